@@ -1,0 +1,133 @@
+/* ncb_blob.h -- "compiled material" interchange format (plain C, no dependencies).
+ *
+ * A compiled material is the flat, POD image of what NCrystal's scatter factory
+ * hands to the hot path: the ordered list of (scale, leaf process) pairs of a
+ * ProcComposition (ref: ncrystal_core/include/NCrystal/interfaces/NCProcImpl.hh:310-373,
+ * flattened by ProcComposition::consumeAndCombine, src/interfaces/NCProcImpl.cc:410-454)
+ * with, per leaf, exactly the immutable tables its crossSection/sampleScatter
+ * methods read.  Producing it (NCMAT parsing, HKL lists, VDOS->S(alpha,beta)) is
+ * the reference's setup pipeline and is out of scope here; the reference-side
+ * producer is oracle/matcompile.cc (the binding a maintainer would add, see
+ * INTEGRATION.md).  Everything derived that the hot path needs beyond these
+ * inputs (S(alpha,beta) sampler tables) is built natively at load time
+ * (csrc/sab_build.cpp).
+ *
+ * Layout: one contiguous little-endian buffer.  ncb_header_t at offset 0, then
+ * one payload per component at comp[i].off (byte offset from the start of the
+ * buffer, 16-byte aligned).  Arrays follow their payload struct directly in the
+ * order documented below; all arrays are fp64.
+ */
+#ifndef NCB_BLOB_H
+#define NCB_BLOB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCB_MAGIC    0x0030303242434eULL /* "NCB200\0" */
+#define NCB_VERSION  2u
+#define NCB_MAXCOMP  8
+
+enum ncb_kind {
+  NCB_KIND_POWDERBRAGG = 1, /* ref: src/powderbragg/NCPowderBragg.cc */
+  NCB_KIND_ELINC       = 2, /* ref: src/elincscatter/NCElIncScatter.cc + src/phys_utils/NCElIncXS.cc */
+  NCB_KIND_SAB         = 3, /* ref: src/sabscatter/NCSABScatter.cc + src/sab */
+  NCB_KIND_FREEGAS     = 4, /* ref: src/freegas/NCFreeGas.cc + src/phys_utils/NCFreeGasUtils.cc */
+  NCB_KIND_SCBRAGG     = 5  /* ref: src/scbragg/NCSCBragg.cc + src/phys_utils/NCGaussMos.cc */
+};
+
+typedef struct {
+  uint32_t kind;       /* enum ncb_kind */
+  uint32_t reserved;
+  double   scale;      /* ProcComposition::Component::scale */
+  double   dom_lo;     /* leaf Process::domain() (EnergyDomain, NCTypes.hh:427-439) */
+  double   dom_hi;
+  uint64_t off;        /* byte offset of the payload */
+  uint64_t nbytes;     /* payload size incl. arrays */
+} ncb_comp_t;
+
+typedef struct {
+  uint64_t   magic;
+  uint32_t   version;
+  uint32_t   ncomp;
+  uint32_t   oriented; /* 1 if MaterialType::Anisotropic */
+  uint32_t   reserved;
+  uint64_t   nbytes;   /* total size of the buffer */
+  double     dom_lo;   /* ProcComposition::domain() */
+  double     dom_hi;
+  char       cfg[208]; /* the cfg-string the material was compiled from (NUL terminated) */
+  ncb_comp_t comp[NCB_MAXCOMP];
+} ncb_header_t;
+
+/* PowderBragg: followed by e2d[nplanes] (= m_2dE, ascending energies wl2ekin(2d)),
+ * fdm[nplanes] (= m_fdm_commul).  NCPowderBragg.cc:68-108. */
+typedef struct {
+  uint64_t nplanes;
+  double   threshold;  /* m_threshold = e2d[0] */
+} ncb_powderbragg_t;
+
+/* ElIncScatter: followed by msd[nelem], bixs[nelem] (= ElIncXS::m_elm_data
+ * .first / .second, second already multiplied by the element scale;
+ * NCElIncXS.cc:59-79). */
+typedef struct {
+  uint64_t nelem;
+  uint64_t reserved;
+} ncb_elinc_t;
+
+/* FreeGas leaf (NCFreeGas.cc:28-41) = FreeGasXSProvider{m_sigmaFree,m_ca} +
+ * temperature + target mass. */
+typedef struct {
+  double sigma_free;   /* FreeGasXSProvider::m_sigmaFree */
+  double ca;           /* FreeGasXSProvider::m_ca = A/kT */
+  double temperature;  /* kelvin */
+  double mass_amu;     /* target mass */
+} ncb_freegas_t;
+
+/* SABScatter.  Followed by egrid[negrid], xs[negrid] (SABXSProvider::m_egrid/m_xs,
+ * identical to SABSampler::m_egrid), alpha[nalpha], beta[nbeta],
+ * sab[nbeta*nalpha] (SABData, row = beta index; NCSABData.hh). */
+typedef struct {
+  double   scale;          /* SABScatter::m_scale (NCSABScatter.cc:87) */
+  double   temperature;    /* SABData::temperature() [K] */
+  double   mass_amu;       /* SABData::elementMassAMU() */
+  double   bound_xs;       /* SABData::boundXS() */
+  double   suggested_emax; /* SABData::suggestedEmax() */
+  double   ext_sigma_free; /* extender: SABFGExtender::m_xsprovider.m_sigmaFree */
+  double   ext_ca;         /* extender: m_ca */
+  double   ext_temperature;/* extender: m_t */
+  double   ext_mass_amu;   /* extender: m_m */
+  double   k_extension;    /* SABXSProvider::m_kExtension (NCSABXSProvider.cc:50) */
+  double   xs_at_emax;     /* SABSampler::m_xsAtEmax */
+  double   k1, k2;         /* SABSampler::m_k1, m_k2 (NCSABSampler.cc:51-52) */
+  double   egrid_margin;   /* SABSampler::m_egridMargin (1.05) */
+  uint64_t negrid, nalpha, nbeta;
+  uint64_t reserved;
+} ncb_sab_t;
+
+/* SCBragg (mosaic single crystal).  Followed by, in order:
+ *   fam_xsfact[nfam], fam_inv2d[nfam], fam_first[nfam+1] (as doubles; index of the
+ *   family's first demi-normal), normals[3*nnormals] (x,y,z interleaved, lab frame),
+ *   then the two GaussOnSphere spline lookup tables (see ncb_splinelut_t). */
+typedef struct {
+  double   threshold_ekin;     /* SCBragg domain low edge */
+  double   gm_mos_fwhm;        /* GaussMos parameters (NCGaussMos.hh) */
+  double   gm_mos_sigma;
+  double   gm_mos_truncN;
+  double   gm_prec;
+  double   gos_sigma;          /* GaussOnSphere state (NCGaussOnSphere.hh) */
+  double   gos_trunc_angle;
+  double   gos_cta, gos_sta;   /* cos/sin of truncation angle */
+  double   gos_circleint_k1, gos_circleint_k2;
+  double   gos_norm, gos_expfact, gos_prec;
+  double   gos_spare[6];
+  uint64_t nfam, nnormals;
+  uint64_t lut_sofcosd_n, lut_circleint_n;
+} ncb_scbragg_t;
+
+static inline uint64_t ncb_align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
+
+#ifdef __cplusplus
+}
+#endif
+#endif

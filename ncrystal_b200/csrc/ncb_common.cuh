@@ -1,0 +1,96 @@
+// ncb_common.cuh -- shared definitions for the sm_100a hot path.
+//
+// All per-neutron physics below is written as NCB_HD functions so that the very
+// same source is (a) inlined into the CUDA kernels of ncb_kernels.cu (the
+// product) and (b) compilable by a plain host compiler for the CPU-side unit
+// tests in tests/hostsim (test-only; the product never dispatches to it).
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <cfloat>
+
+#if defined(__CUDACC__)
+#  define NCB_HD __host__ __device__ __forceinline__
+#  define NCB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#  define NCB_HD inline
+#  define NCB_HD_NOINLINE
+#endif
+
+namespace ncb {
+
+  // Constants, ref: ncrystal_core/include/NCrystal/core/NCDefs.hh:79-120,834-868
+  constexpr double kBoltzmann       = 8.6173303e-5;      // eV/K
+  constexpr double kNeutronMassAmu  = 1.00866491588;
+  constexpr double kInvNeutronMassAmu = 1.0/kNeutronMassAmu;
+  constexpr double kPi              = 3.1415926535897932384626433832795028841971694;
+  constexpr double kPiSq            = 9.86960440108935861883449099987615113531369941;
+  constexpr double kInvSqrtPi       = 0.564189583547756286948079451560772585844050629;
+  constexpr double kEkin2WlSqInv    = 12.22430978582345950656; // 1/0.081804209605330899
+  constexpr double kWl2Ekin         = 0.081804209605330899;
+  constexpr double kInf             = HUGE_VAL;
+  constexpr double kDblMin          = 2.2250738585072014e-308; // numeric_limits<double>::min()
+
+  NCB_HD double dmin( double a, double b ) { return a < b ? a : b; }       // ncmin
+  NCB_HD double dmax( double a, double b ) { return a > b ? a : b; }       // ncmax
+  NCB_HD double dclamp( double v, double lo, double hi ) { return dmin( dmax( v, lo ), hi ); } // ncclamp (NCMath.hh)
+  NCB_HD bool isFinite( double x ) { return fabs(x) <= DBL_MAX; } // std::isfinite (false for NaN/inf)
+  NCB_HD bool inInterval( double a, double b, double x ) { return ( a <= x ) & ( x <= b ); }   // valueInInterval
+
+  // EnergyDomain::contains, ref: NCTypes.hh:435,833-842
+  NCB_HD bool domainContains( double lo, double hi, double e )
+  {
+    const bool isnull = ( lo > DBL_MAX ) || ( lo == hi );
+    return !isnull && e >= lo && e <= hi;
+  }
+
+  // Neumaier summation, ref: NCMath.hh:526-537 (StableSum)
+  struct StableSum {
+    double s = 0.0, c = 0.0;
+    NCB_HD void add( double x )
+    {
+      double t = s + x;
+      c += ( fabs(s) >= fabs(x) ) ? ( (s-t) + x ) : ( (x-t) + s );
+      s = t;
+    }
+    NCB_HD double sum() const { return s + c; }
+  };
+
+  // std::upper_bound / std::lower_bound over a sorted fp64 array, returning indices.
+  template <class Ptr>
+  NCB_HD int upperBound( Ptr a, int lo, int hi, double v )
+  {
+    // first index i in [lo,hi) with a[i] > v  (hi if none)
+    while ( lo < hi ) {
+      int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( !( v < a[mid] ) ) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+  template <class Ptr>
+  NCB_HD int lowerBound( Ptr a, int lo, int hi, double v )
+  {
+    // first index i in [lo,hi) with !(a[i] < v)  (hi if none)
+    while ( lo < hi ) {
+      int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( a[mid] < v ) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+
+  // pickRandIdxByWeight, ref: NCRandUtils.cc:198-220 (n>=2; caller handles n==1 w/o draw)
+  template <class Ptr>
+  NCB_HD int pickIdxByWeight( double rand01, Ptr cumul, int n )
+  {
+    if ( n < 5 ) {
+      const double choice = cumul[n-1] * rand01;
+      for ( int i = 0; i < n; ++i )
+        if ( cumul[i] > choice )
+          return i;
+      return n-1;
+    }
+    int i = lowerBound( cumul, 0, n, cumul[n-1] * rand01 );
+    return i < n-1 ? i : n-1;
+  }
+
+}

@@ -1,0 +1,203 @@
+// ncb_loader.h -- host side: compiled-material blob (ncb_blob.h) -> arena image +
+// Material descriptor (ncb_tables.h).  Header-only, no CUDA: the C-ABI library
+// uploads the arena to HBM and runs the table-build kernels there; the CPU-side
+// unit tests (tests/hostsim) run the same image in host memory.
+//
+// The arena is ONE contiguous allocation holding every array of the material
+// (inputs copied from the blob, derived tables zero-initialised and filled by
+// the SAB build stages), 256-byte aligned sections.
+#pragma once
+#include "ncb_blob.h"
+#include "ncb_tables.h"
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ncb {
+
+  struct SabBuildPlan {       // what the build stages need for one SAB leaf
+    int sab_index;            // index into Material::sab
+    size_t off_logsab, off_cumul, off_ep, off_bx, off_bpdf, off_bcdf, off_ainfo, off_rows, off_xscheck;
+  };
+
+  struct LoadedMaterial {
+    Material mat;                       // pointers are OFFSETS into the arena until relocate()
+    std::vector<unsigned char> arena;   // host image
+    std::vector<SabBuildPlan> sabplans;
+    std::string cfg;
+    bool relocated = false;
+
+    size_t reserve( size_t nbytes )
+    {
+      size_t off = ( arena.size() + 255u ) & ~(size_t)255u;
+      arena.resize( off + nbytes, 0 );
+      return off;
+    }
+    size_t put( const void* src, size_t nbytes )
+    {
+      size_t off = reserve( nbytes );
+      std::memcpy( arena.data() + off, src, nbytes );
+      return off;
+    }
+  };
+
+  template <class T> inline const T* offAsPtr( size_t off ) { return reinterpret_cast<const T*>( off ); }
+  template <class T> inline void relocPtr( const T*& p, const unsigned char* base )
+  {
+    p = reinterpret_cast<const T*>( base + reinterpret_cast<size_t>( p ) );
+  }
+
+  // Convert offsets in lm.mat to pointers based at `base` (device or host address of the arena copy).
+  inline Material relocated( const LoadedMaterial& lm, const void* base_ )
+  {
+    const unsigned char* base = static_cast<const unsigned char*>( base_ );
+    Material m = lm.mat;
+    int npb = 0, nsab = 0;
+    for ( int i = 0; i < m.ncomp; ++i ) {
+      if ( m.comp[i].kind == KIND_POWDERBRAGG ) ++npb;
+      if ( m.comp[i].kind == KIND_SAB ) ++nsab;
+    }
+    for ( int i = 0; i < npb; ++i ) {
+      relocPtr( m.pb[i].e2d, base );
+      relocPtr( m.pb[i].fdm, base );
+    }
+    for ( int i = 0; i < nsab; ++i ) {
+      SabT& s = m.sab[i];
+      relocPtr( s.egrid, base ); relocPtr( s.xs, base ); relocPtr( s.alpha, base ); relocPtr( s.beta, base );
+      relocPtr( s.sab, base ); relocPtr( s.logsab, base ); relocPtr( s.cumul, base );
+      relocPtr( s.ep, base ); relocPtr( s.bx, base ); relocPtr( s.bpdf, base ); relocPtr( s.bcdf, base );
+      relocPtr( s.ainfo, base );
+    }
+    if ( m.sc )
+      relocPtr( m.sc, base );
+    return m;
+  }
+
+  void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
+
+  inline void loadBlob( const void* blob_, size_t nbytes, LoadedMaterial& lm )
+  {
+    const unsigned char* blob = static_cast<const unsigned char*>( blob_ );
+    if ( nbytes < sizeof(ncb_header_t) )
+      throw std::runtime_error( "compiled material: buffer too small" );
+    ncb_header_t hdr;
+    std::memcpy( &hdr, blob, sizeof(hdr) );
+    if ( hdr.magic != NCB_MAGIC )
+      throw std::runtime_error( "compiled material: bad magic" );
+    if ( hdr.version != NCB_VERSION )
+      throw std::runtime_error( "compiled material: unsupported version" );
+    if ( hdr.nbytes > nbytes || hdr.ncomp == 0 || hdr.ncomp > (uint32_t)kMaxComp )
+      throw std::runtime_error( "compiled material: inconsistent header" );
+    hdr.cfg[sizeof(hdr.cfg)-1] = 0;
+    lm.cfg = hdr.cfg;
+    Material& m = lm.mat;
+    std::memset( &m, 0, sizeof(m) );
+    m.ncomp = (int)hdr.ncomp;
+    m.oriented = (int)hdr.oriented;
+    m.dom_lo = hdr.dom_lo;
+    m.dom_hi = hdr.dom_hi;
+    lm.reserve( 256 ); // offset 0 is never a valid array => null stays null
+    int npb = 0, nel = 0, nfg = 0, nsab = 0;
+    for ( int i = 0; i < m.ncomp; ++i ) {
+      const ncb_comp_t& c = hdr.comp[i];
+      if ( c.off + c.nbytes > hdr.nbytes )
+        throw std::runtime_error( "compiled material: component out of bounds" );
+      Comp& k = m.comp[i];
+      k.kind = (int)c.kind;
+      k.scale = c.scale;
+      k.dom_lo = c.dom_lo;
+      k.dom_hi = c.dom_hi;
+      const unsigned char* p = blob + c.off;
+      switch ( c.kind ) {
+      case NCB_KIND_POWDERBRAGG: {
+        if ( npb >= (int)( sizeof(m.pb)/sizeof(m.pb[0]) ) ) throw std::runtime_error( "too many PowderBragg components" );
+        ncb_powderbragg_t h; std::memcpy( &h, p, sizeof(h) );
+        const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
+        PowderBraggT& T = m.pb[npb];
+        T.n = (int)h.nplanes;
+        T.threshold = h.threshold;
+        T.e2d = offAsPtr<double>( lm.put( arr, h.nplanes*8 ) );
+        T.fdm = offAsPtr<double>( lm.put( arr + h.nplanes, h.nplanes*8 ) );
+        k.idx = npb++;
+        break;
+      }
+      case NCB_KIND_ELINC: {
+        if ( nel >= 1 ) throw std::runtime_error( "too many ElIncScatter components" );
+        ncb_elinc_t h; std::memcpy( &h, p, sizeof(h) );
+        if ( h.nelem > (uint64_t)kMaxElIncElems ) throw std::runtime_error( "too many ElInc elements" );
+        const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
+        ElIncT& T = m.elinc[nel];
+        T.n = (int)h.nelem;
+        for ( int j = 0; j < T.n; ++j ) { T.msd[j] = arr[j]; T.bixs[j] = arr[h.nelem+j]; }
+        k.idx = nel++;
+        break;
+      }
+      case NCB_KIND_FREEGAS: {
+        if ( nfg >= (int)( sizeof(m.fg)/sizeof(m.fg[0]) ) ) throw std::runtime_error( "too many FreeGas components" );
+        ncb_freegas_t h; std::memcpy( &h, p, sizeof(h) );
+        FreeGasT& T = m.fg[nfg];
+        T.sigma_free = h.sigma_free;
+        T.ca = h.ca;
+        T.kT = 8.6173303e-5 * h.temperature; // Temperature::kT(), NCTypes.hh:754
+        T.mass_amu = h.mass_amu;
+        k.idx = nfg++;
+        break;
+      }
+      case NCB_KIND_SAB: {
+        if ( nsab >= (int)( sizeof(m.sab)/sizeof(m.sab[0]) ) ) throw std::runtime_error( "too many SABScatter components" );
+        ncb_sab_t h; std::memcpy( &h, p, sizeof(h) );
+        const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
+        SabT& T = m.sab[nsab];
+        T.scale = h.scale;
+        T.kT = 8.6173303e-5 * h.temperature;
+        T.k_extension = h.k_extension;
+        T.k1 = h.k1; T.k2 = h.k2;
+        T.egrid_margin = h.egrid_margin;
+        T.bound_xs = h.bound_xs;
+        T.ext.sigma_free = h.ext_sigma_free;
+        T.ext.ca = h.ext_ca;
+        T.ext.kT = 8.6173303e-5 * h.ext_temperature;
+        T.ext.mass_amu = h.ext_mass_amu;
+        T.negrid = (int)h.negrid; T.nalpha = (int)h.nalpha; T.nbeta = (int)h.nbeta;
+        const size_t ne = h.negrid, na = h.nalpha, nb = h.nbeta;
+        if ( ne < 2 || na < 2 || nb < 2 ) throw std::runtime_error( "compiled material: degenerate SAB grids" );
+        T.egrid = offAsPtr<double>( lm.put( arr, ne*8 ) );
+        T.xs    = offAsPtr<double>( lm.put( arr + ne, ne*8 ) );
+        T.alpha = offAsPtr<double>( lm.put( arr + 2*ne, na*8 ) );
+        T.beta  = offAsPtr<double>( lm.put( arr + 2*ne + na, nb*8 ) );
+        T.sab   = offAsPtr<double>( lm.put( arr + 2*ne + na + nb, na*nb*8 ) );
+        SabBuildPlan pl;
+        pl.sab_index = nsab;
+        pl.off_logsab = lm.reserve( na*nb*8 );
+        pl.off_cumul  = lm.reserve( na*nb*8 );
+        pl.off_ep     = lm.reserve( ne*sizeof(SabEPoint) );
+        pl.off_bx     = lm.reserve( ne*(nb+1)*8 );
+        pl.off_bpdf   = lm.reserve( ne*(nb+1)*8 );
+        pl.off_bcdf   = lm.reserve( ne*(nb+1)*8 );
+        pl.off_ainfo  = lm.reserve( ne*nb*sizeof(SabAlphaInfo) );
+        pl.off_rows   = lm.reserve( ne*nb*16 );
+        pl.off_xscheck= lm.reserve( ne*8 + ne*4 );
+        T.logsab = offAsPtr<double>( pl.off_logsab );
+        T.cumul  = offAsPtr<double>( pl.off_cumul );
+        T.ep     = offAsPtr<SabEPoint>( pl.off_ep );
+        T.bx     = offAsPtr<double>( pl.off_bx );
+        T.bpdf   = offAsPtr<double>( pl.off_bpdf );
+        T.bcdf   = offAsPtr<double>( pl.off_bcdf );
+        T.ainfo  = offAsPtr<SabAlphaInfo>( pl.off_ainfo );
+        lm.sabplans.push_back( pl );
+        k.idx = nsab++;
+        break;
+      }
+      case NCB_KIND_SCBRAGG:
+        loadScBragg( lm, blob, c );
+        k.idx = 0;
+        break;
+      default:
+        throw std::runtime_error( "compiled material: unknown component kind" );
+      }
+    }
+    lm.reserve( 0 );
+  }
+
+}

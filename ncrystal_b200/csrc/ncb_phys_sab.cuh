@@ -1,0 +1,290 @@
+// ncb_phys_sab.cuh -- S(alpha,beta) rejection sampling (Cai et al., JCP 2019, Alg. 1).
+// Restates, per neutron,
+//   SABSampler::sampleAlphaBeta / sampleHighE / sampleDeltaEMu   ref: src/sab/NCSABSampler.cc:59-236
+//   SABSamplerAtE_Alg1::sampleAlphaBeta / sampleAlpha            ref: src/sab/NCSABSamplerModels.cc:48-233
+//   PointwiseDist::percentileWithIndex                           ref: src/utils/NCPointwiseDist.cc:76-105
+//   SABUtils::sampleLogLinDist_fast                              ref: include/NCrystal/internal/sab/NCSABUtils.hh:282-303
+//   SABScatter::sampleScatterIsotropic                           ref: src/sabscatter/NCSABScatter.cc:93-100
+#pragma once
+#include "ncb_phys_freegas.cuh"
+
+namespace ncb {
+
+  enum SampleErr : int {
+    ERR_NONE = 0,
+    ERR_KIN_DENOM = 1,       // convertAlphaBetaToDeltaEMu: beta == -E/kT
+    ERR_SAB_LOOP_OUTER = 2,  // SABSampler::sampleAlphaBeta: 100 tries (NCSABSampler.cc:226)
+    ERR_SAB_LOOP_INNER = 4,  // SABSamplerAtE_Alg1: 100 tries (NCSABSamplerModels.cc:150)
+    ERR_SAB_DISCARD = 8,     // sampleHighE: P_discardinside > 0.95 (NCSABSampler.cc:112)
+    ERR_SAB_ISOFALLBACK = 16 // (warning only) isotropic fallback after 30 tries (NCSABSamplerModels.cc:99)
+  };
+
+  // sampleLogLinDist_fast, ref: NCSABUtils.hh:282-303
+  NCB_HD double sampleLogLinDistFast( double a, double fa, double b, double fb, double rand, double logfa, double logfb )
+  {
+    double df = fb - fa;
+    if ( fa*fb*df != 0.0 ) {
+      const double a_sub_b = a - b;
+      const double logfa_fb = logfb - logfa;
+      if ( a_sub_b * logfa_fb != 0.0 )
+        return a_sub_b * log( fa*exp( a*logfa_fb/a_sub_b ) / ( fa + rand*df ) ) / logfa_fb;
+      df = 0.0;
+    }
+    if ( !df )
+      return a + rand*(b-a);
+    const double x = (b-a)*sqrt(rand);
+    return ( fa ? b-x : a+x );
+  }
+
+  // PointwiseDist::percentileWithIndex, ref: NCPointwiseDist.cc:76-105
+  NCB_HD double pwdPercentileWithIndex( const double* x, const double* y, const double* cdf, int n, double p, int& idx )
+  {
+    if ( p == 1. ) {
+      idx = n-2;
+      return x[n-1];
+    }
+    int i = lowerBound( cdf, 0, n, p );
+    i = i < n-1 ? i : n-1;
+    i = i > 1 ? i : 1;
+    const double dx = x[i] - x[i-1];
+    const double c = ( p - cdf[i-1] );
+    const double a = y[i-1];
+    const double d = y[i] - a;
+    double zdx;
+    if ( !a ) {
+      zdx = d > 0.0 ? sqrt( ( 2.0 * c * dx ) / d ) : 0.5*dx;
+    } else {
+      const double e = d * c / ( dx * a * a );
+      if ( fabs(e) > 1e-7 )
+        zdx = ( sqrt( 1.0 + 2.0 * e ) - 1.0 ) * dx * a / d;
+      else
+        zdx = ( 1 + 0.5 * e * ( e - 1.0 ) ) * c / a;
+    }
+    idx = i-1;
+    return dclamp( x[i-1] + zdx, x[i-1], x[i] );
+  }
+
+  // SABSamplerAtE_Alg1::sampleAlpha, ref: NCSABSamplerModels.cc:157-233
+  NCB_HD double sabSampleAlpha( const SabT& T, const SabEPoint& ep, int ibeta, double rand_percentile )
+  {
+    const SabAlphaInfo& info = T.ainfo[ ep.off_i + ( ibeta - ep.ibeta_off ) ];
+    const int nalpha = T.nalpha;
+    const double* cumul  = T.cumul  + (size_t)ibeta*nalpha;
+    const double* sab    = T.sab    + (size_t)ibeta*nalpha;
+    const double* logsab = T.logsab + (size_t)ibeta*nalpha;
+    const double* agrid  = T.alpha;
+
+    if ( rand_percentile <= info.prob_front ) {
+      if ( info.prob_front == 2.0 ) {
+        const double da = info.b_alpha - info.f_alpha;
+        return info.f_alpha + rand_percentile*da;
+      } else if ( info.prob_front == 1.0 ) {
+        return sampleLogLinDistFast( info.f_alpha, info.f_sval, info.b_alpha, info.b_sval,
+                                     rand_percentile, info.f_logsval, info.b_logsval );
+      } else {
+        const double percentile2 = dclamp( rand_percentile / info.prob_front, kDblMin, 1.0 );
+        return sampleLogLinDistFast( info.f_alpha, info.f_sval,
+                                     agrid[info.f_idx], sab[info.f_idx],
+                                     percentile2,
+                                     info.f_logsval, logsab[info.f_idx] );
+      }
+    } else if ( rand_percentile <= info.prob_notback ) {
+      const double percentile2 = dclamp( ( rand_percentile - info.prob_front ) / ( info.prob_notback - info.prob_front ), 0.0, 1.0 );
+      const int ilow = info.f_idx, iupp = info.b_idx;
+      const double clow = cumul[ilow], cupp = cumul[iupp];
+      const double selectedArea = clow + percentile2 * ( cupp - clow );
+      const int isel_upp = upperBound( cumul, ilow, iupp+1, selectedArea );
+      if ( isel_upp > iupp )
+        return agrid[iupp];
+      if ( isel_upp <= ilow )
+        return agrid[ilow];
+      const int a0 = isel_upp - 1;
+      const int a1 = isel_upp;
+      const double c0 = cumul[a0], c1 = cumul[a1];
+      const double binArea = c1 - c0;
+      const double rand_rescaled = dclamp( ( selectedArea - c0 ) / binArea, kDblMin, 1.0 );
+      return sampleLogLinDistFast( agrid[a0], sab[a0], agrid[a1], sab[a1], rand_rescaled, logsab[a0], logsab[a1] );
+    } else {
+      const double percentile2 = dclamp( ( rand_percentile - info.prob_notback ) / ( 1.0 - info.prob_notback ), kDblMin, 1.0 );
+      return sampleLogLinDistFast( agrid[info.b_idx], sab[info.b_idx],
+                                   info.b_alpha, info.b_sval,
+                                   percentile2,
+                                   logsab[info.b_idx], info.b_logsval );
+    }
+  }
+
+  // SABSamplerAtE_Alg1::sampleAlphaBeta, ref: NCSABSamplerModels.cc:48-155
+  // (npts==0 is SABSamplerAtE_NoScatter: returns (0,0), NCSABSamplerModels.hh:86)
+  NCB_HD void sabSampleAtE( const SabT& T, const SabEPoint& ep, double ekin_div_kT, Rng& rng,
+                            double& alpha_out, double& beta_out, int& err )
+  {
+    if ( ep.npts == 0 ) {
+      alpha_out = 0.0; beta_out = 0.0;
+      return;
+    }
+    const double* bx = T.bx + ep.off_b;
+    const double* bpdf = T.bpdf + ep.off_b;
+    const double* bcdf = T.bcdf + ep.off_b;
+    const double* betaGrid = T.beta;
+    const double firstBin = ep.first_bin_endpoint;
+
+    for ( int iloop = 0; iloop < 100; ++iloop ) {
+      int ibetaSampled;
+      double beta = pwdPercentileWithIndex( bx, bpdf, bcdf, ep.npts, rng.generate(), ibetaSampled );
+
+      if ( ibetaSampled == 0 && firstBin <= 0.0 ) {
+        const double b0 = firstBin;
+        const double b1 = bx[1];
+        if ( b1 < -ekin_div_kT )
+          continue;
+        const double delta_beta = b1 - b0;
+        double alphaval = 0.0;
+        constexpr int nsampletries = 30;
+        for ( int iii = 0; iii < nsampletries; ++iii ) {
+          beta = dmax( firstBin, b0 + delta_beta*rng.generate() );
+          if ( beta < -ekin_div_kT )
+            break;
+          alphaval = sabSampleAlpha( T, ep, ep.ibeta_off, rng.generate() );
+          AlphaLimits alims = getAlphaLimits( -firstBin, beta );
+          if ( inInterval( alims.first, alims.second, alphaval ) )
+            break;
+          if ( iii == nsampletries-1 ) {
+            err |= ERR_SAB_ISOFALLBACK;
+            alphaval = 0.5*( alims.first + alims.second );
+            break;
+          }
+        }
+        if ( beta < -ekin_div_kT )
+          continue;
+        AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+        if ( inInterval( alimits.first, alimits.second, alphaval ) ) {
+          alpha_out = alphaval; beta_out = beta;
+          return;
+        }
+        continue;
+      }
+
+      if ( beta <= dmax( -ekin_div_kT, betaGrid[0] ) )
+        continue;
+
+      const double rand_percentile = rng.generate();
+      const int ibeta = ep.ibeta_off + ibetaSampled;
+      const double bl = betaGrid[ibeta-1];
+      const double alphal = sabSampleAlpha( T, ep, ibeta-1, rand_percentile );
+      const double bh = betaGrid[ibeta];
+      const double alphah = sabSampleAlpha( T, ep, ibeta, rand_percentile );
+      const double alpha = alphal + (alphah-alphal) * (beta-bl)/(bh-bl);
+      AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+      if ( inInterval( alimits.first, alimits.second, alpha ) ) {
+        alpha_out = alpha; beta_out = beta;
+        return;
+      }
+    }
+    err |= ERR_SAB_LOOP_INNER;
+    alpha_out = -1.0; beta_out = 0.0;
+  }
+
+  // SABSampler::sampleHighE, ref: NCSABSampler.cc:59-156.  Returns true if (alpha,beta)
+  // was sampled with the free-gas extender; false => sample the table at E=Emax.
+  NCB_HD bool sabSampleHighE( const SabT& T, double ekin, Rng& rng, double& alpha, double& beta, int& err )
+  {
+    const double emax = T.egrid[T.negrid-1];
+    const double extenderXSMultE = ekin * fgXS( T.ext, ekin );
+    const double P_inside = T.k1 / ( (T.k1-T.k2) + extenderXSMultE );
+    const double P_extender_inside = T.k2 / extenderXSMultE;
+    const double P_discardinside = ( P_extender_inside >= P_inside ? (1.0-P_inside/P_extender_inside) : 0.0 );
+    if ( P_discardinside > 0.95 ) {
+      err |= ERR_SAB_DISCARD;
+      alpha = -1.0; beta = 0.0;
+      return true;
+    }
+    if ( P_extender_inside < P_inside ) {
+      const double aa = 1.0 - P_extender_inside;
+      const double P_extrainside = aa > 1e-10 ? (P_inside-P_extender_inside)/aa : 1.0;
+      if ( rng.generate() < P_extrainside )
+        return false;
+    }
+    const double emax_div_kt = emax / T.kT;
+    FreeGasSampler fgs( ekin, T.ext.kT, T.ext.mass_amu );
+    while ( true ) {
+      fgs.sampleAlphaBeta( rng, alpha, beta );
+      if ( beta <= -emax_div_kt )
+        return true;
+      AlphaLimits alims = getAlphaLimits( emax_div_kt, beta );
+      if ( !inInterval( alims.first, alims.second, alpha ) )
+        return true;
+      if ( P_discardinside && rng.generate() < P_discardinside )
+        continue;
+      return false;
+    }
+  }
+
+  // SABSampler::sampleAlphaBeta, ref: NCSABSampler.cc:158-227
+  NCB_HD void sabSampleAlphaBeta( const SabT& T, double ekin, Rng& rng, double& alpha, double& beta, int& err )
+  {
+    const int n = T.negrid;
+    const double* egrid = T.egrid;
+    int iu = upperBound( egrid, 0, n, ekin );
+    int isampler;
+    bool ultra_small_ekin_mode = false;
+    const double ultra_small_ekin = egrid[0];
+    if ( iu == n ) {
+      if ( sabSampleHighE( T, ekin, rng, alpha, beta, err ) )
+        return; // (the reference returns whenever alpha>=0; errors flagged separately)
+      ekin = egrid[n-1];
+      isampler = n-1;
+    } else if ( iu == 0 ) {
+      isampler = 0;
+      ultra_small_ekin_mode = ( ekin < ultra_small_ekin );
+    } else {
+      if ( T.egrid_margin > 1.0 ) {
+        while ( iu+1 != n && ekin*T.egrid_margin > egrid[iu] )
+          ++iu;
+      }
+      isampler = iu;
+    }
+    const SabEPoint ep = T.ep[isampler];
+    const double ekin_div_kT = ekin / T.kT;
+    const double sampling_ekin_div_kT = ( ultra_small_ekin_mode ? ultra_small_ekin/T.kT : ekin_div_kT );
+    for ( int loop = 0; loop < 100; ++loop ) {
+      sabSampleAtE( T, ep, sampling_ekin_div_kT, rng, alpha, beta, err );
+      if ( err & ERR_SAB_LOOP_INNER )
+        return;
+      if ( beta < -ekin_div_kT )
+        continue;
+      AlphaLimits alims = getAlphaLimits( ekin_div_kT, beta );
+      if ( inInterval( alims.first, alims.second, alpha ) )
+        return;
+      if ( ultra_small_ekin_mode ) {
+        alpha = alims.first + rng.generate()*( alims.second - alims.first );
+        return;
+      }
+    }
+    err |= ERR_SAB_LOOP_OUTER;
+  }
+
+  // SABSampler::sampleDeltaEMu (NCSABSampler.cc:229-236) + SABScatter::sampleScatterIsotropic
+  // (NCSABScatter.cc:93-100)
+  NCB_HD void sabSampleScatter( const SabT& T, double ekin, Rng& rng, double& ekin_out, double& mu, int& err )
+  {
+    double alpha = 0.0, beta = 0.0;
+    sabSampleAlphaBeta( T, ekin, rng, alpha, beta, err );
+    if ( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD ) ) {
+      ekin_out = -1.0; mu = -999.0;
+      return;
+    }
+    double deltaE;
+    if ( muIsotropicAtBeta( beta, ekin/T.kT ) ) {
+      deltaE = beta*T.kT;
+      mu = rng.generate()*2.0 - 1.0;
+    } else {
+      alphaBetaToDeltaEMu( alpha, beta, ekin, T.kT, deltaE, mu, err );
+      if ( err & ERR_KIN_DENOM ) {
+        ekin_out = -1.0; mu = -999.0;
+        return;
+      }
+    }
+    ekin_out = dmax( 0.0, ekin + deltaE );
+  }
+
+}

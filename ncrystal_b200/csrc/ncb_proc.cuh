@@ -1,0 +1,104 @@
+// ncb_proc.cuh -- the flattened ProcComposition: fused weighted sum over the
+// components (= phases x leaf processes) and component choice for sampling.
+// Restates ProcComposition::Impl::updateCacheIsotropic (ref: src/interfaces/NCProcImpl.cc:166-204),
+// crossSectionIsotropic (:353-362) and sampleScatterIsotropic (:379-389).
+#pragma once
+#include "ncb_phys_sab.cuh"
+
+namespace ncb {
+
+  // Unscaled isotropic xs of component i.  aux receives the PowderBragg plane index.
+  NCB_HD double compXSIso( const Material& M, int i, double ekin, int& aux )
+  {
+    const Comp& c = M.comp[i];
+    switch ( c.kind ) {
+    case KIND_POWDERBRAGG: {
+      const PowderBraggT& T = M.pb[c.idx];
+      return pbXS( T.e2d, T.fdm, T.n, T.threshold, ekin, aux );
+    }
+    case KIND_ELINC:
+      return elincXS( M.elinc[c.idx], ekin, nullptr );
+    case KIND_SAB: {
+      const SabT& T = M.sab[c.idx];
+      return sabXS( T, T.egrid, T.xs, ekin );
+    }
+    case KIND_FREEGAS:
+      return fgXS( M.fg[c.idx], ekin );
+    default:
+      return 0.0;
+    }
+  }
+
+  // Total xs; fills cumul[0..ncomp) (componentXSectCommul) and aux[] when non-null.
+  NCB_HD double matXSIso( const Material& M, double ekin, double* cumul, int* aux )
+  {
+    if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) )
+      return 0.0;
+    double tot = 0.0;
+    for ( int i = 0; i < M.ncomp; ++i ) {
+      const Comp& c = M.comp[i];
+      int a = -1;
+      const double xs = domainContains( c.dom_lo, c.dom_hi, ekin ) ? compXSIso( M, i, ekin, a ) : 0.0;
+      tot += c.scale * xs;
+      if ( cumul ) cumul[i] = tot;
+      if ( aux ) aux[i] = a;
+    }
+    return tot;
+  }
+
+  // leaf sampleScatterIsotropic dispatch
+  NCB_HD void compSampleIso( const Material& M, int i, int aux, double ekin, Rng& rng,
+                             double& ekin_out, double& mu, int& err )
+  {
+    const Comp& c = M.comp[i];
+    switch ( c.kind ) {
+    case KIND_POWDERBRAGG: {
+      // PowderBragg::sampleScatterIsotropic, ref: NCPowderBragg.cc:202-216
+      const PowderBraggT& T = M.pb[c.idx];
+      ekin_out = ekin;
+      if ( ekin < T.threshold || !isFinite(ekin) ) {
+        mu = 1.0;
+        return;
+      }
+      if ( aux < 0 )
+        aux = pbLastValidPlane( T.e2d, T.n, ekin );
+      mu = pbSampleMu( T.e2d, T.fdm, aux, ekin, rng );
+      return;
+    }
+    case KIND_ELINC:
+      ekin_out = ekin;
+      mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
+      return;
+    case KIND_SAB:
+      sabSampleScatter( M.sab[c.idx], ekin, rng, ekin_out, mu, err );
+      return;
+    case KIND_FREEGAS:
+      fgSampleScatter( M.fg[c.idx], ekin, rng, ekin_out, mu, err );
+      return;
+    default:
+      ekin_out = ekin; mu = 1.0;
+      return;
+    }
+  }
+
+  // ProcComposition::sampleScatterIsotropic.  Also returns the total xs (the
+  // "evalXSAndSampleScatterIsotropic" fused entry of the reference's batch ABI,
+  // ref: include/NCrystal/internal/extd_utils/NCABIUtils.hh:78-100).
+  NCB_HD double matSampleIso( const Material& M, double ekin, Rng& rng,
+                              double& ekin_out, double& mu, int& err, int& ichoice_out )
+  {
+    ichoice_out = -1;
+    if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) ) {
+      ekin_out = ekin; mu = 1.0;
+      return 0.0;
+    }
+    double cumul[kMaxComp];
+    int aux[kMaxComp];
+    const double tot = matXSIso( M, ekin, cumul, aux );
+    const int ichoice = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
+    ichoice_out = ichoice;
+    compSampleIso( M, ichoice, aux[ichoice], ekin, rng, ekin_out, mu, err );
+    return tot;
+  }
+
+}

@@ -1,0 +1,103 @@
+// ncb_tables.h -- resident (HBM) table layout of one compiled material.
+//
+// A Material is passed BY VALUE to every kernel (__grid_constant__, < 4 KB): it
+// holds the flat (scale, leaf) list of the reference's ProcComposition
+// (ref: NCProcImpl.hh:310-373) with, per leaf, scalars inline and pointers to the
+// leaf's fp64 arrays in global memory.  All arrays are immutable after upload.
+#pragma once
+#include <cstdint>
+
+namespace ncb {
+
+  enum Kind : int { KIND_NONE = 0, KIND_POWDERBRAGG = 1, KIND_ELINC = 2, KIND_SAB = 3, KIND_FREEGAS = 4, KIND_SCBRAGG = 5 };
+
+  constexpr int kMaxComp = 8;
+  constexpr int kMaxElIncElems = 12;
+
+  // ref: NCPowderBragg.hh:91-93
+  struct PowderBraggT {
+    const double* e2d;   // m_2dE[n], ascending
+    const double* fdm;   // m_fdm_commul[n]
+    int n;
+    double threshold;
+  };
+
+  // ref: NCElIncXS.hh (m_elm_data)
+  struct ElIncT {
+    int n;
+    double msd[kMaxElIncElems];
+    double bixs[kMaxElIncElems]; // bound incoherent xs * element scale
+  };
+
+  // ref: NCFreeGasUtils.hh:96-141 (FreeGasXSProvider + what FreeGasSampler's ctor needs)
+  struct FreeGasT {
+    double sigma_free; // m_sigmaFree
+    double ca;         // m_ca = A/kT
+    double kT;         // Temperature::kT()
+    double mass_amu;
+  };
+
+  // Per-energy-point overlay sampler (SABSamplerAtE_Alg1, ref: NCSABSamplerModels.hh:30-80)
+  struct SabEPoint {
+    int32_t  npts;       // points of the beta sampler (0: SABSamplerAtE_NoScatter)
+    int32_t  ibeta_off;  // m_ibetaOffset
+    uint32_t off_b;      // offset of this point's (x,pdf,cdf) rows in the packed beta arrays
+    uint32_t off_i;      // offset of this point's AlphaInfo entries (npts-1 of them)
+    double   first_bin_endpoint; // m_firstBinKinematicEndpointValue
+  };
+
+  // AlphaSampleInfo, ref: NCSABSamplerModels.hh:47-57
+  struct SabAlphaInfo {
+    double f_alpha, f_sval, f_logsval;  // pt_front
+    double b_alpha, b_sval, b_logsval;  // pt_back
+    double prob_front, prob_notback;
+    int32_t f_idx, b_idx;               // pt_front.alpha_idx, pt_back.alpha_idx
+    double pad;                         // 80 bytes
+  };
+
+  struct SabT {
+    // SABScatter / SABXSProvider / SABSampler scalars
+    double scale;          // SABScatter::m_scale
+    double kT;             // SABSampler::m_kT
+    double k_extension;    // SABXSProvider::m_kExtension
+    double k1, k2;         // SABSampler::m_k1/m_k2
+    double egrid_margin;
+    double bound_xs;       // SABData::boundXS (table builder only)
+    FreeGasT ext;          // SABFGExtender
+    int negrid, nalpha, nbeta;
+    const double* egrid;   // [negrid]
+    const double* xs;      // [negrid]
+    const double* alpha;   // [nalpha]
+    const double* beta;    // [nbeta]
+    const double* sab;     // [nbeta*nalpha]
+    const double* logsab;  // [nbeta*nalpha]  (CommonCache::logsab)
+    const double* cumul;   // [nbeta*nalpha]  (CommonCache::alphaintegrals_cumul)
+    const SabEPoint* ep;   // [negrid]
+    const double* bx;      // packed beta-sampler x
+    const double* bpdf;    // packed normalised pdf
+    const double* bcdf;    // packed cdf
+    const SabAlphaInfo* ainfo; // packed
+  };
+
+  struct ScBraggT; // oriented path, see ncb_phys_scbragg.cuh
+
+  struct Comp {
+    int kind;
+    int idx;       // index into the per-kind arrays of Material
+    double scale;
+    double dom_lo, dom_hi;
+  };
+
+  struct Material {
+    int ncomp;
+    int oriented;
+    double dom_lo, dom_hi;
+    Comp comp[kMaxComp];
+    PowderBraggT pb[2];
+    ElIncT elinc[1];
+    FreeGasT fg[2];
+    SabT sab[4];
+    const ScBraggT* sc; // device pointer (oriented materials only)
+  };
+
+}

@@ -1,0 +1,29 @@
+// oracle/matcompile.cc -- command-line front end of the material compiler
+// (refdrv_compile in refdrv.cc):  ncb200_matcompile "<cfg-string>" out.ncb
+// TEST INFRASTRUCTURE / reference-side tooling; links the unmodified reference.
+#include <cstdio>
+#include <cstdint>
+extern "C" {
+  void* refdrv_create( const char* cfg );
+  void refdrv_destroy( void* );
+  void* refdrv_compile( void*, uint64_t* nbytes );
+  void refdrv_free( void* );
+  const char* refdrv_lasterror();
+}
+int main( int argc, char** argv )
+{
+  if ( argc != 3 ) { std::fprintf(stderr,"usage: %s \"<cfg-string>\" out.ncb\n",argv[0]); return 2; }
+  void* h = refdrv_create( argv[1] );
+  if (!h) { std::fprintf(stderr,"error: %s\n",refdrv_lasterror()); return 1; }
+  uint64_t n = 0;
+  void* blob = refdrv_compile( h, &n );
+  if (!blob) { std::fprintf(stderr,"error: %s\n",refdrv_lasterror()); return 1; }
+  FILE* f = std::fopen( argv[2], "wb" );
+  if (!f) { std::perror("fopen"); return 1; }
+  std::fwrite( blob, 1, n, f );
+  std::fclose(f);
+  std::printf("%s: %llu bytes\n",argv[2],(unsigned long long)n);
+  refdrv_free(blob);
+  refdrv_destroy(h);
+  return 0;
+}
