@@ -1,0 +1,183 @@
+/* ncrystal_b200.h -- C ABI of libncrystal_b200.so: NCrystal's batched cross-section
+ * evaluation + scatter sampling on B200 (sm_100a).
+ *
+ * Part 1 re-declares, with IDENTICAL names and signatures, the entry points of the
+ * reference C-API that sit on the hot path (ref: ncrystal_core/include/NCrystal/
+ * cinterface/ncrystal.h, line numbers given per function), so a caller written
+ * against NCrystal's C-API (ctypes/_chooks.py, McStas NCrystal_sample, Geant4
+ * bindings, examples/ncrystal_example_c.c) binds unchanged.
+ *
+ * Part 2 (prefix ncb200_) adds what the reference ABI lacks for an accelerator:
+ * handles from a compiled material, device-pointer variants (inputs/outputs
+ * resident in HBM, caller's CUDA stream), batched ORIENTED calls with
+ * per-neutron (E,dir) (modelled on the reference's experimental batch ABI,
+ * ProcImpl::Process::evalManyXS, NCProcImpl.hh:136-140), a fused xs+sample call
+ * (NCABIUtils.hh:78-100), RNG stream control and the tally histogram kernel.
+ *
+ * Plain C: pointers and sizes only.  All arrays are fp64, caller-owned, no aliasing.
+ */
+#ifndef NCRYSTAL_B200_H
+#define NCRYSTAL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================== Part 1: NCrystal C-API (same symbols) ===================== */
+
+/* ncrystal.h:666-670 */
+typedef struct { void * internal; } ncrystal_process_t;
+typedef struct { void * internal; } ncrystal_scatter_t;
+
+/* ncrystal.h:672-676 -- all take the ADDRESS of a handle */
+int  ncrystal_refcount( void* object );
+void ncrystal_ref( void* object );
+void ncrystal_unref( void* object );
+int  ncrystal_valid( void* object );
+void ncrystal_invalidate( void* object );
+
+/* ncrystal.h:680,682 */
+ncrystal_process_t ncrystal_cast_scat2proc( ncrystal_scatter_t );
+ncrystal_scatter_t ncrystal_cast_proc2scat( ncrystal_process_t );
+
+/* ncrystal.h:699,708 -- cfgstr is resolved to a compiled material (see
+ * ncb200_create_scatter_from_blob and INTEGRATION.md) */
+ncrystal_scatter_t ncrystal_create_scatter( const char * cfgstr );
+ncrystal_scatter_t ncrystal_create_scatter_builtinrng( const char * cfgstr, unsigned long seed );
+
+/* ncrystal.h:718-731 -- clones share the immutable device tables and get an
+ * independent random stream */
+ncrystal_scatter_t ncrystal_clone_scatter( ncrystal_scatter_t );
+ncrystal_scatter_t ncrystal_clone_scatter_rngbyidx( ncrystal_scatter_t, unsigned long rngstreamidx );
+ncrystal_scatter_t ncrystal_clone_scatter_rngforcurrentthread( ncrystal_scatter_t );
+
+/* ncrystal.h:759-773 */
+const char * ncrystal_name( ncrystal_process_t );
+int  ncrystal_isnonoriented( ncrystal_process_t );
+void ncrystal_domain( ncrystal_process_t, double* ekin_low, double* ekin_high );
+
+/* ncrystal.h:765,768 */
+void ncrystal_crosssection_nonoriented( ncrystal_process_t, double ekin, double* result );
+void ncrystal_crosssection( ncrystal_process_t, double ekin, const double (*direction)[3], double* result );
+
+/* ncrystal.h:777,782 */
+void ncrystal_samplescatterisotropic( ncrystal_scatter_t, double ekin, double* ekin_final, double* cos_scat_angle );
+void ncrystal_samplescatter( ncrystal_scatter_t, double ekin, const double (*direction)[3],
+                             double* ekin_final, double (*direction_final)[3] );
+
+/* ncrystal.h:1305 -- results[r*n_ekin+i] */
+void ncrystal_crosssection_nonoriented_many( ncrystal_process_t, const double * ekin, unsigned long n_ekin,
+                                             unsigned long repeat, double* results );
+/* ncrystal.h:1289 -- results[r*n_ekin+i] */
+void ncrystal_samplescatterisotropic_many( ncrystal_scatter_t, const double * ekin, unsigned long n_ekin,
+                                           unsigned long repeat, double* results_ekin, double* results_cos_scat_angle );
+/* ncrystal.h:1296 -- fixed (ekin,direction), `repeat` samples */
+void ncrystal_samplescatter_many( ncrystal_scatter_t, double ekin, const double (*direction)[3], unsigned long repeat,
+                                  double* results_ekin, double * results_dirx, double * results_diry, double * results_dirz );
+
+/* ncrystal.h:1030-1045 -- error state: global, message printed unless quiet, process
+ * exit(1) unless ncrystal_sethaltonerror(0); non-halting calls fill outputs with
+ * -1.0 (xs, ekin) / -999 (mu) / 0-vector (direction). */
+int  ncrystal_error(void);
+const char * ncrystal_lasterror(void);
+const char * ncrystal_lasterrortype(void);
+void ncrystal_clearerror(void);
+int  ncrystal_setquietonerror( int );
+int  ncrystal_sethaltonerror( int );
+void ncrystal_seterrhandler( void (*handler)(char*,char*) );
+
+/* ncrystal.h:1067-1087 -- RNG control.  Host callbacks cannot be honoured on the
+ * device: ncrystal_setrandgen raises an error.  State strings serialise
+ * (seed, stream id, next neutron index). */
+void ncrystal_setrandgen( double (*rg)(void) );
+void ncrystal_setbuiltinrandgen(void);
+void ncrystal_setbuiltinrandgen_withseed( unsigned long seed );
+int  ncrystal_rngsupportsstatemanip_ofscatter( ncrystal_scatter_t );
+char* ncrystal_getrngstate_ofscatter( ncrystal_scatter_t );  /* free with ncrystal_dealloc_string */
+void ncrystal_setrngstate_ofscatter( ncrystal_scatter_t, const char* );
+void ncrystal_dealloc_string( char* );
+
+/* ===================== Part 2: B200 extensions ===================== */
+
+/* Handle from a compiled material (ncrystal_b200/csrc/ncb_blob.h), the call the
+ * reference-side binding makes after flattening its ProcComposition.  The tables
+ * are uploaded to the CURRENT CUDA device; S(alpha,beta) sampler tables are built
+ * there.  Returns {NULL} on error. */
+ncrystal_scatter_t ncb200_create_scatter_from_blob( const void* blob, size_t nbytes, unsigned long seed );
+ncrystal_scatter_t ncb200_create_scatter_from_file( const char* path, unsigned long seed );
+/* Directory list (':'-separated) searched by ncrystal_create_scatter for
+ * "<sanitised cfgstr>.ncb"; default: $NCB200_DATA_PATH then <libdir>/../data. */
+void ncb200_set_data_path( const char* path );
+/* writes the sanitised file stem for a cfg string into buf (returns needed length) */
+int  ncb200_cfg_to_filestem( const char* cfgstr, char* buf, int buflen );
+
+/* Random stream of a scatter handle: neutron j of the next sampling call draws
+ * from Philox stream (seed, stream_id, next_index + j). */
+void ncb200_set_rng_stream( ncrystal_scatter_t, uint64_t seed, uint32_t stream_id, uint64_t next_index );
+void ncb200_get_rng_stream( ncrystal_scatter_t, uint64_t* seed, uint32_t* stream_id, uint64_t* next_index );
+
+/* Device-pointer variants: all arrays are device pointers on the handle's device;
+ * `stream` is a cudaStream_t (NULL = default stream).  Asynchronous: no host
+ * synchronisation; errors raised by the device are collected with
+ * ncb200_check_device_errors. */
+void ncb200_crosssection_nonoriented_many_dev( ncrystal_process_t, const double* d_ekin, uint64_t n,
+                                               double* d_results, void* stream );
+void ncb200_samplescatterisotropic_many_dev( ncrystal_scatter_t, const double* d_ekin, uint64_t n,
+                                             double* d_ekin_final, double* d_mu, void* stream );
+/* fused: also returns the total cross section (d_xs may be NULL) */
+void ncb200_xs_and_samplescatterisotropic_many_dev( ncrystal_scatter_t, const double* d_ekin, uint64_t n,
+                                                    double* d_xs, double* d_ekin_final, double* d_mu, void* stream );
+
+/* Batched oriented calls, per-neutron (E,dir), SoA (host pointers / device pointers). */
+void ncb200_crosssection_many( ncrystal_process_t, const double* ekin, const double* ux, const double* uy, const double* uz,
+                               uint64_t n, double* results );
+void ncb200_samplescatter_manydir( ncrystal_scatter_t, const double* ekin, const double* ux, const double* uy, const double* uz,
+                                   uint64_t n, double* ekin_final, double* ox, double* oy, double* oz );
+void ncb200_crosssection_many_dev( ncrystal_process_t, const double* d_ekin, const double* d_ux, const double* d_uy,
+                                   const double* d_uz, uint64_t n, double* d_results, void* stream );
+void ncb200_samplescatter_manydir_dev( ncrystal_scatter_t, const double* d_ekin, const double* d_ux, const double* d_uy,
+                                       const double* d_uz, uint64_t n, double* d_ekin_final,
+                                       double* d_ox, double* d_oy, double* d_oz, void* stream );
+
+/* Synchronises `stream`, then reports (through the ncrystal_error machinery) any
+ * error raised on the device since the last check.  Returns the raw flag word
+ * (0 = none; bits: ncb::SampleErr in csrc/ncb_phys_sab.cuh). */
+int  ncb200_check_device_errors( ncrystal_scatter_t, void* stream );
+
+/* Per-neutron diagnostics of the NEXT sampling call on this handle (device pointers,
+ * may be NULL): number of uniforms consumed, chosen component index. */
+void ncb200_set_diagnostics_dev( ncrystal_scatter_t, uint32_t* d_ndraws, int32_t* d_component );
+
+/* Synthetic source used by the benchmarks: ekin[i] = 10^(log10(lo)+(log10(hi)-log10(lo))*u_i),
+ * u_i = first uniform of Philox stream (seed, 0xE0, first_index+i); isotropic directions
+ * z=2u-1, phi=2*pi*u' from the next two uniforms (d_u* may be NULL). */
+void ncb200_generate_source_dev( uint64_t seed, uint64_t first_index, uint64_t n, double lo, double hi,
+                                 double* d_ekin, double* d_ux, double* d_uy, double* d_uz, void* stream );
+
+/* Tally: weighted 1D histogram with under/overflow bins (d_hist, d_sumw2: nbins+2 doubles,
+ * ACCUMULATED into; d_weights/d_sumw2 may be NULL).  Analogue of the reference's
+ * Hist1D filling in MiniMC tallies (NCHists.hh); merging across GPUs is an
+ * element-wise sum (NCCL all-reduce), like Tally::merge (NCMMC_Tally.hh:40-62). */
+void ncb200_tally_hist_dev( const double* d_values, const double* d_weights, uint64_t n,
+                            double lo, double hi, uint32_t nbins, double* d_hist, double* d_sumw2, void* stream );
+
+/* Introspection */
+int      ncb200_ncomponents( ncrystal_process_t );
+int      ncb200_component_kind( ncrystal_process_t, int i ); /* enum ncb_kind */
+double   ncb200_component_scale( ncrystal_process_t, int i );
+uint64_t ncb200_kernel_launch_count(void);   /* kernels launched by this library so far */
+uint64_t ncb200_table_bytes( ncrystal_process_t ); /* HBM footprint of the material tables */
+const char* ncb200_version(void);
+/* SAB table builder check: per-energy-point total xs recomputed on the device while
+ * building the sampler tables (compare with the xs grid of the compiled material). */
+int      ncb200_sab_xscheck( ncrystal_process_t, int component, double* out, int nmax );
+/* Copy of built sampler tables for one energy point (layout as oracle refdrv_sab_sampler_dump) */
+int      ncb200_sab_sampler_dump( ncrystal_process_t, int component, int iE, double* x, double* pdf, double* cdf,
+                                  double* infos, double* meta );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

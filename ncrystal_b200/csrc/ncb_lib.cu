@@ -1,0 +1,925 @@
+// ncb_lib.cu -- libncrystal_b200.so: host runtime + C ABI (include/ncrystal_b200.h)
+// over the sm_100a kernels of ncb_kernels.cuh.
+//
+// Host side mirrors the reference's C interface layer (ref: ncrystal_core/src/
+// cinterface/ncrystal.cc): ref-counted opaque handles with a 32-bit type tag as
+// first member (:138-191), global error state with halt/quiet switches (:280-306),
+// sentinel outputs on error (:1095,:1136-1140,:1239-1245).
+//
+// There is NO CPU fallback: every compute entry point launches CUDA kernels and
+// raises an error when no usable device is present.
+#include "ncb_kernels.cuh"
+#include "ncb_loader.h"
+#include "ncb_loader_sc.h"
+#include "../../include/ncrystal_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ncb {
+  double g_erfc_lut_host[kErfcLutLen];
+}
+
+namespace {
+
+  using namespace ncb;
+
+  // ------------------------------------------------------------------ error state
+  // ref: ncrystal.cc:280-306
+  int g_quietonerror = 0;
+  int g_haltonerror = 1;
+  int g_waserror = 0;
+  char g_errmsg[512];
+  char g_errtype[64];
+  void (*g_custom_error_handler)(char*,char*) = nullptr;
+
+  void setError( const char* msg, const char* etype = nullptr ) noexcept
+  {
+    if ( !etype ) etype = "ncrystal_c-interface";
+    std::strncpy( g_errmsg, msg, sizeof(g_errmsg)-1 );
+    std::strncpy( g_errtype, etype, sizeof(g_errtype)-1 );
+    g_errmsg[sizeof(g_errmsg)-1] = '\0';
+    g_errtype[sizeof(g_errtype)-1] = '\0';
+    if ( g_custom_error_handler )
+      (*g_custom_error_handler)( g_errtype, g_errmsg );
+    g_waserror = 1;
+    if ( !g_quietonerror )
+      std::fprintf( stdout, "NCrystal ERROR [%s]: %s\n", g_errtype, g_errmsg );
+    if ( g_haltonerror ) {
+      std::fprintf( stdout, "NCrystal terminating due to ERROR\n" );
+      std::fflush( stdout );
+      std::exit(1);
+    }
+  }
+
+  struct Err : public std::runtime_error {
+    std::string type;
+    Err( const std::string& t, const std::string& m ) : std::runtime_error(m), type(t) {}
+  };
+  void handleError( const std::exception& e ) noexcept
+  {
+    if ( auto x = dynamic_cast<const Err*>( &e ) ) setError( x->what(), x->type.c_str() );
+    else if ( dynamic_cast<const std::runtime_error*>( &e ) ) setError( e.what(), "std::runtime_error" );
+    else setError( "<unknown>", "std::exception" );
+  }
+#define NCBCATCH catch ( std::exception& e ) { handleError(e); }
+
+  void cudaCheck( cudaError_t e, const char* what )
+  {
+    if ( e != cudaSuccess )
+      throw Err( "CalcError", std::string("CUDA failure in ")+what+": "+cudaGetErrorString(e) );
+  }
+#define CUDA_OK(x) cudaCheck( (x), #x )
+
+  std::atomic<uint64_t> g_launches{0};
+
+  // ------------------------------------------------------------------ material on device
+  struct DeviceMaterial {
+    int device = 0;
+    void* d_arena = nullptr;
+    size_t arena_bytes = 0;
+    Material mat;            // device pointers
+    StagePlan sp;            // smem staging plan for the hot tables
+    std::string cfg;
+    std::vector<SabBuildPlan> sabplans;
+    std::atomic<uint32_t> clone_counter{0};
+    ~DeviceMaterial() { if ( d_arena ) cudaFree( d_arena ); }
+  };
+
+  std::once_flag g_lut_once;
+  std::mutex g_lutdev_mtx;
+  std::vector<int> g_lut_devices;
+
+  void ensureErfcLut( int device )
+  {
+    std::call_once( g_lut_once, [](){ fillErfcLutHost( g_erfc_lut_host ); } );
+    std::lock_guard<std::mutex> g( g_lutdev_mtx );
+    for ( int d : g_lut_devices ) if ( d == device ) return;
+    CUDA_OK( cudaMemcpyToSymbol( g_erfc_lut_dev, g_erfc_lut_host, sizeof(g_erfc_lut_host) ) );
+    g_lut_devices.push_back( device );
+  }
+
+  void buildStagePlan( DeviceMaterial& dm )
+  {
+    StagePlan& sp = dm.sp;
+    std::memset( &sp, 0, sizeof(sp) );
+    const Material& M = dm.mat;
+    // Budget: keep >= 2 CTAs/SM worth of shared memory (227 KB per SM usable).
+    const uint32_t budget = 100u*1024u;
+    uint32_t off = 0;
+    auto add = [&]( int slot, const double* p, int n ) {
+      if ( !p || n <= 0 ) return;
+      const uint32_t nb = (uint32_t)( ( (size_t)n*8 + 15 ) & ~(size_t)15 ); // arena sections are 256B padded
+      if ( off + nb > budget ) return;
+      sp.src[slot] = p; sp.nbytes[slot] = nb; sp.off[slot] = off;
+      off += ( nb + 127u ) & ~127u;
+      sp.copy_bytes += nb;
+    };
+    int npb = 0, nsab = 0;
+    for ( int i = 0; i < M.ncomp; ++i ) {
+      if ( M.comp[i].kind == KIND_POWDERBRAGG ) ++npb;
+      if ( M.comp[i].kind == KIND_SAB ) ++nsab;
+    }
+    // small SAB grids first, then the (possibly large) Bragg tables
+    for ( int i = 0; i < nsab; ++i ) {
+      add( 2*kMaxPB + i, M.sab[i].egrid, M.sab[i].negrid );
+      add( 2*kMaxPB + kMaxSab + i, M.sab[i].xs, M.sab[i].negrid );
+    }
+    for ( int i = 0; i < npb; ++i ) {
+      // both or none, so a lookup never mixes memory spaces
+      const uint32_t need = 2u*( ( (uint32_t)M.pb[i].n*8u + 127u ) & ~127u );
+      if ( off + need <= budget ) {
+        add( i, M.pb[i].e2d, M.pb[i].n );
+        add( kMaxPB + i, M.pb[i].fdm, M.pb[i].n );
+      }
+    }
+    sp.total = off;
+  }
+
+  template <class K>
+  void setSmemAttr( K kernel, uint32_t bytes )
+  {
+    if ( bytes > 48u*1024u )
+      CUDA_OK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes ) );
+  }
+
+  int numSMs( int device )
+  {
+    static std::mutex m; static std::vector<std::pair<int,int>> cache;
+    std::lock_guard<std::mutex> g(m);
+    for ( auto& e : cache ) if ( e.first == device ) return e.second;
+    int n = 0;
+    CUDA_OK( cudaDeviceGetAttribute( &n, cudaDevAttrMultiProcessorCount, device ) );
+    cache.emplace_back( device, n );
+    return n;
+  }
+
+  void buildSabTablesOnDevice( DeviceMaterial& dm, cudaStream_t st )
+  {
+    unsigned char* base = static_cast<unsigned char*>( dm.d_arena );
+    for ( auto& pl : dm.sabplans ) {
+      const SabT& T = dm.mat.sab[pl.sab_index];
+      const int na = T.nalpha, nb = T.nbeta, ne = T.negrid;
+      double* logsab = reinterpret_cast<double*>( base + pl.off_logsab );
+      double* cumul = reinterpret_cast<double*>( base + pl.off_cumul );
+      SabRow* rows = reinterpret_cast<SabRow*>( base + pl.off_rows );
+      SabAlphaInfo* ainfo = reinterpret_cast<SabAlphaInfo*>( base + pl.off_ainfo );
+      SabEPoint* ep = reinterpret_cast<SabEPoint*>( base + pl.off_ep );
+      double* bx = reinterpret_cast<double*>( base + pl.off_bx );
+      double* bpdf = reinterpret_cast<double*>( base + pl.off_bpdf );
+      double* bcdf = reinterpret_cast<double*>( base + pl.off_bcdf );
+      double* xscheck = reinterpret_cast<double*>( base + pl.off_xscheck );
+      int* errs = reinterpret_cast<int*>( base + pl.off_xscheck + (size_t)ne*8 );
+      const size_t ntot = (size_t)na*nb;
+      k_sab_logs<<< (unsigned)( ( ntot + 255 )/256 ), 256, 0, st >>>( T.sab, logsab, ntot );
+      k_sab_cumul<<< ( nb + 63 )/64, 64, 0, st >>>( T.alpha, T.sab, logsab, na, nb, cumul );
+      k_sab_rows<<< dim3( ( nb + 127 )/128, ne ), 128, 0, st >>>( T, rows, ainfo );
+      k_sab_epoints<<< ( ne + 31 )/32, 32, 0, st >>>( T, rows, ep, bx, bpdf, bcdf, xscheck, errs );
+      g_launches += 4;
+      CUDA_OK( cudaGetLastError() );
+      std::vector<int> herrs( ne );
+      CUDA_OK( cudaMemcpyAsync( herrs.data(), errs, (size_t)ne*4, cudaMemcpyDeviceToHost, st ) );
+      CUDA_OK( cudaStreamSynchronize( st ) );
+      for ( int e : herrs )
+        if ( e )
+          throw Err( "CalcError", "S(alpha,beta) sampler table build failed on device (code "+std::to_string(e)+")" );
+    }
+  }
+
+  std::shared_ptr<DeviceMaterial> uploadMaterial( const void* blob, size_t nbytes )
+  {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount( &ndev );
+    if ( ce != cudaSuccess || ndev <= 0 )
+      throw Err( "CalcError", std::string("ncrystal_b200 requires a CUDA device (no CPU fallback): ")
+                 + ( ce != cudaSuccess ? cudaGetErrorString(ce) : "no devices found" ) );
+    LoadedMaterial lm;
+    try {
+      loadBlob( blob, nbytes, lm );
+    } catch ( std::runtime_error& e ) {
+      throw Err( "BadInput", e.what() );
+    }
+    auto dm = std::make_shared<DeviceMaterial>();
+    CUDA_OK( cudaGetDevice( &dm->device ) );
+    ensureErfcLut( dm->device );
+    dm->arena_bytes = lm.arena.size();
+    CUDA_OK( cudaMalloc( &dm->d_arena, dm->arena_bytes ) );
+    CUDA_OK( cudaMemcpy( dm->d_arena, lm.arena.data(), dm->arena_bytes, cudaMemcpyHostToDevice ) );
+    dm->mat = relocated( lm, dm->d_arena );
+    dm->cfg = lm.cfg;
+    dm->sabplans = lm.sabplans;
+    buildStagePlan( *dm );
+    setSmemAttr( k_xs_iso, dm->sp.total );
+    setSmemAttr( k_sample_iso, dm->sp.total );
+    buildSabTablesOnDevice( *dm, 0 );
+    return dm;
+  }
+
+  // ------------------------------------------------------------------ handles
+  constexpr uint32_t kScatterTag = 0x7d6b0637u; // same tag value as the reference's Scatter wrapper (ncrystal.cc:228)
+
+  struct Scatter;
+  struct FingerPrint { uint32_t tag; Scatter* self; };
+
+  constexpr size_t kChunk = (size_t)1 << 21; // neutrons per pipeline chunk of the host-pointer path
+  constexpr int kSlots = 2;
+  constexpr int kStageArrays = 8;            // up to 4 in + 4 out
+
+  struct Scatter {
+    FingerPrint fp;
+    std::atomic<int> refcount{1};
+    std::shared_ptr<DeviceMaterial> dm;
+    uint64_t seed = 0;
+    uint32_t sid = 0;
+    uint64_t next_index = 0;
+    int* d_err = nullptr;
+    uint32_t* d_diag_ndraws = nullptr;
+    int32_t* d_diag_comp = nullptr;
+    // host-pointer pipeline resources (lazily created)
+    cudaStream_t streams[kSlots] = { nullptr, nullptr };
+    double* d_stage[kSlots] = { nullptr, nullptr };
+
+    Scatter() { fp.tag = kScatterTag; fp.self = this; }
+    ~Scatter()
+    {
+      if ( d_err ) cudaFree( d_err );
+      for ( int s = 0; s < kSlots; ++s ) {
+        if ( d_stage[s] ) cudaFree( d_stage[s] );
+        if ( streams[s] ) cudaStreamDestroy( streams[s] );
+      }
+    }
+    void ensureErrWord()
+    {
+      if ( !d_err ) {
+        CUDA_OK( cudaMalloc( &d_err, sizeof(int) ) );
+        CUDA_OK( cudaMemset( d_err, 0, sizeof(int) ) );
+      }
+    }
+    void ensurePipeline()
+    {
+      for ( int s = 0; s < kSlots; ++s ) {
+        if ( !streams[s] ) CUDA_OK( cudaStreamCreateWithFlags( &streams[s], cudaStreamNonBlocking ) );
+        if ( !d_stage[s] ) CUDA_OK( cudaMalloc( &d_stage[s], kStageArrays*kChunk*sizeof(double) ) );
+      }
+    }
+  };
+
+  Scatter* fromInternal( void* internal, const char* fct )
+  {
+    if ( !internal )
+      throw Err( "LogicError", std::string("Invalid (null) handle passed to ")+fct );
+    auto fp = static_cast<FingerPrint*>( internal );
+    if ( fp->tag != kScatterTag )
+      throw Err( "LogicError", std::string("Invalid object handle type passed to ")+fct );
+    return fp->self;
+  }
+
+  struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard( int dev ) { cudaGetDevice( &prev ); if ( prev != dev ) CUDA_OK( cudaSetDevice( dev ) ); else prev = -1; }
+    ~DeviceGuard() { if ( prev >= 0 ) cudaSetDevice( prev ); }
+  };
+
+  std::atomic<uint32_t> g_default_stream_counter{0};
+  constexpr uint64_t kDefaultSeed = 0x4e4372797374616cULL; // "NCrystal"
+
+  ncrystal_scatter_t newHandle( std::shared_ptr<DeviceMaterial> dm, uint64_t seed, uint32_t sid )
+  {
+    auto s = new Scatter;
+    s->dm = std::move( dm );
+    s->seed = seed;
+    s->sid = sid;
+    return { &s->fp };
+  }
+
+  // ------------------------------------------------------------------ material lookup
+  std::mutex g_path_mtx;
+  std::string g_data_path;
+
+  std::string libDir()
+  {
+    Dl_info info;
+    if ( dladdr( (void*)&libDir, &info ) && info.dli_fname ) {
+      std::string p( info.dli_fname );
+      auto pos = p.rfind( '/' );
+      if ( pos != std::string::npos ) return p.substr( 0, pos );
+    }
+    return ".";
+  }
+
+  std::string cfgToStem( const char* cfg )
+  {
+    std::string out;
+    for ( const char* c = cfg; *c; ++c ) {
+      const char ch = *c;
+      if ( ch == ' ' || ch == '\t' ) continue;
+      const bool ok = ( ch >= 'a' && ch <= 'z' ) || ( ch >= 'A' && ch <= 'Z' ) || ( ch >= '0' && ch <= '9' )
+                      || ch == '.' || ch == '_' || ch == '-' || ch == '=' || ch == ',' || ch == '@';
+      out += ok ? ch : ( ch == ';' ? '+' : '_' );
+    }
+    return out;
+  }
+
+  std::vector<unsigned char> readFile( const std::string& path )
+  {
+    std::vector<unsigned char> d;
+    FILE* f = std::fopen( path.c_str(), "rb" );
+    if ( !f ) return d;
+    std::fseek( f, 0, SEEK_END );
+    long n = std::ftell( f );
+    std::fseek( f, 0, SEEK_SET );
+    if ( n > 0 ) {
+      d.resize( (size_t)n );
+      if ( std::fread( d.data(), 1, (size_t)n, f ) != (size_t)n ) d.clear();
+    }
+    std::fclose( f );
+    return d;
+  }
+
+  std::vector<unsigned char> findCompiledMaterial( const char* cfg )
+  {
+    std::vector<std::string> dirs;
+    {
+      std::lock_guard<std::mutex> g( g_path_mtx );
+      std::string p = g_data_path;
+      if ( p.empty() ) { const char* e = std::getenv( "NCB200_DATA_PATH" ); if ( e ) p = e; }
+      std::stringstream ss( p );
+      std::string item;
+      while ( std::getline( ss, item, ':' ) ) if ( !item.empty() ) dirs.push_back( item );
+    }
+    dirs.push_back( libDir() + "/../data" );
+    dirs.push_back( libDir() + "/data" );
+    const std::string stem = cfgToStem( cfg );
+    std::string tried;
+    for ( auto& d : dirs ) {
+      const std::string path = d + "/" + stem + ".ncb";
+      auto data = readFile( path );
+      if ( !data.empty() ) return data;
+      tried += " " + path;
+    }
+    throw Err( "FileNotFound", std::string("No compiled material for cfg \"")+cfg+"\" (looked for:"+tried
+               +"). Material setup is done by the NCrystal reference: compile it with oracle/_ref/bin/ncb200_matcompile"
+               " or hand the tables over with ncb200_create_scatter_from_blob (see INTEGRATION.md)." );
+  }
+
+  // ------------------------------------------------------------------ launches
+  unsigned gridFor( uint64_t n, int threads, int device, int ctas_per_sm )
+  {
+    const uint64_t need = ( n + threads - 1 ) / threads;
+    const uint64_t cap = (uint64_t)numSMs( device ) * ctas_per_sm;
+    return (unsigned)( need < cap ? ( need ? need : 1 ) : cap );
+  }
+
+  void launchXSIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_out, cudaStream_t st )
+  {
+    if ( !n ) return;
+    const DeviceMaterial& dm = *s->dm;
+    if ( dm.mat.oriented )
+      throw Err( "LogicError", "ncrystal_crosssection_nonoriented called for an oriented process" );
+    const int threads = 256;
+    const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
+    k_xs_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, n, d_out );
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
+  }
+
+  void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu, cudaStream_t st )
+  {
+    if ( !n ) return;
+    const DeviceMaterial& dm = *s->dm;
+    if ( dm.mat.oriented )
+      throw Err( "LogicError", "ncrystal_samplescatterisotropic called for an oriented process" );
+    s->ensureErrWord();
+    SampleArgs A;
+    A.ekin = d_ekin; A.n = n; A.seed = s->seed; A.first_index = s->next_index; A.sid = s->sid;
+    A.xs_out = d_xs; A.ekin_out = d_eout; A.mu_out = d_mu;
+    A.ndraws = s->d_diag_ndraws; A.component = s->d_diag_comp; A.err_flags = s->d_err;
+    s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
+    s->next_index += n;
+    const int threads = 128;
+    const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
+    k_sample_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, A );
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
+  }
+
+  int fetchDeviceErrors( Scatter* s, cudaStream_t st )
+  {
+    CUDA_OK( cudaStreamSynchronize( st ) );
+    if ( !s->d_err ) return 0;
+    int flags = 0;
+    CUDA_OK( cudaMemcpy( &flags, s->d_err, sizeof(int), cudaMemcpyDeviceToHost ) );
+    if ( flags & ~ERR_SAB_ISOFALLBACK )
+      CUDA_OK( cudaMemset( s->d_err, 0, sizeof(int) ) );
+    return flags;
+  }
+
+  void raiseDeviceErrors( int flags )
+  {
+    // same conditions under which the reference throws CalcError / BadInput
+    if ( flags & ERR_SAB_DISCARD )
+      throw Err( "BadInput", "Scattering Kernel does not appear to match up very well with the chosen extrapolation model at Emax." );
+    if ( flags & ERR_SAB_LOOP_INNER )
+      throw Err( "CalcError", "Rejection method failed to sample kinematically valid (alpha,beta) point after 100 attempts." );
+    if ( flags & ERR_SAB_LOOP_OUTER )
+      throw Err( "CalcError", "Infinite looping in sampleAlphaBeta" );
+    if ( flags & ERR_KIN_DENOM )
+      throw Err( "CalcError", "convertAlphaBetaToDeltaEMu invalid for beta=-E/kT" );
+  }
+
+  // Host-pointer pipeline: chunks of kChunk neutrons alternate between two streams so
+  // that the H2D copy of chunk c+1 overlaps the kernel and D2H copy of chunk c.
+  // `launch(chunk_n, in_dev[], out_dev[], stream)` enqueues the kernel(s).
+  void runHostPipeline( Scatter* s, uint64_t n, int nin, const double* const* in, int nout, double* const* out,
+                        const std::function<void(uint64_t,double* const*,double* const*,cudaStream_t)>& launch )
+  {
+    if ( !n ) return;
+    s->ensurePipeline();
+    uint64_t done = 0;
+    int slot = 0;
+    while ( done < n ) {
+      const uint64_t m = std::min<uint64_t>( kChunk, n - done );
+      cudaStream_t st = s->streams[slot];
+      double* base = s->d_stage[slot];
+      double* din[4]; double* dout[4];
+      for ( int k = 0; k < nin; ++k ) {
+        din[k] = base + (size_t)k*kChunk;
+        CUDA_OK( cudaMemcpyAsync( din[k], in[k] + done, m*sizeof(double), cudaMemcpyHostToDevice, st ) );
+      }
+      for ( int k = 0; k < nout; ++k )
+        dout[k] = base + (size_t)(4+k)*kChunk;
+      launch( m, din, dout, st );
+      for ( int k = 0; k < nout; ++k )
+        CUDA_OK( cudaMemcpyAsync( out[k] + done, dout[k], m*sizeof(double), cudaMemcpyDeviceToHost, st ) );
+      done += m;
+      slot = ( slot + 1 ) % kSlots;
+      // the slot we are about to reuse must have drained
+      if ( done < n )
+        CUDA_OK( cudaStreamSynchronize( s->streams[slot] ) );
+    }
+    for ( int k = 0; k < kSlots; ++k )
+      CUDA_OK( cudaStreamSynchronize( s->streams[k] ) );
+  }
+
+  void xsIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* results )
+  {
+    if ( !n || !repeat ) return;
+    DeviceGuard dg( s->dm->device );
+    const double* in[1] = { ekin };
+    double* out[1] = { results };
+    runHostPipeline( s, n, 1, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st ) {
+      launchXSIso( s, di[0], m, dout[0], st );
+    } );
+    // deterministic: further repeats are copies (ref loop order: results[r*n+i], ncrystal.cc:1125-1133)
+    for ( uint64_t r = 1; r < repeat; ++r )
+      std::memcpy( results + r*n, results, n*sizeof(double) );
+  }
+
+  void sampleIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* eout, double* mu )
+  {
+    if ( !n || !repeat ) return;
+    DeviceGuard dg( s->dm->device );
+    for ( uint64_t r = 0; r < repeat; ++r ) {
+      const double* in[1] = { ekin };
+      double* out[2] = { eout + r*n, mu + r*n };
+      runHostPipeline( s, n, 1, in, 2, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st ) {
+        launchSampleIso( s, di[0], m, nullptr, dout[0], dout[1], st );
+      } );
+    }
+    raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );
+  }
+
+}
+
+// =============================================================================
+//                                  C ABI
+// =============================================================================
+extern "C" {
+
+  // ---- error API (ref: ncrystal.cc:396-440)
+  void ncrystal_seterrhandler( void (*handler)(char*,char*) ) { g_custom_error_handler = handler; }
+  int ncrystal_error(void) { return g_waserror; }
+  const char* ncrystal_lasterror(void) { return g_waserror ? g_errmsg : nullptr; }
+  const char* ncrystal_lasterrortype(void) { return g_waserror ? g_errtype : nullptr; }
+  void ncrystal_clearerror(void) { g_waserror = 0; }
+  int ncrystal_setquietonerror( int q ) { int old = g_quietonerror; g_quietonerror = q; return old; }
+  int ncrystal_sethaltonerror( int h ) { int old = g_haltonerror; g_haltonerror = h; return old; }
+
+  // ---- handle management (ref: ncrystal.cc:442-545)
+  int ncrystal_valid( void* object )
+  {
+    if ( !object ) return 0;
+    return *reinterpret_cast<void**>( object ) ? 1 : 0;
+  }
+  int ncrystal_refcount( void* object )
+  {
+    try { return fromInternal( *reinterpret_cast<void**>( object ), "ncrystal_refcount" )->refcount.load(); } NCBCATCH;
+    return -999;
+  }
+  void ncrystal_ref( void* object )
+  {
+    try { ++fromInternal( *reinterpret_cast<void**>( object ), "ncrystal_ref" )->refcount; } NCBCATCH;
+  }
+  void ncrystal_unref( void* object )
+  {
+    try {
+      void*& internal = *reinterpret_cast<void**>( object );
+      Scatter* s = fromInternal( internal, "ncrystal_unref" );
+      if ( s->refcount.fetch_sub(1) == 1 ) {
+        { DeviceGuard dg( s->dm->device ); delete s; }
+        internal = nullptr;
+      }
+    } NCBCATCH;
+  }
+  void ncrystal_invalidate( void* object )
+  {
+    if ( !ncrystal_valid( object ) ) return;
+    *reinterpret_cast<void**>( object ) = nullptr;
+  }
+  ncrystal_process_t ncrystal_cast_scat2proc( ncrystal_scatter_t s )
+  {
+    try { fromInternal( s.internal, "ncrystal_cast_scat2proc" ); return { s.internal }; } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncrystal_cast_proc2scat( ncrystal_process_t p )
+  {
+    try { fromInternal( p.internal, "ncrystal_cast_proc2scat" ); return { p.internal }; } NCBCATCH;
+    return { nullptr };
+  }
+
+  // ---- creation
+  ncrystal_scatter_t ncb200_create_scatter_from_blob( const void* blob, size_t nbytes, unsigned long seed )
+  {
+    try { return newHandle( uploadMaterial( blob, nbytes ), seed, 0 ); } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncb200_create_scatter_from_file( const char* path, unsigned long seed )
+  {
+    try {
+      auto d = readFile( path );
+      if ( d.empty() ) throw Err( "FileNotFound", std::string("Could not read compiled material file ")+path );
+      return newHandle( uploadMaterial( d.data(), d.size() ), seed, 0 );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  void ncb200_set_data_path( const char* path )
+  {
+    std::lock_guard<std::mutex> g( g_path_mtx );
+    g_data_path = path ? path : "";
+  }
+  int ncb200_cfg_to_filestem( const char* cfgstr, char* buf, int buflen )
+  {
+    const std::string s = cfgToStem( cfgstr );
+    if ( buf && buflen > 0 ) std::snprintf( buf, (size_t)buflen, "%s", s.c_str() );
+    return (int)s.size();
+  }
+  ncrystal_scatter_t ncrystal_create_scatter( const char* cfgstr )
+  {
+    try {
+      auto d = findCompiledMaterial( cfgstr );
+      // every handle created without explicit seed gets its own stream, like the reference's
+      // default RNG producer (NCFact.cc:28-35)
+      return newHandle( uploadMaterial( d.data(), d.size() ), kDefaultSeed, 0x10000000u + g_default_stream_counter++ );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncrystal_create_scatter_builtinrng( const char* cfgstr, unsigned long seed )
+  {
+    try {
+      auto d = findCompiledMaterial( cfgstr );
+      return newHandle( uploadMaterial( d.data(), d.size() ), seed, 0 );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncrystal_clone_scatter( ncrystal_scatter_t o )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncrystal_clone_scatter" );
+      return newHandle( s->dm, s->seed, 0x20000000u + ( ++s->dm->clone_counter ) );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncrystal_clone_scatter_rngbyidx( ncrystal_scatter_t o, unsigned long idx )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncrystal_clone_scatter_rngbyidx" );
+      return newHandle( s->dm, s->seed, 0x40000000u + (uint32_t)( idx & 0x3fffffffu ) );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_scatter_t ncrystal_clone_scatter_rngforcurrentthread( ncrystal_scatter_t o )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncrystal_clone_scatter_rngforcurrentthread" );
+      const size_t h = std::hash<std::thread::id>()( std::this_thread::get_id() );
+      return newHandle( s->dm, s->seed, 0x80000000u + (uint32_t)( h & 0x7fffffffu ) );
+    } NCBCATCH;
+    return { nullptr };
+  }
+
+  // ---- queries (ref: ncrystal.cc:1040-1087)
+  const char* ncrystal_name( ncrystal_process_t p )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncrystal_name" );
+      if ( s->dm->mat.ncomp > 1 ) return "ProcComposition";
+      switch ( s->dm->mat.comp[0].kind ) {
+      case KIND_POWDERBRAGG: return "PowderBragg";
+      case KIND_ELINC: return "ElIncScatter";
+      case KIND_SAB: return "SABScatter";
+      case KIND_FREEGAS: return "FreeGas";
+      case KIND_SCBRAGG: return "SCBragg";
+      default: return "Process";
+      }
+    } NCBCATCH;
+    return nullptr;
+  }
+  int ncrystal_isnonoriented( ncrystal_process_t p )
+  {
+    try { return fromInternal( p.internal, "ncrystal_isnonoriented" )->dm->mat.oriented ? 0 : 1; } NCBCATCH;
+    return -1;
+  }
+  void ncrystal_domain( ncrystal_process_t p, double* ekin_low, double* ekin_high )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncrystal_domain" );
+      *ekin_low = s->dm->mat.dom_lo;
+      *ekin_high = s->dm->mat.dom_hi;
+      return;
+    } NCBCATCH;
+    *ekin_low = *ekin_high = -1.0;
+  }
+
+  // ---- cross sections
+  void ncrystal_crosssection_nonoriented_many( ncrystal_process_t o, const double* ekin, unsigned long n_ekin,
+                                               unsigned long repeat, double* results )
+  {
+    try {
+      xsIsoHost( fromInternal( o.internal, "ncrystal_crosssection_nonoriented_many" ), ekin, n_ekin, repeat, results );
+      return;
+    } NCBCATCH;
+    for ( unsigned long i = 0; i < n_ekin*repeat; ++i ) results[i] = -1.0;
+  }
+  void ncrystal_crosssection_nonoriented( ncrystal_process_t o, double ekin, double* result )
+  {
+    try {
+      xsIsoHost( fromInternal( o.internal, "ncrystal_crosssection_nonoriented" ), &ekin, 1, 1, result );
+      return;
+    } NCBCATCH;
+    *result = -1.0;
+  }
+
+  // ---- sampling
+  void ncrystal_samplescatterisotropic_many( ncrystal_scatter_t o, const double* ekin, unsigned long n_ekin,
+                                             unsigned long repeat, double* results_ekin, double* results_cos_scat_angle )
+  {
+    try {
+      sampleIsoHost( fromInternal( o.internal, "ncrystal_samplescatterisotropic_many" ), ekin, n_ekin, repeat,
+                     results_ekin, results_cos_scat_angle );
+      return;
+    } NCBCATCH;
+    for ( unsigned long i = 0; i < n_ekin*repeat; ++i ) { results_ekin[i] = -1.0; results_cos_scat_angle[i] = -999.0; }
+  }
+  void ncrystal_samplescatterisotropic( ncrystal_scatter_t o, double ekin, double* ekin_final, double* cos_scat_angle )
+  {
+    try {
+      sampleIsoHost( fromInternal( o.internal, "ncrystal_samplescatterisotropic" ), &ekin, 1, 1, ekin_final, cos_scat_angle );
+      return;
+    } NCBCATCH;
+    *ekin_final = -1.0;
+    *cos_scat_angle = -999;
+  }
+
+  // ---- device-pointer variants
+  void ncb200_crosssection_nonoriented_many_dev( ncrystal_process_t o, const double* d_ekin, uint64_t n,
+                                                 double* d_results, void* stream )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_crosssection_nonoriented_many_dev" );
+      DeviceGuard dg( s->dm->device );
+      launchXSIso( s, d_ekin, n, d_results, static_cast<cudaStream_t>( stream ) );
+    } NCBCATCH;
+  }
+  void ncb200_samplescatterisotropic_many_dev( ncrystal_scatter_t o, const double* d_ekin, uint64_t n,
+                                               double* d_ekin_final, double* d_mu, void* stream )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_samplescatterisotropic_many_dev" );
+      DeviceGuard dg( s->dm->device );
+      launchSampleIso( s, d_ekin, n, nullptr, d_ekin_final, d_mu, static_cast<cudaStream_t>( stream ) );
+    } NCBCATCH;
+  }
+  void ncb200_xs_and_samplescatterisotropic_many_dev( ncrystal_scatter_t o, const double* d_ekin, uint64_t n,
+                                                      double* d_xs, double* d_ekin_final, double* d_mu, void* stream )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_xs_and_samplescatterisotropic_many_dev" );
+      DeviceGuard dg( s->dm->device );
+      launchSampleIso( s, d_ekin, n, d_xs, d_ekin_final, d_mu, static_cast<cudaStream_t>( stream ) );
+    } NCBCATCH;
+  }
+  int ncb200_check_device_errors( ncrystal_scatter_t o, void* stream )
+  {
+    int flags = 0;
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_check_device_errors" );
+      DeviceGuard dg( s->dm->device );
+      flags = fetchDeviceErrors( s, static_cast<cudaStream_t>( stream ) );
+      raiseDeviceErrors( flags );
+    } NCBCATCH;
+    return flags;
+  }
+  void ncb200_set_diagnostics_dev( ncrystal_scatter_t o, uint32_t* d_ndraws, int32_t* d_component )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_set_diagnostics_dev" );
+      s->d_diag_ndraws = d_ndraws;
+      s->d_diag_comp = d_component;
+    } NCBCATCH;
+  }
+
+  // ---- RNG control
+  void ncb200_set_rng_stream( ncrystal_scatter_t o, uint64_t seed, uint32_t stream_id, uint64_t next_index )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_set_rng_stream" );
+      s->seed = seed; s->sid = stream_id; s->next_index = next_index;
+    } NCBCATCH;
+  }
+  void ncb200_get_rng_stream( ncrystal_scatter_t o, uint64_t* seed, uint32_t* stream_id, uint64_t* next_index )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_get_rng_stream" );
+      if ( seed ) *seed = s->seed;
+      if ( stream_id ) *stream_id = s->sid;
+      if ( next_index ) *next_index = s->next_index;
+    } NCBCATCH;
+  }
+  void ncrystal_setrandgen( double (*)(void) )
+  {
+    try {
+      throw Err( "LogicError", "ncrystal_setrandgen: host RNG callbacks cannot be evaluated on the GPU; "
+                 "ncrystal_b200 uses per-neutron counter-based streams (see ncb200_set_rng_stream)" );
+    } NCBCATCH;
+  }
+  void ncrystal_setbuiltinrandgen(void) {}
+  void ncrystal_setbuiltinrandgen_withseed( unsigned long ) {}
+  int ncrystal_rngsupportsstatemanip_ofscatter( ncrystal_scatter_t ) { return 1; }
+  char* ncrystal_getrngstate_ofscatter( ncrystal_scatter_t o )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncrystal_getrngstate_ofscatter" );
+      char buf[96];
+      // 64-bit seed, 32-bit stream id, 64-bit next index, then a 4-byte type id (cf. the
+      // reference's hex state + type UID, NCRNG.cc:89,165-186)
+      std::snprintf( buf, sizeof(buf), "%016llx%08x%016llxb2005eed", (unsigned long long)s->seed, s->sid,
+                     (unsigned long long)s->next_index );
+      char* out = static_cast<char*>( std::malloc( std::strlen(buf)+1 ) );
+      std::strcpy( out, buf );
+      return out;
+    } NCBCATCH;
+    return nullptr;
+  }
+  void ncrystal_setrngstate_ofscatter( ncrystal_scatter_t o, const char* st )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncrystal_setrngstate_ofscatter" );
+      unsigned long long seed, idx; unsigned sid;
+      if ( !st || std::strlen(st) != 48 || std::strcmp( st+40, "b2005eed" ) != 0
+           || std::sscanf( st, "%16llx%8x%16llx", &seed, &sid, &idx ) != 3 )
+        throw Err( "BadInput", "ncrystal_setrngstate_ofscatter: not a state string of this RNG type" );
+      s->seed = seed; s->sid = sid; s->next_index = idx;
+    } NCBCATCH;
+  }
+  void ncrystal_dealloc_string( char* p ) { std::free( p ); }
+
+  // ---- source + tally
+  void ncb200_generate_source_dev( uint64_t seed, uint64_t first_index, uint64_t n, double lo, double hi,
+                                   double* d_ekin, double* d_ux, double* d_uy, double* d_uz, void* stream )
+  {
+    try {
+      if ( !n ) return;
+      int dev = 0; CUDA_OK( cudaGetDevice( &dev ) );
+      const double loglo = std::log10( lo ), logspan = std::log10( hi ) - std::log10( lo );
+      k_gen_source<<< gridFor( n, 256, dev, 8 ), 256, 0, static_cast<cudaStream_t>( stream ) >>>(
+        seed, first_index, n, loglo, logspan, d_ekin, d_ux, d_uy, d_uz );
+      ++g_launches;
+      CUDA_OK( cudaGetLastError() );
+    } NCBCATCH;
+  }
+  void ncb200_tally_hist_dev( const double* d_values, const double* d_weights, uint64_t n,
+                              double lo, double hi, uint32_t nbins, double* d_hist, double* d_sumw2, void* stream )
+  {
+    try {
+      if ( !n ) return;
+      if ( !( hi > lo ) || nbins == 0 || nbins > 12000 )
+        throw Err( "BadInput", "ncb200_tally_hist_dev: need hi>lo and 1<=nbins<=12000" );
+      int dev = 0; CUDA_OK( cudaGetDevice( &dev ) );
+      const uint32_t smem = ( nbins + 2 ) * 8u * ( d_sumw2 ? 2u : 1u );
+      setSmemAttr( k_tally_hist, smem );
+      k_tally_hist<<< gridFor( n, 256, dev, 4 ), 256, smem, static_cast<cudaStream_t>( stream ) >>>(
+        d_values, d_weights, n, lo, (double)nbins/( hi - lo ), nbins, d_hist, d_sumw2 );
+      ++g_launches;
+      CUDA_OK( cudaGetLastError() );
+    } NCBCATCH;
+  }
+
+  // ---- introspection
+  int ncb200_ncomponents( ncrystal_process_t p )
+  {
+    try { return fromInternal( p.internal, "ncb200_ncomponents" )->dm->mat.ncomp; } NCBCATCH;
+    return -1;
+  }
+  int ncb200_component_kind( ncrystal_process_t p, int i )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_component_kind" );
+      if ( i < 0 || i >= s->dm->mat.ncomp ) throw Err( "BadInput", "component index out of range" );
+      return s->dm->mat.comp[i].kind;
+    } NCBCATCH;
+    return -1;
+  }
+  double ncb200_component_scale( ncrystal_process_t p, int i )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_component_scale" );
+      if ( i < 0 || i >= s->dm->mat.ncomp ) throw Err( "BadInput", "component index out of range" );
+      return s->dm->mat.comp[i].scale;
+    } NCBCATCH;
+    return -1.0;
+  }
+  uint64_t ncb200_kernel_launch_count(void) { return g_launches.load(); }
+  uint64_t ncb200_table_bytes( ncrystal_process_t p )
+  {
+    try { return fromInternal( p.internal, "ncb200_table_bytes" )->dm->arena_bytes; } NCBCATCH;
+    return 0;
+  }
+  const char* ncb200_version(void) { return "ncrystal_b200 0.1 (sm_100a; hot path of NCrystal 4.4.2)"; }
+
+  int ncb200_sab_xscheck( ncrystal_process_t p, int component, double* out, int nmax )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_sab_xscheck" );
+      const Material& M = s->dm->mat;
+      if ( component < 0 || component >= M.ncomp || M.comp[component].kind != KIND_SAB ) return -1;
+      const int isab = M.comp[component].idx;
+      for ( auto& pl : s->dm->sabplans )
+        if ( pl.sab_index == isab ) {
+          const int ne = M.sab[isab].negrid;
+          const int m = ne < nmax ? ne : nmax;
+          DeviceGuard dg( s->dm->device );
+          CUDA_OK( cudaMemcpy( out, static_cast<unsigned char*>( s->dm->d_arena ) + pl.off_xscheck, (size_t)m*8, cudaMemcpyDeviceToHost ) );
+          return ne;
+        }
+    } NCBCATCH;
+    return -1;
+  }
+
+  int ncb200_sab_sampler_dump( ncrystal_process_t p, int component, int iE, double* x, double* pdf, double* cdf,
+                               double* infos, double* meta )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_sab_sampler_dump" );
+      const Material& M = s->dm->mat;
+      if ( component < 0 || component >= M.ncomp || M.comp[component].kind != KIND_SAB ) return -1;
+      const SabT& T = M.sab[M.comp[component].idx];
+      if ( iE < 0 || iE >= T.negrid ) return -1;
+      DeviceGuard dg( s->dm->device );
+      SabEPoint ep;
+      CUDA_OK( cudaMemcpy( &ep, T.ep + iE, sizeof(ep), cudaMemcpyDeviceToHost ) );
+      const int n = ep.npts;
+      if ( n <= 0 ) return 0;
+      if ( x ) CUDA_OK( cudaMemcpy( x, T.bx + ep.off_b, (size_t)n*8, cudaMemcpyDeviceToHost ) );
+      if ( pdf ) CUDA_OK( cudaMemcpy( pdf, T.bpdf + ep.off_b, (size_t)n*8, cudaMemcpyDeviceToHost ) );
+      if ( cdf ) CUDA_OK( cudaMemcpy( cdf, T.bcdf + ep.off_b, (size_t)n*8, cudaMemcpyDeviceToHost ) );
+      if ( infos ) {
+        std::vector<SabAlphaInfo> v( n-1 );
+        CUDA_OK( cudaMemcpy( v.data(), T.ainfo + ep.off_i, (size_t)(n-1)*sizeof(SabAlphaInfo), cudaMemcpyDeviceToHost ) );
+        for ( int i = 0; i+1 < n; ++i ) {
+          const SabAlphaInfo& f = v[i];
+          double* o = infos + 10*i;
+          o[0]=f.f_alpha; o[1]=f.f_sval; o[2]=f.f_logsval; o[3]=f.f_idx;
+          o[4]=f.b_alpha; o[5]=f.b_sval; o[6]=f.b_logsval; o[7]=f.b_idx;
+          o[8]=f.prob_front; o[9]=f.prob_notback;
+        }
+      }
+      if ( meta ) { meta[0] = ep.ibeta_off; meta[1] = ep.first_bin_endpoint; }
+      return n;
+    } NCBCATCH;
+    return -1;
+  }
+
+  // ---- oriented entry points: see ncb_lib_oriented.inc
+#include "ncb_lib_oriented.inc"
+
+}

@@ -18,7 +18,8 @@ namespace ncb {
   // the same libm erfc the reference uses, uploaded once per device).
   constexpr int kErfcLutLen = 1103; // = 3+(9.0-(-2.0))/0.01
 #if defined(__CUDACC__)
-  extern __device__ double g_erfc_lut_dev[kErfcLutLen];
+  // defined here: the library is a single translation unit (no relocatable device code)
+  __device__ double g_erfc_lut_dev[kErfcLutLen];
 #endif
   extern double g_erfc_lut_host[kErfcLutLen];
 

@@ -7,20 +7,36 @@
 
 namespace ncb {
 
+  // The small, hot lookup tables of the cross-section path.  The pointers are either
+  // the material's global-memory arrays or their per-CTA copies staged into shared
+  // memory by TMA bulk copies (ncb_kernels.cu: stageHotTabs).
+  constexpr int kMaxPB = 2, kMaxSab = 4;
+  struct HotTabs {
+    const double* pb_e2d[kMaxPB];
+    const double* pb_fdm[kMaxPB];
+    const double* sab_egrid[kMaxSab];
+    const double* sab_xs[kMaxSab];
+  };
+  NCB_HD void hotTabsFromMaterial( const Material& M, HotTabs& H )
+  {
+    for ( int i = 0; i < kMaxPB; ++i ) { H.pb_e2d[i] = M.pb[i].e2d; H.pb_fdm[i] = M.pb[i].fdm; }
+    for ( int i = 0; i < kMaxSab; ++i ) { H.sab_egrid[i] = M.sab[i].egrid; H.sab_xs[i] = M.sab[i].xs; }
+  }
+
   // Unscaled isotropic xs of component i.  aux receives the PowderBragg plane index.
-  NCB_HD double compXSIso( const Material& M, int i, double ekin, int& aux )
+  NCB_HD double compXSIso( const Material& M, const HotTabs& H, int i, double ekin, int& aux )
   {
     const Comp& c = M.comp[i];
     switch ( c.kind ) {
     case KIND_POWDERBRAGG: {
       const PowderBraggT& T = M.pb[c.idx];
-      return pbXS( T.e2d, T.fdm, T.n, T.threshold, ekin, aux );
+      return pbXS( H.pb_e2d[c.idx], H.pb_fdm[c.idx], T.n, T.threshold, ekin, aux );
     }
     case KIND_ELINC:
       return elincXS( M.elinc[c.idx], ekin, nullptr );
     case KIND_SAB: {
       const SabT& T = M.sab[c.idx];
-      return sabXS( T, T.egrid, T.xs, ekin );
+      return sabXS( T, H.sab_egrid[c.idx], H.sab_xs[c.idx], ekin );
     }
     case KIND_FREEGAS:
       return fgXS( M.fg[c.idx], ekin );
@@ -30,7 +46,7 @@ namespace ncb {
   }
 
   // Total xs; fills cumul[0..ncomp) (componentXSectCommul) and aux[] when non-null.
-  NCB_HD double matXSIso( const Material& M, double ekin, double* cumul, int* aux )
+  NCB_HD double matXSIso( const Material& M, const HotTabs& H, double ekin, double* cumul, int* aux )
   {
     if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) )
       return 0.0;
@@ -38,7 +54,7 @@ namespace ncb {
     for ( int i = 0; i < M.ncomp; ++i ) {
       const Comp& c = M.comp[i];
       int a = -1;
-      const double xs = domainContains( c.dom_lo, c.dom_hi, ekin ) ? compXSIso( M, i, ekin, a ) : 0.0;
+      const double xs = domainContains( c.dom_lo, c.dom_hi, ekin ) ? compXSIso( M, H, i, ekin, a ) : 0.0;
       tot += c.scale * xs;
       if ( cumul ) cumul[i] = tot;
       if ( aux ) aux[i] = a;
@@ -47,7 +63,7 @@ namespace ncb {
   }
 
   // leaf sampleScatterIsotropic dispatch
-  NCB_HD void compSampleIso( const Material& M, int i, int aux, double ekin, Rng& rng,
+  NCB_HD void compSampleIso( const Material& M, const HotTabs& H, int i, int aux, double ekin, Rng& rng,
                              double& ekin_out, double& mu, int& err )
   {
     const Comp& c = M.comp[i];
@@ -61,8 +77,8 @@ namespace ncb {
         return;
       }
       if ( aux < 0 )
-        aux = pbLastValidPlane( T.e2d, T.n, ekin );
-      mu = pbSampleMu( T.e2d, T.fdm, aux, ekin, rng );
+        aux = pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+      mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], aux, ekin, rng );
       return;
     }
     case KIND_ELINC:
@@ -84,7 +100,7 @@ namespace ncb {
   // ProcComposition::sampleScatterIsotropic.  Also returns the total xs (the
   // "evalXSAndSampleScatterIsotropic" fused entry of the reference's batch ABI,
   // ref: include/NCrystal/internal/extd_utils/NCABIUtils.hh:78-100).
-  NCB_HD double matSampleIso( const Material& M, double ekin, Rng& rng,
+  NCB_HD double matSampleIso( const Material& M, const HotTabs& H, double ekin, Rng& rng,
                               double& ekin_out, double& mu, int& err, int& ichoice_out )
   {
     ichoice_out = -1;
@@ -94,10 +110,10 @@ namespace ncb {
     }
     double cumul[kMaxComp];
     int aux[kMaxComp];
-    const double tot = matXSIso( M, ekin, cumul, aux );
+    const double tot = matXSIso( M, H, ekin, cumul, aux );
     const int ichoice = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
     ichoice_out = ichoice;
-    compSampleIso( M, ichoice, aux[ichoice], ekin, rng, ekin_out, mu, err );
+    compSampleIso( M, H, ichoice, aux[ichoice], ekin, rng, ekin_out, mu, err );
     return tot;
   }
 

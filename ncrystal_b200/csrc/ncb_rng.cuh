@@ -3,7 +3,7 @@
 // The reference draws from ONE sequential xoroshiro128+ stream per handle
 // (ref: NCRandUtils.hh:208-245, NCDefs.hh:1276), with data-dependent draw
 // counts -- not reproducible in parallel.  Here every neutron owns a stream
-//     key = 64-bit seed, counter = (global neutron index, block number)
+//     key = 64-bit seed, counter = (global neutron index, block number, stream id)
 // and its k'th uniform is word (k&1) of Philox block (k>>1), mapped to (0,1]
 // exactly like the reference maps its 64 random bits (randUInt64ToFP01,
 // NCDefs.hh:1308-1330).  Results are therefore independent of launch shape and
@@ -26,11 +26,13 @@ namespace ncb {
   struct Rng {
     uint32_t k0, k1;   // key  (seed)
     uint32_t c0, c1;   // counter words 0,1 (neutron index)
+    uint32_t sid;      // counter word 3: stream id (0 for a fresh handle, k for its k'th clone)
     uint32_t ndraws;   // uniforms consumed
     uint32_t b2, b3;   // second half of the current block
 
-    NCB_HD void init( uint64_t seed, uint64_t index )
+    NCB_HD void init( uint64_t seed, uint64_t index, uint32_t stream_id = 0 )
     {
+      sid = stream_id;
       k0 = (uint32_t)seed; k1 = (uint32_t)( seed >> 32 );
       c0 = (uint32_t)index; c1 = (uint32_t)( index >> 32 );
       ndraws = 0; b2 = b3 = 0;
@@ -50,7 +52,7 @@ namespace ncb {
       const uint32_t k = ndraws++;
       if ( k & 1u )
         return toFP01( b2, b3 );
-      uint32_t x0 = c0, x1 = c1, x2 = k >> 1, x3 = 0u;
+      uint32_t x0 = c0, x1 = c1, x2 = k >> 1, x3 = sid;
       uint32_t ka = k0, kb = k1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll

@@ -9,7 +9,8 @@
  *
  * Stream definition (must match ncrystal_b200/csrc/ncb_rng.cuh):
  *   key      = (seed_lo, seed_hi)
- *   counter  = (index_lo, index_hi, k>>1, 0)     index = global neutron index
+ *   counter  = (index_lo, index_hi, k>>1, sid)   index = global neutron index, sid = stream id
+ *                                                (0 for a fresh handle, k for its k'th clone)
  *   draw k   = 64-bit word (k&1) of that block: w0 = r1:r0, w1 = r3:r2
  *   uniform  = randUInt64ToFP01(word)  in (0,1]  (ref: NCDefs.hh:1308-1330)
  */
@@ -49,12 +50,17 @@ typedef struct {
   uint32_t ndraws;   /* draws consumed so far */
 } ncb_stream_t;
 
-static inline void ncb_stream_init(ncb_stream_t* s, uint64_t seed, uint64_t index)
+static inline void ncb_stream_init_sid(ncb_stream_t* s, uint64_t seed, uint64_t index, uint32_t sid)
 {
   s->key[0] = (uint32_t)seed; s->key[1] = (uint32_t)(seed >> 32);
   s->ctr[0] = (uint32_t)index; s->ctr[1] = (uint32_t)(index >> 32);
-  s->ctr[2] = 0; s->ctr[3] = 0;
+  s->ctr[2] = 0; s->ctr[3] = sid;
   s->ndraws = 0;
+}
+
+static inline void ncb_stream_init(ncb_stream_t* s, uint64_t seed, uint64_t index)
+{
+  ncb_stream_init_sid(s, seed, index, 0);
 }
 
 static inline double ncb_stream_next(ncb_stream_t* s)

@@ -1,0 +1,49 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref, built from
+/root/reference by oracle/Makefile).  Run here (the reference sources are not on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Per isotropic config: N energies (log-uniform 1e-5..10 eV + edge cases), total and per-component
+cross sections, and scatter outcomes under replay of the per-neutron Philox streams
+(seed=GOLDEN_SEED, index=i) through the reference's RNG interface, incl. the number of
+uniforms each neutron consumed.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from _libs import RefDrv, loguniform_energies  # noqa: E402
+from __graft_entry__ import CONFIGS  # noqa: E402
+
+GOLDEN_SEED = 20261017
+N = 4000
+
+
+def energies(n):
+    e = loguniform_energies(n, seed=777)
+    # edge cases the reference tests exercise: below/above SAB grid, Bragg thresholds, tiny and large
+    e[:12] = [1e-5, 1e-3, 0.0253, 1.0, 10.0, 1e-9, 1e-7, 4.9999, 5.0001, 0.0037, 0.00375, 100.0]
+    return e
+
+
+def main():
+    for key, cfg in CONFIGS.items():
+        r = RefDrv(cfg)
+        if RefDrv.lib().refdrv_isoriented(r.h):
+            continue
+        e = energies(N)
+        xs = r.xs_iso(e)
+        xsc = r.xs_iso_components(e)
+        eo, mu, nd = r.sample_iso(e, seed=GOLDEN_SEED, first_index=0)
+        out = os.path.join(HERE, "iso_%s.npz" % key)
+        np.savez_compressed(out, cfg=cfg, seed=GOLDEN_SEED, ekin=e, xs=xs, xs_components=xsc,
+                            comp_names=np.array(r.compnames()), ekin_out=eo, mu=mu, ndraws=nd)
+        print(out, os.path.getsize(out), "bytes; mean draws %.2f" % nd.mean())
+
+
+if __name__ == "__main__":
+    main()

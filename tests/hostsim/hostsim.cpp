@@ -21,6 +21,7 @@ namespace {
   struct Handle {
     ncb::LoadedMaterial lm;
     ncb::Material mat;
+    ncb::HotTabs H;
   };
   struct LutInit { LutInit() { ncb::fillErfcLutHost( ncb::g_erfc_lut_host ); } } s_lutinit;
   thread_local std::string g_err;
@@ -70,6 +71,7 @@ extern "C" {
       auto h = std::make_unique<Handle>();
       ncb::loadBlob( blob, nbytes, h->lm );
       h->mat = ncb::relocated( h->lm, h->lm.arena.data() );
+      ncb::hotTabsFromMaterial( h->mat, h->H );
       buildSabHost( *h );
       return h.release();
     } catch ( std::exception& e ) {
@@ -84,18 +86,20 @@ extern "C" {
   void hostsim_xs_iso( void* vh, const double* ekin, uint64_t n, double* out )
   {
     auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
     for ( uint64_t i = 0; i < n; ++i )
-      out[i] = ncb::matXSIso( M, ekin[i], nullptr, nullptr );
+      out[i] = ncb::matXSIso( M, H, ekin[i], nullptr, nullptr );
   }
 
   // per-component unscaled xs out[c*n+i]
   void hostsim_xs_iso_components( void* vh, const double* ekin, uint64_t n, double* out )
   {
     auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
     for ( int c = 0; c < M.ncomp; ++c )
       for ( uint64_t i = 0; i < n; ++i ) {
         int aux;
-        out[c*n+i] = ncb::domainContains( M.comp[c].dom_lo, M.comp[c].dom_hi, ekin[i] ) ? ncb::compXSIso( M, c, ekin[i], aux ) : 0.0;
+        out[c*n+i] = ncb::domainContains( M.comp[c].dom_lo, M.comp[c].dom_hi, ekin[i] ) ? ncb::compXSIso( M, H, c, ekin[i], aux ) : 0.0;
       }
   }
 
@@ -103,10 +107,11 @@ extern "C" {
                            double* ekin_out, double* mu_out, uint32_t* ndraws, int32_t* errs )
   {
     auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
     for ( uint64_t i = 0; i < n; ++i ) {
       ncb::Rng rng; rng.init( seed, first_index + i );
       int err = 0, ich;
-      ncb::matSampleIso( M, ekin[i], rng, ekin_out[i], mu_out[i], err, ich );
+      ncb::matSampleIso( M, H, ekin[i], rng, ekin_out[i], mu_out[i], err, ich );
       if ( ndraws ) ndraws[i] = rng.ndraws;
       if ( errs ) errs[i] = err;
     }
@@ -116,10 +121,11 @@ extern "C" {
                                 double* ekin_out, double* mu_out, uint32_t* ndraws, int32_t* errs )
   {
     auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
     for ( uint64_t i = 0; i < n; ++i ) {
       ncb::Rng rng; rng.init( seed, first_index + i );
       int err = 0;
-      ncb::compSampleIso( M, c, -1, ekin[i], rng, ekin_out[i], mu_out[i], err );
+      ncb::compSampleIso( M, H, c, -1, ekin[i], rng, ekin_out[i], mu_out[i], err );
       if ( ndraws ) ndraws[i] = rng.ndraws;
       if ( errs ) errs[i] = err;
     }

@@ -1,0 +1,114 @@
+"""CPU tests of the compiled-material format and of the C-ABI library's exported surface."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HDR_FMT = "<QIIIIQdd208s"
+COMP_FMT = "<IIdddQQ"
+
+
+def parse_header(blob):
+    magic, version, ncomp, oriented, _r, nbytes, dlo, dhi, cfg = struct.unpack_from(HDR_FMT, blob, 0)
+    off = struct.calcsize(HDR_FMT)
+    comps = []
+    for i in range(8):
+        kind, _r2, scale, clo, chi, coff, cn = struct.unpack_from(COMP_FMT, blob, off + i * struct.calcsize(COMP_FMT))
+        if i < ncomp:
+            comps.append(dict(kind=kind, scale=scale, dom=(clo, chi), off=coff, nbytes=cn))
+    return dict(magic=magic, version=version, ncomp=ncomp, oriented=oriented, nbytes=nbytes, dom=(dlo, dhi),
+                cfg=cfg.split(b"\0")[0].decode(), comps=comps)
+
+
+def sab_grids(blob, icomp):
+    h = parse_header(blob)
+    c = h["comps"][icomp]
+    assert c["kind"] == 3
+    off = c["off"]
+    vals = struct.unpack_from("<14d4Q", blob, off)
+    negrid = vals[14]
+    base = off + 14 * 8 + 4 * 8
+    egrid = np.frombuffer(blob, dtype=np.float64, count=negrid, offset=base)
+    xs = np.frombuffer(blob, dtype=np.float64, count=negrid, offset=base + 8 * negrid)
+    return egrid, xs
+
+
+def test_header_declares_only_exported_symbols():
+    """Every function include/ncrystal_b200.h declares is exported by the built library
+    (no compute calls here: there is no GPU on this box)."""
+    hdr = open(os.path.join(ROOT, "include", "ncrystal_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ncrystal_[a-z0-9_]+|ncb200_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"ncrystal_process_t", "ncrystal_scatter_t"}
+    assert len(names) > 50
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(_lib.SIGNATURES) == names, sorted(set(_lib.SIGNATURES) ^ names)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ncrystal_b200 as nc
+    with pytest.raises(nc.NCException) as ei:
+        nc.Scatter.fromBlob(b"\0" * 1024)
+    assert "CUDA device" in str(ei.value) or "magic" in str(ei.value)
+
+
+def test_error_state_machinery():
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    L.ncrystal_clearerror()
+    assert L.ncrystal_error() == 0
+    h = _lib.ncrystal_scatter_t(None)
+    p = L.ncrystal_cast_scat2proc(h)   # invalid handle -> error state, null result
+    assert L.ncrystal_error() == 1 and not p.internal
+    assert b"Invalid" in L.ncrystal_lasterror()
+    assert L.ncrystal_lasterrortype() == b"LogicError"
+    L.ncrystal_clearerror()
+    assert L.ncrystal_error() == 0 and L.ncrystal_lasterror() is None
+    out = np.zeros(6)
+    e = np.ones(3)
+    dp = C.POINTER(C.c_double)
+    L.ncrystal_crosssection_nonoriented_many(_lib.ncrystal_process_t(None), e.ctypes.data_as(dp), 3, 2, out.ctypes.data_as(dp))
+    assert L.ncrystal_error() == 1 and np.all(out == -1.0)   # sentinel fill, ref: ncrystal.cc:1136-1140
+    L.ncrystal_clearerror()
+    eo = np.zeros(3)
+    mu = np.zeros(3)
+    L.ncrystal_samplescatterisotropic_many(_lib.ncrystal_scatter_t(None), e.ctypes.data_as(dp), 3, 1,
+                                           eo.ctypes.data_as(dp), mu.ctypes.data_as(dp))
+    assert np.all(eo == -1.0) and np.all(mu == -999.0)       # ref: ncrystal.cc:1239-1245
+    L.ncrystal_clearerror()
+    L.ncrystal_setrandgen(None)
+    assert L.ncrystal_error() == 1
+    L.ncrystal_clearerror()
+
+
+def test_cfg_filestem():
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    buf = C.create_string_buffer(256)
+    L.ncb200_cfg_to_filestem(b"Al_sg225.ncmat ; temp=293.15K", buf, 256)
+    assert buf.value == b"Al_sg225.ncmat+temp=293.15K"
+
+
+def test_blob_layout_al(configs):
+    from oracle_check import material_path
+    p = material_path(configs["Al"])
+    if not os.path.exists(p):
+        pytest.skip("compiled material not built")
+    blob = open(p, "rb").read()
+    h = parse_header(blob)
+    assert h["magic"] == 0x0030303242434e and h["ncomp"] == 3 and h["oriented"] == 0
+    assert [c["kind"] for c in h["comps"]] == [2, 1, 3]       # ElInc, PowderBragg, SAB (reference order)
+    assert h["nbytes"] == len(blob)
+    egrid, xs = sab_grids(blob, 2)
+    assert egrid.size == 300 and np.all(np.diff(egrid) > 0) and abs(egrid[-1] - 5.0) < 1e-9
