@@ -14,7 +14,7 @@
 #  define NCB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #  define NCB_HD inline
-#  define NCB_HD_NOINLINE
+#  define NCB_HD_NOINLINE inline
 #endif
 
 namespace ncb {
@@ -30,6 +30,22 @@ namespace ncb {
   constexpr double kWl2Ekin         = 0.081804209605330899;
   constexpr double kInf             = HUGE_VAL;
   constexpr double kDblMin          = 2.2250738585072014e-308; // numeric_limits<double>::min()
+
+  // Out-of-line fp64 libm: CUDA inlines the (large) double-precision implementations of
+  // exp/log/erf/... at every call site; with ~40 call sites on the sampling path that made
+  // the kernels >64 KB of SASS and instruction-fetch bound (ncu: stall_no_instruction).
+  // One shared copy per function keeps the hot loops inside the instruction cache.
+#if defined(__CUDACC__)
+#  define NCB_MATHFN __host__ __device__ __noinline__
+#else
+#  define NCB_MATHFN inline
+#endif
+  NCB_MATHFN double m_exp( double x ) { return exp(x); }
+  NCB_MATHFN double m_log( double x ) { return log(x); }
+  NCB_MATHFN double m_expm1( double x ) { return expm1(x); }
+  NCB_MATHFN double m_log1p( double x ) { return log1p(x); }
+  NCB_MATHFN double m_erf( double x ) { return erf(x); }
+  NCB_MATHFN double m_erfc( double x ) { return erfc(x); }
 
   NCB_HD double dmin( double a, double b ) { return a < b ? a : b; }       // ncmin
   NCB_HD double dmax( double a, double b ) { return a > b ? a : b; }       // ncmax

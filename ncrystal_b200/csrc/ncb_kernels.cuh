@@ -130,6 +130,199 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
+  // ------------------------------------------------------- sampling (isotropic), v2
+  // Three launches per batch instead of one divergent kernel:
+  //   k_sample_classify  xs + component pick; the cheap elastic leaves (PowderBragg, ElInc) are
+  //                      sampled in place; S(alpha,beta) table neutrons and free-gas neutrons
+  //                      (FreeGas leaf, SAB above Emax) are appended to two index queues with
+  //                      warp-aggregated atomics
+  //   k_sample_sab       the S(alpha,beta) table path (Alg. 1) over its queue
+  //   k_sample_fg        the free-gas rejection samplers over their queue
+  // Each queue holds homogeneous work, so warps no longer serialise over unrelated code paths.
+  // Because the random streams are counter based, a later kernel resumes a neutron's stream
+  // simply by re-deriving block 0 (no RNG state is stored).
+  constexpr uint32_t kQueueIdxBits = 28;
+  constexpr uint32_t kQueueIdxMask = ( 1u << kQueueIdxBits ) - 1u;   // <= 2^28 neutrons per launch
+
+  struct QueueArgs {
+    uint32_t* q_sab;    // S(alpha,beta) table path, E < Emax
+    uint32_t* q_fg;     // free-gas leaf and S(alpha,beta) above Emax
+    uint32_t* q_emax;   // pairs (entry, draws consumed): table sampling at E=Emax requested by the high-E analysis
+    uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs)
+  };
+
+  __device__ __forceinline__ void warpPush( bool pred, uint32_t* q, uint32_t* counter, uint32_t entry )
+  {
+    const uint32_t mask = __ballot_sync( 0xffffffffu, pred );
+    if ( !mask ) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs( mask ) - 1;
+    uint32_t base = 0;
+    if ( lane == leader )
+      base = atomicAdd( counter, (uint32_t)__popc( mask ) );
+    base = __shfl_sync( 0xffffffffu, base, leader );
+    if ( pred )
+      q[ base + __popc( mask & ( ( 1u << lane ) - 1u ) ) ] = entry;
+  }
+
+  __global__ void __launch_bounds__(256)
+  k_sample_classify( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                     const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int errs = 0;
+    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < A.n; base += stride ) {
+      const uint64_t i = base + threadIdx.x;
+      int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue
+      uint32_t entry = 0;
+      if ( i < A.n ) {
+        const double ekin = A.ekin[i];
+        double eout = ekin, mu = 1.0, tot = 0.0;
+        int ich = -1;
+        uint32_t nd = 0;
+        if ( domainContains( M.dom_lo, M.dom_hi, ekin ) ) {
+          double cumul[kMaxComp];
+          int aux[kMaxComp];
+          tot = matXSIso( M, H, ekin, cumul, aux );
+          Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+          ich = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
+          const Comp& c = M.comp[ich];
+          if ( c.kind == KIND_SAB ) {
+            const SabT& T = M.sab[c.idx];
+            // upper_bound(egrid,E)==end  <=>  !(E < egrid.back())  (NCSABSampler.cc:166-171)
+            cls = ( ekin < H.sab_egrid[c.idx][T.negrid-1] ) ? 1 : 2;
+          } else if ( c.kind == KIND_FREEGAS ) {
+            cls = 2;
+          } else if ( c.kind == KIND_POWDERBRAGG ) {
+            // PowderBragg::sampleScatterIsotropic, ref: NCPowderBragg.cc:202-216
+            const PowderBraggT& T = M.pb[c.idx];
+            if ( !( ekin < T.threshold || !isFinite(ekin) ) ) {
+              const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+              mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
+            }
+            nd = rng.ndraws;
+          } else if ( c.kind == KIND_ELINC ) {
+            mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
+            nd = rng.ndraws;
+          }
+          entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
+        }
+        if ( A.xs_out ) A.xs_out[i] = tot;
+        if ( A.component ) A.component[i] = ich;
+        if ( cls == 0 ) {
+          A.ekin_out[i] = eout;
+          A.mu_out[i] = mu;
+          if ( A.ndraws ) A.ndraws[i] = nd;
+        }
+      }
+      warpPush( cls == 1, Q.q_sab, Q.counts + 0, entry );
+      warpPush( cls == 2, Q.q_fg, Q.counts + 1, entry );
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
+  // S(alpha,beta) table path over a queue.  kAtEmax=false: entries of q_sab (E < Emax, stream
+  // resumes after the component pick); kAtEmax=true: (entry, ndraws) pairs of q_emax.
+  template <bool kAtEmax>
+  __global__ void __launch_bounds__(128)
+  k_sample_sab( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count )
+  {
+    const uint32_t nq = *count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    int errs = 0;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
+      const uint32_t entry = kAtEmax ? queue[2*j] : queue[j];
+      const uint32_t i = entry & kQueueIdxMask;
+      const int ich = (int)( entry >> kQueueIdxBits );
+      const double ekin = A.ekin[i];
+      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      rng.seek( kAtEmax ? queue[2*j+1] : ( M.ncomp > 1 ? 1u : 0u ) );
+      const SabT& T = M.sab[M.comp[ich].idx];
+      double eout, mu;
+      int err = 0;
+      if ( kAtEmax )
+        sabSampleScatterAtEmax( T, ekin, rng, eout, mu, err );
+      else
+        sabSampleScatter<false>( T, ekin, rng, eout, mu, err );
+      A.ekin_out[i] = eout;
+      A.mu_out[i] = mu;
+      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+      errs |= err;
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
+  // Free-gas samplers over q_fg: the FreeGas leaf, and for S(alpha,beta) above Emax the
+  // high-E analysis (SABSampler::sampleHighE); neutrons it sends back to the tabulated kernel
+  // are appended to q_emax together with their stream position.
+  __global__ void __launch_bounds__(128)
+  k_sample_fg( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+               const __grid_constant__ QueueArgs Q )
+  {
+    const uint32_t nq = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nq_up = ( nq + 31u ) & ~31u;   // warp-uniform trip count (warpPush uses full-mask ballots)
+    int errs = 0;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq_up; j += stride ) {
+      bool to_emax = false;
+      uint32_t entry = 0, nd = 0;
+      if ( j < nq ) {
+        entry = Q.q_fg[j];
+        const uint32_t i = entry & kQueueIdxMask;
+        const int ich = (int)( entry >> kQueueIdxBits );
+        const double ekin = A.ekin[i];
+        Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+        rng.seek( M.ncomp > 1 ? 1u : 0u );
+        const Comp& c = M.comp[ich];
+        double eout = -1.0, mu = -999.0;
+        int err = 0;
+        if ( c.kind == KIND_FREEGAS ) {
+          fgSampleScatter( M.fg[c.idx], ekin, rng, eout, mu, err );
+        } else {
+          const SabT& T = M.sab[c.idx];
+          double alpha, beta;
+          if ( sabSampleHighE( T, ekin, rng, alpha, beta, err ) ) {
+            if ( !( err & ERR_SAB_DISCARD ) )
+              sabFinishScatter( T, ekin, alpha, beta, rng, eout, mu, err );
+          } else {
+            to_emax = true;
+          }
+        }
+        nd = rng.ndraws;
+        if ( !to_emax ) {
+          A.ekin_out[i] = eout;
+          A.mu_out[i] = mu;
+          if ( A.ndraws ) A.ndraws[i] = nd;
+        }
+        errs |= err;
+      }
+      // paired push: entry and stream position
+      const uint32_t mask = __ballot_sync( 0xffffffffu, to_emax );
+      if ( mask ) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs( mask ) - 1;
+        uint32_t base = 0;
+        if ( lane == leader )
+          base = atomicAdd( Q.counts + 2, (uint32_t)__popc( mask ) );
+        base = __shfl_sync( 0xffffffffu, base, leader );
+        if ( to_emax ) {
+          const uint32_t pos = base + __popc( mask & ( ( 1u << lane ) - 1u ) );
+          Q.q_emax[2*pos] = entry;
+          Q.q_emax[2*pos+1] = nd;
+        }
+      }
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
   // ------------------------------------------------------------ SAB table builder
   __global__ void k_sab_logs( const double* __restrict__ sab, double* __restrict__ logsab, size_t n )
   {

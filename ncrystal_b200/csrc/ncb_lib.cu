@@ -221,6 +221,7 @@ namespace {
     buildStagePlan( *dm );
     setSmemAttr( k_xs_iso, dm->sp.total );
     setSmemAttr( k_sample_iso, dm->sp.total );
+    setSmemAttr( k_sample_classify, dm->sp.total );
     buildSabTablesOnDevice( *dm, 0 );
     return dm;
   }
@@ -248,11 +249,16 @@ namespace {
     // host-pointer pipeline resources (lazily created)
     cudaStream_t streams[kSlots] = { nullptr, nullptr };
     double* d_stage[kSlots] = { nullptr, nullptr };
+    // work queues of the split sampling path: one context per pipeline slot + one for the
+    // device-pointer entry points (a handle has at most one launch sequence in flight per context)
+    struct QueueCtx { uint32_t* q = nullptr; uint32_t* counts = nullptr; size_t cap = 0; };
+    QueueCtx qctx[kSlots+1];
 
     Scatter() { fp.tag = kScatterTag; fp.self = this; }
     ~Scatter()
     {
       if ( d_err ) cudaFree( d_err );
+      for ( auto& c : qctx ) { if ( c.q ) cudaFree( c.q ); if ( c.counts ) cudaFree( c.counts ); }
       for ( int s = 0; s < kSlots; ++s ) {
         if ( d_stage[s] ) cudaFree( d_stage[s] );
         if ( streams[s] ) cudaStreamDestroy( streams[s] );
@@ -264,6 +270,17 @@ namespace {
         CUDA_OK( cudaMalloc( &d_err, sizeof(int) ) );
         CUDA_OK( cudaMemset( d_err, 0, sizeof(int) ) );
       }
+    }
+    QueueCtx& ensureQueues( int ictx, size_t n )
+    {
+      QueueCtx& c = qctx[ictx];
+      if ( !c.counts ) CUDA_OK( cudaMalloc( &c.counts, 4*sizeof(uint32_t) ) );
+      if ( c.cap < n ) {
+        if ( c.q ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( c.q ) ); c.q = nullptr; }
+        c.cap = n + n/8 + 1024;
+        CUDA_OK( cudaMalloc( &c.q, 4*c.cap*sizeof(uint32_t) ) );
+      }
+      return c;
     }
     void ensurePipeline()
     {
@@ -393,24 +410,52 @@ namespace {
     CUDA_OK( cudaGetLastError() );
   }
 
-  void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu, cudaStream_t st )
+  bool useSampleV1()
+  {
+    static const bool v1 = []{ const char* e = std::getenv( "NCB200_SAMPLE_V1" ); return e && *e && *e != '0'; }();
+    return v1;
+  }
+
+  void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu,
+                        cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     if ( dm.mat.oriented )
       throw Err( "LogicError", "ncrystal_samplescatterisotropic called for an oriented process" );
     s->ensureErrWord();
-    SampleArgs A;
-    A.ekin = d_ekin; A.n = n; A.seed = s->seed; A.first_index = s->next_index; A.sid = s->sid;
-    A.xs_out = d_xs; A.ekin_out = d_eout; A.mu_out = d_mu;
-    A.ndraws = s->d_diag_ndraws; A.component = s->d_diag_comp; A.err_flags = s->d_err;
+    uint32_t* diag_nd = s->d_diag_ndraws;
+    int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
+    const uint64_t maxn = useSampleV1() ? n : ( (uint64_t)1 << kQueueIdxBits );
+    for ( uint64_t done = 0; done < n; done += maxn ) {
+      const uint64_t m = std::min<uint64_t>( maxn, n - done );
+      SampleArgs A;
+      A.ekin = d_ekin + done; A.n = m; A.seed = s->seed; A.first_index = s->next_index + done; A.sid = s->sid;
+      A.xs_out = d_xs ? d_xs + done : nullptr; A.ekin_out = d_eout + done; A.mu_out = d_mu + done;
+      A.ndraws = diag_nd ? diag_nd + done : nullptr; A.component = diag_comp ? diag_comp + done : nullptr;
+      A.err_flags = s->d_err;
+      const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
+      if ( useSampleV1() ) {
+        k_sample_iso<<< gridFor( m, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A );
+        ++g_launches;
+      } else {
+        Scatter::QueueCtx& qc = s->ensureQueues( ictx, m );
+        QueueArgs Q;
+        Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
+        CUDA_OK( cudaMemsetAsync( qc.counts, 0, 4*sizeof(uint32_t), st ) );
+        k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q );
+        const unsigned nsm = (unsigned)numSMs( dm.device );
+        const unsigned gsab = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
+        const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*4 );
+        k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
+        k_sample_fg<<< gfg, 128, 0, st >>>( dm.mat, A, Q );
+        k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
+        g_launches += 4;
+      }
+      CUDA_OK( cudaGetLastError() );
+    }
     s->next_index += n;
-    const int threads = 128;
-    const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
-    k_sample_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, A );
-    ++g_launches;
-    CUDA_OK( cudaGetLastError() );
   }
 
   int fetchDeviceErrors( Scatter* s, cudaStream_t st )
@@ -441,7 +486,7 @@ namespace {
   // that the H2D copy of chunk c+1 overlaps the kernel and D2H copy of chunk c.
   // `launch(chunk_n, in_dev[], out_dev[], stream)` enqueues the kernel(s).
   void runHostPipeline( Scatter* s, uint64_t n, int nin, const double* const* in, int nout, double* const* out,
-                        const std::function<void(uint64_t,double* const*,double* const*,cudaStream_t)>& launch )
+                        const std::function<void(uint64_t,double* const*,double* const*,cudaStream_t,int)>& launch )
   {
     if ( !n ) return;
     s->ensurePipeline();
@@ -458,7 +503,7 @@ namespace {
       }
       for ( int k = 0; k < nout; ++k )
         dout[k] = base + (size_t)(4+k)*kChunk;
-      launch( m, din, dout, st );
+      launch( m, din, dout, st, slot );
       for ( int k = 0; k < nout; ++k )
         CUDA_OK( cudaMemcpyAsync( out[k] + done, dout[k], m*sizeof(double), cudaMemcpyDeviceToHost, st ) );
       done += m;
@@ -477,7 +522,7 @@ namespace {
     DeviceGuard dg( s->dm->device );
     const double* in[1] = { ekin };
     double* out[1] = { results };
-    runHostPipeline( s, n, 1, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st ) {
+    runHostPipeline( s, n, 1, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int ) {
       launchXSIso( s, di[0], m, dout[0], st );
     } );
     // deterministic: further repeats are copies (ref loop order: results[r*n+i], ncrystal.cc:1125-1133)
@@ -492,8 +537,8 @@ namespace {
     for ( uint64_t r = 0; r < repeat; ++r ) {
       const double* in[1] = { ekin };
       double* out[2] = { eout + r*n, mu + r*n };
-      runHostPipeline( s, n, 1, in, 2, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st ) {
-        launchSampleIso( s, di[0], m, nullptr, dout[0], dout[1], st );
+      runHostPipeline( s, n, 1, in, 2, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int slot ) {
+        launchSampleIso( s, di[0], m, nullptr, dout[0], dout[1], st, slot );
       } );
     }
     raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );

@@ -50,7 +50,7 @@ namespace ncb {
     if ( t > 24.0 )
       return 1.0 / t;
     t = -t;
-    return expm1(t) / t;
+    return m_expm1(t) / t;
   }
 
   // evaluate / evalXSContribsCommul, ref: NCElIncXS.cc:117-141.  `contribs` may be null.
@@ -75,7 +75,7 @@ namespace ncb {
   }
 
   // sampleMuMonoAtomic, ref: NCElIncXS.cc:81-115
-  NCB_HD double elincSampleMuMono( Rng& rng, double ekin, double msd )
+  NCB_HD_NOINLINE double elincSampleMuMono( Rng& rng, double ekin, double msd )
   {
     constexpr double kkk = 8.0 * kPiSq * kEkin2WlSqInv;
     const double twoksq = kkk * ekin;
@@ -88,7 +88,7 @@ namespace ncb {
           return mu;
       }
     }
-    return dclamp( log1p( rng.generate() * expm1( 2.0*a ) ) / a - 1.0, -1.0, 1.0 );
+    return dclamp( m_log1p( rng.generate() * m_expm1( 2.0*a ) ) / a - 1.0, -1.0, 1.0 );
   }
 
   // EPointAnalysis::sampleMu, ref: NCElIncXS.cc:178-190 (+ ElIncScatter::sampleScatterIsotropic,
@@ -105,7 +105,7 @@ namespace ncb {
 
   // ------------------------------------------------------------ free-gas xs
   // FreeGasXSProvider::evalXSShapeASq, ref: src/phys_utils/NCFreeGasUtils.cc:64-83
-  NCB_HD double fgXSShapeASq( double a_squared )
+  NCB_HD_NOINLINE double fgXSShapeASq( double a_squared )
   {
     if ( a_squared > 36.0 )
       return 1.0 + 0.5 / a_squared;
@@ -122,7 +122,7 @@ namespace ncb {
       return kInvSqrtPi * ( 2.0 / a + a *( c1- a2*(c2-a2*(c3-a2*(c4-a2*c5)))));
     }
     const double inva = 1.0 / a;
-    return ( 1.0 + 0.5*inva*inva ) * erf(a) + kInvSqrtPi * exp(-a_squared)*inva;
+    return ( 1.0 + 0.5*inva*inva ) * m_erf(a) + kInvSqrtPi * m_exp(-a_squared)*inva;
   }
 
   // FreeGasXSProvider::crossSection, ref: include/NCrystal/internal/phys_utils/NCFreeGasUtils.hh:122-125

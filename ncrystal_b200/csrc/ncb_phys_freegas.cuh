@@ -76,15 +76,15 @@ namespace ncb {
       a = -a;
       const double t = a; a = b; b = t;
     }
-    const double erfca = a > 27.3 ? 0.0 : erfc(a);
+    const double erfca = a > 27.3 ? 0.0 : m_erfc(a);
     if ( b > a+4.0 && ( a >= 4 || ( a < 0.0 && b > 6.0 ) ) )
       return erfca;
-    const double erfcb = b > 27.3 ? 0.0 : erfc(b);
+    const double erfcb = b > 27.3 ? 0.0 : m_erfc(b);
     return erfca - erfcb;
   }
 
   // erfcdiff, ref: NCMath.cc:363-390
-  NCB_HD double erfcdiff( double a, double b )
+  NCB_HD_NOINLINE double erfcdiff( double a, double b )
   {
     if ( dmax( fabs(a), fabs(b) ) < 0.32 ) {
       constexpr double c1  = - 2.0 * kInvSqrtPi;
@@ -105,12 +105,12 @@ namespace ncb {
   }
 
   // erfc_rescaled, ref: NCMath.cc:393-415
-  NCB_HD double erfcRescaled( double x, double b )
+  NCB_HD_NOINLINE double erfcRescaled( double x, double b )
   {
     if ( b < -745.1 )
       return 0.0;
     if ( ( x < 23.0 && fabs(b) < 700 ) || x < 5 )
-      return exp(b) * erfc(x);
+      return m_exp(b) * m_erfc(x);
     const double bxx = b - x*x;
     if ( bxx < -745.1 )
       return 0.0;
@@ -121,19 +121,19 @@ namespace ncb {
     const double c11 = -29.53125;
     const double y = 1/x;
     const double y2 = y*y;
-    return kInvSqrtPi*exp(bxx)*(y+y2*(c3+y2*(c5+y2*(c7+y2*(c9+y2*c11)))));
+    return kInvSqrtPi*m_exp(bxx)*(y+y2*(c3+y2*(c5+y2*(c7+y2*(c9+y2*c11)))));
   }
 
   // RandExpIntervalSampler, ref: NCRandUtils.hh:180-215
   struct ExpIntervalSampler {
     double a = 0, c1 = 0, c2 = 0;
-    NCB_HD void set( double a_, double b_, double c_ ) { a = a_; c1 = -1.0/c_; c2 = expm1( -c_*(b_-a_) ); }
+    NCB_HD void set( double a_, double b_, double c_ ) { a = a_; c1 = -1.0/c_; c2 = m_expm1( -c_*(b_-a_) ); }
     NCB_HD void invalidate() { a = c1 = c2 = 0.0; }
     NCB_HD bool isValid() const { return c1 < 0.0; }
-    NCB_HD double sample( Rng& rng ) const { return a + c1 * log( 1.0 + rng.generate() * c2 ); }
+    NCB_HD double sample( Rng& rng ) const { return a + c1 * m_log( 1.0 + rng.generate() * c2 ); }
   };
 
-  // randExpDivSqrt, ref: NCRandUtils.cc:224-380.  Sample exp(-c*x)/sqrt(x) on [a,b].
+  // randExpDivSqrt, ref: NCRandUtils.cc:224-380.  Sample m_exp(-c*x)/sqrt(x) on [a,b].
   NCB_HD_NOINLINE double randExpDivSqrt( Rng& rng, double c, double a, double b )
   {
     const double A = c*a;
@@ -182,7 +182,7 @@ namespace ncb {
           if ( ugen > 4.0 && Raccept > 0.0183156388887343 )
             continue;
         }
-        if ( Raccept < exp(-ugen) )
+        if ( Raccept < m_exp(-ugen) )
           break;
       }
       return dclamp( (ugen+A)/c, a, b );
@@ -190,16 +190,16 @@ namespace ncb {
   }
 
   // f_eval lambda of randExpMInvXMCXDivSqrtX, ref: NCFreeGasUtils.cc:314-322
-  NCB_HD double fgFEval( double xmax, double c, double x )
+  NCB_HD_NOINLINE double fgFEval( double xmax, double c, double x )
   {
     const double exparg = (x-xmax)/(x*xmax) - c*(x-xmax);
     if ( exparg >= 706.0 )
       return 1.0;
-    return exparg < -745.1 ? 0.0 : exp(exparg)*sqrt(xmax/x);
+    return exparg < -745.1 ? 0.0 : m_exp(exparg)*sqrt(xmax/x);
   }
 
   // randExpMInvXMCXDivSqrtX, ref: NCFreeGasUtils.cc:237-490.
-  // Sample f(x)=exp(-1/x-c*x)/sqrt(x) over [xm,xp].
+  // Sample f(x)=m_exp(-1/x-c*x)/sqrt(x) over [xm,xp].
   NCB_HD_NOINLINE double randExpMInvXMCXDivSqrtX( Rng& rng, double c, double xm, double xp )
   {
     if ( xp == xm )
@@ -297,7 +297,7 @@ namespace ncb {
           return xgen;
       } else {
         const double xgen = randExpDivSqrt( rng, c, xswitch, xp );
-        if ( rng.generate() < exp( (xgen-xp)/(xgen*xp) ) )
+        if ( rng.generate() < m_exp( (xgen-xp)/(xgen*xp) ) )
           return xgen;
       }
     }
@@ -333,9 +333,9 @@ namespace ncb {
     NCB_HD void evalExpMBeta()
     {
       if ( expmbeta < 0 )
-        expmbeta = beta < -700.0 ? 0.0 : exp(-beta);
+        expmbeta = beta < -700.0 ? 0.0 : m_exp(-beta);
     }
-    NCB_HD double evalExact()
+    NCB_HD_NOINLINE double evalExact()
     {
       double t1 = erfcdiff( k11, k12 );
       evalExpMBeta();
@@ -344,7 +344,7 @@ namespace ncb {
       double t2 = erfcdiff( k21, k22 );
       return normfact*( t1 + t2*expmbeta );
     }
-    NCB_HD PairDD evalQuickBounds()
+    NCB_HD_NOINLINE PairDD evalQuickBounds()
     {
       PairDD e11 = erfcQuickBounds( k11 );
       PairDD e12 = erfcQuickBounds( k12 );
@@ -373,7 +373,7 @@ namespace ncb {
       const double A = kInvNeutronMassAmu * mass_amu; // AtomMass::relativeToNeutronMass, NCTypes.hh:815
       m_invA = 1.0/A;
       m_Adiv4 = 0.25*A;
-      m_normfact = 0.5/erf( sqrt( m_c*m_invA ) );
+      m_normfact = 0.5/m_erf( sqrt( m_c*m_invA ) );
       m_c_real = ekin/kT;
     }
 
@@ -399,7 +399,7 @@ namespace ncb {
           constexpr double c7 =  1./5040.;
           area_closetail = b * (1.0+b*(c2+b*(c3+b*(c4+b*(c5+b*(c6+b*c7))))));
         } else {
-          area_fartail = Tlim_k1 - exp(-bbb);
+          area_fartail = Tlim_k1 - m_exp(-bbb);
           area_closetail = Tlim_k2;
         }
         const double invareatot = 1.0 / ( area_downscat + area_closetail + area_fartail );
@@ -467,7 +467,7 @@ namespace ncb {
             if ( !ov.expsampler.isValid() )
               ov.expsampler.set( Tlim, ov.b, 1.0 );
             beta = ov.expsampler.sample( rng );
-            foverlay = exp(-beta);
+            foverlay = m_exp(-beta);
           } else {
             const double bmax = dmin( ov.b, Tlim );
             while ( true ) {
@@ -548,8 +548,8 @@ namespace ncb {
           const double alpha = xx * fourA;
           if ( alpha < am || alpha > ap )
             continue;
-          // randExp(rng) = -log(rng.generate()), NCRandUtils.hh:175-178
-          if ( alpha*ap*( -log( rng.generate() ) ) >= t*(ap-alpha) )
+          // randExp(rng) = -m_log(rng.generate()), NCRandUtils.hh:175-178
+          if ( alpha*ap*( -m_log( rng.generate() ) ) >= t*(ap-alpha) )
             return alpha;
         }
       } else {

@@ -16,18 +16,19 @@ namespace ncb {
     ERR_SAB_LOOP_OUTER = 2,  // SABSampler::sampleAlphaBeta: 100 tries (NCSABSampler.cc:226)
     ERR_SAB_LOOP_INNER = 4,  // SABSamplerAtE_Alg1: 100 tries (NCSABSamplerModels.cc:150)
     ERR_SAB_DISCARD = 8,     // sampleHighE: P_discardinside > 0.95 (NCSABSampler.cc:112)
-    ERR_SAB_ISOFALLBACK = 16 // (warning only) isotropic fallback after 30 tries (NCSABSamplerModels.cc:99)
+    ERR_SAB_ISOFALLBACK = 16,// (warning only) isotropic fallback after 30 tries (NCSABSamplerModels.cc:99)
+    ERR_SAB_ROUTING = 32     // internal: E > Emax neutron reached the table-only kernel
   };
 
   // sampleLogLinDist_fast, ref: NCSABUtils.hh:282-303
-  NCB_HD double sampleLogLinDistFast( double a, double fa, double b, double fb, double rand, double logfa, double logfb )
+  NCB_HD_NOINLINE double sampleLogLinDistFast( double a, double fa, double b, double fb, double rand, double logfa, double logfb )
   {
     double df = fb - fa;
     if ( fa*fb*df != 0.0 ) {
       const double a_sub_b = a - b;
       const double logfa_fb = logfb - logfa;
       if ( a_sub_b * logfa_fb != 0.0 )
-        return a_sub_b * log( fa*exp( a*logfa_fb/a_sub_b ) / ( fa + rand*df ) ) / logfa_fb;
+        return a_sub_b * m_log( fa*m_exp( a*logfa_fb/a_sub_b ) / ( fa + rand*df ) ) / logfa_fb;
       df = 0.0;
     }
     if ( !df )
@@ -65,7 +66,7 @@ namespace ncb {
   }
 
   // SABSamplerAtE_Alg1::sampleAlpha, ref: NCSABSamplerModels.cc:157-233
-  NCB_HD double sabSampleAlpha( const SabT& T, const SabEPoint& ep, int ibeta, double rand_percentile )
+  NCB_HD_NOINLINE double sabSampleAlpha( const SabT& T, const SabEPoint& ep, int ibeta, double rand_percentile )
   {
     const SabAlphaInfo& info = T.ainfo[ ep.off_i + ( ibeta - ep.ibeta_off ) ];
     const int nalpha = T.nalpha;
@@ -219,7 +220,11 @@ namespace ncb {
     }
   }
 
-  // SABSampler::sampleAlphaBeta, ref: NCSABSampler.cc:158-227
+  // SABSampler::sampleAlphaBeta, ref: NCSABSampler.cc:158-227.
+  // kHighE=false instantiates the tabulated-kernel path only (E <= Emax): the kernels route
+  // E > Emax neutrons to a separate launch, which keeps the free-gas extender code (and its
+  // register footprint) out of the table-sampling kernel.
+  template <bool kHighE>
   NCB_HD void sabSampleAlphaBeta( const SabT& T, double ekin, Rng& rng, double& alpha, double& beta, int& err )
   {
     const int n = T.negrid;
@@ -229,6 +234,11 @@ namespace ncb {
     bool ultra_small_ekin_mode = false;
     const double ultra_small_ekin = egrid[0];
     if ( iu == n ) {
+      if ( !kHighE ) {
+        err |= ERR_SAB_ROUTING;
+        alpha = -1.0; beta = 0.0;
+        return;
+      }
       if ( sabSampleHighE( T, ekin, rng, alpha, beta, err ) )
         return; // (the reference returns whenever alpha>=0; errors flagged separately)
       ekin = egrid[n-1];
@@ -263,13 +273,61 @@ namespace ncb {
     err |= ERR_SAB_LOOP_OUTER;
   }
 
+  // Tail of SABSampler::sampleDeltaEMu (NCSABSampler.cc:229-236) + SABScatter::sampleScatterIsotropic
+  // (NCSABScatter.cc:93-100): (alpha,beta) at the neutron's own energy -> (E_final, mu).
+  NCB_HD void sabFinishScatter( const SabT& T, double ekin, double alpha, double beta, Rng& rng,
+                                double& ekin_out, double& mu, int& err )
+  {
+    double deltaE;
+    if ( muIsotropicAtBeta( beta, ekin/T.kT ) ) {
+      deltaE = beta*T.kT;
+      mu = rng.generate()*2.0 - 1.0;
+    } else {
+      alphaBetaToDeltaEMu( alpha, beta, ekin, T.kT, deltaE, mu, err );
+      if ( err & ERR_KIN_DENOM ) {
+        ekin_out = -1.0; mu = -999.0;
+        return;
+      }
+    }
+    ekin_out = dmax( 0.0, ekin + deltaE );
+  }
+
+  // Table sampling for a neutron above Emax whose high-E analysis (sabSampleHighE) asked for
+  // the tabulated kernel at E=Emax (NCSABSampler.cc:173-178): (alpha,beta) from the last
+  // overlay sampler with ekin:=Emax, then the outcome at the neutron's own energy.
+  NCB_HD void sabSampleScatterAtEmax( const SabT& T, double ekin_orig, Rng& rng, double& ekin_out, double& mu, int& err )
+  {
+    double alpha = 0.0, beta = 0.0;
+    const double emax = T.egrid[T.negrid-1];
+    // upper_bound(egrid, Emax) == end, so run the in-grid branch by hand on the last sampler:
+    const SabEPoint ep = T.ep[T.negrid-1];
+    const double ekin_div_kT = emax / T.kT;
+    bool ok = false;
+    for ( int loop = 0; loop < 100; ++loop ) {
+      sabSampleAtE( T, ep, ekin_div_kT, rng, alpha, beta, err );
+      if ( err & ERR_SAB_LOOP_INNER )
+        break;
+      if ( beta < -ekin_div_kT )
+        continue;
+      AlphaLimits alims = getAlphaLimits( ekin_div_kT, beta );
+      if ( inInterval( alims.first, alims.second, alpha ) ) { ok = true; break; }
+    }
+    if ( !ok ) {
+      if ( !( err & ERR_SAB_LOOP_INNER ) ) err |= ERR_SAB_LOOP_OUTER;
+      ekin_out = -1.0; mu = -999.0;
+      return;
+    }
+    sabFinishScatter( T, ekin_orig, alpha, beta, rng, ekin_out, mu, err );
+  }
+
   // SABSampler::sampleDeltaEMu (NCSABSampler.cc:229-236) + SABScatter::sampleScatterIsotropic
   // (NCSABScatter.cc:93-100)
+  template <bool kHighE = true>
   NCB_HD void sabSampleScatter( const SabT& T, double ekin, Rng& rng, double& ekin_out, double& mu, int& err )
   {
     double alpha = 0.0, beta = 0.0;
-    sabSampleAlphaBeta( T, ekin, rng, alpha, beta, err );
-    if ( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD ) ) {
+    sabSampleAlphaBeta<kHighE>( T, ekin, rng, alpha, beta, err );
+    if ( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD | ERR_SAB_ROUTING ) ) {
       ekin_out = -1.0; mu = -999.0;
       return;
     }

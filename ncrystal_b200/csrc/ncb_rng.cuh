@@ -38,6 +38,13 @@ namespace ncb {
       ndraws = 0; b2 = b3 = 0;
     }
 
+    // Position the stream so that the next generate() returns uniform number k.
+    NCB_HD void seek( uint32_t k )
+    {
+      if ( k & 1u ) { ndraws = k - 1u; generate(); }  // refill the second half of block k>>1
+      else ndraws = k;
+    }
+
     NCB_HD static double toFP01( uint32_t lo, uint32_t hi )
     {
       // x = hi:lo ; r1 = (x>>11)*2^-53 ; r2 = (x&0x7FF)*2^-64 ; (1-r1)-r2

@@ -46,15 +46,15 @@ namespace ncb {
     const bool linlin_mode = ( fa*fb == 0.0 );
     if ( x < midpoint ) {
       const double r = (x-a) / bma;
-      return ( linlin_mode ? ( fa + (fb-fa)*r ) : exp( logfa+(logfb-logfa)*r ) );
+      return ( linlin_mode ? ( fa + (fb-fa)*r ) : m_exp( logfa+(logfb-logfa)*r ) );
     } else {
       const double s = (b-x) / bma;
-      return ( linlin_mode ? ( fb + (fa-fb)*s ) : exp( logfb+(logfa-logfb)*s ) );
+      return ( linlin_mode ? ( fb + (fa-fb)*s ) : m_exp( logfb+(logfa-logfb)*s ) );
     }
   }
 
-  // stage 0a: log(S), ref: NCSABIntegrator.cc:113-117
-  NCB_HD double sabLogS( double s ) { return s > 0.0 ? log(s) : -kInf; }
+  // stage 0a: m_log(S), ref: NCSABIntegrator.cc:113-117
+  NCB_HD double sabLogS( double s ) { return s > 0.0 ? m_log(s) : -kInf; }
 
   // stage 0b: cumulative alpha integrals of one beta row, ref: NCSABIntegrator.cc:119-133
   NCB_HD void sabCumulRow( const double* agrid, const double* sab_row, const double* logsab_row, int nalpha, double* cumul_row )
@@ -79,7 +79,7 @@ namespace ncb {
   {
     t_alpha = alpha;
     t_sval = interpLogLinFast( agrid[aidx], sab[aidx], agrid[aidx+1], sab[aidx+1], alpha, logsab[aidx], logsab[aidx+1] );
-    t_logsval = log( dmax( t_sval, kDblMin ) );
+    t_logsval = m_log( dmax( t_sval, kDblMin ) );
   }
 
   // Stage 1.  Per-row part of activeGridRanges (NCSABUtils.cc:460-536), of
