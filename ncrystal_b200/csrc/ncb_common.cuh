@@ -46,6 +46,8 @@ namespace ncb {
   NCB_MATHFN double m_log1p( double x ) { return log1p(x); }
   NCB_MATHFN double m_erf( double x ) { return erf(x); }
   NCB_MATHFN double m_erfc( double x ) { return erfc(x); }
+  NCB_MATHFN double m_sqrt( double x ) { return sqrt(x); }   // (used on the free-gas path only)
+  NCB_MATHFN double m_div( double a, double b ) { return a / b; }
 
   NCB_HD double dmin( double a, double b ) { return a < b ? a : b; }       // ncmin
   NCB_HD double dmax( double a, double b ) { return a > b ? a : b; }       // ncmax

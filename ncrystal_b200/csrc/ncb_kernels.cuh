@@ -259,6 +259,111 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
+  // S(alpha,beta) table path, attempt-level scheduling ("lane refill").  The reference's
+  // sampler is two nested rejection loops (NCSABSampler.cc:203-225 around
+  // NCSABSamplerModels.cc:62-148) with ~75% acceptance: run neutron-per-lane, a warp waits
+  // for its unluckiest lane.  Here every pass of the loop below executes exactly ONE
+  // rejection attempt for every lane; a lane whose neutron is done pulls the next queue
+  // entry (warp-aggregated atomic on a global cursor) before the next pass, so lanes stay
+  // converged on the same code and busy until the queue drains.  The arithmetic and the
+  // order in which each neutron consumes its uniforms are unchanged.
+  template <bool kAtEmax>
+  __global__ void __launch_bounds__(128)
+  k_sample_sab_refill( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+                       const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
+                       uint32_t* __restrict__ cursor )
+  {
+    const uint32_t nq = *count;
+    const int lane = threadIdx.x & 31;
+    int errs = 0;
+    // per-lane work item
+    bool have = false;
+    uint32_t idx = 0;
+    int isab = 0, isampler = 0, inner = 0, outer = 0;
+    bool ultra = false;
+    double ekin_orig = 0.0, ekin_div_kT = 0.0, sampling_ediv = 0.0;
+    Rng rng; rng.init( A.seed, A.first_index, A.sid );
+    while ( true ) {
+      // ---- refill
+      const uint32_t need = __ballot_sync( 0xffffffffu, !have );
+      if ( need ) {
+        uint32_t base = 0;
+        const int leader = __ffs( need ) - 1;
+        if ( lane == leader )
+          base = atomicAdd( cursor, (uint32_t)__popc( need ) );
+        base = __shfl_sync( 0xffffffffu, base, leader );
+        if ( !have ) {
+          const uint32_t j = base + __popc( need & ( ( 1u << lane ) - 1u ) );
+          if ( j < nq ) {
+            const uint32_t entry = kAtEmax ? queue[2*j] : queue[j];
+            idx = entry & kQueueIdxMask;
+            isab = M.comp[ entry >> kQueueIdxBits ].idx;
+            const SabT& T = M.sab[isab];
+            ekin_orig = A.ekin[idx];
+            rng.init( A.seed, A.first_index + idx, A.sid );
+            rng.seek( kAtEmax ? queue[2*j+1] : ( M.ncomp > 1 ? 1u : 0u ) );
+            double ekin_eff;
+            if ( kAtEmax ) {
+              ekin_eff = T.egrid[T.negrid-1];
+              isampler = T.negrid-1;
+              ultra = false;
+            } else {
+              ekin_eff = ekin_orig;
+              isampler = sabPickSampler( T, T.egrid, ekin_orig, ultra );
+            }
+            ekin_div_kT = ekin_eff / T.kT;
+            sampling_ediv = ultra ? T.egrid[0] / T.kT : ekin_div_kT;
+            inner = outer = 0;
+            have = true;
+          }
+        }
+      }
+      if ( !__ballot_sync( 0xffffffffu, have ) )
+        break;
+      // ---- one attempt
+      if ( have ) {
+        const SabT& T = M.sab[isab];
+        const SabEPoint ep = T.ep[isampler];
+        double alpha = 0.0, beta = 0.0;
+        int err = 0;
+        bool done = false, failed = false;
+        bool inner_ok = true;
+        if ( ep.npts != 0 )
+          inner_ok = sabAttemptAtE( T, ep, sampling_ediv, rng, alpha, beta, err );
+        if ( !inner_ok ) {
+          if ( ++inner == 100 ) { err |= ERR_SAB_LOOP_INNER; failed = true; }
+        } else {
+          inner = 0;
+          // outer acceptance at the neutron's (effective) energy, NCSABSampler.cc:205-224
+          bool acc = false;
+          if ( !( beta < -ekin_div_kT ) ) {
+            AlphaLimits al = getAlphaLimits( ekin_div_kT, beta );
+            if ( inInterval( al.first, al.second, alpha ) ) {
+              acc = true;
+            } else if ( ultra ) {
+              alpha = al.first + rng.generate()*( al.second - al.first );
+              acc = true;
+            }
+          }
+          if ( acc ) done = true;
+          else if ( ++outer == 100 ) { err |= ERR_SAB_LOOP_OUTER; failed = true; }
+        }
+        if ( done || failed ) {
+          double eout = -1.0, mu = -999.0;
+          if ( done )
+            sabFinishScatter( T, ekin_orig, alpha, beta, rng, eout, mu, err );
+          A.ekin_out[idx] = eout;
+          A.mu_out[idx] = mu;
+          if ( A.ndraws ) A.ndraws[idx] = rng.ndraws;
+          have = false;
+        }
+        errs |= err;
+      }
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
   // Free-gas samplers over q_fg: the FreeGas leaf, and for S(alpha,beta) above Emax the
   // high-E analysis (SABSampler::sampleHighE); neutrons it sends back to the tabulated kernel
   // are appended to q_emax together with their stream position.

@@ -274,7 +274,7 @@ namespace {
     QueueCtx& ensureQueues( int ictx, size_t n )
     {
       QueueCtx& c = qctx[ictx];
-      if ( !c.counts ) CUDA_OK( cudaMalloc( &c.counts, 4*sizeof(uint32_t) ) );
+      if ( !c.counts ) CUDA_OK( cudaMalloc( &c.counts, 8*sizeof(uint32_t) ) );
       if ( c.cap < n ) {
         if ( c.q ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( c.q ) ); c.q = nullptr; }
         c.cap = n + n/8 + 1024;
@@ -443,14 +443,26 @@ namespace {
         Scatter::QueueCtx& qc = s->ensureQueues( ictx, m );
         QueueArgs Q;
         Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
-        CUDA_OK( cudaMemsetAsync( qc.counts, 0, 4*sizeof(uint32_t), st ) );
+        CUDA_OK( cudaMemsetAsync( qc.counts, 0, 8*sizeof(uint32_t), st ) );
         k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q );
         const unsigned nsm = (unsigned)numSMs( dm.device );
         const unsigned gsab = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
         const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*4 );
-        k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
-        k_sample_fg<<< gfg, 128, 0, st >>>( dm.mat, A, Q );
-        k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
+        static const int sabmode = []{ const char* e = std::getenv( "NCB200_SAB_MODE" ); return e ? std::atoi(e) : 1; }();
+        static const int sabctas = []{ const char* e = std::getenv( "NCB200_SAB_CTAS" ); return e ? std::atoi(e) : 5; }();
+        static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 8; }();
+        const unsigned gfg2 = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
+        if ( sabmode == 0 ) {
+          k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
+          k_sample_fg<<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
+          k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
+        } else {
+          // counts[3] / counts[4..] : cursors of the refill kernels
+          const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*sabctas );
+          k_sample_sab_refill<false><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+          k_sample_fg<<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
+          k_sample_sab_refill<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2, Q.counts + 4 );
+        }
         g_launches += 4;
       }
       CUDA_OK( cudaGetLastError() );

@@ -133,7 +133,7 @@ namespace ncb {
     NCB_HD double sample( Rng& rng ) const { return a + c1 * m_log( 1.0 + rng.generate() * c2 ); }
   };
 
-  // randExpDivSqrt, ref: NCRandUtils.cc:224-380.  Sample m_exp(-c*x)/sqrt(x) on [a,b].
+  // randExpDivSqrt, ref: NCRandUtils.cc:224-380.  Sample m_exp(-c*x)/m_sqrt(x) on [a,b].
   NCB_HD_NOINLINE double randExpDivSqrt( Rng& rng, double c, double a, double b )
   {
     const double A = c*a;
@@ -155,8 +155,8 @@ namespace ncb {
       const double B = U+A;
       if ( !(B>A) )
         return a;
-      const double sqrtA = sqrt(A);
-      const double sqrtB = sqrt(B);
+      const double sqrtA = m_sqrt(A);
+      const double sqrtB = m_sqrt(B);
       const double sqrtB_minus_sqrtA = sqrtB - sqrtA;
       const double twosqrtA = 2*sqrtA;
       double ugen;
@@ -195,27 +195,27 @@ namespace ncb {
     const double exparg = (x-xmax)/(x*xmax) - c*(x-xmax);
     if ( exparg >= 706.0 )
       return 1.0;
-    return exparg < -745.1 ? 0.0 : m_exp(exparg)*sqrt(xmax/x);
+    return exparg < -745.1 ? 0.0 : m_exp(exparg)*m_sqrt(xmax/x);
   }
 
   // randExpMInvXMCXDivSqrtX, ref: NCFreeGasUtils.cc:237-490.
-  // Sample f(x)=m_exp(-1/x-c*x)/sqrt(x) over [xm,xp].
+  // Sample f(x)=m_exp(-1/x-c*x)/m_sqrt(x) over [xm,xp].
   NCB_HD_NOINLINE double randExpMInvXMCXDivSqrtX( Rng& rng, double c, double xm, double xp )
   {
     if ( xp == xm )
       return xm;
-    const double sqrtc = sqrt(c);
+    const double sqrtc = m_sqrt(c);
     const double invsqrtc = 1/sqrtc;
     const double xpeak = ( c > 1e-5
-                           ? ( c > 1e200 ? invsqrtc : (sqrt(16.0*c+1.0)-1.0)/(4.0*c) )
+                           ? ( c > 1e200 ? invsqrtc : (m_sqrt(16.0*c+1.0)-1.0)/(4.0*c) )
                            : ( 2.0-c*(8.0-c*(64.0-c*(640.0-c*7168.0))) ) );
     if ( xpeak == 0.0 )
       return xm > 0.0 ? xm : dmin( kDblMin, xp );
     const double xmax = ( xm > xpeak ? xm : dmin( xp, xpeak ) );
     if ( !(xmax > 0.0) )
       return xm;
-    double xlarge = dmax( 5.0/sqrt(c), 2*xpeak );
-    double xsmall = dmin( 0.2/sqrt(c), 0.5*xpeak );
+    double xlarge = dmax( 5.0/m_sqrt(c), 2*xpeak );
+    double xsmall = dmin( 0.2/m_sqrt(c), 0.5*xpeak );
     if ( xp > xlarge )
       xp = dmin( xp, dmax( xm, xlarge ) + 15.0/c );
     if ( xm < xsmall ) {
@@ -248,8 +248,8 @@ namespace ncb {
       xswitch = xlarge;
       const double area_left = (xswitch-xm);
       const double B = c*xmax+1/xmax-1/xp;
-      area_right = ( erfcRescaled( sqrtc*sqrt(xswitch), B )
-                     - erfcRescaled( sqrtc*sqrt(xp), B ) ) * sqrt( kPi*(xmax/c) );
+      area_right = ( erfcRescaled( sqrtc*m_sqrt(xswitch), B )
+                     - erfcRescaled( sqrtc*m_sqrt(xp), B ) ) * m_sqrt( kPi*(xmax/c) );
       probability_flat = area_left/(area_left+area_right);
     }
     // eval_probability lambda, :399-407
@@ -308,13 +308,17 @@ namespace ncb {
     double beta, normfact, expmbeta;
     double k11, k12, k21, k22;
     NCB_HD FGBetaDist( double c, double invA, double sqrtAc, double beta_, double normfact_ )
-      : beta(beta_), normfact(normfact_), expmbeta(-1.0)
     {
+      init( c, invA, sqrtAc, beta_, normfact_ );
+    }
+    NCB_HD_NOINLINE void init( double c, double invA, double sqrtAc, double beta_, double normfact_ )
+    {
+      beta = beta_; normfact = normfact_; expmbeta = -1.0;
       const double eps = beta/c;
-      const double sqrt1pluseps = sqrt(1+eps);
+      const double sqrt1pluseps = m_sqrt(1+eps);
       const double S = ( beta < 0.0 ? -1.0 : 1.0 );
       const double sqrtepsprime = ( eps >= 0.0 ? 1.0 : sqrt1pluseps );
-      const double sqrtgammaplus = sqrt( 2.0+eps+2.0*sqrt1pluseps );
+      const double sqrtgammaplus = m_sqrt( 2.0+eps+2.0*sqrt1pluseps );
       const double SP = 0.5*(S+invA);
       const double SM = 0.5*(S-invA);
       const double invA_sqrtepsprime = invA*sqrtepsprime;
@@ -369,11 +373,11 @@ namespace ncb {
     {
       m_c = dmin( 1e14, dmax( 1e-10, ekin/kT ) );
       m_kT = kT;
-      m_sqrtAc = sqrt( mass_amu*m_c/kNeutronMassAmu );
+      m_sqrtAc = m_sqrt( mass_amu*m_c/kNeutronMassAmu );
       const double A = kInvNeutronMassAmu * mass_amu; // AtomMass::relativeToNeutronMass, NCTypes.hh:815
       m_invA = 1.0/A;
       m_Adiv4 = 0.25*A;
-      m_normfact = 0.5/m_erf( sqrt( m_c*m_invA ) );
+      m_normfact = 0.5/m_erf( m_sqrt( m_c*m_invA ) );
       m_c_real = ekin/kT;
     }
 
@@ -381,7 +385,7 @@ namespace ncb {
     struct Overlay {
       double a, b, prob_downscat, prob_notclosetail;
       ExpIntervalSampler expsampler;
-      NCB_HD void setAB( double aaa, double bbb )
+      NCB_HD_NOINLINE void setAB( double aaa, double bbb )
       {
         constexpr double Tlim = 2.0;
         constexpr double Tlim_k1 = 0.135335283236612691893999494972484403407;

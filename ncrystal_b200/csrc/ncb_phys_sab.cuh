@@ -114,6 +114,68 @@ namespace ncb {
     }
   }
 
+  // One pass of the rejection loop body of SABSamplerAtE_Alg1::sampleAlphaBeta
+  // (ref: NCSABSamplerModels.cc:62-148; requires ep.npts>0).  Returns true when a point was
+  // accepted (the reference `return`s), false where it `continue`s.
+  NCB_HD bool sabAttemptAtE( const SabT& T, const SabEPoint& ep, double ekin_div_kT, Rng& rng,
+                             double& alpha_out, double& beta_out, int& err )
+  {
+    const double* bx = T.bx + ep.off_b;
+    const double* betaGrid = T.beta;
+    const double firstBin = ep.first_bin_endpoint;
+    int ibetaSampled;
+    double beta = pwdPercentileWithIndex( bx, T.bpdf + ep.off_b, T.bcdf + ep.off_b, ep.npts, rng.generate(), ibetaSampled );
+
+    if ( ibetaSampled == 0 && firstBin <= 0.0 ) {
+      const double b0 = firstBin;
+      const double b1 = bx[1];
+      if ( b1 < -ekin_div_kT )
+        return false;
+      const double delta_beta = b1 - b0;
+      double alphaval = 0.0;
+      constexpr int nsampletries = 30;
+      for ( int iii = 0; iii < nsampletries; ++iii ) {
+        beta = dmax( firstBin, b0 + delta_beta*rng.generate() );
+        if ( beta < -ekin_div_kT )
+          break;
+        alphaval = sabSampleAlpha( T, ep, ep.ibeta_off, rng.generate() );
+        AlphaLimits alims = getAlphaLimits( -firstBin, beta );
+        if ( inInterval( alims.first, alims.second, alphaval ) )
+          break;
+        if ( iii == nsampletries-1 ) {
+          err |= ERR_SAB_ISOFALLBACK;
+          alphaval = 0.5*( alims.first + alims.second );
+          break;
+        }
+      }
+      if ( beta < -ekin_div_kT )
+        return false;
+      AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+      if ( inInterval( alimits.first, alimits.second, alphaval ) ) {
+        alpha_out = alphaval; beta_out = beta;
+        return true;
+      }
+      return false;
+    }
+
+    if ( beta <= dmax( -ekin_div_kT, betaGrid[0] ) )
+      return false;
+
+    const double rand_percentile = rng.generate();
+    const int ibeta = ep.ibeta_off + ibetaSampled;
+    const double bl = betaGrid[ibeta-1];
+    const double alphal = sabSampleAlpha( T, ep, ibeta-1, rand_percentile );
+    const double bh = betaGrid[ibeta];
+    const double alphah = sabSampleAlpha( T, ep, ibeta, rand_percentile );
+    const double alpha = alphal + (alphah-alphal) * (beta-bl)/(bh-bl);
+    AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+    if ( inInterval( alimits.first, alimits.second, alpha ) ) {
+      alpha_out = alpha; beta_out = beta;
+      return true;
+    }
+    return false;
+  }
+
   // SABSamplerAtE_Alg1::sampleAlphaBeta, ref: NCSABSamplerModels.cc:48-155
   // (npts==0 is SABSamplerAtE_NoScatter: returns (0,0), NCSABSamplerModels.hh:86)
   NCB_HD void sabSampleAtE( const SabT& T, const SabEPoint& ep, double ekin_div_kT, Rng& rng,
@@ -123,66 +185,29 @@ namespace ncb {
       alpha_out = 0.0; beta_out = 0.0;
       return;
     }
-    const double* bx = T.bx + ep.off_b;
-    const double* bpdf = T.bpdf + ep.off_b;
-    const double* bcdf = T.bcdf + ep.off_b;
-    const double* betaGrid = T.beta;
-    const double firstBin = ep.first_bin_endpoint;
-
-    for ( int iloop = 0; iloop < 100; ++iloop ) {
-      int ibetaSampled;
-      double beta = pwdPercentileWithIndex( bx, bpdf, bcdf, ep.npts, rng.generate(), ibetaSampled );
-
-      if ( ibetaSampled == 0 && firstBin <= 0.0 ) {
-        const double b0 = firstBin;
-        const double b1 = bx[1];
-        if ( b1 < -ekin_div_kT )
-          continue;
-        const double delta_beta = b1 - b0;
-        double alphaval = 0.0;
-        constexpr int nsampletries = 30;
-        for ( int iii = 0; iii < nsampletries; ++iii ) {
-          beta = dmax( firstBin, b0 + delta_beta*rng.generate() );
-          if ( beta < -ekin_div_kT )
-            break;
-          alphaval = sabSampleAlpha( T, ep, ep.ibeta_off, rng.generate() );
-          AlphaLimits alims = getAlphaLimits( -firstBin, beta );
-          if ( inInterval( alims.first, alims.second, alphaval ) )
-            break;
-          if ( iii == nsampletries-1 ) {
-            err |= ERR_SAB_ISOFALLBACK;
-            alphaval = 0.5*( alims.first + alims.second );
-            break;
-          }
-        }
-        if ( beta < -ekin_div_kT )
-          continue;
-        AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
-        if ( inInterval( alimits.first, alimits.second, alphaval ) ) {
-          alpha_out = alphaval; beta_out = beta;
-          return;
-        }
-        continue;
-      }
-
-      if ( beta <= dmax( -ekin_div_kT, betaGrid[0] ) )
-        continue;
-
-      const double rand_percentile = rng.generate();
-      const int ibeta = ep.ibeta_off + ibetaSampled;
-      const double bl = betaGrid[ibeta-1];
-      const double alphal = sabSampleAlpha( T, ep, ibeta-1, rand_percentile );
-      const double bh = betaGrid[ibeta];
-      const double alphah = sabSampleAlpha( T, ep, ibeta, rand_percentile );
-      const double alpha = alphal + (alphah-alphal) * (beta-bl)/(bh-bl);
-      AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
-      if ( inInterval( alimits.first, alimits.second, alpha ) ) {
-        alpha_out = alpha; beta_out = beta;
+    for ( int iloop = 0; iloop < 100; ++iloop )
+      if ( sabAttemptAtE( T, ep, ekin_div_kT, rng, alpha_out, beta_out, err ) )
         return;
-      }
-    }
     err |= ERR_SAB_LOOP_INNER;
     alpha_out = -1.0; beta_out = 0.0;
+  }
+
+  // Choice of the overlay sampler for an in-grid or below-grid energy
+  // (SABSampler::sampleAlphaBeta, ref: NCSABSampler.cc:166-192; E < Emax only).
+  NCB_HD int sabPickSampler( const SabT& T, const double* egrid, double ekin, bool& ultra_small_ekin_mode )
+  {
+    const int n = T.negrid;
+    int iu = upperBound( egrid, 0, n, ekin );
+    ultra_small_ekin_mode = false;
+    if ( iu == 0 ) {
+      ultra_small_ekin_mode = ( ekin < egrid[0] );
+      return 0;
+    }
+    if ( T.egrid_margin > 1.0 ) {
+      while ( iu+1 != n && ekin*T.egrid_margin > egrid[iu] )
+        ++iu;
+    }
+    return iu;
   }
 
   // SABSampler::sampleHighE, ref: NCSABSampler.cc:59-156.  Returns true if (alpha,beta)
@@ -243,15 +268,8 @@ namespace ncb {
         return; // (the reference returns whenever alpha>=0; errors flagged separately)
       ekin = egrid[n-1];
       isampler = n-1;
-    } else if ( iu == 0 ) {
-      isampler = 0;
-      ultra_small_ekin_mode = ( ekin < ultra_small_ekin );
     } else {
-      if ( T.egrid_margin > 1.0 ) {
-        while ( iu+1 != n && ekin*T.egrid_margin > egrid[iu] )
-          ++iu;
-      }
-      isampler = iu;
+      isampler = sabPickSampler( T, egrid, ekin, ultra_small_ekin_mode );
     }
     const SabEPoint ep = T.ep[isampler];
     const double ekin_div_kT = ekin / T.kT;
