@@ -105,24 +105,28 @@ typedef struct {
   uint64_t reserved;
 } ncb_sab_t;
 
-/* SCBragg (mosaic single crystal).  Followed by, in order:
- *   fam_xsfact[nfam], fam_inv2d[nfam], fam_first[nfam+1] (as doubles; index of the
- *   family's first demi-normal), normals[3*nnormals] (x,y,z interleaved, lab frame),
- *   then the two GaussOnSphere spline lookup tables (see ncb_splinelut_t). */
+/* SCBragg (mosaic single crystal; NCSCBragg.cc:33-90 pimpl + GaussMos + GaussOnSphere).
+ * Followed by, in order:
+ *   fam_xsfact[nfam], fam_inv2d[nfam]   ReflectionFamily::xsfact / inv2d (families sorted by
+ *                                       d-spacing descending, NCSCBragg.cc:50-56)
+ *   fam_first[nfam+1]                   (as doubles) index of each family's first demi-normal
+ *   normals[3*nnormals]                 demi-normals in the lab frame, xyz interleaved
+ *   lut_sofcosd[2*(lut_sofcosd_n)]      CubicSpline::m_data pairs (value, second derivative)
+ *   lut_evalcosx[2*(lut_evalcosx_n)]    of GaussOnSphere::m_lt_sofcosd / m_lt_evalcosx */
 typedef struct {
-  double   threshold_ekin;     /* SCBragg domain low edge */
-  double   gm_mos_fwhm;        /* GaussMos parameters (NCGaussMos.hh) */
-  double   gm_mos_sigma;
-  double   gm_mos_truncN;
-  double   gm_prec;
-  double   gos_sigma;          /* GaussOnSphere state (NCGaussOnSphere.hh) */
-  double   gos_trunc_angle;
-  double   gos_cta, gos_sta;   /* cos/sin of truncation angle */
+  double   threshold_ekin;     /* SCBragg::pimpl::m_threshold_ekin */
+  double   gos_cta;            /* GaussOnSphere::m_cta (NCGaussOnSphere.hh) */
+  double   gos_sta;
   double   gos_circleint_k1, gos_circleint_k2;
-  double   gos_norm, gos_expfact, gos_prec;
-  double   gos_spare[6];
+  double   gos_norm, gos_expfact, gos_truncangle, gos_sigma;
+  double   gos_numint_accuracy;
+  double   gos_prec;
+  double   sofcosd_a, sofcosd_invdelta;     /* SplinedLookupTable::m_a / m_invdelta */
+  double   evalcosx_a, evalcosx_invdelta;
+  double   mos_fwhm, mos_truncN;            /* GaussMos (informational) */
+  double   reserved[3];
   uint64_t nfam, nnormals;
-  uint64_t lut_sofcosd_n, lut_circleint_n;
+  uint64_t lut_sofcosd_n, lut_evalcosx_n;   /* number of (value,d2) pairs; CubicSpline::m_nm2 = n-2 */
 } ncb_scbragg_t;
 
 static inline uint64_t ncb_align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }

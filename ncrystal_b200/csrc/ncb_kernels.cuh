@@ -428,6 +428,59 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
+  // ------------------------------------------------------------ oriented (single crystal)
+  // Per-neutron (E, direction), SoA.  One neutron per thread: the lanes of a warp walk the
+  // reflection-family / demi-normal tables in lockstep (same addresses -> broadcast loads);
+  // only normals inside the mosaic truncation cone (a handful per neutron) reach the
+  // circle-integral code.
+  struct DirArgs {
+    const double* ux; const double* uy; const double* uz;   // in
+    double* ox; double* oy; double* oz;                      // out (sampling only)
+  };
+
+  __global__ void __launch_bounds__(128)
+  k_xs_aniso( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+              const double* __restrict__ ekin, const __grid_constant__ DirArgs D, uint64_t n, double* __restrict__ out )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride )
+      out[i] = matXS( M, H, ekin[i], Vec3{ D.ux[i], D.uy[i], D.uz[i] }, nullptr, nullptr, nullptr );
+  }
+
+  __global__ void __launch_bounds__(128)
+  k_sample_aniso( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                  const __grid_constant__ SampleArgs A, const __grid_constant__ DirArgs D )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int errs = 0;
+    for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += stride ) {
+      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      double eout;
+      Vec3 o;
+      int err = 0, ich;
+      const double xs = matSample( M, H, A.ekin[i], Vec3{ D.ux[i], D.uy[i], D.uz[i] }, rng, eout, o, err, ich );
+      if ( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD | ERR_KIN_DENOM ) ) {
+        eout = -1.0; o = { 0.0, 0.0, 0.0 };
+      }
+      A.ekin_out[i] = eout;
+      D.ox[i] = o.x; D.oy[i] = o.y; D.oz[i] = o.z;
+      if ( A.xs_out ) A.xs_out[i] = xs;
+      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+      if ( A.component ) A.component[i] = ich;
+      errs |= err;
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
   // ------------------------------------------------------------ SAB table builder
   __global__ void k_sab_logs( const double* __restrict__ sab, double* __restrict__ logsab, size_t n )
   {

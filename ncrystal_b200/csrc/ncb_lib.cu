@@ -222,6 +222,8 @@ namespace {
     setSmemAttr( k_xs_iso, dm->sp.total );
     setSmemAttr( k_sample_iso, dm->sp.total );
     setSmemAttr( k_sample_classify, dm->sp.total );
+    setSmemAttr( k_xs_aniso, dm->sp.total );
+    setSmemAttr( k_sample_aniso, dm->sp.total );
     buildSabTablesOnDevice( *dm, 0 );
     return dm;
   }
@@ -402,7 +404,7 @@ namespace {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     if ( dm.mat.oriented )
-      throw Err( "LogicError", "ncrystal_crosssection_nonoriented called for an oriented process" );
+      throw Err( "LogicError", "Process::crossSectionIsotropic can only be called for isotropic materials." );
     const int threads = 256;
     const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
     k_xs_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, n, d_out );
@@ -422,7 +424,7 @@ namespace {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     if ( dm.mat.oriented )
-      throw Err( "LogicError", "ncrystal_samplescatterisotropic called for an oriented process" );
+      throw Err( "LogicError", "Process::sampleScatterIsotropic can only be called for isotropic materials." );
     s->ensureErrWord();
     uint32_t* diag_nd = s->d_diag_ndraws;
     int32_t* diag_comp = s->d_diag_comp;
@@ -468,6 +470,37 @@ namespace {
       CUDA_OK( cudaGetLastError() );
     }
     s->next_index += n;
+  }
+
+  void launchXSAniso( Scatter* s, const double* d_ekin, const double* ux, const double* uy, const double* uz,
+                      uint64_t n, double* d_out, cudaStream_t st )
+  {
+    if ( !n ) return;
+    const DeviceMaterial& dm = *s->dm;
+    DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = D.oy = D.oz = nullptr;
+    const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
+    k_xs_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, D, n, d_out );
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
+  }
+
+  void launchSampleAniso( Scatter* s, const double* d_ekin, const double* ux, const double* uy, const double* uz,
+                          uint64_t n, double* d_eout, double* ox, double* oy, double* oz, cudaStream_t st )
+  {
+    if ( !n ) return;
+    const DeviceMaterial& dm = *s->dm;
+    s->ensureErrWord();
+    SampleArgs A;
+    A.ekin = d_ekin; A.n = n; A.seed = s->seed; A.first_index = s->next_index; A.sid = s->sid;
+    A.xs_out = nullptr; A.ekin_out = d_eout; A.mu_out = nullptr;
+    A.ndraws = s->d_diag_ndraws; A.component = s->d_diag_comp; A.err_flags = s->d_err;
+    s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
+    s->next_index += n;
+    DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = ox; D.oy = oy; D.oz = oz;
+    const int ctas = dm.sp.total > 56u*1024u ? 2 : 4;
+    k_sample_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A, D );
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
   }
 
   int fetchDeviceErrors( Scatter* s, cudaStream_t st )
@@ -553,6 +586,31 @@ namespace {
         launchSampleIso( s, di[0], m, nullptr, dout[0], dout[1], st, slot );
       } );
     }
+    raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );
+  }
+
+  void xsAnisoHost( Scatter* s, const double* ekin, const double* ux, const double* uy, const double* uz,
+                    uint64_t n, double* results )
+  {
+    if ( !n ) return;
+    DeviceGuard dg( s->dm->device );
+    const double* in[4] = { ekin, ux, uy, uz };
+    double* out[1] = { results };
+    runHostPipeline( s, n, 4, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int ) {
+      launchXSAniso( s, di[0], di[1], di[2], di[3], m, dout[0], st );
+    } );
+  }
+
+  void sampleAnisoHost( Scatter* s, const double* ekin, const double* ux, const double* uy, const double* uz,
+                        uint64_t n, double* eout, double* ox, double* oy, double* oz )
+  {
+    if ( !n ) return;
+    DeviceGuard dg( s->dm->device );
+    const double* in[4] = { ekin, ux, uy, uz };
+    double* out[4] = { eout, ox, oy, oz };
+    runHostPipeline( s, n, 4, in, 4, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int ) {
+      launchSampleAniso( s, di[0], di[1], di[2], di[3], m, dout[0], dout[1], dout[2], dout[3], st );
+    } );
     raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );
   }
 

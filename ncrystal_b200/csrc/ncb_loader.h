@@ -69,8 +69,10 @@ namespace ncb {
       relocPtr( s.ep, base ); relocPtr( s.bx, base ); relocPtr( s.bpdf, base ); relocPtr( s.bcdf, base );
       relocPtr( s.ainfo, base );
     }
-    if ( m.sc )
-      relocPtr( m.sc, base );
+    if ( m.sc.nfam ) {
+      relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
+      relocPtr( m.sc.normals, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
+    }
     return m;
   }
 

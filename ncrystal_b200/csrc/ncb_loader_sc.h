@@ -2,8 +2,35 @@
 #pragma once
 #include "ncb_loader.h"
 namespace ncb {
-  inline void loadScBragg( LoadedMaterial&, const unsigned char*, const ncb_comp_t& )
+  inline void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c )
   {
-    throw std::runtime_error( "compiled material: SCBragg components not supported yet" );
+    ncb_scbragg_t h; std::memcpy( &h, blob + c.off, sizeof(h) );
+    const double* arr = reinterpret_cast<const double*>( blob + c.off + sizeof(h) );
+    ScBraggT& S = lm.mat.sc;
+    if ( S.nfam != 0 )
+      throw std::runtime_error( "compiled material: more than one SCBragg component" );
+    const size_t nf = h.nfam, nn = h.nnormals;
+    if ( nf == 0 || nn == 0 || h.lut_sofcosd_n < 4 || h.lut_evalcosx_n < 4 )
+      throw std::runtime_error( "compiled material: degenerate SCBragg tables" );
+    S.threshold_ekin = h.threshold_ekin;
+    S.cta = h.gos_cta;
+    S.circleint_k1 = h.gos_circleint_k1; S.circleint_k2 = h.gos_circleint_k2;
+    S.numint_accuracy = h.gos_numint_accuracy;
+    S.nfam = (int)nf; S.nnormals = (int)nn;
+    S.fam_xsfact = offAsPtr<double>( lm.put( arr, nf*8 ) );
+    S.fam_inv2d = offAsPtr<double>( lm.put( arr + nf, nf*8 ) );
+    std::vector<int> first( nf+1 );
+    for ( size_t i = 0; i <= nf; ++i ) first[i] = (int)arr[2*nf+i];
+    S.fam_first = offAsPtr<int>( lm.put( first.data(), (nf+1)*sizeof(int) ) );
+    const double* pn = arr + 2*nf + nf + 1;
+    S.normals = offAsPtr<double>( lm.put( pn, 3*nn*8 ) );
+    const double* l1 = pn + 3*nn;
+    const double* l2 = l1 + 2*h.lut_sofcosd_n;
+    S.sofcosd.data = offAsPtr<double>( lm.put( l1, 2*h.lut_sofcosd_n*8 ) );
+    S.sofcosd.nm2 = (int)h.lut_sofcosd_n - 2;
+    S.sofcosd.a = h.sofcosd_a; S.sofcosd.invdelta = h.sofcosd_invdelta;
+    S.evalcosx.data = offAsPtr<double>( lm.put( l2, 2*h.lut_evalcosx_n*8 ) );
+    S.evalcosx.nm2 = (int)h.lut_evalcosx_n - 2;
+    S.evalcosx.a = h.evalcosx_a; S.evalcosx.invdelta = h.evalcosx_invdelta;
   }
 }

@@ -4,6 +4,7 @@
 // crossSectionIsotropic (:353-362) and sampleScatterIsotropic (:379-389).
 #pragma once
 #include "ncb_phys_sab.cuh"
+#include "ncb_phys_scbragg.cuh"
 
 namespace ncb {
 
@@ -114,6 +115,66 @@ namespace ncb {
     const int ichoice = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
     ichoice_out = ichoice;
     compSampleIso( M, H, ichoice, aux[ichoice], ekin, rng, ekin_out, mu, err );
+    return tot;
+  }
+
+  // ------------------------------------------------------------------ oriented API
+  // ProcComposition::crossSection (ref: NCProcImpl.cc:340-351) with updateCacheAnisotropic
+  // (:206-249): isotropic leaves answer crossSection(E,dir) with their isotropic value
+  // (NCProcImpl.hh:463).  aux[i]: PowderBragg plane index, or for SCBragg the number of
+  // contributing normals (entries of xs_commul); sc_total: SCBragg's unscaled xs.
+  NCB_HD double matXS( const Material& M, const HotTabs& H, double ekin, const Vec3& dir,
+                       double* cumul, int* aux, double* sc_total )
+  {
+    if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) )
+      return 0.0;
+    double tot = 0.0;
+    for ( int i = 0; i < M.ncomp; ++i ) {
+      const Comp& c = M.comp[i];
+      int a = -1;
+      double xs = 0.0;
+      if ( domainContains( c.dom_lo, c.dom_hi, ekin ) ) {
+        if ( c.kind == KIND_SCBRAGG ) {
+          xs = scXS( M.sc, ekin, dir, a );
+          if ( sc_total ) *sc_total = xs;
+        } else {
+          xs = compXSIso( M, H, i, ekin, a );
+        }
+      }
+      tot += c.scale * xs;
+      if ( cumul ) cumul[i] = tot;
+      if ( aux ) aux[i] = a;
+    }
+    return tot;
+  }
+
+  // ProcComposition::sampleScatter, ref: NCProcImpl.cc:364-377.  Returns the total xs.
+  NCB_HD double matSample( const Material& M, const HotTabs& H, double ekin, const Vec3& dir, Rng& rng,
+                           double& ekin_out, Vec3& outdir, int& err, int& ichoice_out )
+  {
+    ichoice_out = -1;
+    ekin_out = ekin;
+    outdir = dir;
+    if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) )
+      return 0.0;
+    double cumul[kMaxComp];
+    int aux[kMaxComp];
+    double sc_total = 0.0;
+    const double tot = matXS( M, H, ekin, dir, cumul, aux, &sc_total );
+    const int ichoice = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
+    ichoice_out = ichoice;
+    if ( M.comp[ichoice].kind == KIND_SCBRAGG ) {
+      // (when the component's domain excludes E its xs pass was skipped: aux = -1 -> no entries)
+      scSampleScatter( M.sc, ekin, dir, aux[ichoice] > 0 ? aux[ichoice] : 0, sc_total, rng, outdir );
+    } else {
+      // ScatterIsotropicMat::sampleScatter, ref: NCProcImpl.cc:29-37
+      double mu;
+      compSampleIso( M, H, ichoice, aux[ichoice], ekin, rng, ekin_out, mu, err );
+      if ( !( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD | ERR_KIN_DENOM ) ) )
+        outdir = randDirectionGivenScatterMu( rng, mu, dir );
+      else
+        outdir = { 0.0, 0.0, 0.0 };
+    }
     return tot;
   }
 

@@ -79,7 +79,24 @@ namespace ncb {
     const SabAlphaInfo* ainfo; // packed
   };
 
-  struct ScBraggT; // oriented path, see ncb_phys_scbragg.cuh
+  // ref: NCSCBragg.cc:33-90 (pimpl), NCGaussOnSphere.hh (private members), NCSpline.hh:40-46
+  struct SplineLutT {
+    const double* data;  // (value, second derivative) pairs, CubicSpline::m_data
+    int nm2;             // CubicSpline::m_nm2
+    double a, invdelta;  // SplinedLookupTable::m_a / m_invdelta
+  };
+  struct ScBraggT {
+    double threshold_ekin;
+    double cta;                       // GaussOnSphere::m_cta
+    double circleint_k1, circleint_k2;
+    double numint_accuracy;
+    int nfam, nnormals;
+    const double* fam_xsfact;         // [nfam]
+    const double* fam_inv2d;          // [nfam] ascending
+    const int* fam_first;             // [nfam+1]
+    const double* normals;            // [3*nnormals] lab frame
+    SplineLutT sofcosd, evalcosx;
+  };
 
   struct Comp {
     int kind;
@@ -97,7 +114,7 @@ namespace ncb {
     ElIncT elinc[1];
     FreeGasT fg[2];
     SabT sab[4];
-    const ScBraggT* sc; // device pointer (oriented materials only)
+    ScBraggT sc;   // at most one SCBragg component (oriented materials only)
   };
 
 }

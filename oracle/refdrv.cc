@@ -82,6 +82,53 @@ namespace {
     uint64_t appendv( const std::vector<double>& v ) { return append(v.data(),v.size()*sizeof(double)); }
   };
 
+  bool refdrv_compile_scbragg( const NCPI::Process* p, ncb_comp_t& comp, Buf& buf, std::string& err )
+  {
+    auto sc = dynamic_cast<const NC::SCBragg*>( p );
+    if ( !sc )
+      return false;
+    static_assert( sizeof(SCBraggMirrorFamily) == sizeof(std::vector<NC::Vector>) + 2*sizeof(double), "layout" );
+    auto pm = reinterpret_cast<const SCBraggMirrorPimpl*>( sc->m_pimpl.get() );
+    const NC::GaussMos& gm = pm->m_gm;
+    const NC::GaussOnSphere& gos = gm.m_gos;
+    if ( pm->m_threshold_ekin != p->domain().elow.dbl() ) { err = "SCBragg pimpl mirror mismatch"; return true; }
+    comp.kind = NCB_KIND_SCBRAGG;
+    ncb_scbragg_t h; std::memset(&h,0,sizeof(h));
+    h.threshold_ekin = pm->m_threshold_ekin;
+    h.gos_cta = gos.m_cta; h.gos_sta = gos.m_sta;
+    h.gos_circleint_k1 = gos.m_circleint_k1; h.gos_circleint_k2 = gos.m_circleint_k2;
+    h.gos_norm = gos.m_norm; h.gos_expfact = gos.m_expfact; h.gos_truncangle = gos.m_truncangle; h.gos_sigma = gos.m_sigma;
+    h.gos_numint_accuracy = gos.m_numint_accuracy;
+    h.gos_prec = gos.m_prec;
+    h.sofcosd_a = gos.m_lt_sofcosd.m_a; h.sofcosd_invdelta = gos.m_lt_sofcosd.m_invdelta;
+    h.evalcosx_a = gos.m_lt_evalcosx.m_a; h.evalcosx_invdelta = gos.m_lt_evalcosx.m_invdelta;
+    h.mos_fwhm = gm.m_mos_fwhm.dbl(); h.mos_truncN = gm.m_mos_truncN;
+    h.nfam = pm->m_reflfamilies.size();
+    std::vector<double> xsfact, inv2d, first, normals;
+    uint64_t nn = 0;
+    for ( auto& f : pm->m_reflfamilies ) {
+      xsfact.push_back( f.xsfact ); inv2d.push_back( f.inv2d ); first.push_back( (double)nn );
+      for ( auto& v : f.deminormals ) { normals.push_back(v.x()); normals.push_back(v.y()); normals.push_back(v.z()); ++nn; }
+    }
+    first.push_back( (double)nn );
+    h.nnormals = nn;
+    auto lutdata = []( const NC::SplinedLookupTable& L ) {
+      std::vector<double> d;
+      for ( auto& e : L.m_spline.m_data ) { d.push_back(e.first); d.push_back(e.second); }
+      return d;
+    };
+    auto d1 = lutdata( gos.m_lt_sofcosd ), d2 = lutdata( gos.m_lt_evalcosx );
+    h.lut_sofcosd_n = d1.size()/2; h.lut_evalcosx_n = d2.size()/2;
+    if ( gos.m_lt_sofcosd.m_spline.m_nm2 + 2 != h.lut_sofcosd_n || gos.m_lt_evalcosx.m_spline.m_nm2 + 2 != h.lut_evalcosx_n ) {
+      err = "unexpected spline layout"; return true;
+    }
+    comp.off = buf.reserve(sizeof(h));
+    buf.put(comp.off,&h,sizeof(h));
+    buf.appendv(xsfact); buf.appendv(inv2d); buf.appendv(first); buf.appendv(normals);
+    buf.appendv(d1); buf.appendv(d2);
+    return true;
+  }
+
   const NC::SAB::SABSamplerAtE_Alg1* firstAlg1( const NC::SABSampler& s )
   {
     for ( auto& up : s.m_samplers ) {
@@ -162,7 +209,8 @@ namespace {
       buf.appendv(sd.betaGrid());
       buf.appendv(sd.sab());
     } else if ( refdrv_compile_scbragg( p, comp, buf, err ) ) {
-      //done
+      if ( !err.empty() )
+        return false;
     } else {
       if (err.empty())
         err = std::string("unsupported leaf process type: ")+p->name();

@@ -171,6 +171,9 @@ class HostSim:
             L.hostsim_sample_iso.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, C.c_uint64, _dp, _dp, _u32p, _i32p]
             L.hostsim_sample_iso_leaf.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _dp, C.c_uint64, _dp, _dp,
                                                   _u32p, _i32p]
+            L.hostsim_xs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_uint64, _dp]
+            L.hostsim_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, C.c_uint64,
+                                         _dp, _dp, _dp, _dp, _u32p, _i32p]
             L.hostsim_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, _dp]
             L.hostsim_sab_sampler_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
             L.hostsim_sab_xscheck.argtypes = [C.c_void_p, C.c_int, _dp]
@@ -218,6 +221,21 @@ class HostSim:
                                                nd.ctypes.data_as(_u32p), er.ctypes.data_as(_i32p))
         return eo, mu, nd, er
 
+    def xs(self, ekin, ux, uy, uz):
+        ekin, ux, uy, uz = [np.ascontiguousarray(a, dtype=np.float64) for a in (ekin, ux, uy, uz)]
+        out = np.empty_like(ekin)
+        self.lib().hostsim_xs(self.h, _d(ekin), _d(ux), _d(uy), _d(uz), ekin.size, _d(out))
+        return out
+
+    def sample(self, ekin, ux, uy, uz, seed=1, first_index=0):
+        ekin, ux, uy, uz = [np.ascontiguousarray(a, dtype=np.float64) for a in (ekin, ux, uy, uz)]
+        eo, ox, oy, oz = [np.empty_like(ekin) for _ in range(4)]
+        nd = np.zeros(ekin.size, dtype=np.uint32)
+        er = np.zeros(ekin.size, dtype=np.int32)
+        self.lib().hostsim_sample(self.h, seed, first_index, _d(ekin), _d(ux), _d(uy), _d(uz), ekin.size,
+                                  _d(eo), _d(ox), _d(oy), _d(oz), nd.ctypes.data_as(_u32p), er.ctypes.data_as(_i32p))
+        return eo, ox, oy, oz, nd, er
+
     def uniforms(self, seed, index, n):
         out = np.empty(n)
         self.lib().hostsim_uniforms(seed, index, n, _d(out))
@@ -232,6 +250,14 @@ class HostSim:
         if n < 0:
             raise RuntimeError("xscheck failed")
         return out[:n]
+
+
+def isotropic_directions(n, seed=54321):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    z = 2.0 * rng.random(n) - 1.0
+    phi = 2.0 * np.pi * rng.random(n)
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    return r * np.cos(phi), r * np.sin(phi), z
 
 
 def loguniform_energies(n, seed=12345, lo=1e-5, hi=10.0):

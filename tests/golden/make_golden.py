@@ -16,7 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from _libs import RefDrv, loguniform_energies  # noqa: E402
+from _libs import RefDrv, loguniform_energies, isotropic_directions  # noqa: E402
 from __graft_entry__ import CONFIGS  # noqa: E402
 
 GOLDEN_SEED = 20261017
@@ -30,10 +30,38 @@ def energies(n):
     return e
 
 
+def oriented_inputs(n):
+    """Isotropic directions + log-uniform energies, with a quarter of the neutrons placed close to
+    Bragg conditions of the Ge config (dir ~ (0,1,1)/sqrt2 at 1.54 Aa, within ~3e-4 rad) so that the
+    mosaic Gaussian, both circle-integral branches and the scatter generation are exercised."""
+    e = loguniform_energies(n, seed=778)
+    ux, uy, uz = isotropic_directions(n, seed=779)
+    k = n // 4
+    rng = np.random.Generator(np.random.Philox(key=780))
+    e0 = 0.081804209605330899 / 1.54 ** 2
+    ux[:k] = rng.normal(0, 3e-4, k)
+    uy[:k] = 1 / np.sqrt(2) + rng.normal(0, 3e-4, k)
+    uz[:k] = 1 / np.sqrt(2) + rng.normal(0, 3e-4, k)
+    e[:k] = e0 * (1 + rng.normal(0, 1e-3, k))
+    # exact known-answer points of the reference's own tests (_testimpl.py:253-254)
+    e[k:k + 3] = e0
+    ux[k:k + 3] = [0, 1, 0]
+    uy[k:k + 3] = [1, 1, 0]
+    uz[k:k + 3] = [1, 0, 1]
+    return e, ux, uy, uz
+
+
 def main():
     for key, cfg in CONFIGS.items():
         r = RefDrv(cfg)
         if RefDrv.lib().refdrv_isoriented(r.h):
+            e, ux, uy, uz = oriented_inputs(N)
+            xs = r.xs(e, ux, uy, uz)
+            eo, ox, oy, oz, nd = r.sample(e, ux, uy, uz, seed=GOLDEN_SEED, first_index=0)
+            out = os.path.join(HERE, "aniso_%s.npz" % key)
+            np.savez_compressed(out, cfg=cfg, seed=GOLDEN_SEED, ekin=e, ux=ux, uy=uy, uz=uz, xs=xs,
+                                comp_names=np.array(r.compnames()), ekin_out=eo, ox=ox, oy=oy, oz=oz, ndraws=nd)
+            print(out, os.path.getsize(out), "bytes; mean draws %.2f; n(xs>10 barn)=%d" % (nd.mean(), (xs > 10).sum()))
             continue
         e = energies(N)
         xs = r.xs_iso(e)

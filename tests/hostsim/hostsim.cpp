@@ -131,6 +131,31 @@ extern "C" {
     }
   }
 
+  void hostsim_xs( void* vh, const double* ekin, const double* ux, const double* uy, const double* uz, uint64_t n, double* out )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
+    for ( uint64_t i = 0; i < n; ++i )
+      out[i] = ncb::matXS( M, H, ekin[i], ncb::Vec3{ ux[i], uy[i], uz[i] }, nullptr, nullptr, nullptr );
+  }
+
+  void hostsim_sample( void* vh, uint64_t seed, uint64_t first_index, const double* ekin,
+                       const double* ux, const double* uy, const double* uz, uint64_t n,
+                       double* ekin_out, double* ox, double* oy, double* oz, uint32_t* ndraws, int32_t* errs )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
+    for ( uint64_t i = 0; i < n; ++i ) {
+      ncb::Rng rng; rng.init( seed, first_index + i );
+      int err = 0, ich;
+      ncb::Vec3 o;
+      ncb::matSample( M, H, ekin[i], ncb::Vec3{ ux[i], uy[i], uz[i] }, rng, ekin_out[i], o, err, ich );
+      ox[i] = o.x; oy[i] = o.y; oz[i] = o.z;
+      if ( ndraws ) ndraws[i] = rng.ndraws;
+      if ( errs ) errs[i] = err;
+    }
+  }
+
   void hostsim_uniforms( uint64_t seed, uint64_t index, uint32_t n, double* out )
   {
     ncb::Rng rng; rng.init( seed, index );
