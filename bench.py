@@ -192,7 +192,8 @@ def main():
     # inputs: 3 rotating device buffers (3 x 80 MB) so that a step's input is never L2-resident from
     # the previous step; per-step working set (in+out) = 320 MB > 126 MB L2.
     NBUF = 3
-    first = rank * n
+    from ncrystal_b200.sharding import shard_range, merge_tallies
+    first = shard_range(world * n, rank, world)[0]   # weak scaling: n neutrons per GPU, contiguous global index ranges
     d_e = [nc.generateSource(n, seed=SEED + b, first_index=first, device=dev) for b in range(NBUF)]
     d_xs = torch.empty(n, dtype=torch.float64, device=dev)
     d_eo = torch.empty(n, dtype=torch.float64, device=dev)
@@ -206,7 +207,7 @@ def main():
         k = step_counter[0]
         step_counter[0] += 1
         e = d_e[k % NBUF]
-        sc.setRNGStream(SEED, 0, (k * world + rank) * n)
+        sc.setRNGStream(SEED, 0, k * world * n + first)
         if events is not None:
             events[0].record(stream)
         L.ncb200_crosssection_nonoriented_many_dev(sc._p, e.data_ptr(), n, d_xs.data_ptr(), sp)
@@ -240,8 +241,7 @@ def main():
     t_begin.record(stream)
     for k in range(args.steps):
         step(ev[k])
-    if world > 1:
-        dist.all_reduce(d_hist)           # the only collective: tally merge (NCCL over NVLink)
+    merge_tallies(d_hist)                 # the only collective: tally merge (NCCL all-reduce over NVLink)
     t_end.record(stream)
     barrier()
     launches = nc.kernelLaunchCount() - launches0

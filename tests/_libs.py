@@ -135,6 +135,18 @@ class RefDrv:
     def sab_sampler_dump(self, c, iE, nbeta):
         return _sab_dump(self.lib().refdrv_sab_sampler_dump, self.h, c, iE, nbeta)
 
+    @classmethod
+    def capi_sample_iso(cls, cfg, ekin, nthreads=None):
+        """Independent-stream sampling through the reference's own C-API and builtin RNG
+        (ncrystal_samplescatterisotropic_many on cloned handles, one per host thread)."""
+        ekin = np.ascontiguousarray(ekin, dtype=np.float64)
+        nthreads = nthreads or len(os.sched_getaffinity(0))
+        eo, mu = np.empty_like(ekin), np.empty_like(ekin)
+        null = C.cast(None, _dp)
+        cls.lib().refdrv_bench_capi(cfg.encode(), 1, nthreads, 0, _d(ekin), null, null, null, ekin.size,
+                                    _d(eo), _d(mu), null, null)
+        return eo, mu
+
 
 def _sab_dump(fn, h, c, iE, nbeta):
     x = np.zeros(nbeta + 1)
