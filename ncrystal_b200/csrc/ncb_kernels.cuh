@@ -267,8 +267,8 @@ namespace ncb {
   // entry (warp-aggregated atomic on a global cursor) before the next pass, so lanes stay
   // converged on the same code and busy until the queue drains.  The arithmetic and the
   // order in which each neutron consumes its uniforms are unchanged.
-  template <bool kAtEmax>
-  __global__ void __launch_bounds__(128)
+  template <bool kAtEmax, int kMinBlocks>
+  __global__ void __launch_bounds__(128, kMinBlocks)
   k_sample_sab_refill( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
                        const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count,
                        uint32_t* __restrict__ cursor )

@@ -234,8 +234,8 @@ namespace {
   struct Scatter;
   struct FingerPrint { uint32_t tag; Scatter* self; };
 
-  constexpr size_t kChunk = (size_t)1 << 21; // neutrons per pipeline chunk of the host-pointer path
-  constexpr int kSlots = 2;
+  constexpr size_t kChunk = (size_t)1 << 20; // neutrons per pipeline chunk of the host-pointer path
+  constexpr int kSlots = 3;
   constexpr int kStageArrays = 8;            // up to 4 in + 4 out
 
   struct Scatter {
@@ -249,18 +249,28 @@ namespace {
     uint32_t* d_diag_ndraws = nullptr;
     int32_t* d_diag_comp = nullptr;
     // host-pointer pipeline resources (lazily created)
-    cudaStream_t streams[kSlots] = { nullptr, nullptr };
-    double* d_stage[kSlots] = { nullptr, nullptr };
+    cudaStream_t streams[kSlots] = {};
+    double* d_stage[kSlots] = {};
     // work queues of the split sampling path: one context per pipeline slot + one for the
     // device-pointer entry points (a handle has at most one launch sequence in flight per context)
-    struct QueueCtx { uint32_t* q = nullptr; uint32_t* counts = nullptr; size_t cap = 0; };
+    struct QueueCtx {
+      uint32_t* q = nullptr; uint32_t* counts = nullptr; size_t cap = 0;
+      cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
+      cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    };
     QueueCtx qctx[kSlots+1];
 
     Scatter() { fp.tag = kScatterTag; fp.self = this; }
     ~Scatter()
     {
       if ( d_err ) cudaFree( d_err );
-      for ( auto& c : qctx ) { if ( c.q ) cudaFree( c.q ); if ( c.counts ) cudaFree( c.counts ); }
+      for ( auto& c : qctx ) {
+        if ( c.q ) cudaFree( c.q );
+        if ( c.counts ) cudaFree( c.counts );
+        if ( c.side ) cudaStreamDestroy( c.side );
+        if ( c.ev_fork ) cudaEventDestroy( c.ev_fork );
+        if ( c.ev_join ) cudaEventDestroy( c.ev_join );
+      }
       for ( int s = 0; s < kSlots; ++s ) {
         if ( d_stage[s] ) cudaFree( d_stage[s] );
         if ( streams[s] ) cudaStreamDestroy( streams[s] );
@@ -277,6 +287,11 @@ namespace {
     {
       QueueCtx& c = qctx[ictx];
       if ( !c.counts ) CUDA_OK( cudaMalloc( &c.counts, 8*sizeof(uint32_t) ) );
+      if ( !c.side ) {
+        CUDA_OK( cudaStreamCreateWithFlags( &c.side, cudaStreamNonBlocking ) );
+        CUDA_OK( cudaEventCreateWithFlags( &c.ev_fork, cudaEventDisableTiming ) );
+        CUDA_OK( cudaEventCreateWithFlags( &c.ev_join, cudaEventDisableTiming ) );
+      }
       if ( c.cap < n ) {
         if ( c.q ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( c.q ) ); c.q = nullptr; }
         c.cap = n + n/8 + 1024;
@@ -451,19 +466,41 @@ namespace {
         const unsigned gsab = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
         const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*4 );
         static const int sabmode = []{ const char* e = std::getenv( "NCB200_SAB_MODE" ); return e ? std::atoi(e) : 1; }();
-        static const int sabctas = []{ const char* e = std::getenv( "NCB200_SAB_CTAS" ); return e ? std::atoi(e) : 5; }();
+        static const int sabctas = []{ const char* e = std::getenv( "NCB200_SAB_CTAS" ); return e ? std::atoi(e) : 0; }();
         static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 8; }();
+        static const bool overlap = []{ const char* e = std::getenv( "NCB200_FG_OVERLAP" ); return e ? std::atoi(e) != 0 : true; }();
         const unsigned gfg2 = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
         if ( sabmode == 0 ) {
           k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
           k_sample_fg<<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
           k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
         } else {
-          // counts[3] / counts[4..] : cursors of the refill kernels
-          const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*sabctas );
-          k_sample_sab_refill<false><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
-          k_sample_fg<<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
-          k_sample_sab_refill<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2, Q.counts + 4 );
+          // counts[3] / counts[4] : cursors of the refill kernels
+          static const int sabminb = []{ const char* e = std::getenv( "NCB200_SAB_MINB" ); return e ? std::atoi(e) : 8; }();
+          const int ctas_eff = sabctas > 0 ? sabctas : sabminb;
+          const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*ctas_eff );
+          auto launchRefill = [&]( auto kern, unsigned grid, const uint32_t* q, const uint32_t* cnt, uint32_t* cur, cudaStream_t s2 ) {
+            kern<<< grid, 128, 0, s2 >>>( dm.mat, A, q, cnt, cur );
+          };
+          cudaStream_t st_fg = st;
+          if ( overlap ) {
+            // fork: free-gas queue (+ its E=Emax follow-up) on the side stream, S(alpha,beta) table queue on `st`
+            CUDA_OK( cudaEventRecord( qc.ev_fork, st ) );
+            CUDA_OK( cudaStreamWaitEvent( qc.side, qc.ev_fork, 0 ) );
+            st_fg = qc.side;
+          }
+          switch ( sabminb ) {
+          case 4: launchRefill( k_sample_sab_refill<false,4>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          case 6: launchRefill( k_sample_sab_refill<false,6>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          case 8: launchRefill( k_sample_sab_refill<false,8>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          default: launchRefill( k_sample_sab_refill<false,5>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          }
+          k_sample_fg<<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
+          launchRefill( k_sample_sab_refill<true,5>, gfg, Q.q_emax, Q.counts + 2, Q.counts + 4, st_fg );
+          if ( overlap ) {
+            CUDA_OK( cudaEventRecord( qc.ev_join, qc.side ) );
+            CUDA_OK( cudaStreamWaitEvent( st, qc.ev_join, 0 ) );
+          }
         }
         g_launches += 4;
       }

@@ -54,12 +54,12 @@ namespace ncb {
       return ( 1.0 - r1 ) - r2;
     }
 
-    NCB_HD double generate()
+    // One Philox4x32-10 block (counter = (c0, c1, block, sid)); kept out of line: generate() has
+    // ~40 call sites on the sampling path and the 10 inlined rounds per site made those kernels
+    // instruction-fetch bound (ncu: ~30% of the free-gas kernel's samples sat in inlined rounds).
+    NCB_HD_NOINLINE double refill( uint32_t block )
     {
-      const uint32_t k = ndraws++;
-      if ( k & 1u )
-        return toFP01( b2, b3 );
-      uint32_t x0 = c0, x1 = c1, x2 = k >> 1, x3 = sid;
+      uint32_t x0 = c0, x1 = c1, x2 = block, x3 = sid;
       uint32_t ka = k0, kb = k1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -74,6 +74,14 @@ namespace ncb {
       }
       b2 = x2; b3 = x3;
       return toFP01( x0, x1 );
+    }
+
+    NCB_HD double generate()
+    {
+      const uint32_t k = ndraws++;
+      if ( k & 1u )
+        return toFP01( b2, b3 );
+      return refill( k >> 1 );
     }
   };
 
