@@ -204,21 +204,33 @@ def main():
     step_counter = [0]
 
     def step(events=None):
+        # One pass of the hot path over one batch: total cross section AND sampled scattering for every
+        # neutron (the fused entry point, cf. the reference's evalXSAndSampleScatterIsotropic batch ABI,
+        # NCABIUtils.hh:78-100), then the mu tally.
         k = step_counter[0]
         step_counter[0] += 1
         e = d_e[k % NBUF]
         sc.setRNGStream(SEED, 0, k * world * n + first)
         if events is not None:
             events[0].record(stream)
-        L.ncb200_crosssection_nonoriented_many_dev(sc._p, e.data_ptr(), n, d_xs.data_ptr(), sp)
+        L.ncb200_xs_and_samplescatterisotropic_many_dev(sc._h, e.data_ptr(), n, d_xs.data_ptr(), d_eo.data_ptr(),
+                                                        d_mu.data_ptr(), sp)
         if events is not None:
             events[1].record(stream)
-        L.ncb200_samplescatterisotropic_many_dev(sc._h, e.data_ptr(), n, d_eo.data_ptr(), d_mu.data_ptr(), sp)
-        if events is not None:
-            events[2].record(stream)
         L.ncb200_tally_hist_dev(d_mu.data_ptr(), None, n, -1.0, 1.0, NBINS, d_hist.data_ptr(), None, sp)
         if events is not None:
-            events[3].record(stream)
+            events[2].record(stream)
+
+    def timed_loop(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(0)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for r in range(reps):
+            fn(r)
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
 
     def barrier():
         if world > 1:
@@ -233,7 +245,7 @@ def main():
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = nc.kernelLaunchCount()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -252,9 +264,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    ms_xs = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    ms_sm = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    ms_ta = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
+    ms_fused = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    ms_ta = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    # the two reference calls separately (outside the headline timed region): xs-evaluations/s, scatter-samples/s
+    ms_xs = timed_loop(lambda r: L.ncb200_crosssection_nonoriented_many_dev(
+        sc._p, d_e[r % NBUF].data_ptr(), n, d_xs.data_ptr(), sp), args.steps)
+    ms_sm = timed_loop(lambda r: L.ncb200_samplescatterisotropic_many_dev(
+        sc._h, d_e[r % NBUF].data_ptr(), n, d_eo.data_ptr(), d_mu.data_ptr(), sp), args.steps)
     hist_total = float(d_hist.sum().item())
 
     # ---- e2e: reference-facing C entry points, pinned host buffers, copies inside the timed region
@@ -293,7 +309,8 @@ def main():
 
     value = world * n * args.steps / (ms_total * 1e-3)
     peak, peak_kind = peaks()
-    ach = n * BYTES_SAMPLE / (ms_sm * 1e-3) / 1e9
+    BYTES_FUSED = 32   # 8 in + 8 xs + 8 E' + 8 mu (fused xs+sample_iso)
+    ach = n * BYTES_FUSED / (ms_fused * 1e-3) / 1e9
     out = {
         "metric": "neutrons/sec (xs eval + sampleScatter)", "value": value, "unit": "neutrons/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -304,7 +321,8 @@ def main():
             "neutrons_per_gpu_per_step": n, "parallelism": "neutron index range sharded over %d GPU(s)" % world,
             "l2": "3 rotating 80 MB input buffers; per-step working set 320 MB > 126 MB L2",
             "xs_per_s": world * n / (ms_xs * 1e-3), "samples_per_s": world * n / (ms_sm * 1e-3),
-            "ms_xs": ms_xs, "ms_sample": ms_sm, "ms_tally": ms_ta,
+            "step": "fused xs+sample (ncb200_xs_and_samplescatterisotropic_many_dev) + mu tally",
+            "ms_fused_xs_sample": ms_fused, "ms_xs": ms_xs, "ms_sample": ms_sm, "ms_tally": ms_ta,
             "rng": "Philox4x32-10 per-neutron streams", "device_error_flags": flags,
             "tally_total": hist_total, "mean_mu_e2e": mean_mu,
         },
@@ -312,9 +330,12 @@ def main():
                 "steps": e2e_steps, "api": "ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "k_sample_iso", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "fused xs+sample launch sequence (k_sample_classify, k_queue_scan/scatter, "
+                                               "k_sample_sab_refill, k_sample_fg); dominant: k_sample_sab_refill",
+                     "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": None, "peak_source": peak_kind,
-                     "algorithmic_bytes_per_launch": n * BYTES_SAMPLE,
+                     "algorithmic_bytes_per_launch": n * BYTES_FUSED,
+                     "note": "latency/FP64-issue bound, not HBM bound (SURVEY 8d): see profiles/ for ncu stall and pipe evidence",
                      "xs_kernel": {"achieved": n * BYTES_XS / (ms_xs * 1e-3) / 1e9,
                                    "frac": n * BYTES_XS / (ms_xs * 1e-3) / 1e9 / peak}},
     }

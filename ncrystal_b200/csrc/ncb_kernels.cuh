@@ -144,12 +144,24 @@ namespace ncb {
   constexpr uint32_t kQueueIdxBits = 28;
   constexpr uint32_t kQueueIdxMask = ( 1u << kQueueIdxBits ) - 1u;   // <= 2^28 neutrons per launch
 
+  constexpr int kSortBins = 1024;   // energy-sort keys: 16 bins per octave from 2^-24 eV upwards
   struct QueueArgs {
     uint32_t* q_sab;    // S(alpha,beta) table path, E < Emax
     uint32_t* q_fg;     // free-gas leaf and S(alpha,beta) above Emax
     uint32_t* q_emax;   // pairs (entry, draws consumed): table sampling at E=Emax requested by the high-E analysis
-    uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs)
+    uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs), [3],[4] refill cursors
+    uint32_t* q_sab_sorted;  // the two queues reordered by energy bin (counting sort), or null
+    uint32_t* q_fg_sorted;
+    uint32_t* hist;     // [2*kSortBins] per-bin counts, then turned into running cursors by k_queue_scan
   };
+
+  // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave;
+  // the SAB energy grids have ~16 points per octave, so one bin ~ one overlay sampler).
+  __device__ __forceinline__ uint32_t sortKey( double ekin )
+  {
+    const int k = (int)( ( (unsigned long long)__double_as_longlong( ekin ) >> 48 ) & 0x7FFFull ) - ( 999 << 4 );
+    return (uint32_t)( k < 0 ? 0 : ( k > kSortBins-1 ? kSortBins-1 : k ) );
+  }
 
   __device__ __forceinline__ void warpPush( bool pred, uint32_t* q, uint32_t* counter, uint32_t entry )
   {
@@ -171,8 +183,14 @@ namespace ncb {
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
+    __shared__ uint32_t sh_hist[2*kSortBins];
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
+    const bool do_sort = ( Q.hist != nullptr );
+    if ( do_sort ) {
+      for ( int b = threadIdx.x; b < 2*kSortBins; b += blockDim.x ) sh_hist[b] = 0;
+      __syncthreads();
+    }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     int errs = 0;
     for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < A.n; base += stride ) {
@@ -210,6 +228,8 @@ namespace ncb {
             nd = rng.ndraws;
           }
           entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
+          if ( do_sort && cls )
+            atomicAdd( &sh_hist[ ( cls - 1 )*kSortBins + sortKey( ekin ) ], 1u );
         }
         if ( A.xs_out ) A.xs_out[i] = tot;
         if ( A.component ) A.component[i] = ich;
@@ -222,8 +242,59 @@ namespace ncb {
       warpPush( cls == 1, Q.q_sab, Q.counts + 0, entry );
       warpPush( cls == 2, Q.q_fg, Q.counts + 1, entry );
     }
+    if ( do_sort ) {
+      __syncthreads();
+      for ( int b = threadIdx.x; b < 2*kSortBins; b += blockDim.x )
+        if ( sh_hist[b] ) atomicAdd( &Q.hist[b], sh_hist[b] );
+    }
     if ( errs )
       atomicOr( A.err_flags, errs );
+  }
+
+  // Counting sort of the two queues by energy bin, so that neighbouring lanes of the sampling
+  // kernels work on the same overlay sampler (same beta-CDF rows -> L1 hits, same search
+  // lengths -> converged warps).  k_queue_scan: per-queue exclusive prefix sum of the bin
+  // histogram (one CTA, 1024 threads); k_queue_scatter: entry -> its bin's running cursor.
+  __global__ void __launch_bounds__(1024)
+  k_queue_scan( uint32_t* __restrict__ hist )
+  {
+    __shared__ uint32_t warp_tot[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for ( int q = 0; q < 2; ++q ) {
+      const uint32_t v = hist[q*kSortBins + t];
+      uint32_t incl = v;
+      for ( int d = 1; d < 32; d <<= 1 ) {
+        const uint32_t o = __shfl_up_sync( 0xffffffffu, incl, d );
+        if ( lane >= d ) incl += o;
+      }
+      if ( lane == 31 ) warp_tot[w] = incl;
+      __syncthreads();
+      if ( w == 0 ) {
+        uint32_t x = warp_tot[lane];
+        for ( int d = 1; d < 32; d <<= 1 ) {
+          const uint32_t o = __shfl_up_sync( 0xffffffffu, x, d );
+          if ( lane >= d ) x += o;
+        }
+        warp_tot[lane] = x;
+      }
+      __syncthreads();
+      hist[q*kSortBins + t] = incl - v + ( w ? warp_tot[w-1] : 0u );
+      __syncthreads();
+    }
+  }
+
+  __global__ void __launch_bounds__(256)
+  k_queue_scatter( const double* __restrict__ ekin, const __grid_constant__ QueueArgs Q )
+  {
+    const uint32_t n0 = Q.counts[0], n1 = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n0 + n1; j += stride ) {
+      const bool fg = ( j >= n0 );
+      const uint32_t entry = fg ? Q.q_fg[j - n0] : Q.q_sab[j];
+      const uint32_t key = sortKey( ekin[ entry & kQueueIdxMask ] );
+      const uint32_t pos = atomicAdd( &Q.hist[ ( fg ? kSortBins : 0 ) + key ], 1u );
+      ( fg ? Q.q_fg_sorted : Q.q_sab_sorted )[pos] = entry;
+    }
   }
 
   // S(alpha,beta) table path over a queue.  kAtEmax=false: entries of q_sab (E < Emax, stream

@@ -65,7 +65,11 @@ namespace ncb {
     return dclamp( x[i-1] + zdx, x[i-1], x[i] );
   }
 
-  // SABSamplerAtE_Alg1::sampleAlpha, ref: NCSABSamplerModels.cc:157-233
+  // SABSamplerAtE_Alg1::sampleAlpha, ref: NCSABSamplerModels.cc:157-233.
+  // The reference's three cases (front tail / whole bins / back tail) each end in a call of
+  // sampleLogLinDist_fast; here the cases only select its arguments and all lanes then meet at
+  // ONE call site, so a warp whose lanes fall into different cases evaluates the expensive
+  // log/exp sequence once instead of up to three times.  Same arithmetic, same results.
   NCB_HD_NOINLINE double sabSampleAlpha( const SabT& T, const SabEPoint& ep, int ibeta, double rand_percentile )
   {
     const SabAlphaInfo& info = T.ainfo[ ep.off_i + ( ibeta - ep.ibeta_off ) ];
@@ -74,23 +78,24 @@ namespace ncb {
     const double* sab    = T.sab    + (size_t)ibeta*nalpha;
     const double* logsab = T.logsab + (size_t)ibeta*nalpha;
     const double* agrid  = T.alpha;
+    double a, fa, b, fb, r, la, lb;
+    const double prob_front = info.prob_front, prob_notback = info.prob_notback;
 
-    if ( rand_percentile <= info.prob_front ) {
-      if ( info.prob_front == 2.0 ) {
+    if ( rand_percentile <= prob_front ) {
+      if ( prob_front == 2.0 ) {
         const double da = info.b_alpha - info.f_alpha;
         return info.f_alpha + rand_percentile*da;
-      } else if ( info.prob_front == 1.0 ) {
-        return sampleLogLinDistFast( info.f_alpha, info.f_sval, info.b_alpha, info.b_sval,
-                                     rand_percentile, info.f_logsval, info.b_logsval );
+      } else if ( prob_front == 1.0 ) {
+        a = info.f_alpha; fa = info.f_sval; b = info.b_alpha; fb = info.b_sval;
+        r = rand_percentile; la = info.f_logsval; lb = info.b_logsval;
       } else {
-        const double percentile2 = dclamp( rand_percentile / info.prob_front, kDblMin, 1.0 );
-        return sampleLogLinDistFast( info.f_alpha, info.f_sval,
-                                     agrid[info.f_idx], sab[info.f_idx],
-                                     percentile2,
-                                     info.f_logsval, logsab[info.f_idx] );
+        const int fi = info.f_idx;
+        a = info.f_alpha; fa = info.f_sval; b = agrid[fi]; fb = sab[fi];
+        r = dclamp( rand_percentile / prob_front, kDblMin, 1.0 );
+        la = info.f_logsval; lb = logsab[fi];
       }
-    } else if ( rand_percentile <= info.prob_notback ) {
-      const double percentile2 = dclamp( ( rand_percentile - info.prob_front ) / ( info.prob_notback - info.prob_front ), 0.0, 1.0 );
+    } else if ( rand_percentile <= prob_notback ) {
+      const double percentile2 = dclamp( ( rand_percentile - prob_front ) / ( prob_notback - prob_front ), 0.0, 1.0 );
       const int ilow = info.f_idx, iupp = info.b_idx;
       const double clow = cumul[ilow], cupp = cumul[iupp];
       const double selectedArea = clow + percentile2 * ( cupp - clow );
@@ -103,15 +108,14 @@ namespace ncb {
       const int a1 = isel_upp;
       const double c0 = cumul[a0], c1 = cumul[a1];
       const double binArea = c1 - c0;
-      const double rand_rescaled = dclamp( ( selectedArea - c0 ) / binArea, kDblMin, 1.0 );
-      return sampleLogLinDistFast( agrid[a0], sab[a0], agrid[a1], sab[a1], rand_rescaled, logsab[a0], logsab[a1] );
+      r = dclamp( ( selectedArea - c0 ) / binArea, kDblMin, 1.0 );
+      a = agrid[a0]; fa = sab[a0]; b = agrid[a1]; fb = sab[a1]; la = logsab[a0]; lb = logsab[a1];
     } else {
-      const double percentile2 = dclamp( ( rand_percentile - info.prob_notback ) / ( 1.0 - info.prob_notback ), kDblMin, 1.0 );
-      return sampleLogLinDistFast( agrid[info.b_idx], sab[info.b_idx],
-                                   info.b_alpha, info.b_sval,
-                                   percentile2,
-                                   logsab[info.b_idx], info.b_logsval );
+      const int bi = info.b_idx;
+      r = dclamp( ( rand_percentile - prob_notback ) / ( 1.0 - prob_notback ), kDblMin, 1.0 );
+      a = agrid[bi]; fa = sab[bi]; b = info.b_alpha; fb = info.b_sval; la = logsab[bi]; lb = info.b_logsval;
     }
+    return sampleLogLinDistFast( a, fa, b, fb, r, la, lb );
   }
 
   // One pass of the rejection loop body of SABSamplerAtE_Alg1::sampleAlphaBeta
