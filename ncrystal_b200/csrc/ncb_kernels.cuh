@@ -438,7 +438,8 @@ namespace ncb {
   // Free-gas samplers over q_fg: the FreeGas leaf, and for S(alpha,beta) above Emax the
   // high-E analysis (SABSampler::sampleHighE); neutrons it sends back to the tabulated kernel
   // are appended to q_emax together with their stream position.
-  __global__ void __launch_bounds__(128)
+  template <int kMinBlocks>
+  __global__ void __launch_bounds__(128, kMinBlocks)
   k_sample_fg( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
                const __grid_constant__ QueueArgs Q )
   {

@@ -479,12 +479,14 @@ namespace {
         const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*4 );
         static const int sabmode = []{ const char* e = std::getenv( "NCB200_SAB_MODE" ); return e ? std::atoi(e) : 1; }();
         static const int sabctas = []{ const char* e = std::getenv( "NCB200_SAB_CTAS" ); return e ? std::atoi(e) : 0; }();
-        static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 8; }();
-        static const bool overlap = []{ const char* e = std::getenv( "NCB200_FG_OVERLAP" ); return e ? std::atoi(e) != 0 : true; }();
+        static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
+        // running the free-gas kernels on a side stream concurrently with the table kernel was measured
+        // to be no faster (each kernel alone already fills the SMs); off by default
+        static const bool overlap = []{ const char* e = std::getenv( "NCB200_FG_OVERLAP" ); return e ? std::atoi(e) != 0 : false; }();
         const unsigned gfg2 = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
         if ( sabmode == 0 ) {
           k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
-          k_sample_fg<<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
+          k_sample_fg<4><<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
           k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
         } else {
           // counts[3] / counts[4] : cursors of the refill kernels
@@ -494,6 +496,8 @@ namespace {
           auto launchRefill = [&]( auto kern, unsigned grid, const uint32_t* q, const uint32_t* cnt, uint32_t* cur, cudaStream_t s2 ) {
             kern<<< grid, 128, 0, s2 >>>( dm.mat, A, q, cnt, cur );
           };
+          static const int fgminb = []{ const char* e = std::getenv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
+          static const bool fgfirst = []{ const char* e = std::getenv( "NCB200_FG_FIRST" ); return e ? std::atoi(e) != 0 : false; }();
           cudaStream_t st_fg = st;
           if ( overlap ) {
             // fork: free-gas queue (+ its E=Emax follow-up) on the side stream, S(alpha,beta) table queue on `st`
@@ -501,13 +505,18 @@ namespace {
             CUDA_OK( cudaStreamWaitEvent( qc.side, qc.ev_fork, 0 ) );
             st_fg = qc.side;
           }
+          auto launchFG = [&]() {
+            if ( fgminb >= 8 ) k_sample_fg<8><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
+            else k_sample_fg<4><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
+          };
+          if ( fgfirst ) launchFG();
           switch ( sabminb ) {
           case 4: launchRefill( k_sample_sab_refill<false,4>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 6: launchRefill( k_sample_sab_refill<false,6>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 8: launchRefill( k_sample_sab_refill<false,8>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           default: launchRefill( k_sample_sab_refill<false,5>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           }
-          k_sample_fg<<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
+          if ( !fgfirst ) launchFG();
           launchRefill( k_sample_sab_refill<true,5>, gfg, Q.q_emax, Q.counts + 2, Q.counts + 4, st_fg );
           if ( overlap ) {
             CUDA_OK( cudaEventRecord( qc.ev_join, qc.side ) );
