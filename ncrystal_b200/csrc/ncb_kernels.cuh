@@ -17,11 +17,13 @@
 
 namespace ncb {
 
-  constexpr int kHotSlots = 2*kMaxPB + 2*kMaxSab;
+  constexpr int kHotSlotsIso = 2*kMaxPB + 2*kMaxSab;
+  // + SCBragg: demi-normals, family xsfact / inv2d / first-index arrays, the two spline LUTs
+  constexpr int kHotSlots = kHotSlotsIso + 6;
 
   // Host-computed staging plan: slot -> (source, bytes, smem offset). bytes==0: not staged.
   struct StagePlan {
-    const double* src[kHotSlots];
+    const void* src[kHotSlots];
     uint32_t nbytes[kHotSlots];   // multiple of 16
     uint32_t off[kHotSlots];      // 16-byte aligned offsets into dynamic smem
     uint32_t total;               // dynamic smem bytes
@@ -61,13 +63,23 @@ namespace ncb {
       asm volatile( "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                     : "=r"(done) : "r"(mb) : "memory" );
     }
-    for ( int s = 0; s < kHotSlots; ++s ) {
+    for ( int s = 0; s < kHotSlotsIso; ++s ) {
       if ( !sp.nbytes[s] ) continue;
       const double* p = reinterpret_cast<const double*>( smem + sp.off[s] );
       if ( s < kMaxPB ) H.pb_e2d[s] = p;
       else if ( s < 2*kMaxPB ) H.pb_fdm[s-kMaxPB] = p;
       else if ( s < 2*kMaxPB+kMaxSab ) H.sab_egrid[s-2*kMaxPB] = p;
       else H.sab_xs[s-2*kMaxPB-kMaxSab] = p;
+    }
+    if ( sp.nbytes[kHotSlotsIso] ) {   // SCBragg tables are staged all-or-nothing
+      H.scv = M.sc;
+      H.scv.normals      = reinterpret_cast<const double*>( smem + sp.off[kHotSlotsIso+0] );
+      H.scv.fam_xsfact   = reinterpret_cast<const double*>( smem + sp.off[kHotSlotsIso+1] );
+      H.scv.fam_inv2d    = reinterpret_cast<const double*>( smem + sp.off[kHotSlotsIso+2] );
+      H.scv.fam_first    = reinterpret_cast<const int*>( smem + sp.off[kHotSlotsIso+3] );
+      H.scv.sofcosd.data = reinterpret_cast<const double*>( smem + sp.off[kHotSlotsIso+4] );
+      H.scv.evalcosx.data= reinterpret_cast<const double*>( smem + sp.off[kHotSlotsIso+5] );
+      H.sc = &H.scv;
     }
   }
 

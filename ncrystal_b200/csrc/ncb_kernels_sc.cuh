@@ -1,0 +1,376 @@
+// ncb_kernels_sc.cuh -- warp-cooperative kernels for oriented materials (SCBragg).
+//
+// For every neutron (E, direction) SCBragg tests ALL demi-normals of the reflection families with
+// wl < 2d (Ge: up to 1119) against the mosaic truncation cone and integrates the few that pass
+// (NCSCBragg.cc:233-275, NCGaussMos.cc:147-194).  One neutron per lane makes a warp (a) run as long
+// as its highest-energy lane and (b) wait for every lane's rare circle-integral in turn.  Here ONE
+// WARP handles one neutron: lane l tests normals l, l+32, ... (the family/normal tables are staged
+// in shared memory by TMA bulk copies), candidates are compacted in order with ballots, their
+// integrals are evaluated by different lanes in parallel, and the running cumulative sums
+// ("xs_commul") are then formed in the reference's order.
+//
+//   k_sc_scan        per neutron: SCBragg cross section + number of contributing normals
+//   k_classify_aniso per neutron (one per lane): composition sum with that result, component pick,
+//                    PowderBragg/ElInc sampled in place (+direction), S(a,b)/free-gas -> queues,
+//                    SCBragg-chosen -> queue
+//   k_sc_sample      per queued neutron (one per warp): pick the normal, GaussMos::genScat
+//   k_dir_from_mu    outgoing direction for the neutrons sampled by the isotropic queue kernels
+//                    (ScatterIsotropicMat::sampleScatter, NCProcImpl.cc:29-37): uniform azimuth
+#pragma once
+#include "ncb_kernels.cuh"
+
+namespace ncb {
+
+  constexpr int kScMaxFam = 128;      // families whose per-neutron parameters fit the per-warp scratch
+  constexpr int kScCandCap = 64;
+  constexpr int kScWarps = 8;         // warps per CTA (they share the staged tables)
+
+  struct ScWarpScratch {
+    double cptsq[kScMaxFam];
+    double spt[kScMaxFam];
+    double vals[2*kScCandCap];        // raw xs of (-normal, +normal) per candidate
+    uint16_t cand[kScCandCap];
+  };
+
+  // state of the ordered accumulation (warp-uniform)
+  struct ScAccum {
+    int cur_fam, n;
+    double xsoffset, xssum, commul_last;
+    // mode 1
+    bool found;
+    int chosen_in, chosen_sign;
+  };
+
+  // Evaluate the `count` recorded candidates (lanes in parallel), then accumulate in order.
+  // mode 0: total/count.  mode 1: stop at the entry selected by `choice` (rule: linear '>' / lower_bound '>=').
+  __device__ __forceinline__ void scFlush( const ScBraggT& S, ScWarpScratch& ws, const uint8_t* fam_of,
+                                           double wl, const Vec3& d, int count, ScAccum& acc,
+                                           int mode, bool linear, double choice )
+  {
+    const int lane = threadIdx.x & 31;
+    for ( int k0 = 0; k0 < count; k0 += 32 ) {
+      const int k = k0 + lane;
+      if ( k < count ) {
+        const int in = ws.cand[k];
+        const int f = fam_of[in];
+        InteractionPars ip;
+        ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+        const double nx = S.normals[3*in], ny = S.normals[3*in+1], nz = S.normals[3*in+2];
+        const double dot = nx*d.x + ny*d.y + nz*d.z;
+        const double sdotcptsq = ( 1.0 - dot*dot )*ip.cos_perfect_theta_sq;
+        const double ds = dot * ip.sin_perfect_theta;
+        double xm = 0.0, xp = 0.0;
+        const double Am = dmax( 0.0, S.cta - ds );
+        if ( sdotcptsq > Am*Am ) xm = gmRawXS( S, ip, dot );     // anti-normal
+        const double Ap = dmax( 0.0, S.cta + ds );
+        if ( sdotcptsq > Ap*Ap ) xp = gmRawXS( S, ip, -dot );    // normal
+        ws.vals[2*k] = xm; ws.vals[2*k+1] = xp;
+      }
+    }
+    __syncwarp();
+    // ordered accumulation, all lanes redundantly (<= 128 values)
+    for ( int k = 0; k < count && !( mode && acc.found ); ++k ) {
+      const int in = ws.cand[k];
+      const int f = fam_of[in];
+      if ( f != acc.cur_fam ) { acc.cur_fam = f; acc.xsoffset = acc.commul_last; acc.xssum = 0.0; }
+      for ( int sgn = 0; sgn < 2; ++sgn ) {
+        const double xs = ws.vals[2*k+sgn];
+        if ( xs ) {
+          acc.commul_last = acc.xsoffset + ( acc.xssum += xs );
+          ++acc.n;
+          if ( mode ) {
+            acc.chosen_in = in; acc.chosen_sign = sgn;
+            if ( linear ? ( acc.commul_last > choice ) : !( acc.commul_last < choice ) ) { acc.found = true; break; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // One walk for the neutron owned by this warp.  Returns through acc.
+  __device__ __forceinline__ void scWalkWarp( const ScBraggT& S, ScWarpScratch& ws, const uint8_t* fam_of,
+                                              double ekin_raw, const Vec3& d, double& wl_out, ScAccum& acc,
+                                              int mode, bool linear, double choice )
+  {
+    const int lane = threadIdx.x & 31;
+    acc.cur_fam = -1; acc.n = 0; acc.xsoffset = acc.xssum = acc.commul_last = 0.0;
+    acc.found = false; acc.chosen_in = 0; acc.chosen_sign = 1;
+    const double ekin = scCacheRound( ekin_raw );
+    const double wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+    wl_out = wl;
+    if ( wl == 0 ) return;
+    const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
+    // number of active families (sorted by inv2d ascending) and their scan parameters
+    int nfam_act = 0;
+    for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
+      const int f = f0 + lane;
+      const bool act = ( f < S.nfam ) && ( S.fam_inv2d[f] < inv2dcutoff );
+      if ( act ) {
+        InteractionPars ip;
+        ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+        ws.cptsq[f] = ip.cos_perfect_theta_sq;
+        ws.spt[f] = ip.sin_perfect_theta;
+      }
+      const uint32_t m = __ballot_sync( 0xffffffffu, act );
+      nfam_act += __popc( m );
+      if ( m != 0xffffffffu ) break;
+    }
+    __syncwarp();
+    if ( nfam_act == 0 ) return;
+    const int n_act = S.fam_first[nfam_act];
+    const double cta = S.cta;
+    int count = 0;
+    for ( int base = 0; base < n_act; base += 32 ) {
+      const int in = base + lane;
+      bool is_cand = false;
+      if ( in < n_act ) {
+        const int f = fam_of[in];
+        const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
+        double sd, ds;
+        is_cand = scIsCandidate( cta, ws.cptsq[f], ws.spt[f], dot, sd, ds );
+      }
+      const uint32_t m = __ballot_sync( 0xffffffffu, is_cand );
+      if ( m ) {
+        if ( is_cand )
+          ws.cand[ count + __popc( m & ( ( 1u << lane ) - 1u ) ) ] = (uint16_t)in;
+        count += __popc( m );
+        __syncwarp();
+        if ( count > kScCandCap - 32 ) {
+          scFlush( S, ws, fam_of, wl, d, count, acc, mode, linear, choice );
+          count = 0;
+          if ( mode && acc.found ) return;
+        }
+      }
+    }
+    if ( count )
+      scFlush( S, ws, fam_of, wl, d, count, acc, mode, linear, choice );
+  }
+
+  // shared set-up of the SC kernels: staged tables + normal->family map
+  __device__ __forceinline__ void scBlockSetup( const Material& M, const StagePlan& sp, unsigned char* smem, uint64_t* mbar,
+                                                HotTabs& H, uint8_t* fam_of )
+  {
+    stageHotTabs( M, sp, smem, mbar, H );
+    const ScBraggT& S = *H.sc;
+    for ( int f = threadIdx.x; f < S.nfam; f += blockDim.x )
+      for ( int in = S.fam_first[f]; in < S.fam_first[f+1]; ++in )
+        fam_of[in] = (uint8_t)f;
+    __syncthreads();
+  }
+
+  struct ScScanArgs {
+    const double* ekin; const double* ux; const double* uy; const double* uz;
+    uint64_t n;
+    double* sc_xs;     // out: unscaled SCBragg xs
+    int32_t* sc_n;     // out: entries of xs_commul
+    double dom_lo, dom_hi;   // the SCBragg component's domain
+  };
+
+  // dynamic smem layout: [staged tables (sp.total)] [fam_of: nnormals bytes, 16-aligned] [kScWarps x ScWarpScratch]
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_scan( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+             const __grid_constant__ ScScanArgs A, uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const int lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kScWarps;
+    for ( uint64_t i = (uint64_t)blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); i < A.n; i += nwarps ) {
+      const double ekin = A.ekin[i];
+      double xs = 0.0; int nent = 0;
+      if ( domainContains( A.dom_lo, A.dom_hi, ekin ) && !( ekin <= S.threshold_ekin ) ) {
+        Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
+        vnormalise( d );
+        ScAccum acc; double wl;
+        scWalkWarp( S, ws, fam_of, ekin, d, wl, acc, 0, false, 0.0 );
+        xs = acc.commul_last; nent = acc.n;
+      }
+      if ( lane == 0 ) { A.sc_xs[i] = xs; A.sc_n[i] = nent; }
+    }
+  }
+
+  // ---- thread-per-neutron kernels that consume the scan result
+  struct AnisoArgs {
+    DirArgs D;
+    const double* sc_xs; const int32_t* sc_n;   // from k_sc_scan (null for materials without SCBragg)
+    double* mu_tmp;                              // scratch: mu of the isotropic queue kernels
+    uint32_t* nd_tmp;                            // scratch: stream position after isotropic sampling
+    uint32_t* q_sc; uint32_t* q_sc_count;        // neutrons whose chosen component is SCBragg
+  };
+
+  // total xs with precomputed SCBragg part (matXS, ncb_proc.cuh)
+  __device__ __forceinline__ double matXSPre( const Material& M, const HotTabs& H, double ekin, double sc_xs, int sc_n,
+                                              double* cumul, int* aux )
+  {
+    if ( !domainContains( M.dom_lo, M.dom_hi, ekin ) )
+      return 0.0;
+    double tot = 0.0;
+    for ( int i = 0; i < M.ncomp; ++i ) {
+      const Comp& c = M.comp[i];
+      int a = -1;
+      double xs = 0.0;
+      if ( domainContains( c.dom_lo, c.dom_hi, ekin ) ) {
+        if ( c.kind == KIND_SCBRAGG ) { xs = sc_xs; a = sc_n; }
+        else xs = compXSIso( M, H, i, ekin, a );
+      }
+      tot += c.scale * xs;
+      if ( cumul ) cumul[i] = tot;
+      if ( aux ) aux[i] = a;
+    }
+    return tot;
+  }
+
+  __global__ void __launch_bounds__(256)
+  k_xs_aniso_pre( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                  const double* __restrict__ ekin, const double* __restrict__ sc_xs, const int32_t* __restrict__ sc_n,
+                  uint64_t n, double* __restrict__ out )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride )
+      out[i] = matXSPre( M, H, ekin[i], sc_xs ? sc_xs[i] : 0.0, sc_n ? sc_n[i] : 0, nullptr, nullptr );
+  }
+
+  __global__ void __launch_bounds__(256)
+  k_classify_aniso( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                    const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q,
+                    const __grid_constant__ AnisoArgs X )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int errs = 0;
+    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < A.n; base += stride ) {
+      const uint64_t i = base + threadIdx.x;
+      int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue, 3: SCBragg queue
+      uint32_t entry = 0;
+      if ( i < A.n ) {
+        const double ekin = A.ekin[i];
+        const Vec3 dir = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
+        double eout = ekin, tot = 0.0;
+        Vec3 o = dir;
+        int ich = -1;
+        uint32_t nd = 0;
+        if ( domainContains( M.dom_lo, M.dom_hi, ekin ) ) {
+          double cumul[kMaxComp];
+          int aux[kMaxComp];
+          tot = matXSPre( M, H, ekin, X.sc_xs ? X.sc_xs[i] : 0.0, X.sc_n ? X.sc_n[i] : 0, cumul, aux );
+          Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+          ich = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
+          const Comp& c = M.comp[ich];
+          if ( c.kind == KIND_SCBRAGG ) {
+            // no-scatter cases of SCBragg::sampleScatter (NCSCBragg.cc:306-318) finish here
+            if ( !( ekin <= M.sc.threshold_ekin ) && aux[ich] > 0 && X.sc_xs[i] > 0.0 )
+              cls = 3;
+          } else if ( c.kind == KIND_SAB ) {
+            const SabT& T = M.sab[c.idx];
+            cls = ( ekin < H.sab_egrid[c.idx][T.negrid-1] ) ? 1 : 2;
+          } else if ( c.kind == KIND_FREEGAS ) {
+            cls = 2;
+          } else {
+            double mu = 1.0;
+            if ( c.kind == KIND_POWDERBRAGG ) {
+              const PowderBraggT& T = M.pb[c.idx];
+              if ( !( ekin < T.threshold || !isFinite(ekin) ) ) {
+                const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+                mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
+              }
+            } else if ( c.kind == KIND_ELINC ) {
+              mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
+            }
+            o = randDirectionGivenScatterMu( rng, mu, dir );
+          }
+          nd = rng.ndraws;
+          entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
+        }
+        if ( A.xs_out ) A.xs_out[i] = tot;
+        if ( A.component ) A.component[i] = ich;
+        if ( cls == 0 ) {
+          A.ekin_out[i] = eout;
+          X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
+          if ( A.ndraws ) A.ndraws[i] = nd;
+        }
+      }
+      warpPush( cls == 1, Q.q_sab, Q.counts + 0, entry );
+      warpPush( cls == 2, Q.q_fg, Q.counts + 1, entry );
+      warpPush( cls == 3, X.q_sc, X.q_sc_count, entry );
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
+  // one queued neutron per warp: choose the normal (second walk) and generate the scattering
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_sample( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+               const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X,
+               uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const int lane = threadIdx.x & 31;
+    const uint32_t nq = *X.q_sc_count;
+    const uint32_t nwarps = gridDim.x * kScWarps;
+    for ( uint32_t j = blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); j < nq; j += nwarps ) {
+      const uint32_t i = X.q_sc[j] & kQueueIdxMask;
+      const double ekin = A.ekin[i];
+      Vec3 d = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
+      vnormalise( d );
+      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      rng.seek( M.ncomp > 1 ? 1u : 0u );
+      const int nent = X.sc_n[i];
+      const double total = X.sc_xs[i];
+      // pickRandIdxByWeight over xs_commul (NCSCBragg.cc:283; NCRandUtils.cc:198-220)
+      double choice = -1.0; bool linear = true;
+      if ( nent > 1 ) { choice = total * rng.generate(); linear = ( nent < 5 ); }
+      ScAccum acc; double wl;
+      scWalkWarp( S, ws, fam_of, ekin, d, wl, acc, 1, linear, choice );
+      const int in = acc.chosen_in;
+      const double sg = acc.chosen_sign ? 1.0 : -1.0;   // vals[2k] = anti-normal, vals[2k+1] = normal
+      const Vec3 pn = { sg*S.normals[3*in], sg*S.normals[3*in+1], sg*S.normals[3*in+2] };
+      const double inv2dsp = gmCacheRound( S.fam_inv2d[ fam_of[in] ] );   // ip.m_inv2dsp (NCGaussMos.cc:258)
+      Vec3 o;
+      gmGenScat( S, rng, pn, inv2dsp, wl, d, o );
+      if ( lane == 0 ) {
+        A.ekin_out[i] = ekin;
+        X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
+        if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+      }
+    }
+  }
+
+  // direction for neutrons sampled by the isotropic queue kernels (entries of q_sab and q_fg)
+  __global__ void __launch_bounds__(256)
+  k_dir_from_mu( const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q, const __grid_constant__ AnisoArgs X )
+  {
+    const uint32_t n0 = Q.counts[0], n1 = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n0 + n1; j += stride ) {
+      const uint32_t i = ( j < n0 ? Q.q_sab[j] : Q.q_fg[j - n0] ) & kQueueIdxMask;
+      Vec3 o = { 0.0, 0.0, 0.0 };
+      if ( A.ekin_out[i] >= 0.0 ) {     // (-1: the sampler raised an error for this neutron)
+        Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+        rng.seek( X.nd_tmp[i] );
+        o = randDirectionGivenScatterMu( rng, X.mu_tmp[i], Vec3{ X.D.ux[i], X.D.uy[i], X.D.uz[i] } );
+        if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+      }
+      X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
+    }
+  }
+
+}

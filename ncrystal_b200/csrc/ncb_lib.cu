@@ -9,6 +9,7 @@
 // There is NO CPU fallback: every compute entry point launches CUDA kernels and
 // raises an error when no usable device is present.
 #include "ncb_kernels.cuh"
+#include "ncb_kernels_sc.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
 #include "../../include/ncrystal_b200.h"
@@ -90,6 +91,10 @@ namespace {
     size_t arena_bytes = 0;
     Material mat;            // device pointers
     StagePlan sp;            // smem staging plan for the hot tables
+    StagePlan sp_sc;         // staging plan of the warp-cooperative SCBragg kernels (SCBragg tables only)
+    StagePlan sp_iso;        // hot tables of the isotropic leaves only
+    bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
+    uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0;
     std::string cfg;
     std::vector<SabBuildPlan> sabplans;
     std::atomic<uint32_t> clone_counter{0};
@@ -117,9 +122,9 @@ namespace {
     // Budget: keep >= 2 CTAs/SM worth of shared memory (227 KB per SM usable).
     const uint32_t budget = 100u*1024u;
     uint32_t off = 0;
-    auto add = [&]( int slot, const double* p, int n ) {
+    auto add = [&]( int slot, const void* p, int n, int elem = 8 ) {
       if ( !p || n <= 0 ) return;
-      const uint32_t nb = (uint32_t)( ( (size_t)n*8 + 15 ) & ~(size_t)15 ); // arena sections are 256B padded
+      const uint32_t nb = (uint32_t)( ( (size_t)n*elem + 15 ) & ~(size_t)15 ); // arena sections are 256B padded
       if ( off + nb > budget ) return;
       sp.src[slot] = p; sp.nbytes[slot] = nb; sp.off[slot] = off;
       off += ( nb + 127u ) & ~127u;
@@ -143,7 +148,41 @@ namespace {
         add( kMaxPB + i, M.pb[i].fdm, M.pb[i].n );
       }
     }
+    if ( M.sc.nfam ) {
+      const ScBraggT& S = M.sc;
+      auto al = []( size_t b ) { return (uint32_t)( ( b + 127 ) & ~(size_t)127 ); };
+      const uint32_t need = al( (size_t)S.nnormals*24 ) + 2*al( (size_t)S.nfam*8 ) + al( (size_t)( S.nfam+1 )*4 )
+                          + al( (size_t)( S.sofcosd.nm2+2 )*16 ) + al( (size_t)( S.evalcosx.nm2+2 )*16 );
+      if ( off + need <= budget ) {
+        add( kHotSlotsIso+0, S.normals, 3*S.nnormals );
+        add( kHotSlotsIso+1, S.fam_xsfact, S.nfam );
+        add( kHotSlotsIso+2, S.fam_inv2d, S.nfam );
+        add( kHotSlotsIso+3, S.fam_first, S.nfam+1, 4 );
+        add( kHotSlotsIso+4, S.sofcosd.data, 2*( S.sofcosd.nm2+2 ) );
+        add( kHotSlotsIso+5, S.evalcosx.data, 2*( S.evalcosx.nm2+2 ) );
+      }
+    }
     sp.total = off;
+    // derived plans
+    dm.sp_iso = sp; dm.sp_sc = sp;
+    std::memset( &dm.sp_sc, 0, sizeof(StagePlan) );
+    if ( sp.nbytes[kHotSlotsIso] ) {
+      uint32_t o2 = 0;
+      for ( int sl = kHotSlotsIso; sl < kHotSlots; ++sl ) {
+        dm.sp_sc.src[sl] = sp.src[sl]; dm.sp_sc.nbytes[sl] = sp.nbytes[sl]; dm.sp_sc.off[sl] = o2;
+        o2 += ( sp.nbytes[sl] + 127u ) & ~127u;
+        dm.sp_sc.copy_bytes += sp.nbytes[sl];
+        // the isotropic-only plan drops the SCBragg slots (they were appended last)
+        dm.sp_iso.copy_bytes -= sp.nbytes[sl];
+        dm.sp_iso.nbytes[sl] = 0;
+      }
+      dm.sp_iso.total = sp.off[kHotSlotsIso];
+      dm.sp_sc.total = o2;
+      dm.sc_warp_ok = ( M.sc.nfam <= kScMaxFam && M.sc.nfam <= 255 && M.sc.nnormals <= 65535 );
+      dm.sc_famof_off = o2;
+      dm.sc_scratch_off = ( o2 + (uint32_t)M.sc.nnormals + 127u ) & ~127u;
+      dm.sc_smem = dm.sc_scratch_off + (uint32_t)( kScWarps*sizeof(ScWarpScratch) );
+    }
   }
 
   template <class K>
@@ -224,6 +263,10 @@ namespace {
     setSmemAttr( k_sample_classify, dm->sp.total );
     setSmemAttr( k_xs_aniso, dm->sp.total );
     setSmemAttr( k_sample_aniso, dm->sp.total );
+    setSmemAttr( k_xs_aniso_pre, dm->sp_iso.total );
+    setSmemAttr( k_classify_aniso, dm->sp_iso.total );
+    setSmemAttr( k_sc_scan, dm->sc_smem );
+    setSmemAttr( k_sc_sample, dm->sc_smem );
     buildSabTablesOnDevice( *dm, 0 );
     return dm;
   }
@@ -255,6 +298,9 @@ namespace {
     // device-pointer entry points (a handle has at most one launch sequence in flight per context)
     struct QueueCtx {
       uint32_t* q = nullptr; uint32_t* counts = nullptr; size_t cap = 0;
+      // oriented path scratch (per neutron): SCBragg scan results, mu / stream position of the isotropic samplers
+      double* sc_xs = nullptr; int32_t* sc_n = nullptr; double* mu_tmp = nullptr; uint32_t* nd_tmp = nullptr;
+      uint32_t* q_sc = nullptr; size_t acap = 0;
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
@@ -267,6 +313,7 @@ namespace {
       for ( auto& c : qctx ) {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
+        if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc ); }
         if ( c.side ) cudaStreamDestroy( c.side );
         if ( c.ev_fork ) cudaEventDestroy( c.ev_fork );
         if ( c.ev_join ) cudaEventDestroy( c.ev_join );
@@ -296,6 +343,23 @@ namespace {
         if ( c.q ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( c.q ) ); c.q = nullptr; }
         c.cap = n + n/8 + 1024;
         CUDA_OK( cudaMalloc( &c.q, 6*c.cap*sizeof(uint32_t) ) );
+      }
+      return c;
+    }
+    QueueCtx& ensureAnisoBuffers( int ictx, size_t n )
+    {
+      QueueCtx& c = ensureQueues( ictx, n );
+      if ( c.acap < n ) {
+        if ( c.sc_xs ) {
+          CUDA_OK( cudaDeviceSynchronize() );
+          cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
+        }
+        c.acap = n + n/8 + 1024;
+        CUDA_OK( cudaMalloc( &c.sc_xs, c.acap*sizeof(double) ) );
+        CUDA_OK( cudaMalloc( &c.sc_n, c.acap*sizeof(int32_t) ) );
+        CUDA_OK( cudaMalloc( &c.mu_tmp, c.acap*sizeof(double) ) );
+        CUDA_OK( cudaMalloc( &c.nd_tmp, c.acap*sizeof(uint32_t) ) );
+        CUDA_OK( cudaMalloc( &c.q_sc, c.acap*sizeof(uint32_t) ) );
       }
       return c;
     }
@@ -530,35 +594,118 @@ namespace {
     s->next_index += n;
   }
 
+  bool useAnisoV1()
+  {
+    static const bool v1 = []{ const char* e = std::getenv( "NCB200_ANISO_V1" ); return e && *e && *e != '0'; }();
+    return v1;
+  }
+
+  int scCompIndex( const Material& M )
+  {
+    for ( int i = 0; i < M.ncomp; ++i ) if ( M.comp[i].kind == KIND_SCBRAGG ) return i;
+    return -1;
+  }
+
+  // SCBragg scan (one warp per neutron) -> sc_xs / sc_n
+  void launchScScan( const DeviceMaterial& dm, const double* d_ekin, const double* ux, const double* uy, const double* uz,
+                     uint64_t n, double* sc_xs, int32_t* sc_n, cudaStream_t st )
+  {
+    const int isc = scCompIndex( dm.mat );
+    ScScanArgs SA;
+    SA.ekin = d_ekin; SA.ux = ux; SA.uy = uy; SA.uz = uz; SA.n = n; SA.sc_xs = sc_xs; SA.sc_n = sc_n;
+    SA.dom_lo = dm.mat.comp[isc].dom_lo; SA.dom_hi = dm.mat.comp[isc].dom_hi;
+    const int ctas = std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) );
+    const uint64_t need = ( n + kScWarps - 1 ) / kScWarps;
+    const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)numSMs( dm.device )*std::min( ctas, 8 ) );
+    k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off );
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
+  }
+
   void launchXSAniso( Scatter* s, const double* d_ekin, const double* ux, const double* uy, const double* uz,
-                      uint64_t n, double* d_out, cudaStream_t st )
+                      uint64_t n, double* d_out, cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
-    DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = D.oy = D.oz = nullptr;
-    const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
-    k_xs_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, D, n, d_out );
+    const bool has_sc = scCompIndex( dm.mat ) >= 0;
+    if ( useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) ) {
+      DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = D.oy = D.oz = nullptr;
+      const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
+      k_xs_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, D, n, d_out );
+      ++g_launches;
+      CUDA_OK( cudaGetLastError() );
+      return;
+    }
+    const double* sc_xs = nullptr; const int32_t* sc_n = nullptr;
+    if ( has_sc ) {
+      Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, n );
+      launchScScan( dm, d_ekin, ux, uy, uz, n, qc.sc_xs, qc.sc_n, st );
+      sc_xs = qc.sc_xs; sc_n = qc.sc_n;
+    }
+    const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
+    k_xs_aniso_pre<<< gridFor( n, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, d_ekin, sc_xs, sc_n, n, d_out );
     ++g_launches;
     CUDA_OK( cudaGetLastError() );
   }
 
   void launchSampleAniso( Scatter* s, const double* d_ekin, const double* ux, const double* uy, const double* uz,
-                          uint64_t n, double* d_eout, double* ox, double* oy, double* oz, cudaStream_t st )
+                          uint64_t n, double* d_eout, double* ox, double* oy, double* oz, cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     s->ensureErrWord();
-    SampleArgs A;
-    A.ekin = d_ekin; A.n = n; A.seed = s->seed; A.first_index = s->next_index; A.sid = s->sid;
-    A.xs_out = nullptr; A.ekin_out = d_eout; A.mu_out = nullptr;
-    A.ndraws = s->d_diag_ndraws; A.component = s->d_diag_comp; A.err_flags = s->d_err;
+    uint32_t* diag_nd = s->d_diag_ndraws;
+    int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
+    const bool has_sc = scCompIndex( dm.mat ) >= 0;
+    const bool v1 = useAnisoV1() || ( has_sc && !dm.sc_warp_ok );
+    const uint64_t maxn = v1 ? n : ( (uint64_t)1 << kQueueIdxBits );
+    for ( uint64_t done = 0; done < n; done += maxn ) {
+      const uint64_t m = std::min<uint64_t>( maxn, n - done );
+      SampleArgs A;
+      A.ekin = d_ekin + done; A.n = m; A.seed = s->seed; A.first_index = s->next_index + done; A.sid = s->sid;
+      A.xs_out = nullptr; A.ekin_out = d_eout + done; A.mu_out = nullptr;
+      A.ndraws = diag_nd ? diag_nd + done : nullptr; A.component = diag_comp ? diag_comp + done : nullptr;
+      A.err_flags = s->d_err;
+      DirArgs D; D.ux = ux + done; D.uy = uy + done; D.uz = uz + done; D.ox = ox + done; D.oy = oy + done; D.oz = oz + done;
+      if ( v1 ) {
+        const int ctas = dm.sp.total > 56u*1024u ? 2 : 4;
+        k_sample_aniso<<< gridFor( m, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A, D );
+        ++g_launches;
+        CUDA_OK( cudaGetLastError() );
+        continue;
+      }
+      Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, m );
+      if ( has_sc )
+        launchScScan( dm, A.ekin, D.ux, D.uy, D.uz, m, qc.sc_xs, qc.sc_n, st );
+      QueueArgs Q;
+      Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
+      Q.q_sab_sorted = Q.q_fg_sorted = nullptr; Q.hist = nullptr;
+      AnisoArgs X;
+      X.D = D; X.sc_xs = has_sc ? qc.sc_xs : nullptr; X.sc_n = has_sc ? qc.sc_n : nullptr;
+      X.mu_tmp = qc.mu_tmp; X.nd_tmp = qc.nd_tmp; X.q_sc = qc.q_sc; X.q_sc_count = qc.counts + 5;
+      CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
+      const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
+      k_classify_aniso<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, A, Q, X );
+      // isotropic leaves: same queue kernels as the isotropic path; they leave (E', mu, stream position)
+      SampleArgs Ai = A;
+      Ai.mu_out = qc.mu_tmp; Ai.ndraws = qc.nd_tmp; Ai.component = nullptr;
+      const unsigned nsm = (unsigned)numSMs( dm.device );
+      const unsigned gq = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
+      const unsigned gf = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
+      k_sample_sab_refill<false,8><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+      k_sample_fg<8><<< gf, 128, 0, st >>>( dm.mat, Ai, Q );
+      k_sample_sab_refill<true,5><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_emax, Q.counts + 2, Q.counts + 4 );
+      k_dir_from_mu<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A, Q, X );
+      g_launches += 5;
+      if ( has_sc ) {
+        const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kScWarps - 1 )/kScWarps, (uint64_t)nsm*3 );
+        k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off );
+        ++g_launches;
+      }
+      CUDA_OK( cudaGetLastError() );
+    }
     s->next_index += n;
-    DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = ox; D.oy = oy; D.oz = oz;
-    const int ctas = dm.sp.total > 56u*1024u ? 2 : 4;
-    k_sample_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A, D );
-    ++g_launches;
-    CUDA_OK( cudaGetLastError() );
   }
 
   int fetchDeviceErrors( Scatter* s, cudaStream_t st )
@@ -654,8 +801,8 @@ namespace {
     DeviceGuard dg( s->dm->device );
     const double* in[4] = { ekin, ux, uy, uz };
     double* out[1] = { results };
-    runHostPipeline( s, n, 4, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int ) {
-      launchXSAniso( s, di[0], di[1], di[2], di[3], m, dout[0], st );
+    runHostPipeline( s, n, 4, in, 1, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int slot ) {
+      launchXSAniso( s, di[0], di[1], di[2], di[3], m, dout[0], st, slot );
     } );
   }
 
@@ -666,8 +813,8 @@ namespace {
     DeviceGuard dg( s->dm->device );
     const double* in[4] = { ekin, ux, uy, uz };
     double* out[4] = { eout, ox, oy, oz };
-    runHostPipeline( s, n, 4, in, 4, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int ) {
-      launchSampleAniso( s, di[0], di[1], di[2], di[3], m, dout[0], dout[1], dout[2], dout[3], st );
+    runHostPipeline( s, n, 4, in, 4, out, [s]( uint64_t m, double* const* di, double* const* dout, cudaStream_t st, int slot ) {
+      launchSampleAniso( s, di[0], di[1], di[2], di[3], m, dout[0], dout[1], dout[2], dout[3], st, slot );
     } );
     raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );
   }

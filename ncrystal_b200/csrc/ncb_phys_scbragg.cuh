@@ -337,57 +337,97 @@ namespace ncb {
     return ip.Q * gosCircleIntegral( S, cos_angle_indir_normal, sin_angle_indir_normal, ip.sin_perfect_theta, ip.cos_perfect_theta );
   }
 
-  // Walk over all contributing (signed) normals in the reference's order
-  // (SCBragg::pimpl::updateCache NCSCBragg.cc:233-275 + GaussMos::calcCrossSections NCGaussMos.cc:147-194).
-  // The running cumulative value reproduces xs_commul: xsoffset + (xssum += xs) per family.
-  // Visitor: bool visit( double commul, Vec3 signed_normal, double inv2dsp ) -> true to stop.
-  template <class Visitor>
-  NCB_HD void scWalk( const ScBraggT& S, double ekin_raw, const Vec3& dir_norm, double& wl_out, Visitor&& visit )
+  // State of one walk over the contributing (signed) normals, in the reference's order
+  // (SCBragg::pimpl::updateCache NCSCBragg.cc:233-275 + GaussMos::calcCrossSections
+  // NCGaussMos.cc:147-194).  The running cumulative value reproduces xs_commul:
+  // xsoffset + (xssum += xs) per family.  mode 0: total + number of entries;
+  // mode 1: stop at the entry picked by pickRandIdxByWeight (linear rule '>' for n<5,
+  // lower_bound '>=' otherwise; falls through to the last entry = clamp n-1).
+  struct ScWalkState {
+    int mode;
+    bool linear;
+    double choice;
+    double commul_last, xsoffset, xssum;
+    int n;
+    Vec3 chosen_n;
+    double chosen_inv2d;
+  };
+
+  // Slow path for one candidate normal (inside the truncation cone for +n or -n); returns true to stop.
+  NCB_HD_NOINLINE bool scCandidate( const ScBraggT& S, InteractionPars& ip, ScWalkState& W,
+                                    double nx, double ny, double nz, double dot, double sdotcptsq, double ds )
+  {
+    const double cta = S.cta;
+    const double Am = dmax( 0.0, cta - ds );
+    if ( sdotcptsq > Am*Am ) {
+      const double xs = gmRawXS( S, ip, dot );
+      if ( xs ) {
+        W.commul_last = W.xsoffset + ( W.xssum += xs );
+        ++W.n;
+        if ( W.mode ) {
+          W.chosen_n = Vec3{ -nx, -ny, -nz }; W.chosen_inv2d = ip.inv2dsp;
+          if ( W.linear ? ( W.commul_last > W.choice ) : !( W.commul_last < W.choice ) ) return true;
+        }
+      }
+    }
+    const double Ap = dmax( 0.0, cta + ds );
+    if ( sdotcptsq > Ap*Ap ) {
+      const double xs = gmRawXS( S, ip, -dot );
+      if ( xs ) {
+        W.commul_last = W.xsoffset + ( W.xssum += xs );
+        ++W.n;
+        if ( W.mode ) {
+          W.chosen_n = Vec3{ nx, ny, nz }; W.chosen_inv2d = ip.inv2dsp;
+          if ( W.linear ? ( W.commul_last > W.choice ) : !( W.commul_last < W.choice ) ) return true;
+        }
+      }
+    }
+    return false;
+  }
+
+  // Per-family scan parameters of one neutron (InteractionPars::set, NCGaussMos.cc:252-280) and the
+  // combined truncation test of GaussMos::calcCrossSections (NCGaussMos.cc:160-170).
+  NCB_HD bool scIsCandidate( double cta, double cptsq, double spt, double dot, double& sdotcptsq, double& ds )
+  {
+    sdotcptsq = ( 1.0 - dot*dot )*cptsq;
+    ds = dot * spt;
+    const double A0 = dmax( 0.0, cta - fabs(ds) );
+    return !( sdotcptsq <= A0*A0 );
+  }
+
+  // Sequential walk (one neutron per thread / host loop): candidates are evaluated where found.
+  // The device kernels for oriented materials use the warp-cooperative form in ncb_kernels_sc.cuh.
+  NCB_HD void scWalk( const ScBraggT& S, double ekin_raw, const Vec3& dir_norm, double& wl_out, ScWalkState& W )
   {
     const double ekin = scCacheRound( ekin_raw );
     const double wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;   // ekin2wl, NCDefs.hh:840-845
     wl_out = wl;
+    W.commul_last = 0.0; W.n = 0;
     if ( wl == 0 )
       return;
     const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
     const double cta = S.cta;
-    double commul_last = 0.0;  // xs_commul.back() (0 when empty)
+    const double dx = dir_norm.x, dy = dir_norm.y, dz = dir_norm.z;
     for ( int ifam = 0; ifam < S.nfam; ++ifam ) {
       const double inv2d = S.fam_inv2d[ifam];
       if ( inv2d >= inv2dcutoff )
         break;
       InteractionPars ip;
       ip.set( wl, inv2d, S.fam_xsfact[ifam] );
-      const double xsoffset = commul_last;
-      double xssum = 0.0;
+      W.xsoffset = W.commul_last;
+      W.xssum = 0.0;
       const double cptsq = ip.cos_perfect_theta_sq;
+      const double spt = ip.sin_perfect_theta;
       const int n0 = S.fam_first[ifam], n1 = S.fam_first[ifam+1];
-      for ( int in = n0; in < n1; ++in ) {
-        const Vec3 normal = { S.normals[3*in], S.normals[3*in+1], S.normals[3*in+2] };
-        const double dot = vdot( normal, dir_norm );
-        const double sdotcptsq = ( 1.0 - dot*dot )*cptsq;
-        const double ds = dot * ip.sin_perfect_theta;
-        const double A0 = dmax( 0.0, cta - fabs(ds) );
-        if ( sdotcptsq <= A0*A0 )
+      const double* nrm = S.normals + 3*n0;
+      for ( int in = n0; in < n1; ++in, nrm += 3 ) {
+        const double nx = nrm[0], ny = nrm[1], nz = nrm[2];
+        const double dot = nx*dx + ny*dy + nz*dz;
+        double sdotcptsq, ds;
+        if ( !scIsCandidate( cta, cptsq, spt, dot, sdotcptsq, ds ) )
           continue;
-        const double Am = dmax( 0.0, cta - ds );
-        if ( sdotcptsq > Am*Am ) {
-          const double xs = gmRawXS( S, ip, dot );
-          if ( xs ) {
-            commul_last = xsoffset + ( xssum += xs );
-            if ( visit( commul_last, Vec3{ -normal.x, -normal.y, -normal.z }, ip.inv2dsp ) )
-              return;
-          }
-        }
-        const double Ap = dmax( 0.0, cta + ds );
-        if ( sdotcptsq > Ap*Ap ) {
-          const double xs = gmRawXS( S, ip, -dot );
-          if ( xs ) {
-            commul_last = xsoffset + ( xssum += xs );
-            if ( visit( commul_last, normal, ip.inv2dsp ) )
-              return;
-          }
-        }
+        if ( scCandidate( S, ip, W, nx, ny, nz, dot, sdotcptsq, ds ) )
+          return;
       }
     }
   }
@@ -400,11 +440,11 @@ namespace ncb {
       return 0.0;
     Vec3 d = dir;
     vnormalise( d );
-    double total = 0.0, wl;
-    int n = 0;
-    scWalk( S, ekin, d, wl, [&]( double commul, const Vec3&, double ) { total = commul; ++n; return false; } );
-    n_out = n;
-    return total;
+    double wl;
+    ScWalkState W; W.mode = 0; W.linear = false; W.choice = 0.0;
+    scWalk( S, ekin, d, wl, W );
+    n_out = W.n;
+    return W.commul_last;
   }
 
   // randPointOnUnitCircle, ref: NCRandUtils.cc:98-112
@@ -543,20 +583,17 @@ namespace ncb {
     Vec3 d = indir_raw;
     vnormalise( d );
     // pickRandIdxByWeight over xs_commul (NCRandUtils.hh:130, .cc:198-220), without storing the list
-    Vec3 chosen_n = { 0, 0, 1 };
-    double chosen_inv2d = 0.0, wl = 0.0;
+    double wl = 0.0;
+    ScWalkState W; W.mode = 1; W.chosen_n = Vec3{ 0, 0, 1 }; W.chosen_inv2d = 0.0;
     if ( n_entries == 1 ) {
-      scWalk( S, ekin, d, wl, [&]( double, const Vec3& nn, double i2d ) { chosen_n = nn; chosen_inv2d = i2d; return true; } );
+      W.linear = true; W.choice = -1.0;   // first entry is taken (no draw)
     } else {
-      const double choice = total * rng.generate();
-      const bool linear = ( n_entries < 5 );   // '>' for the linear rule, '>=' (lower_bound) otherwise
-      int k = 0;
-      scWalk( S, ekin, d, wl, [&]( double commul, const Vec3& nn, double i2d ) {
-        ++k;
-        chosen_n = nn; chosen_inv2d = i2d;            // falls through to the last entry (clamp n-1)
-        return linear ? ( commul > choice ) : !( commul < choice );
-      } );
+      W.choice = total * rng.generate();
+      W.linear = ( n_entries < 5 );
     }
+    scWalk( S, ekin, d, wl, W );
+    const Vec3 chosen_n = W.chosen_n;
+    const double chosen_inv2d = W.chosen_inv2d;
     gmGenScat( S, rng, chosen_n, chosen_inv2d, wl, d, outdir );
   }
 

@@ -17,11 +17,14 @@ namespace ncb {
     const double* pb_fdm[kMaxPB];
     const double* sab_egrid[kMaxSab];
     const double* sab_xs[kMaxSab];
+    const ScBraggT* sc;   // the material's SCBragg tables, or `scv` (arrays staged in shared memory)
+    ScBraggT scv;
   };
   NCB_HD void hotTabsFromMaterial( const Material& M, HotTabs& H )
   {
     for ( int i = 0; i < kMaxPB; ++i ) { H.pb_e2d[i] = M.pb[i].e2d; H.pb_fdm[i] = M.pb[i].fdm; }
     for ( int i = 0; i < kMaxSab; ++i ) { H.sab_egrid[i] = M.sab[i].egrid; H.sab_xs[i] = M.sab[i].xs; }
+    H.sc = &M.sc;
   }
 
   // Unscaled isotropic xs of component i.  aux receives the PowderBragg plane index.
@@ -135,7 +138,7 @@ namespace ncb {
       double xs = 0.0;
       if ( domainContains( c.dom_lo, c.dom_hi, ekin ) ) {
         if ( c.kind == KIND_SCBRAGG ) {
-          xs = scXS( M.sc, ekin, dir, a );
+          xs = scXS( *H.sc, ekin, dir, a );
           if ( sc_total ) *sc_total = xs;
         } else {
           xs = compXSIso( M, H, i, ekin, a );
@@ -165,7 +168,7 @@ namespace ncb {
     ichoice_out = ichoice;
     if ( M.comp[ichoice].kind == KIND_SCBRAGG ) {
       // (when the component's domain excludes E its xs pass was skipped: aux = -1 -> no entries)
-      scSampleScatter( M.sc, ekin, dir, aux[ichoice] > 0 ? aux[ichoice] : 0, sc_total, rng, outdir );
+      scSampleScatter( *H.sc, ekin, dir, aux[ichoice] > 0 ? aux[ichoice] : 0, sc_total, rng, outdir );
     } else {
       // ScatterIsotropicMat::sampleScatter, ref: NCProcImpl.cc:29-37
       double mu;
