@@ -189,6 +189,29 @@ namespace ncb {
       q[ base + __popc( mask & ( ( 1u << lane ) - 1u ) ) ] = entry;
   }
 
+  // Block-aggregated variant for two queues at once: one global atomic per queue per CTA iteration
+  // (per-warp atomics on the two hot counters were ~8% of k_sample_classify's stall samples).
+  // Must be called by all threads of the CTA (contains __syncthreads).
+  __device__ __forceinline__ void blockPush2( int cls, uint32_t entry, uint32_t* q1, uint32_t* q2, uint32_t* counts,
+                                              uint32_t (*s_cnt)[2], uint32_t* s_base )
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t m1 = __ballot_sync( 0xffffffffu, cls == 1 );
+    const uint32_t m2 = __ballot_sync( 0xffffffffu, cls == 2 );
+    if ( lane == 0 ) { s_cnt[w][0] = __popc( m1 ); s_cnt[w][1] = __popc( m2 ); }
+    __syncthreads();
+    if ( threadIdx.x < 2 ) {
+      uint32_t tot = 0;
+      for ( int k = 0; k < nw; ++k ) { const uint32_t c = s_cnt[k][threadIdx.x]; s_cnt[k][threadIdx.x] = tot; tot += c; }
+      s_base[threadIdx.x] = tot ? atomicAdd( counts + threadIdx.x, tot ) : 0u;
+    }
+    __syncthreads();
+    const uint32_t lt = ( 1u << lane ) - 1u;
+    if ( cls == 1 ) q1[ s_base[0] + s_cnt[w][0] + __popc( m1 & lt ) ] = entry;
+    if ( cls == 2 ) q2[ s_base[1] + s_cnt[w][1] + __popc( m2 & lt ) ] = entry;
+    __syncthreads();   // s_cnt / s_base are reused by the next iteration
+  }
+
   __global__ void __launch_bounds__(256)
   k_sample_classify( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
                      const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q )
@@ -196,6 +219,8 @@ namespace ncb {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t sh_hist[2*kSortBins];
+    __shared__ uint32_t s_cnt[8][2];
+    __shared__ uint32_t s_base[2];
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
     const bool do_sort = ( Q.hist != nullptr );
@@ -251,8 +276,7 @@ namespace ncb {
           if ( A.ndraws ) A.ndraws[i] = nd;
         }
       }
-      warpPush( cls == 1, Q.q_sab, Q.counts + 0, entry );
-      warpPush( cls == 2, Q.q_fg, Q.counts + 1, entry );
+      blockPush2( cls, entry, Q.q_sab, Q.q_fg, Q.counts, s_cnt, s_base );
     }
     if ( do_sort ) {
       __syncthreads();
@@ -606,6 +630,31 @@ namespace ncb {
                                      off_b, (uint32_t)( (size_t)ie*T.nbeta ), e, bx + off_b, bpdf + off_b, bcdf + off_b, err );
     ep[ie] = e;
     errs[ie] = err;
+  }
+
+  // guide tables: blockIdx.y = energy point (beta guides) or beta row - negrid (alpha guides)
+  __global__ void k_sab_guides( SabT T, SabEPoint* __restrict__ ep, uint16_t* __restrict__ bguide,
+                                uint16_t* __restrict__ aguide, double* __restrict__ ascale )
+  {
+    const int y = blockIdx.y;
+    if ( y < T.negrid ) {
+      const SabEPoint e = ep[y];
+      const double* cdf = T.bcdf + e.off_b;
+      uint16_t* g = bguide + (size_t)y*( kSabGB+1 );
+      for ( int b = blockIdx.x*blockDim.x + threadIdx.x; b <= kSabGB; b += gridDim.x*blockDim.x )
+        g[b] = sabBetaGuideEntry( cdf, e.npts, b );
+      if ( blockIdx.x == 0 && threadIdx.x == 0 )
+        ep[y].guide = e.npts > 0 ? g : nullptr;
+    } else {
+      const int ib = y - T.negrid;
+      const double* row = T.cumul + (size_t)ib*T.nalpha;
+      const double sc = sabAlphaScale( row, T.nalpha );
+      uint16_t* g = aguide + (size_t)ib*( kSabGA+1 );
+      for ( int b = blockIdx.x*blockDim.x + threadIdx.x; b <= kSabGA; b += gridDim.x*blockDim.x )
+        g[b] = sabAlphaGuideEntry( row, T.nalpha, sc, b );
+      if ( blockIdx.x == 0 && threadIdx.x == 0 )
+        ascale[ib] = sc;
+    }
   }
 
   // ------------------------------------------------------------ synthetic source

@@ -224,7 +224,10 @@ namespace {
       k_sab_cumul<<< ( nb + 63 )/64, 64, 0, st >>>( T.alpha, T.sab, logsab, na, nb, cumul );
       k_sab_rows<<< dim3( ( nb + 127 )/128, ne ), 128, 0, st >>>( T, rows, ainfo );
       k_sab_epoints<<< ( ne + 31 )/32, 32, 0, st >>>( T, rows, ep, bx, bpdf, bcdf, xscheck, errs );
-      g_launches += 4;
+      k_sab_guides<<< dim3( 4, ne + nb ), 256, 0, st >>>( T, ep, reinterpret_cast<uint16_t*>( base + pl.off_bguide ),
+                                                       reinterpret_cast<uint16_t*>( base + pl.off_aguide ),
+                                                       reinterpret_cast<double*>( base + pl.off_ascale ) );
+      g_launches += 5;
       CUDA_OK( cudaGetLastError() );
       std::vector<int> herrs( ne );
       CUDA_OK( cudaMemcpyAsync( herrs.data(), errs, (size_t)ne*4, cudaMemcpyDeviceToHost, st ) );

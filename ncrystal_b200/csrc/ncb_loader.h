@@ -19,6 +19,7 @@ namespace ncb {
   struct SabBuildPlan {       // what the build stages need for one SAB leaf
     int sab_index;            // index into Material::sab
     size_t off_logsab, off_cumul, off_ep, off_bx, off_bpdf, off_bcdf, off_ainfo, off_rows, off_xscheck;
+    size_t off_bguide, off_aguide, off_ascale;
   };
 
   struct LoadedMaterial {
@@ -68,6 +69,7 @@ namespace ncb {
       relocPtr( s.sab, base ); relocPtr( s.logsab, base ); relocPtr( s.cumul, base );
       relocPtr( s.ep, base ); relocPtr( s.bx, base ); relocPtr( s.bpdf, base ); relocPtr( s.bcdf, base );
       relocPtr( s.ainfo, base );
+      relocPtr( s.bguide, base ); relocPtr( s.aguide, base ); relocPtr( s.ascale, base );
     }
     if ( m.sc.nfam ) {
       relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
@@ -180,6 +182,10 @@ namespace ncb {
         pl.off_ainfo  = lm.reserve( ne*nb*sizeof(SabAlphaInfo) );
         pl.off_rows   = lm.reserve( ne*nb*16 );
         pl.off_xscheck= lm.reserve( ne*8 + ne*4 );
+        pl.off_bguide = lm.reserve( ne*( kSabGB+1 )*sizeof(uint16_t) );
+        pl.off_aguide = lm.reserve( nb*( kSabGA+1 )*sizeof(uint16_t) );
+        pl.off_ascale = lm.reserve( nb*8 );
+        if ( nb + 1 > 65535 || na > 65535 ) throw std::runtime_error( "compiled material: SAB grids too large for 16-bit guide tables" );
         T.logsab = offAsPtr<double>( pl.off_logsab );
         T.cumul  = offAsPtr<double>( pl.off_cumul );
         T.ep     = offAsPtr<SabEPoint>( pl.off_ep );
@@ -187,6 +193,9 @@ namespace ncb {
         T.bpdf   = offAsPtr<double>( pl.off_bpdf );
         T.bcdf   = offAsPtr<double>( pl.off_bcdf );
         T.ainfo  = offAsPtr<SabAlphaInfo>( pl.off_ainfo );
+        T.bguide = offAsPtr<uint16_t>( pl.off_bguide );
+        T.aguide = offAsPtr<uint16_t>( pl.off_aguide );
+        T.ascale = offAsPtr<double>( pl.off_ascale );
         lm.sabplans.push_back( pl );
         k.idx = nsab++;
         break;

@@ -197,7 +197,7 @@ namespace ncb {
     for ( int i = 0; i < nbeta; ++i )
       if ( rows[i].has_range ) { ibeta_low = i; break; }
 
-    ep.npts = 0; ep.ibeta_off = 0; ep.off_b = off_b; ep.off_i = off_i_base; ep.first_bin_endpoint = 1.0;
+    ep.npts = 0; ep.ibeta_off = 0; ep.off_b = off_b; ep.off_i = off_i_base; ep.first_bin_endpoint = 1.0; ep.guide = nullptr;
     if ( ibeta_low >= nbeta )
       return 0.0; // SABSamplerAtE_NoScatter
 
@@ -260,6 +260,25 @@ namespace ncb {
     ep.off_i = off_i_base + (uint32_t)ibeta_low;
     ep.first_bin_endpoint = ( starts_at_kinematic_endpoint ? beta_lower_limit : 1.0 );
     return xs_total;
+  }
+
+  // ---- stage 3: guide tables (an acceleration structure of the product, not part of the reference)
+  // beta guide of one energy point: g[b] = lower_bound( cdf, b/kSabGB )
+  NCB_HD uint16_t sabBetaGuideEntry( const double* cdf, int npts, int b )
+  {
+    if ( npts <= 0 ) return 0;
+    return (uint16_t)lowerBound( cdf, 0, npts, (double)b / (double)kSabGB );
+  }
+  // alpha guide of one beta row: g[b] = upper_bound( cumul_row, b/scale ), scale = kSabGA/cumul_row[last]
+  NCB_HD double sabAlphaScale( const double* cumul_row, int nalpha )
+  {
+    const double tot = cumul_row[nalpha-1];
+    return ( tot > 0.0 && isFinite( (double)kSabGA / tot ) ) ? (double)kSabGA / tot : 0.0;
+  }
+  NCB_HD uint16_t sabAlphaGuideEntry( const double* cumul_row, int nalpha, double scale, int b )
+  {
+    if ( !( scale > 0.0 ) ) return (uint16_t)( b == 0 ? 0 : nalpha );
+    return (uint16_t)upperBound( cumul_row, 0, nalpha, (double)b / scale );
   }
 
 }

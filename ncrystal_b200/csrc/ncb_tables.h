@@ -44,6 +44,7 @@ namespace ncb {
     uint32_t off_b;      // offset of this point's (x,pdf,cdf) rows in the packed beta arrays
     uint32_t off_i;      // offset of this point's AlphaInfo entries (npts-1 of them)
     double   first_bin_endpoint; // m_firstBinKinematicEndpointValue
+    const uint16_t* guide;       // this point's beta guide table (kSabGB+1 entries), or null
   };
 
   // AlphaSampleInfo, ref: NCSABSamplerModels.hh:47-57
@@ -77,7 +78,14 @@ namespace ncb {
     const double* bpdf;    // packed normalised pdf
     const double* bcdf;    // packed cdf
     const SabAlphaInfo* ainfo; // packed
+    // Guide tables (inverse-CDF bucket index -> first candidate position) that replace most steps of the
+    // two binary searches of a sampling attempt; the search result is unchanged (see ncb_phys_sab.cuh).
+    const uint16_t* bguide;    // [negrid][kSabGB+1]  over each energy point's beta CDF
+    const uint16_t* aguide;    // [nbeta][kSabGA+1]   over each beta row of the cumulative alpha integrals
+    const double* ascale;      // [nbeta]  kSabGA / cumul[row][nalpha-1]  (0 for an all-zero row)
   };
+  constexpr int kSabGB = 1024;
+  constexpr int kSabGA = 256;
 
   // ref: NCSCBragg.cc:33-90 (pimpl), NCGaussOnSphere.hh (private members), NCSpline.hh:40-46
   struct SplineLutT {

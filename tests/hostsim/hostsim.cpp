@@ -57,6 +57,22 @@ namespace {
         if ( err )
           throw std::runtime_error( "SAB table build failed (err="+std::to_string(err)+")" );
       }
+      // stage 3: guide tables
+      uint16_t* bguide = reinterpret_cast<uint16_t*>( base + pl.off_bguide );
+      uint16_t* aguide = reinterpret_cast<uint16_t*>( base + pl.off_aguide );
+      double* ascale = reinterpret_cast<double*>( base + pl.off_ascale );
+      for ( int ie = 0; ie < ne; ++ie ) {
+        uint16_t* g = bguide + (size_t)ie*( kSabGB+1 );
+        for ( int b = 0; b <= kSabGB; ++b )
+          g[b] = sabBetaGuideEntry( bcdf + ep[ie].off_b, ep[ie].npts, b );
+        ep[ie].guide = ep[ie].npts > 0 ? g : nullptr;
+      }
+      for ( int ib = 0; ib < nb; ++ib ) {
+        const double* row = cumul + (size_t)ib*na;
+        ascale[ib] = sabAlphaScale( row, na );
+        for ( int b = 0; b <= kSabGA; ++b )
+          aguide[(size_t)ib*( kSabGA+1 ) + b] = sabAlphaGuideEntry( row, na, ascale[ib], b );
+      }
     }
   }
 }
