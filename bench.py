@@ -107,6 +107,22 @@ def cpu_reference(cfg, n, nthreads, nrep, seed=SEED):
     return t_xs, t_sm
 
 
+def cpu_port_baseline(cfg, n=4_000_000):
+    """Fallback when the compiled reference is absent: the plain-C oracle port on all host threads, bounded sample."""
+    from _libs import loguniform_energies
+    try:
+        from oracle_check import oracle_for
+        o = oracle_for(cfg, prefer="port")
+        nt = host_threads()
+        ekin = loguniform_energies(n, seed=SEED)
+        t_xs = o.bench(0, nt, ekin)
+        t_sm = o.bench(1, nt, ekin)
+        return {"value": n / (t_xs + t_sm), "unit": "neutrons/s", "cores": nt, "kind": "port",
+                "sample": "%d neutrons, xs + sample, oracle/ C port" % n, "xs_per_s": n / t_xs, "samples_per_s": n / t_sm}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "neutrons/s", "cores": 0, "kind": "port", "sample": "oracle unavailable: %s" % e}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -122,10 +138,30 @@ def run_reference(args, cfg):
     nthreads = host_threads()
     n = N_PER_GPU
     if not have_refdrv():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
+        # the compiled reference did not travel: time the oracle port instead (kind "port")
+        for _ in range(max(args.warmup, 1)):
+            cb = cpu_port_baseline(cfg)
+        vals = [cpu_port_baseline(cfg) for _ in range(args.steps)]
+        if vals[0]["value"] is None:
+            print(json.dumps({"impl": "reference", "unavailable": vals[0]["sample"]}))
+            return
+        val = sum(v["value"] for v in vals) / len(vals)
+        cb = dict(vals[0], value=val)
+        print(json.dumps({
+            "impl": "reference", "metric": "neutrons/sec (xs eval + sampleScatter)", "value": val, "unit": "neutrons/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 4_000_000 / val,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Al_sg225.ncmat;temp=293.15K powder, isotropic crossSection + sampleScatter, "
+                                   "log-uniform 1e-5..10 eV", "neutrons_per_step": 4_000_000},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "neutrons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    # each step: the full 1e7-neutron workload through ncrystal_crosssection_nonoriented_many +
-    # ncrystal_samplescatterisotropic_many on all host cores (best-of handled by steps here)
+    # each step: a bounded sample of the 1e7-neutron workload through ncrystal_crosssection_nonoriented_many +
+    # ncrystal_samplescatterisotropic_many on all host cores; the sample is sized from a probe so that the
+    # whole --steps run stays within ~2 minutes (full 1e7 when that fits).
+    a, b = cpu_reference(cfg, 1_000_000, nthreads, 1)
+    rate = 1_000_000 / (a + b)
+    n = int(min(N_PER_GPU, max(200_000, 120.0 * rate / max(args.steps + args.warmup, 1))))
     for _ in range(max(args.warmup, 1)):
         cpu_reference(cfg, n, nthreads, 1)
     t0 = time.perf_counter()
@@ -140,12 +176,12 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "neutrons/sec (xs eval + sampleScatter)", "value": val, "unit": "neutrons/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Al_sg225.ncmat;temp=293.15K powder, 1e7 isotropic crossSection + sampleScatter, "
-                               "log-uniform 1e-5..10 eV", "neutrons_per_step": n,
+        "config": {"workload": "Al_sg225.ncmat;temp=293.15K powder, isotropic crossSection + sampleScatter, "
+                               "log-uniform 1e-5..10 eV (BASELINE.json configs[0])", "neutrons_per_step": n,
                    "xs_per_s": n * args.steps / txs, "samples_per_s": n * args.steps / tsm,
                    "note": "reference NCrystal 4.4.2 C-API *_many on host cores; wall %.1fs incl. handle setup" % wall},
         "cpu_baseline": {"value": val, "unit": "neutrons/s", "cores": nthreads, "kind": "reference",
-                         "sample": "full workload: 1e7 neutrons per step"},
+                         "sample": "%d neutrons per step (of the 1e7-neutron workload)" % n},
         "e2e": {"value": val, "unit": "neutrons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -153,7 +189,7 @@ def run_reference(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="neutrons per GPU per step")
@@ -257,7 +293,6 @@ def main():
     t_end.record(stream)
     barrier()
     launches = nc.kernelLaunchCount() - launches0
-    clk = clocks.stop() if clocks else None
     flags = sc.checkDeviceErrors(dev)
     ms_total = t_begin.elapsed_time(t_end)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -272,6 +307,21 @@ def main():
     ms_sm = timed_loop(lambda r: L.ncb200_samplescatterisotropic_many_dev(
         sc._h, d_e[r % NBUF].data_ptr(), n, d_eo.data_ptr(), d_mu.data_ptr(), sp), args.steps)
     hist_total = float(d_hist.sum().item())
+    clk = clocks.stop() if clocks else None   # sampled over the timed region + the two single-call loops (all under load)
+
+    # ---- per-kernel durations, live: CUDA events recorded by the library on the launching stream around
+    # each of its kernels (ncb200_kernel_timing), over a short extra loop of the same step.
+    ktimes, qcounts = {}, None
+    L.ncb200_kernel_timing(1)
+    for _ in range(min(args.steps, 20)):
+        step()
+    buf = C.create_string_buffer(4096)
+    if L.ncb200_kernel_timing_report(buf, 4096) > 0:
+        ktimes = json.loads(buf.value.decode())
+    L.ncb200_kernel_timing(0)
+    qc = (C.c_uint32 * 3)()
+    if L.ncb200_last_queue_counts(sc._h, qc) == 0:
+        qcounts = [int(qc[i]) for i in range(3)]
 
     # ---- e2e: reference-facing C entry points, pinned host buffers, copies inside the timed region
     h_e = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -286,7 +336,7 @@ def main():
         L.ncrystal_samplescatterisotropic_many(sc._h, C.cast(h_e.data_ptr(), dp), n, 1, C.cast(h_eo.data_ptr(), dp),
                                                C.cast(h_mu.data_ptr(), dp))
 
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -310,7 +360,20 @@ def main():
     value = world * n * args.steps / (ms_total * 1e-3)
     peak, peak_kind = peaks()
     BYTES_FUSED = 32   # 8 in + 8 xs + 8 E' + 8 mu (fused xs+sample_iso)
-    ach = n * BYTES_FUSED / (ms_fused * 1e-3) / 1e9
+    ach_seq = n * BYTES_FUSED / (ms_fused * 1e-3) / 1e9
+    # dominant kernel: k_sample_sab_refill (S(alpha,beta)-table sampling of the neutrons queued for it):
+    # algorithmic bytes per unit = BYTES_SAMPLE (8 B energy in, 16 B (E', mu) out), units = its queue length.
+    dom = ktimes.get("k_sample_sab_refill")
+    if dom and qcounts:
+        dom_units = qcounts[0]
+        dom_ms = dom["ms_avg"]
+        ach = dom_units * BYTES_SAMPLE / (dom_ms * 1e-3) / 1e9
+        dom_bytes = dom_units * BYTES_SAMPLE
+    else:
+        dom_units, dom_ms, ach, dom_bytes = n, ms_fused, ach_seq, n * BYTES_FUSED
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r1_kernels_v6_metrics.csv,
+    # same command, 1e7-neutron Al batch): dram__bytes_read.sum + dram__bytes_write.sum per launch.
+    traffic = 368.6e6 if n == N_PER_GPU else None
     out = {
         "metric": "neutrons/sec (xs eval + sampleScatter)", "value": value, "unit": "neutrons/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -330,12 +393,15 @@ def main():
                 "steps": e2e_steps, "api": "ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "fused xs+sample launch sequence (k_sample_classify, k_queue_scan/scatter, "
-                                               "k_sample_sab_refill, k_sample_fg); dominant: k_sample_sab_refill",
+        "roofline": {"bound": "hbm", "kernel": "k_sample_sab_refill",
                      "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "peak_source": peak_kind,
-                     "algorithmic_bytes_per_launch": n * BYTES_FUSED,
-                     "note": "latency/FP64-issue bound, not HBM bound (SURVEY 8d): see profiles/ for ncu stall and pipe evidence",
+                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": dom_bytes, "units_per_launch": dom_units, "ms_per_launch": dom_ms,
+                     "note": "rejection sampling in fp64: latency/issue bound, not HBM bound (SURVEY 8d); "
+                             "ncu stall and pipe evidence under profiles/",
+                     "kernel_ms": ktimes, "queue_units": qcounts,
+                     "launch_sequence": {"achieved": ach_seq, "frac": ach_seq / peak,
+                                         "algorithmic_bytes_per_step": n * BYTES_FUSED, "ms": ms_fused},
                      "xs_kernel": {"achieved": n * BYTES_XS / (ms_xs * 1e-3) / 1e9,
                                    "frac": n * BYTES_XS / (ms_xs * 1e-3) / 1e9 / peak}},
     }
@@ -348,8 +414,7 @@ def main():
                                    "sample": "full workload (1e7 neutrons), best of 2 after warm-up",
                                    "xs_per_s": n / t_xs, "samples_per_s": n / t_sm}
         else:
-            out["cpu_baseline"] = {"value": None, "unit": "neutrons/s", "cores": 0, "kind": "port",
-                                   "sample": "oracle/_ref not present"}
+            out["cpu_baseline"] = cpu_port_baseline(cfg)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

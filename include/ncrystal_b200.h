@@ -169,6 +169,12 @@ int      ncb200_component_kind( ncrystal_process_t, int i ); /* enum ncb_kind */
 double   ncb200_component_scale( ncrystal_process_t, int i );
 uint64_t ncb200_kernel_launch_count(void);   /* kernels launched by this library so far */
 uint64_t ncb200_table_bytes( ncrystal_process_t ); /* HBM footprint of the material tables */
+/* Per-kernel timing with CUDA events on the launching stream (off by default).  enable!=0 starts a fresh
+ * recording; the report is a JSON object {"kernel": {"launches": n, "ms_avg": t}, ...} (returns its length). */
+void     ncb200_kernel_timing( int enable );
+int      ncb200_kernel_timing_report( char* buf, int buflen );
+/* sizes of the work queues of the most recent isotropic sampling launch: table path, free-gas path, table at Emax */
+int      ncb200_last_queue_counts( ncrystal_scatter_t, uint32_t* out3 );
 const char* ncb200_version(void);
 /* SAB table builder check: per-energy-point total xs recomputed on the device while
  * building the sampler tables (compare with the xs grid of the compiled material). */

@@ -84,6 +84,35 @@ namespace {
 
   std::atomic<uint64_t> g_launches{0};
 
+  // ---- optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+  // Off by default; when on, every timed launch is bracketed by two events.
+  struct KernelTimer {
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    bool enabled = false;
+    std::vector<Rec> recs;
+    std::mutex mtx;
+    void begin( const char* name, cudaStream_t st )
+    {
+      if ( !enabled ) return;
+      Rec r; r.name = name;
+      cudaEventCreate( &r.a ); cudaEventCreate( &r.b );
+      cudaEventRecord( r.a, st );
+      std::lock_guard<std::mutex> g( mtx );
+      recs.push_back( r );
+    }
+    void end( cudaStream_t st )
+    {
+      if ( !enabled ) return;
+      std::lock_guard<std::mutex> g( mtx );
+      cudaEventRecord( recs.back().b, st );
+    }
+  } g_ktimer;
+  struct TimedLaunch {
+    cudaStream_t st;
+    TimedLaunch( const char* name, cudaStream_t s ) : st(s) { g_ktimer.begin( name, s ); }
+    ~TimedLaunch() { g_ktimer.end( st ); }
+  };
+
   // ------------------------------------------------------------------ material on device
   struct DeviceMaterial {
     int device = 0;
@@ -280,7 +309,12 @@ namespace {
   struct Scatter;
   struct FingerPrint { uint32_t tag; Scatter* self; };
 
-  constexpr size_t kChunk = (size_t)1 << 20; // neutrons per pipeline chunk of the host-pointer path
+  constexpr size_t kChunkMax = (size_t)1 << 22; // staging capacity (neutrons) per pipeline slot of the host-pointer path
+  size_t chunkSize()
+  {
+    static const size_t c = []{ const char* e = std::getenv( "NCB200_CHUNK" ); size_t v = e ? (size_t)std::atoll(e) : ( (size_t)1 << 20 ); return std::min( std::max<size_t>( v, 1024 ), kChunkMax ); }();
+    return c;
+  }
   constexpr int kSlots = 3;
   constexpr int kStageArrays = 8;            // up to 4 in + 4 out
 
@@ -292,6 +326,7 @@ namespace {
     uint32_t sid = 0;
     uint64_t next_index = 0;
     int* d_err = nullptr;
+    uint32_t* last_counts_ptr = nullptr;   // queue counters of the most recent split-path launch (diagnostics)
     uint32_t* d_diag_ndraws = nullptr;
     int32_t* d_diag_comp = nullptr;
     // host-pointer pipeline resources (lazily created)
@@ -370,7 +405,7 @@ namespace {
     {
       for ( int s = 0; s < kSlots; ++s ) {
         if ( !streams[s] ) CUDA_OK( cudaStreamCreateWithFlags( &streams[s], cudaStreamNonBlocking ) );
-        if ( !d_stage[s] ) CUDA_OK( cudaMalloc( &d_stage[s], kStageArrays*kChunk*sizeof(double) ) );
+        if ( !d_stage[s] ) CUDA_OK( cudaMalloc( &d_stage[s], kStageArrays*chunkSize()*sizeof(double) ) );
       }
     }
   };
@@ -489,7 +524,8 @@ namespace {
       throw Err( "LogicError", "Process::crossSectionIsotropic can only be called for isotropic materials." );
     const int threads = 256;
     const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
-    k_xs_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, n, d_out );
+    { TimedLaunch tl( "k_xs_iso", st );
+      k_xs_iso<<< gridFor( n, threads, dm.device, ctas ), threads, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, n, d_out ); }
     ++g_launches;
     CUDA_OK( cudaGetLastError() );
   }
@@ -534,7 +570,8 @@ namespace {
         Q.q_fg_sorted = do_sort ? qc.q + 5*qc.cap : nullptr;
         Q.hist = do_sort ? qc.counts + 8 : nullptr;
         CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
-        k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q );
+        { TimedLaunch tl( "k_sample_classify", st );
+          k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
         const unsigned nsm = (unsigned)numSMs( dm.device );
         if ( do_sort ) {
           k_queue_scan<<< 1, 1024, 0, st >>>( Q.hist );
@@ -573,18 +610,22 @@ namespace {
             st_fg = qc.side;
           }
           auto launchFG = [&]() {
+            TimedLaunch tl( "k_sample_fg", st_fg );
             if ( fgminb >= 8 ) k_sample_fg<8><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
             else k_sample_fg<4><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
           };
           if ( fgfirst ) launchFG();
+          { TimedLaunch tl( "k_sample_sab_refill", st );
           switch ( sabminb ) {
           case 4: launchRefill( k_sample_sab_refill<false,4>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 6: launchRefill( k_sample_sab_refill<false,6>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 8: launchRefill( k_sample_sab_refill<false,8>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           default: launchRefill( k_sample_sab_refill<false,5>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          }
+          } }
           if ( !fgfirst ) launchFG();
-          launchRefill( k_sample_sab_refill<true,5>, gfg, Q.q_emax, Q.counts + 2, Q.counts + 4, st_fg );
+          { TimedLaunch tl( "k_sample_sab_refill_emax", st_fg );
+            launchRefill( k_sample_sab_refill<true,5>, gfg, Q.q_emax, Q.counts + 2, Q.counts + 4, st_fg ); }
+          s->last_counts_ptr = Q.counts;
           if ( overlap ) {
             CUDA_OK( cudaEventRecord( qc.ev_join, qc.side ) );
             CUDA_OK( cudaStreamWaitEvent( st, qc.ev_join, 0 ) );
@@ -746,6 +787,7 @@ namespace {
     uint64_t done = 0;
     int slot = 0;
     while ( done < n ) {
+      const size_t kChunk = chunkSize();
       const uint64_t m = std::min<uint64_t>( kChunk, n - done );
       cudaStream_t st = s->streams[slot];
       double* base = s->d_stage[slot];
@@ -1182,6 +1224,57 @@ extern "C" {
     return -1.0;
   }
   uint64_t ncb200_kernel_launch_count(void) { return g_launches.load(); }
+
+  void ncb200_kernel_timing( int enable )
+  {
+    std::lock_guard<std::mutex> g( g_ktimer.mtx );
+    for ( auto& r : g_ktimer.recs ) { cudaEventDestroy( r.a ); cudaEventDestroy( r.b ); }
+    g_ktimer.recs.clear();
+    g_ktimer.enabled = enable != 0;
+  }
+  int ncb200_kernel_timing_report( char* buf, int buflen )
+  {
+    try {
+      CUDA_OK( cudaDeviceSynchronize() );
+      std::lock_guard<std::mutex> g( g_ktimer.mtx );
+      struct Acc { double ms = 0; int n = 0; };
+      std::vector<std::pair<std::string,Acc>> acc;
+      for ( auto& r : g_ktimer.recs ) {
+        float ms = 0.f;
+        if ( cudaEventElapsedTime( &ms, r.a, r.b ) != cudaSuccess ) continue;
+        auto it = acc.begin();
+        for ( ; it != acc.end(); ++it ) if ( it->first == r.name ) break;
+        if ( it == acc.end() ) { acc.emplace_back( r.name, Acc() ); it = acc.end() - 1; }
+        it->second.ms += ms; it->second.n += 1;
+      }
+      std::ostringstream ss;
+      ss << "{";
+      bool first = true;
+      for ( auto& e : acc ) {
+        ss << ( first ? "" : ", " ) << "\"" << e.first << "\": {\"launches\": " << e.second.n << ", \"ms_avg\": "
+           << ( e.second.n ? e.second.ms/e.second.n : 0.0 ) << "}";
+        first = false;
+      }
+      ss << "}";
+      const std::string out = ss.str();
+      if ( buf && buflen > 0 ) std::snprintf( buf, (size_t)buflen, "%s", out.c_str() );
+      return (int)out.size();
+    } NCBCATCH;
+    return -1;
+  }
+  // queue sizes of the most recent isotropic sampling launch: [table path, free-gas path, table-at-Emax]
+  int ncb200_last_queue_counts( ncrystal_scatter_t o, uint32_t* out3 )
+  {
+    try {
+      Scatter* s = fromInternal( o.internal, "ncb200_last_queue_counts" );
+      if ( !s->last_counts_ptr ) return -1;
+      DeviceGuard dg( s->dm->device );
+      CUDA_OK( cudaDeviceSynchronize() );
+      CUDA_OK( cudaMemcpy( out3, s->last_counts_ptr, 3*sizeof(uint32_t), cudaMemcpyDeviceToHost ) );
+      return 0;
+    } NCBCATCH;
+    return -1;
+  }
   uint64_t ncb200_table_bytes( ncrystal_process_t p )
   {
     try { return fromInternal( p.internal, "ncb200_table_bytes" )->dm->arena_bytes; } NCBCATCH;
