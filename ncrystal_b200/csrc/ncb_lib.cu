@@ -316,7 +316,21 @@ namespace {
     return c;
   }
   constexpr int kSlots = 3;
-  constexpr int kStageArrays = 8;            // up to 4 in + 4 out
+  constexpr uint64_t kWindowMax = (uint64_t)1 << 24;   // neutrons staged on the device per window of the host-pointer path
+  struct PipeSchedule { uint64_t first, max; double growth; };
+  PipeSchedule pipeSchedule()
+  {
+    static const PipeSchedule ps = []{
+      PipeSchedule p;
+      const char* e0 = std::getenv( "NCB200_CHUNK0" );
+      const char* eg = std::getenv( "NCB200_CHUNK_GROWTH" );
+      p.max = chunkSize();
+      p.first = std::min<uint64_t>( p.max, std::max<uint64_t>( 4096, e0 ? (uint64_t)std::atoll(e0) : ( (uint64_t)1 << 18 ) ) );
+      p.growth = std::max( 1.0, eg ? std::atof(eg) : 2.0 );
+      return p;
+    }();
+    return ps;
+  }
 
   struct Scatter {
     FingerPrint fp;
@@ -330,8 +344,11 @@ namespace {
     uint32_t* d_diag_ndraws = nullptr;
     int32_t* d_diag_comp = nullptr;
     // host-pointer pipeline resources (lazily created)
-    cudaStream_t streams[kSlots] = {};
-    double* d_stage[kSlots] = {};
+    cudaStream_t streams[kSlots] = {};      // kernel streams, one per slot
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    double* d_win = nullptr;                // staging window: (nin+nout) arrays of win_doubles/(nin+nout) neutrons
+    size_t win_doubles = 0;
+    std::vector<cudaEvent_t> ev_h, ev_c;    // per chunk: copy-in done, kernels done
     // work queues of the split sampling path: one context per pipeline slot + one for the
     // device-pointer entry points (a handle has at most one launch sequence in flight per context)
     struct QueueCtx {
@@ -356,10 +373,13 @@ namespace {
         if ( c.ev_fork ) cudaEventDestroy( c.ev_fork );
         if ( c.ev_join ) cudaEventDestroy( c.ev_join );
       }
-      for ( int s = 0; s < kSlots; ++s ) {
-        if ( d_stage[s] ) cudaFree( d_stage[s] );
+      for ( int s = 0; s < kSlots; ++s )
         if ( streams[s] ) cudaStreamDestroy( streams[s] );
-      }
+      if ( st_h2d ) cudaStreamDestroy( st_h2d );
+      if ( st_d2h ) cudaStreamDestroy( st_d2h );
+      if ( d_win ) cudaFree( d_win );
+      for ( auto e : ev_h ) cudaEventDestroy( e );
+      for ( auto e : ev_c ) cudaEventDestroy( e );
     }
     void ensureErrWord()
     {
@@ -401,11 +421,26 @@ namespace {
       }
       return c;
     }
-    void ensurePipeline()
+    void ensurePipeline( size_t ndoubles )
     {
-      for ( int s = 0; s < kSlots; ++s ) {
+      for ( int s = 0; s < kSlots; ++s )
         if ( !streams[s] ) CUDA_OK( cudaStreamCreateWithFlags( &streams[s], cudaStreamNonBlocking ) );
-        if ( !d_stage[s] ) CUDA_OK( cudaMalloc( &d_stage[s], kStageArrays*chunkSize()*sizeof(double) ) );
+      if ( !st_h2d ) CUDA_OK( cudaStreamCreateWithFlags( &st_h2d, cudaStreamNonBlocking ) );
+      if ( !st_d2h ) CUDA_OK( cudaStreamCreateWithFlags( &st_d2h, cudaStreamNonBlocking ) );
+      if ( ndoubles > win_doubles ) {
+        if ( d_win ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( d_win ) ); d_win = nullptr; }
+        const size_t want = std::max( ndoubles, (size_t)3 << 20 );
+        CUDA_OK( cudaMalloc( &d_win, want*sizeof(double) ) );
+        win_doubles = want;
+      }
+    }
+    void ensureChunkEvents( size_t k )
+    {
+      while ( ev_h.size() < k ) {
+        cudaEvent_t a, b;
+        CUDA_OK( cudaEventCreateWithFlags( &a, cudaEventDisableTiming ) );
+        CUDA_OK( cudaEventCreateWithFlags( &b, cudaEventDisableTiming ) );
+        ev_h.push_back( a ); ev_c.push_back( b );
       }
     }
   };
@@ -776,39 +811,52 @@ namespace {
       throw Err( "CalcError", "convertAlphaBetaToDeltaEMu invalid for beta=-E/kT" );
   }
 
-  // Host-pointer pipeline: chunks of kChunk neutrons alternate between two streams so
-  // that the H2D copy of chunk c+1 overlaps the kernel and D2H copy of chunk c.
-  // `launch(chunk_n, in_dev[], out_dev[], stream)` enqueues the kernel(s).
+  // Host-pointer pipeline.  The call's arrays are staged in one device window (<= kWindowMax neutrons; longer
+  // calls run window after window).  Three kinds of streams: one for H2D copies, kSlots for the kernels
+  // (round robin, so the tail of one chunk's rejection kernels overlaps the next chunk), one for D2H copies;
+  // events order chunk k's copy-in -> kernels -> copy-out, the host only blocks at the end of a window.
+  // Chunks start small (the first D2H starts early) and grow geometrically up to chunkSize() (launch efficiency).
+  // `launch(chunk_n, in_dev[], out_dev[], stream, slot)` enqueues the kernel(s).
   void runHostPipeline( Scatter* s, uint64_t n, int nin, const double* const* in, int nout, double* const* out,
                         const std::function<void(uint64_t,double* const*,double* const*,cudaStream_t,int)>& launch )
   {
     if ( !n ) return;
-    s->ensurePipeline();
-    uint64_t done = 0;
-    int slot = 0;
-    while ( done < n ) {
-      const size_t kChunk = chunkSize();
-      const uint64_t m = std::min<uint64_t>( kChunk, n - done );
-      cudaStream_t st = s->streams[slot];
-      double* base = s->d_stage[slot];
-      double* din[4]; double* dout[4];
-      for ( int k = 0; k < nin; ++k ) {
-        din[k] = base + (size_t)k*kChunk;
-        CUDA_OK( cudaMemcpyAsync( din[k], in[k] + done, m*sizeof(double), cudaMemcpyHostToDevice, st ) );
+    const uint64_t W = std::min<uint64_t>( n, kWindowMax );
+    s->ensurePipeline( (size_t)W * (size_t)( nin + nout ) );
+    const PipeSchedule ps = pipeSchedule();
+    for ( uint64_t w0 = 0; w0 < n; w0 += W ) {
+      const uint64_t wn = std::min<uint64_t>( W, n - w0 );
+      uint64_t done = 0;
+      size_t k = 0;
+      double chunk = (double)ps.first;
+      while ( done < wn ) {
+        uint64_t m = std::min<uint64_t>( (uint64_t)chunk, wn - done );
+        if ( wn - done - m < ps.first/2 ) m = wn - done;      // no tiny last chunk
+        chunk = std::min<double>( chunk*ps.growth, (double)ps.max );
+        s->ensureChunkEvents( k + 1 );
+        const int slot = (int)( k % kSlots );
+        cudaStream_t cs = s->streams[slot];
+        double* din[4]; double* dout[4];
+        for ( int a = 0; a < nin; ++a ) {
+          din[a] = s->d_win + (size_t)a*W + done;
+          CUDA_OK( cudaMemcpyAsync( din[a], in[a] + w0 + done, m*sizeof(double), cudaMemcpyHostToDevice, s->st_h2d ) );
+        }
+        CUDA_OK( cudaEventRecord( s->ev_h[k], s->st_h2d ) );
+        for ( int a = 0; a < nout; ++a )
+          dout[a] = s->d_win + (size_t)(nin+a)*W + done;
+        CUDA_OK( cudaStreamWaitEvent( cs, s->ev_h[k], 0 ) );
+        launch( m, din, dout, cs, slot );
+        CUDA_OK( cudaEventRecord( s->ev_c[k], cs ) );
+        CUDA_OK( cudaStreamWaitEvent( s->st_d2h, s->ev_c[k], 0 ) );
+        for ( int a = 0; a < nout; ++a )
+          CUDA_OK( cudaMemcpyAsync( out[a] + w0 + done, dout[a], m*sizeof(double), cudaMemcpyDeviceToHost, s->st_d2h ) );
+        done += m;
+        ++k;
       }
-      for ( int k = 0; k < nout; ++k )
-        dout[k] = base + (size_t)(4+k)*kChunk;
-      launch( m, din, dout, st, slot );
-      for ( int k = 0; k < nout; ++k )
-        CUDA_OK( cudaMemcpyAsync( out[k] + done, dout[k], m*sizeof(double), cudaMemcpyDeviceToHost, st ) );
-      done += m;
-      slot = ( slot + 1 ) % kSlots;
-      // the slot we are about to reuse must have drained
-      if ( done < n )
-        CUDA_OK( cudaStreamSynchronize( s->streams[slot] ) );
+      CUDA_OK( cudaStreamSynchronize( s->st_d2h ) );
+      for ( int c = 0; c < kSlots; ++c )
+        CUDA_OK( cudaStreamSynchronize( s->streams[c] ) );
     }
-    for ( int k = 0; k < kSlots; ++k )
-      CUDA_OK( cudaStreamSynchronize( s->streams[k] ) );
   }
 
   void xsIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* results )
