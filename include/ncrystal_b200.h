@@ -169,6 +169,17 @@ int      ncb200_component_kind( ncrystal_process_t, int i ); /* enum ncb_kind */
 double   ncb200_component_scale( ncrystal_process_t, int i );
 uint64_t ncb200_kernel_launch_count(void);   /* kernels launched by this library so far */
 uint64_t ncb200_table_bytes( ncrystal_process_t ); /* HBM footprint of the material tables */
+/* Device-resident transport step ("MiniMC" on the device): the reference's ["mmc","run",CFGSTR,GEOMCFG,SRCCFG,
+ * ENGINECFG] query of ncrystal_jsonquery (ncrystal.h:1253; NCMMC_Query.cc:38-56) for the material of a scatter handle.
+ * Same cfg-string vocabulary and result JSON ("NCrystalMiniMCResults_v1"); supported subset documented in
+ * csrc/ncb_lib_mmc.inc.  Returns NULL on error; free the string with ncrystal_dealloc_string.
+ * _slice simulates source neutrons [first, first+count) only -- tallies of disjoint slices add up (multi-GPU). */
+char*    ncb200_minimc_run( ncrystal_scatter_t, const char* geomcfg, const char* srccfg, const char* enginecfg );
+char*    ncb200_minimc_run_slice( ncrystal_scatter_t, const char* geomcfg, const char* srccfg, const char* enginecfg,
+                                  uint64_t first, uint64_t count );
+/* bulk quantities of the compiled material: number density [atoms/Aa^3], AbsOOV constant xs_abs*sqrt(E)
+ * [barn*sqrt(eV)] (NCAbsOOV.cc:33-45), temperature [K] */
+void     ncb200_material_bulk( ncrystal_process_t, double* numdens, double* abs_c, double* temperature );
 /* Per-kernel timing with CUDA events on the launching stream (off by default).  enable!=0 starts a fresh
  * recording; the report is a JSON object {"kernel": {"launches": n, "ms_avg": t}, ...} (returns its length). */
 void     ncb200_kernel_timing( int enable );

@@ -89,6 +89,9 @@ SIGNATURES = {
     "ncb200_component_scale": (C.c_double, [ncrystal_process_t, C.c_int]),
     "ncb200_kernel_launch_count": (_u64, []),
     "ncb200_table_bytes": (_u64, [ncrystal_process_t]),
+    "ncb200_minimc_run": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "ncb200_minimc_run_slice": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p, _u64, _u64]),
+    "ncb200_material_bulk": (None, [ncrystal_process_t, _dblp, _dblp, _dblp]),
     "ncb200_kernel_timing": (None, [C.c_int]),
     "ncb200_kernel_timing_report": (C.c_int, [C.c_char_p, C.c_int]),
     "ncb200_last_queue_counts": (C.c_int, [ncrystal_scatter_t, C.POINTER(C.c_uint32)]),

@@ -358,6 +358,31 @@ class Scatter(Process):
             return self.sampleScatterIsotropic(ekin, repeat)
         return self.sampleScatter(ekin, direction, repeat)
 
+    # -- device-resident transport step (the reference's MiniMC, ncrystal_python/src/NCrystal/minimc.py: run)
+    def minimc(self, geomcfg, srccfg, enginecfg="", first=None, count=None):
+        """Run source neutrons (optionally only the slice [first, first+count)) through a single volume of this
+        material on the device; returns the decoded result dictionary ("NCrystalMiniMCResults_v1").
+        ref: minimc.py run(cfgstr, geomcfg, srccfg, enginecfg) / ncrystal_jsonquery ["mmc","run",...]"""
+        import json
+        if first is None and count is None:
+            p = self._L.ncb200_minimc_run(self._h, geomcfg.encode(), srccfg.encode(), enginecfg.encode())
+        else:
+            p = self._L.ncb200_minimc_run_slice(self._h, geomcfg.encode(), srccfg.encode(), enginecfg.encode(),
+                                                int(first or 0), int(count if count is not None else 2 ** 63))
+        _check_error()
+        if not p:
+            raise NCCalcError("ncb200_minimc_run failed")
+        s = C.string_at(p).decode()
+        self._L.ncrystal_dealloc_string(p)
+        return json.loads(s)
+
+    def materialBulk(self):
+        """(number density [atoms/Aa^3], absorption constant xs*sqrt(E) [barn sqrt(eV)], temperature [K])"""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._L.ncb200_material_bulk(self._p, C.byref(a), C.byref(b), C.byref(c))
+        _check_error()
+        return a.value, b.value, c.value
+
     def checkDeviceErrors(self, device=None):
         """Synchronise torch's current stream and raise if a kernel flagged an error."""
         import torch

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define NCB_MAGIC    0x0030303242434eULL /* "NCB200\0" */
-#define NCB_VERSION  2u
+#define NCB_VERSION  3u
 #define NCB_MAXCOMP  8
 
 enum ncb_kind {
@@ -56,7 +56,14 @@ typedef struct {
   uint64_t   nbytes;   /* total size of the buffer */
   double     dom_lo;   /* ProcComposition::domain() */
   double     dom_hi;
-  char       cfg[208]; /* the cfg-string the material was compiled from (NUL terminated) */
+  /* bulk quantities the transport step needs next to the scatter process (MiniMC MatDef,
+   * ref: include/NCrystal/internal/minimc/NCMMC_Defs.hh; absorption = AbsOOV, src/absoov/NCAbsOOV.cc:33-45) */
+  double     numdens;     /* Info::getNumberDensity() [atoms/Aa^3] */
+  double     abs_c;       /* AbsOOV::m_c = sigma_abs(2200m/s)*sqrt(E_2200): xs_abs(E) = abs_c/sqrt(E) [barn*sqrt(eV)];
+                             0 = no absorption, <0 = absorption is not a 1/v process (unsupported) */
+  double     temperature; /* Info::getTemperature() [K], -1 if not available */
+  double     reserved2;
+  char       cfg[176]; /* the cfg-string the material was compiled from (NUL terminated) */
   ncb_comp_t comp[NCB_MAXCOMP];
 } ncb_header_t;
 

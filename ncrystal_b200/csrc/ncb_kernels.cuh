@@ -114,6 +114,9 @@ namespace ncb {
     uint32_t* ndraws;    // may be null
     int32_t* component;  // may be null
     int* err_flags;      // device word, atomicOr'ed
+    const uint64_t* ids = nullptr;   // optional: random-stream index of neutron i (transport: source particle id);
+                                     // default first_index + i
+    NCB_HD uint64_t streamIndex( uint64_t i ) const { return ids ? ids[i] : first_index + i; }
   };
 
   __global__ void __launch_bounds__(128)
@@ -127,7 +130,7 @@ namespace ncb {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     int errs = 0;
     for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += stride ) {
-      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
       double eout, mu;
       int err = 0, ich;
       const double xs = matSampleIso( M, H, A.ekin[i], rng, eout, mu, err, ich );
@@ -243,7 +246,7 @@ namespace ncb {
           double cumul[kMaxComp];
           int aux[kMaxComp];
           tot = matXSIso( M, H, ekin, cumul, aux );
-          Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+          Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
           ich = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
           const Comp& c = M.comp[ich];
           if ( c.kind == KIND_SAB ) {
@@ -348,7 +351,7 @@ namespace ncb {
       const uint32_t i = entry & kQueueIdxMask;
       const int ich = (int)( entry >> kQueueIdxBits );
       const double ekin = A.ekin[i];
-      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
       rng.seek( kAtEmax ? queue[2*j+1] : ( M.ncomp > 1 ? 1u : 0u ) );
       const SabT& T = M.sab[M.comp[ich].idx];
       double eout, mu;
@@ -407,7 +410,7 @@ namespace ncb {
             isab = M.comp[ entry >> kQueueIdxBits ].idx;
             const SabT& T = M.sab[isab];
             ekin_orig = A.ekin[idx];
-            rng.init( A.seed, A.first_index + idx, A.sid );
+            rng.init( A.seed, A.streamIndex( idx ), A.sid );
             rng.seek( kAtEmax ? queue[2*j+1] : ( M.ncomp > 1 ? 1u : 0u ) );
             double ekin_eff;
             if ( kAtEmax ) {
@@ -491,7 +494,7 @@ namespace ncb {
         const uint32_t i = entry & kQueueIdxMask;
         const int ich = (int)( entry >> kQueueIdxBits );
         const double ekin = A.ekin[i];
-        Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+        Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
         rng.seek( M.ncomp > 1 ? 1u : 0u );
         const Comp& c = M.comp[ich];
         double eout = -1.0, mu = -999.0;
@@ -570,7 +573,7 @@ namespace ncb {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     int errs = 0;
     for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += stride ) {
-      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
       double eout;
       Vec3 o;
       int err = 0, ich;

@@ -1,0 +1,224 @@
+// ncb_kernels_mmc.cuh -- kernels of the device-resident transport step (see ncb_mmc.cuh for the physics and the
+// reference line numbers).  Included by ncb_lib.cu only.
+//
+// Population layout: SoA arrays in HBM (MmcState), two buffers.  One step =
+//   launchXSAniso(A)            scattering cross section at every live neutron's (E, dir)
+//   k_mmc_forward(A -> B)       flight distances, transmission, roulette, weights; survivors are appended to B
+//                               at their scattering point (block-aggregated atomic cursor), wt[] = tallied weight
+//   k_mmc_tally(A, wt)          exit tallies, shared-memory privatised per CTA, one histogram at a time
+//   launchSampleAniso(B)        scattering outcome for every survivor (same kernels as the C-API)
+//   k_mmc_post(B)               new (E, dir), scattering counters
+// then A <-> B.  All per-neutron accesses are coalesced 8-byte streams; the only scattered traffic is the
+// compaction write (contiguous per CTA).
+#pragma once
+#include "ncb_mmc.cuh"
+
+namespace ncb {
+
+  struct MmcState {
+    double *x, *y, *z, *ux, *uy, *uz, *w, *ekin, *e0;
+    int32_t *nscat, *ninel;
+    uint64_t* id;
+  };
+
+  // CTA-wide stream compaction cursor: returns the output slot of every thread with pred (undefined otherwise).
+  // One global atomic per CTA per call.  Must be called by all threads of the CTA.
+  __device__ __forceinline__ uint32_t blockAppend( bool pred, uint32_t* counter, uint32_t* s_warp, uint32_t* s_base )
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t m = __ballot_sync( 0xffffffffu, pred );
+    if ( lane == 0 ) s_warp[w] = __popc( m );
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+      uint32_t tot = 0;
+      for ( int k = 0; k < nw; ++k ) { const uint32_t c = s_warp[k]; s_warp[k] = tot; tot += c; }
+      *s_base = tot ? atomicAdd( counter, tot ) : 0u;
+    }
+    __syncthreads();
+    const uint32_t pos = *s_base + s_warp[w] + __popc( m & ( ( 1u << lane ) - 1u ) );
+    __syncthreads();
+    return pos;
+  }
+
+  // counters: [0] live neutrons appended to A, [1] missed neutrons appended to Miss
+  __global__ void __launch_bounds__(256)
+  k_mmc_source( const __grid_constant__ MmcSource S, const __grid_constant__ MmcGeom G, uint64_t seed, uint64_t first_id,
+                uint32_t n, MmcState A, MmcState Miss, uint32_t* counters, int record_miss )
+  {
+    __shared__ uint32_t s_warp[8], s_base;
+    const uint32_t n_up = ( n + blockDim.x - 1 )/blockDim.x*blockDim.x;
+    for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
+      bool live = false, miss = false;
+      MmcNeutron nt{};
+      if ( i < n ) {
+        Rng rng; rng.init( seed, first_id + i, kMmcSidSrc );
+        nt = mmcGenerate( S, rng );
+        live = true;
+        if ( S.may_be_outside ) {
+          const double d = mmcDistToEntry( G, nt.x, nt.y, nt.z, nt.ux, nt.uy, nt.uz );
+          if ( d < 0.0 ) { live = false; miss = true; }
+          else { nt.x += d*nt.ux; nt.y += d*nt.uy; nt.z += d*nt.uz; }   // detail::propagateDistance
+        }
+      }
+      const uint32_t pa = blockAppend( live, counters + 0, s_warp, &s_base );
+      const uint32_t pm = blockAppend( miss, counters + 1, s_warp, &s_base );
+      if ( live || ( miss && record_miss ) ) {
+        const MmcState& T = live ? A : Miss;
+        const uint32_t p = live ? pa : pm;
+        T.x[p] = nt.x; T.y[p] = nt.y; T.z[p] = nt.z; T.ux[p] = nt.ux; T.uy[p] = nt.uy; T.uz[p] = nt.uz;
+        T.w[p] = nt.w; T.ekin[p] = nt.ekin; T.e0[p] = nt.ekin;
+        T.nscat[p] = live ? 0 : -1;       // markAsMissedTarget, NCMMC_Baskets.cc:81
+        T.ninel[p] = 0;
+        T.id[p] = first_id + i;
+      }
+    }
+  }
+
+  __global__ void __launch_bounds__(256)
+  k_mmc_forward( const __grid_constant__ MmcGeom G, const __grid_constant__ MmcEngine E, uint64_t seed, uint32_t step,
+                 uint32_t n, MmcState A, const double* __restrict__ xs, double* __restrict__ wt,
+                 MmcState B, uint32_t* counter )
+  {
+    __shared__ uint32_t s_warp[8], s_base;
+    const uint32_t n_up = ( n + blockDim.x - 1 )/blockDim.x*blockDim.x;
+    for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
+      MmcStepOut o; o.survives = false;
+      double ux = 0, uy = 0, uz = 0, ekin = 0, e0 = 0; int nscat = 0, ninel = 0; uint64_t id = 0;
+      if ( i < n ) {
+        id = A.id[i];
+        ux = A.ux[i]; uy = A.uy[i]; uz = A.uz[i]; ekin = A.ekin[i]; e0 = A.e0[i];
+        nscat = A.nscat[i]; ninel = A.ninel[i];
+        Rng rng; rng.init( seed, id, kMmcSidBase + 2u*step );
+        o = mmcForward( G, E, rng, A.x[i], A.y[i], A.z[i], ux, uy, uz, A.w[i], ekin, nscat, xs[i] );
+        wt[i] = o.wt;
+      }
+      const uint32_t p = blockAppend( o.survives, counter, s_warp, &s_base );
+      if ( o.survives ) {
+        B.x[p] = o.x; B.y[p] = o.y; B.z[p] = o.z; B.ux[p] = ux; B.uy[p] = uy; B.uz[p] = uz;
+        B.w[p] = o.w; B.ekin[p] = ekin; B.e0[p] = e0; B.nscat[p] = nscat; B.ninel[p] = ninel; B.id[p] = id;
+      }
+    }
+  }
+
+  // after the scattering kernels: SimEngine.cc:392-404
+  __global__ void __launch_bounds__(256)
+  k_mmc_post( uint32_t n, MmcState B, const double* __restrict__ eout, const double* __restrict__ ox,
+              const double* __restrict__ oy, const double* __restrict__ oz )
+  {
+    for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x ) {
+      const double e_new = eout[i];
+      const bool was_elastic = ( B.ekin[i] == e_new );
+      B.ux[i] = ox[i]; B.uy[i] = oy[i]; B.uz[i] = oz[i];
+      B.ekin[i] = e_new;
+      B.nscat[i] += 1;
+      if ( !was_elastic ) B.ninel[i] += 1;
+    }
+  }
+
+  // order-preserving map double -> uint64 (for atomicMin/atomicMax on the running min/max of filled values)
+  __device__ __forceinline__ unsigned long long mmcOrdered( double d )
+  {
+    const unsigned long long b = (unsigned long long)__double_as_longlong( d );
+    return ( b >> 63 ) ? ~b : ( b | 0x8000000000000000ull );
+  }
+
+  // Exit tallies.  wt == nullptr: the records are source neutrons that missed the volume (weight = S.w).
+  // dynamic smem: mmcHistDoubles(max nbins) doubles.
+  __global__ void __launch_bounds__(256)
+  k_mmc_tally( const __grid_constant__ MmcTally T, uint32_t n, MmcState A, const double* __restrict__ wt,
+               double* __restrict__ tally )
+  {
+    extern __shared__ __align__(16) double sh[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_up = ( n + 31u ) & ~31u;
+    for ( int ih = 0; ih < T.nh; ++ih ) {
+      const MmcHist h = T.h[ih];
+      const int nb2 = h.nbins + 2;
+      const uint32_t nd = mmcHistDoubles( h.nbins );
+      double* s_cont = sh;                                  // [class][nb2]
+      double* s_err = sh + kMmcNClass*nb2;                  // [class][nb2]
+      double* s_stat = sh + 2*kMmcNClass*nb2;               // [class][kMmcNStat]
+      unsigned long long* s_statu = reinterpret_cast<unsigned long long*>( s_stat );
+      for ( uint32_t k = threadIdx.x; k < nd; k += blockDim.x ) sh[k] = 0.0;
+      __syncthreads();
+      if ( threadIdx.x < kMmcNClass ) {
+        s_statu[threadIdx.x*kMmcNStat + 3] = ~0ull;         // min
+        s_statu[threadIdx.x*kMmcNStat + 4] = 0ull;          // max
+      }
+      __syncthreads();
+      for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
+        int cls = -1;
+        double val = 0.0, wgt = 0.0;
+        if ( i < n ) {
+          const double w = wt ? wt[i] : A.w[i];
+          const int nscat = A.nscat[i];
+          bool weighted;
+          val = mmcTallyValue( T, h.type, A.ux[i], A.uy[i], A.uz[i], A.ekin[i], w, nscat, A.e0[i], weighted );
+          wgt = weighted ? w : 1.0;
+          if ( wgt > 0.0 ) {
+            cls = mmcClass( nscat, A.ninel[i] );
+            const int bin = mmcValueToBin( h, val );
+            atomicAdd( &s_cont[cls*nb2 + bin], wgt );
+            atomicAdd( &s_err[cls*nb2 + bin], wgt*wgt );
+          }
+        }
+        // running statistics (RunningStats1D): warp-reduce per class, one shared atomic per warp and class
+        for ( int c = 0; c < kMmcNClass; ++c ) {
+          const uint32_t m = __ballot_sync( 0xffffffffu, cls == c );
+          if ( !m ) continue;
+          const bool mine = ( cls == c );
+          double a0 = mine ? wgt : 0.0, a1 = mine ? wgt*val : 0.0, a2 = mine ? wgt*val*val : 0.0;
+          unsigned long long lo = mine ? mmcOrdered( val ) : ~0ull, hi = mine ? mmcOrdered( val ) : 0ull;
+          for ( int d = 16; d; d >>= 1 ) {
+            a0 += __shfl_xor_sync( 0xffffffffu, a0, d );
+            a1 += __shfl_xor_sync( 0xffffffffu, a1, d );
+            a2 += __shfl_xor_sync( 0xffffffffu, a2, d );
+            const unsigned long long l2 = __shfl_xor_sync( 0xffffffffu, lo, d ), h2 = __shfl_xor_sync( 0xffffffffu, hi, d );
+            lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+          }
+          if ( lane == 0 ) {
+            atomicAdd( &s_stat[c*kMmcNStat + 0], a0 );
+            atomicAdd( &s_stat[c*kMmcNStat + 1], a1 );
+            atomicAdd( &s_stat[c*kMmcNStat + 2], a2 );
+            atomicMin( &s_statu[c*kMmcNStat + 3], lo );
+            atomicMax( &s_statu[c*kMmcNStat + 4], hi );
+          }
+        }
+      }
+      __syncthreads();
+      double* g = tally + h.off;
+      unsigned long long* gu = reinterpret_cast<unsigned long long*>( g );
+      const uint32_t nbins_all = 2u*kMmcNClass*nb2;
+      for ( uint32_t k = threadIdx.x; k < nbins_all; k += blockDim.x )
+        if ( sh[k] != 0.0 ) atomicAdd( &g[k], sh[k] );
+      if ( threadIdx.x < kMmcNClass ) {
+        const uint32_t so = threadIdx.x*kMmcNStat;     // within s_stat / s_statu
+        const uint32_t o = nbins_all + so;             // within the histogram's global block
+        if ( s_statu[so+3] != ~0ull ) {
+          atomicAdd( &g[o+0], s_stat[so+0] ); atomicAdd( &g[o+1], s_stat[so+1] ); atomicAdd( &g[o+2], s_stat[so+2] );
+          atomicMin( &gu[o+3], s_statu[so+3] );
+          atomicMax( &gu[o+4], s_statu[so+4] );
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // sum of the tallied weights and record count (metadata "tallied"): block reduction
+  __global__ void __launch_bounds__(256)
+  k_mmc_sum_weights( uint32_t n, const double* __restrict__ w, double* __restrict__ out )
+  {
+    __shared__ double s[8];
+    double a = 0.0;
+    for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x ) a += w[i];
+    for ( int d = 16; d; d >>= 1 ) a += __shfl_xor_sync( 0xffffffffu, a, d );
+    if ( ( threadIdx.x & 31 ) == 0 ) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+      double t = 0.0;
+      for ( int k = 0; k < (int)( blockDim.x >> 5 ); ++k ) t += s[k];
+      atomicAdd( out, t );
+    }
+  }
+
+}

@@ -266,7 +266,7 @@ namespace ncb {
           double cumul[kMaxComp];
           int aux[kMaxComp];
           tot = matXSPre( M, H, ekin, X.sc_xs ? X.sc_xs[i] : 0.0, X.sc_n ? X.sc_n[i] : 0, cumul, aux );
-          Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+          Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
           ich = ( M.ncomp == 1 ? 0 : pickIdxByWeight( rng.generate(), cumul, M.ncomp ) );
           const Comp& c = M.comp[ich];
           if ( c.kind == KIND_SCBRAGG ) {
@@ -331,7 +331,7 @@ namespace ncb {
       const double ekin = A.ekin[i];
       Vec3 d = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
       vnormalise( d );
-      Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
       rng.seek( M.ncomp > 1 ? 1u : 0u );
       const int nent = X.sc_n[i];
       const double total = X.sc_xs[i];
@@ -364,7 +364,7 @@ namespace ncb {
       const uint32_t i = ( j < n0 ? Q.q_sab[j] : Q.q_fg[j - n0] ) & kQueueIdxMask;
       Vec3 o = { 0.0, 0.0, 0.0 };
       if ( A.ekin_out[i] >= 0.0 ) {     // (-1: the sampler raised an error for this neutron)
-        Rng rng; rng.init( A.seed, A.first_index + i, A.sid );
+        Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
         rng.seek( X.nd_tmp[i] );
         o = randDirectionGivenScatterMu( rng, X.mu_tmp[i], Vec3{ X.D.ux[i], X.D.uy[i], X.D.uz[i] } );
         if ( A.ndraws ) A.ndraws[i] = rng.ndraws;

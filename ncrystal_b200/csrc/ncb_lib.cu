@@ -10,6 +10,7 @@
 // raises an error when no usable device is present.
 #include "ncb_kernels.cuh"
 #include "ncb_kernels_sc.cuh"
+#include "ncb_kernels_mmc.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
 #include "../../include/ncrystal_b200.h"
@@ -125,6 +126,7 @@ namespace {
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
     uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0;
     std::string cfg;
+    double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
     std::vector<SabBuildPlan> sabplans;
     std::atomic<uint32_t> clone_counter{0};
     ~DeviceMaterial() { if ( d_arena ) cudaFree( d_arena ); }
@@ -288,6 +290,7 @@ namespace {
     CUDA_OK( cudaMemcpy( dm->d_arena, lm.arena.data(), dm->arena_bytes, cudaMemcpyHostToDevice ) );
     dm->mat = relocated( lm, dm->d_arena );
     dm->cfg = lm.cfg;
+    dm->numdens = lm.numdens; dm->abs_c = lm.abs_c; dm->temperature = lm.temperature;
     dm->sabplans = lm.sabplans;
     buildStagePlan( *dm );
     setSmemAttr( k_xs_iso, dm->sp.total );
@@ -340,6 +343,7 @@ namespace {
     uint32_t sid = 0;
     uint64_t next_index = 0;
     int* d_err = nullptr;
+    const uint64_t* ids_override = nullptr; // transport: device array of random-stream indices for the next sampling launch
     uint32_t* last_counts_ptr = nullptr;   // queue counters of the most recent split-path launch (diagnostics)
     uint32_t* d_diag_ndraws = nullptr;
     int32_t* d_diag_comp = nullptr;
@@ -590,6 +594,7 @@ namespace {
       A.xs_out = d_xs ? d_xs + done : nullptr; A.ekin_out = d_eout + done; A.mu_out = d_mu + done;
       A.ndraws = diag_nd ? diag_nd + done : nullptr; A.component = diag_comp ? diag_comp + done : nullptr;
       A.err_flags = s->d_err;
+      A.ids = s->ids_override ? s->ids_override + done : nullptr;
       const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
       if ( useSampleV1() ) {
         k_sample_iso<<< gridFor( m, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A );
@@ -746,6 +751,7 @@ namespace {
       A.xs_out = nullptr; A.ekin_out = d_eout + done; A.mu_out = nullptr;
       A.ndraws = diag_nd ? diag_nd + done : nullptr; A.component = diag_comp ? diag_comp + done : nullptr;
       A.err_flags = s->d_err;
+      A.ids = s->ids_override ? s->ids_override + done : nullptr;
       DirArgs D; D.ux = ux + done; D.uy = uy + done; D.uz = uz + done; D.ox = ox + done; D.oy = oy + done; D.oz = oz + done;
       if ( v1 ) {
         const int ctas = dm.sp.total > 56u*1024u ? 2 : 4;
@@ -911,6 +917,8 @@ namespace {
     } );
     raiseDeviceErrors( fetchDeviceErrors( s, s->streams[0] ) );
   }
+
+#include "ncb_lib_mmc.inc"
 
 }
 
@@ -1385,5 +1393,10 @@ extern "C" {
 
   // ---- oriented entry points: see ncb_lib_oriented.inc
 #include "ncb_lib_oriented.inc"
+
+  // ---- device-resident transport step: see ncb_lib_mmc.inc
+#define NCB_MMC_CAPI
+#include "ncb_lib_mmc.inc"
+#undef NCB_MMC_CAPI
 
 }

@@ -27,6 +27,7 @@ namespace ncb {
     std::vector<unsigned char> arena;   // host image
     std::vector<SabBuildPlan> sabplans;
     std::string cfg;
+    double numdens = 0.0, abs_c = 0.0, temperature = -1.0;   // bulk quantities for the transport step
     bool relocated = false;
 
     size_t reserve( size_t nbytes )
@@ -95,6 +96,7 @@ namespace ncb {
       throw std::runtime_error( "compiled material: inconsistent header" );
     hdr.cfg[sizeof(hdr.cfg)-1] = 0;
     lm.cfg = hdr.cfg;
+    lm.numdens = hdr.numdens; lm.abs_c = hdr.abs_c; lm.temperature = hdr.temperature;
     Material& m = lm.mat;
     std::memset( &m, 0, sizeof(m) );
     m.ncomp = (int)hdr.ncomp;

@@ -33,6 +33,7 @@
 #include "philox_ref.h"
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -280,6 +281,22 @@ extern "C" {
       hdr.dom_lo = dom.elow.dbl();
       hdr.dom_hi = dom.ehigh.dbl();
       std::snprintf( hdr.cfg, sizeof(hdr.cfg), "%s", h->cfg.c_str() );
+      {
+        // bulk quantities for the transport step (what MiniMC's MatDef holds next to the scatter process)
+        auto info = NC::createInfo( h->cfg.c_str() );
+        hdr.numdens = info->getNumberDensity().dbl();
+        hdr.temperature = info->hasTemperature() ? info->getTemperature().dbl() : -1.0;
+        auto absn = NC::createAbsorption( h->cfg.c_str() );
+        if ( absn.isNull() ) {
+          hdr.abs_c = 0.0;
+        } else {
+          // AbsOOV: xs = c/sqrt(E) (NCAbsOOV.cc:41-45).  c = xs(1 eV); anything that is not 1/v is flagged.
+          const double c = absn.crossSectionIsotropic( NC::NeutronEnergy{1.0} ).dbl();
+          const double x2 = absn.crossSectionIsotropic( NC::NeutronEnergy{0.04} ).dbl();
+          const bool oov = !absn.isOriented() && std::fabs( x2*0.2 - c ) <= 1e-12*std::fabs(c);
+          hdr.abs_c = oov ? c : -1.0;
+        }
+      }
       buf.reserve( sizeof(hdr) );
       for ( unsigned i = 0; i < hdr.ncomp; ++i ) {
         std::string err;

@@ -9,19 +9,20 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-HDR_FMT = "<QIIIIQdd208s"
+HDR_FMT = "<QIIIIQdd4d176s"
 COMP_FMT = "<IIdddQQ"
 
 
 def parse_header(blob):
-    magic, version, ncomp, oriented, _r, nbytes, dlo, dhi, cfg = struct.unpack_from(HDR_FMT, blob, 0)
+    magic, version, ncomp, oriented, _r, nbytes, dlo, dhi, numdens, abs_c, temp, _r3, cfg = struct.unpack_from(HDR_FMT, blob, 0)
     off = struct.calcsize(HDR_FMT)
     comps = []
     for i in range(8):
         kind, _r2, scale, clo, chi, coff, cn = struct.unpack_from(COMP_FMT, blob, off + i * struct.calcsize(COMP_FMT))
         if i < ncomp:
             comps.append(dict(kind=kind, scale=scale, dom=(clo, chi), off=coff, nbytes=cn))
-    return dict(magic=magic, version=version, ncomp=ncomp, oriented=oriented, nbytes=nbytes, dom=(dlo, dhi),
+    return dict(magic=magic, version=version, ncomp=ncomp, oriented=oriented, nbytes=nbytes, dom=(dlo, dhi), numdens=numdens, abs_c=abs_c,
+                temperature=temp,
                 cfg=cfg.split(b"\0")[0].decode(), comps=comps)
 
 
