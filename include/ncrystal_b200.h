@@ -30,6 +30,7 @@ extern "C" {
 /* ncrystal.h:666-670 */
 typedef struct { void * internal; } ncrystal_process_t;
 typedef struct { void * internal; } ncrystal_scatter_t;
+typedef struct { void * internal; } ncrystal_absorption_t;
 
 /* ncrystal.h:672-676 -- all take the ADDRESS of a handle */
 int  ncrystal_refcount( void* object );
@@ -41,6 +42,12 @@ void ncrystal_invalidate( void* object );
 /* ncrystal.h:680,682 */
 ncrystal_process_t ncrystal_cast_scat2proc( ncrystal_scatter_t );
 ncrystal_scatter_t ncrystal_cast_proc2scat( ncrystal_process_t );
+
+/* ncrystal.h:681,684 / :703 -- absorption: the 1/v process (AbsOOV, src/absoov/NCAbsOOV.cc) of the compiled material;
+ * accepted by the cross-section entry points after ncrystal_cast_abs2proc, never by the sampling ones */
+ncrystal_process_t ncrystal_cast_abs2proc( ncrystal_absorption_t );
+ncrystal_absorption_t ncrystal_cast_proc2abs( ncrystal_process_t );
+ncrystal_absorption_t ncrystal_create_absorption( const char * cfgstr );
 
 /* ncrystal.h:699,708 -- cfgstr is resolved to a compiled material (see
  * ncb200_create_scatter_from_blob and INTEGRATION.md) */
@@ -107,6 +114,7 @@ void ncrystal_dealloc_string( char* );
  * there.  Returns {NULL} on error. */
 ncrystal_scatter_t ncb200_create_scatter_from_blob( const void* blob, size_t nbytes, unsigned long seed );
 ncrystal_scatter_t ncb200_create_scatter_from_file( const char* path, unsigned long seed );
+ncrystal_absorption_t ncb200_create_absorption_from_blob( const void* blob, size_t nbytes );
 /* Directory list (':'-separated) searched by ncrystal_create_scatter for
  * "<sanitised cfgstr>.ncb"; default: $NCB200_DATA_PATH then <libdir>/../data. */
 void ncb200_set_data_path( const char* path );

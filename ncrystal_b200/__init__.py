@@ -3,7 +3,7 @@ evaluation and scatter sampling, behind NCrystal's own Scatter / C-API `*_many` 
 
 The package is a thin host layer over libncrystal_b200.so (hand-written CUDA); see DESIGN.md.
 """
-from .core import (Scatter, Process, createScatter, generateSource, tallyHist, kernelLaunchCount,  # noqa: F401
+from .core import (Scatter, Process, Absorption, createScatter, createAbsorption, generateSource, tallyHist, kernelLaunchCount,  # noqa: F401
                    NCException, NCBadInput, NCCalcError, NCLogicError, NCFileNotFound)
 
 __version__ = "0.1.0"

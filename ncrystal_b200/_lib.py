@@ -21,6 +21,10 @@ class ncrystal_process_t(C.Structure):
     _fields_ = [("internal", C.c_void_p)]
 
 
+class ncrystal_absorption_t(C.Structure):
+    _fields_ = [("internal", C.c_void_p)]
+
+
 _dblp = C.POINTER(C.c_double)
 _u64 = C.c_uint64
 _ulong = C.c_ulong
@@ -89,6 +93,10 @@ SIGNATURES = {
     "ncb200_component_scale": (C.c_double, [ncrystal_process_t, C.c_int]),
     "ncb200_kernel_launch_count": (_u64, []),
     "ncb200_table_bytes": (_u64, [ncrystal_process_t]),
+    "ncrystal_cast_abs2proc": (ncrystal_process_t, [ncrystal_absorption_t]),
+    "ncrystal_cast_proc2abs": (ncrystal_absorption_t, [ncrystal_process_t]),
+    "ncrystal_create_absorption": (ncrystal_absorption_t, [C.c_char_p]),
+    "ncb200_create_absorption_from_blob": (ncrystal_absorption_t, [_vp, C.c_size_t]),
     "ncb200_minimc_run": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p]),
     "ncb200_minimc_run_slice": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p, _u64, _u64]),
     "ncb200_material_bulk": (None, [ncrystal_process_t, _dblp, _dblp, _dblp]),

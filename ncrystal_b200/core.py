@@ -78,9 +78,12 @@ class Process:
     """ref: core.py:1226 (class Process)"""
 
     def __init__(self, handle):
-        self._h = handle  # ncrystal_scatter_t
+        self._h = handle  # ncrystal_scatter_t or ncrystal_absorption_t
         self._L = _lib.lib()
-        self._p = self._L.ncrystal_cast_scat2proc(handle)
+        if isinstance(handle, _lib.ncrystal_absorption_t):
+            self._p = self._L.ncrystal_cast_abs2proc(handle)
+        else:
+            self._p = self._L.ncrystal_cast_scat2proc(handle)
         _check_error()
 
     def __del__(self):
@@ -390,6 +393,28 @@ class Scatter(Process):
         flags = self._L.ncb200_check_device_errors(self._h, _stream_ptr(dev))
         _check_error()
         return flags
+
+
+class Absorption(Process):
+    """ref: core.py class Absorption -- here always the 1/v process of the compiled material (AbsOOV)."""
+
+    def __init__(self, cfgstr=None, _handle=None):
+        L = _lib.lib()
+        if _handle is None:
+            _handle = L.ncrystal_create_absorption(cfgstr.encode())
+            _check_error()
+        super().__init__(_handle)
+
+    @classmethod
+    def fromBlob(cls, blob):
+        h = _lib.lib().ncb200_create_absorption_from_blob(blob, len(blob))
+        _check_error()
+        return cls(_handle=h)
+
+
+def createAbsorption(cfgstr):
+    """ref: core.py createAbsorption / C: ncrystal_create_absorption"""
+    return Absorption(cfgstr)
 
 
 def createScatter(cfgstr, seed=None):

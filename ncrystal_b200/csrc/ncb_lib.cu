@@ -308,6 +308,7 @@ namespace {
 
   // ------------------------------------------------------------------ handles
   constexpr uint32_t kScatterTag = 0x7d6b0637u; // same tag value as the reference's Scatter wrapper (ncrystal.cc:228)
+  constexpr uint32_t kAbsorptionTag = 0xede2eb9du; // ... and its Absorption wrapper (ncrystal.cc:243)
 
   struct Scatter;
   struct FingerPrint { uint32_t tag; Scatter* self; };
@@ -454,9 +455,15 @@ namespace {
     if ( !internal )
       throw Err( "LogicError", std::string("Invalid (null) handle passed to ")+fct );
     auto fp = static_cast<FingerPrint*>( internal );
-    if ( fp->tag != kScatterTag )
+    if ( fp->tag != kScatterTag && fp->tag != kAbsorptionTag )
       throw Err( "LogicError", std::string("Invalid object handle type passed to ")+fct );
     return fp->self;
+  }
+  // for entry points that need a scattering process (sampling, transport)
+  void requireScatter( const FingerPrint& fp, const char* fct )
+  {
+    if ( fp.tag != kScatterTag )
+      throw Err( "LogicError", std::string("Invalid object handle type passed to ")+fct+" (absorption processes cannot be sampled)" );
   }
 
   struct DeviceGuard {
@@ -579,6 +586,7 @@ namespace {
                         cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
+    requireScatter( s->fp, "sampleScatterIsotropic" );
     const DeviceMaterial& dm = *s->dm;
     if ( dm.mat.oriented )
       throw Err( "LogicError", "Process::sampleScatterIsotropic can only be called for isotropic materials." );
@@ -736,6 +744,7 @@ namespace {
                           uint64_t n, double* d_eout, double* ox, double* oy, double* oz, cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
+    requireScatter( s->fp, "sampleScatter" );
     const DeviceMaterial& dm = *s->dm;
     s->ensureErrWord();
     uint32_t* diag_nd = s->d_diag_ndraws;
@@ -974,7 +983,54 @@ extern "C" {
   }
   ncrystal_scatter_t ncrystal_cast_proc2scat( ncrystal_process_t p )
   {
+    if ( p.internal && static_cast<FingerPrint*>( p.internal )->tag == kAbsorptionTag ) return { nullptr };
     try { fromInternal( p.internal, "ncrystal_cast_proc2scat" ); return { p.internal }; } NCBCATCH;
+    return { nullptr };
+  }
+
+  // ---- absorption: 1/v process from the compiled material's header (ref: ncrystal.h:703 ncrystal_create_absorption,
+  // :681-684 casts; NCAbsOOV.cc).  Same handle machinery; only the cross-section entry points accept it.
+  ncrystal_absorption_t ncb200_create_absorption_from_blob( const void* blob, size_t nbytes )
+  {
+    try {
+      if ( nbytes < sizeof(ncb_header_t) ) throw Err( "BadInput", "compiled material: buffer too small" );
+      ncb_header_t hdr; std::memcpy( &hdr, blob, sizeof(hdr) );
+      if ( hdr.magic != NCB_MAGIC || hdr.version != NCB_VERSION ) throw Err( "BadInput", "compiled material: bad magic or version" );
+      if ( hdr.abs_c < 0.0 ) throw Err( "BadInput", "the material's absorption process is not of the 1/v type" );
+      auto dm = std::make_shared<DeviceMaterial>();
+      CUDA_OK( cudaGetDevice( &dm->device ) );
+      std::memset( &dm->mat, 0, sizeof(dm->mat) );
+      std::memset( &dm->sp, 0, sizeof(dm->sp) ); std::memset( &dm->sp_sc, 0, sizeof(dm->sp_sc) ); std::memset( &dm->sp_iso, 0, sizeof(dm->sp_iso) );
+      Material& m = dm->mat;
+      m.ncomp = 1; m.oriented = 0;
+      m.dom_lo = 0.0; m.dom_hi = hdr.abs_c > 0.0 ? kInf : 0.0;      // AbsOOV::m_domain, NCAbsOOV.cc:35-37
+      m.comp[0].kind = KIND_ABSOOV; m.comp[0].scale = 1.0; m.comp[0].par = hdr.abs_c;
+      m.comp[0].dom_lo = m.dom_lo; m.comp[0].dom_hi = m.dom_hi;
+      hdr.cfg[sizeof(hdr.cfg)-1] = 0;
+      dm->cfg = hdr.cfg; dm->numdens = hdr.numdens; dm->abs_c = hdr.abs_c; dm->temperature = hdr.temperature;
+      ncrystal_scatter_t h = newHandle( dm, 0, 0 );
+      static_cast<FingerPrint*>( h.internal )->tag = kAbsorptionTag;
+      return { h.internal };
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_absorption_t ncrystal_create_absorption( const char* cfgstr )
+  {
+    try {
+      auto d = findCompiledMaterial( cfgstr );
+      return ncb200_create_absorption_from_blob( d.data(), d.size() );
+    } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_process_t ncrystal_cast_abs2proc( ncrystal_absorption_t a )
+  {
+    try { fromInternal( a.internal, "ncrystal_cast_abs2proc" ); return { a.internal }; } NCBCATCH;
+    return { nullptr };
+  }
+  ncrystal_absorption_t ncrystal_cast_proc2abs( ncrystal_process_t p )
+  {
+    // like the reference: a null handle (no error) when the process is not an absorption process
+    if ( p.internal && static_cast<FingerPrint*>( p.internal )->tag == kAbsorptionTag ) return { p.internal };
     return { nullptr };
   }
 
@@ -1060,6 +1116,7 @@ extern "C" {
       case KIND_SAB: return "SABScatter";
       case KIND_FREEGAS: return "FreeGas";
       case KIND_SCBRAGG: return "SCBragg";
+      case KIND_ABSOOV: return "AbsOOV";
       default: return "Process";
       }
     } NCBCATCH;

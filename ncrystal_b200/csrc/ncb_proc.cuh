@@ -44,6 +44,11 @@ namespace ncb {
     }
     case KIND_FREEGAS:
       return fgXS( M.fg[c.idx], ekin );
+    case KIND_ABSOOV: {
+      // AbsOOV::crossSectionIsotropic, ref: src/absoov/NCAbsOOV.cc:41-45
+      const double sqrtE = sqrt( ekin );
+      return sqrtE ? c.par / sqrtE : kInf;
+    }
     default:
       return 0.0;
     }

@@ -9,7 +9,8 @@
 
 namespace ncb {
 
-  enum Kind : int { KIND_NONE = 0, KIND_POWDERBRAGG = 1, KIND_ELINC = 2, KIND_SAB = 3, KIND_FREEGAS = 4, KIND_SCBRAGG = 5 };
+  enum Kind : int { KIND_NONE = 0, KIND_POWDERBRAGG = 1, KIND_ELINC = 2, KIND_SAB = 3, KIND_FREEGAS = 4, KIND_SCBRAGG = 5,
+                    KIND_ABSOOV = 6 /* 1/v absorption, ref: src/absoov/NCAbsOOV.cc:33-45; not a blob kind */ };
 
   constexpr int kMaxComp = 8;
   constexpr int kMaxElIncElems = 12;
@@ -111,6 +112,7 @@ namespace ncb {
     int idx;       // index into the per-kind arrays of Material
     double scale;
     double dom_lo, dom_hi;
+    double par;    // KIND_ABSOOV: AbsOOV::m_c
   };
 
   struct Material {

@@ -164,3 +164,16 @@ double orc_bench(void* vm, int mode, int nthreads, const double* ekin, uint64_t 
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (t1.tv_sec - t0.tv_sec) + 1e-9*(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* 1/v absorption (AbsOOV::crossSectionIsotropic, ref: ncrystal_core/src/absoov/NCAbsOOV.cc:41-45) with the constant
+ * the material compiler stored in the blob header; domain as AbsOOV::m_domain (:35-37). */
+void orc_abs_xs_many(void* vm, const double* ekin, uint64_t n, double* out)
+{
+  const orc_material* M = (const orc_material*)vm;
+  const double c = ((const ncb_header_t*)M->blob)->abs_c;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (!(c > 0.0) || !(ekin[i] >= 0.0)) { out[i] = 0.0; continue; }   /* outside the (empty or [0,inf]) domain */
+    const double s = sqrt(ekin[i]);
+    out[i] = s ? c / s : INFINITY;
+  }
+}
