@@ -85,6 +85,26 @@ namespace ncb {
     }
     return lo;
   }
+  // upperBound(a,0,n,v) for a grid that is (close to) geometrically spaced: the spacing only supplies the
+  // starting point, the result is verified against the grid itself, so it is the exact upper bound for any
+  // ascending grid (falls back to the binary search when the guess is more than 3 entries off).
+  template <class Ptr>
+  NCB_HD int upperBoundLogGuess( Ptr a, int n, double v, double log_a0, double inv_dlog )
+  {
+    double t = ( m_log( v ) - log_a0 )*inv_dlog + 1.0;
+    int i = t > 0.0 ? ( t < (double)n ? (int)t : n ) : 0;     // (NaN -> 0)
+    int steps = 0;
+    while ( i < n && !( v < a[i] ) ) {
+      ++i;
+      if ( ++steps > 3 ) return upperBound( a, i, n, v );
+    }
+    while ( i > 0 && v < a[i-1] ) {
+      --i;
+      if ( ++steps > 3 ) return upperBound( a, 0, i, v );
+    }
+    return i;
+  }
+
   template <class Ptr>
   NCB_HD int lowerBound( Ptr a, int lo, int hi, double v )
   {

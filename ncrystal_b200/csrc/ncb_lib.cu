@@ -668,6 +668,8 @@ namespace {
           case 4: launchRefill( k_sample_sab_refill<false,4>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 6: launchRefill( k_sample_sab_refill<false,6>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           case 8: launchRefill( k_sample_sab_refill<false,8>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          case 10: launchRefill( k_sample_sab_refill<false,10>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
+          case 12: launchRefill( k_sample_sab_refill<false,12>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           default: launchRefill( k_sample_sab_refill<false,5>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
           } }
           if ( !fgfirst ) launchFG();

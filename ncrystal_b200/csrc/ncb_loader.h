@@ -160,6 +160,12 @@ namespace ncb {
         T.k_extension = h.k_extension;
         T.k1 = h.k1; T.k2 = h.k2;
         T.egrid_margin = h.egrid_margin;
+        {
+          const double* eg = reinterpret_cast<const double*>( p + sizeof(h) );
+          const double l0 = std::log( eg[0] ), l1 = std::log( eg[h.negrid-1] );
+          T.egrid_log0 = l0;
+          T.egrid_invdlog = ( h.negrid > 1 && l1 > l0 ) ? ( (double)h.negrid - 1.0 )/( l1 - l0 ) : 0.0;
+        }
         T.bound_xs = h.bound_xs;
         T.ext.sigma_free = h.ext_sigma_free;
         T.ext.ca = h.ext_ca;

@@ -225,7 +225,8 @@ namespace ncb {
   NCB_HD int sabPickSampler( const SabT& T, const double* egrid, double ekin, bool& ultra_small_ekin_mode )
   {
     const int n = T.negrid;
-    int iu = upperBound( egrid, 0, n, ekin );
+    int iu = T.egrid_invdlog > 0.0 ? upperBoundLogGuess( egrid, n, ekin, T.egrid_log0, T.egrid_invdlog )
+                                   : upperBound( egrid, 0, n, ekin );
     ultra_small_ekin_mode = false;
     if ( iu == 0 ) {
       ultra_small_ekin_mode = ( ekin < egrid[0] );

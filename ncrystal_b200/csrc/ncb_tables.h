@@ -64,6 +64,7 @@ namespace ncb {
     double k_extension;    // SABXSProvider::m_kExtension
     double k1, k2;         // SABSampler::m_k1/m_k2
     double egrid_margin;
+    double egrid_log0, egrid_invdlog; // starting guess for searches in the (geometrically spaced) energy grid
     double bound_xs;       // SABData::boundXS (table builder only)
     FreeGasT ext;          // SABFGExtender
     int negrid, nalpha, nbeta;
