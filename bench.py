@@ -352,6 +352,31 @@ def main():
     e2e_val = world * n * e2e_steps / e2e_s
     mean_mu = float(h_mu.mean())
 
+    # ---- secondary figure: the device-resident transport step (ncb200_minimc_run) on the same
+    # material: 1e7 source neutrons per GPU through a 10 cm Al sphere, tallies all-reduced over the ranks (NCCL)
+    transport = None
+    try:
+        from ncrystal_b200.sharding import minimc_sharded
+        n_src = world * 10_000_000
+        geom, src = "sphere;r=0.05", "constant;wl=1.8;z=-0.05;n=%d" % n_src
+        eng = "tally=theta,mu;seed=%d" % SEED
+        sc.minimc(geom, "constant;wl=1.8;z=-0.05;n=200000", eng)
+        barrier()
+        t0 = time.perf_counter()
+        res = minimc_sharded(sc, geom, src, eng, device=dev)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        md = res["output"]["metadata"]
+        transport = {"workload": "Al sphere r=5cm, pencil beam 1.8 Aa, %d source neutrons, tallies theta+mu" % n_src,
+                     "histories_per_s": n_src / dt, "tally_records_per_s": md["tallied"]["count"] / dt,
+                     "seconds": dt, "tallied_weight_fraction": md["tallied"]["weight"] / n_src}
+    except Exception as e:  # noqa: BLE001
+        transport = {"error": str(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -388,6 +413,7 @@ def main():
             "ms_fused_xs_sample": ms_fused, "ms_xs": ms_xs, "ms_sample": ms_sm, "ms_tally": ms_ta,
             "rng": "Philox4x32-10 per-neutron streams", "device_error_flags": flags,
             "tally_total": hist_total, "mean_mu_e2e": mean_mu,
+            "transport_step": transport,
         },
         "e2e": {"value": e2e_val, "unit": "neutrons/s", "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n,
                 "steps": e2e_steps, "api": "ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many"},

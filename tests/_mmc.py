@@ -298,3 +298,30 @@ def compatible(name, c1, e1, c2, e2, pmin=0.001):
     p, chi, k = chi2_pvalue(c1, e1, c2, e2)
     ok = (chi / k < 4.0) if name in CORRELATED_TALLIES else (p > pmin)
     return ok, "chi2=%.1f dof=%d p=%.2g" % (chi, k, p)
+
+
+def result_dict_from_layout(h, meta, tallies, provided):
+    """device/oracle tally layout -> the result-JSON layout (what Scatter.minimc returns), for host-logic tests"""
+    def one(c, e, st):
+        sw, swx, swx2 = st[..., 0].sum(), st[..., 1].sum(), st[..., 2].sum()
+        stats = dict(integral=0.0, mean=None, rms=None, minfilled=None, maxfilled=None)
+        if sw > 0:
+            m = swx / sw
+            stats = dict(integral=float(sw), mean=float(m), rms=float(max(0.0, swx2 / sw - m * m) ** 0.5),
+                         minfilled=float(st[..., 3].min()), maxfilled=float(st[..., 4].max()))
+        return dict(stats=stats, bindata=dict(nbins=len(c) - 2, content=c[1:-1].tolist(), errorsq=e[1:-1].tolist(),
+                                              underflow=float(c[0]), overflow=float(c[-1]),
+                                              underflow_errorsq=float(e[0]), overflow_errorsq=float(e[-1])))
+    out = {}
+    for name, nb, lo, hi in tallies:
+        v = h[name]
+        filled = v["stats"][:, 0] > 0
+        st_tot = v["stats"][filled] if filled.any() else np.zeros((1, NSTAT))
+        out[name] = dict(total=one(v["content"].sum(axis=0), v["errsq"].sum(axis=0), st_tot),
+                         breakdown={cn: one(v["content"][k], v["errsq"][k],
+                                            v["stats"][k:k + 1] if v["stats"][k, 0] > 0 else np.zeros((1, NSTAT)))
+                                    for k, cn in enumerate(CLASS_NAMES)})
+    md = dict(provided=dict(count=int(provided), weight=float(provided)),
+              miss=dict(count=int(meta["miss_count"]), weight=float(meta["miss_weight"])),
+              tallied=dict(count=int(meta["tallied_count"]), weight=float(meta["tallied_weight"])))
+    return dict(output=dict(tally=out, metadata=md))

@@ -82,3 +82,57 @@ def test_two_rank_gloo_matches_single_process(tmp_path, configs):
     full = _hist(mu)
     for p in parts:
         assert np.array_equal(p["hist"], full) and p["hist"].sum() == N
+
+
+# ---- transport step: per-rank source slices + tally merge (the per-rank compute stand-in is the CPU oracle)
+
+def _mmc_worker(rank, world, port, outdir):
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from ncrystal_b200.sharding import shard_range, merge_minimc_results, source_count
+    from _mmc import all_scenarios, cached_oracle, run_oracle, result_dict_from_layout
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    sc = all_scenarios()["box_yag"]
+    assert source_count(sc.srccfg()) == sc.n
+    b, e = shard_range(sc.n, rank, world)
+    o, _ = cached_oracle(sc.material)
+    h, meta = run_oracle(o, sc, first=b, count=e - b)
+    merged = merge_minimc_results(result_dict_from_layout(h, meta, sc.tallies, e - b))
+    json.dump(merged, open(os.path.join(outdir, "mmc_rank%d.json" % rank), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_transport_tally_merge(tmp_path, configs):
+    import json
+    import torch.multiprocessing as mp
+    from oracle_check import material_path
+    from _mmc import all_scenarios, cached_oracle, run_oracle, result_dict_from_layout
+    if not os.path.exists(material_path(configs["YAG"])):
+        pytest.skip("compiled YAG material not present")
+    port = _free_port()
+    mp.spawn(_mmc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sc = all_scenarios()["box_yag"]
+    o, _ = cached_oracle(sc.material)
+    h, meta = run_oracle(o, sc)
+    whole = result_dict_from_layout(h, meta, sc.tallies, sc.n)
+    parts = [json.load(open(os.path.join(str(tmp_path), "mmc_rank%d.json" % r))) for r in range(2)]
+    assert parts[0] == parts[1]
+    m = parts[0]["output"]
+    assert m["metadata"]["provided"]["count"] == sc.n
+    assert m["metadata"]["miss"]["count"] == whole["output"]["metadata"]["miss"]["count"]
+    assert m["metadata"]["tallied"]["count"] == whole["output"]["metadata"]["tallied"]["count"]
+    for name, *_ in sc.tallies:
+        for which in ["total"] + list(m["tally"][name]["breakdown"]):
+            a = m["tally"][name][which] if which == "total" else m["tally"][name]["breakdown"][which]
+            w = whole["output"]["tally"][name][which] if which == "total" else whole["output"]["tally"][name]["breakdown"][which]
+            assert np.allclose(a["bindata"]["content"], w["bindata"]["content"], rtol=1e-12, atol=1e-9)
+            assert np.allclose(a["bindata"]["errorsq"], w["bindata"]["errorsq"], rtol=1e-12, atol=1e-9)
+            for k in ("integral", "mean", "rms", "minfilled", "maxfilled"):
+                if w["stats"][k] is None:
+                    assert a["stats"][k] is None
+                else:
+                    assert abs(a["stats"][k] - w["stats"][k]) <= 1e-9 * max(1.0, abs(w["stats"][k]))
