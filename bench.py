@@ -360,20 +360,24 @@ def main():
         n_src = world * 10_000_000
         geom, src = "sphere;r=0.05", "constant;wl=1.8;z=-0.05;n=%d" % n_src
         eng = "tally=theta,mu;seed=%d" % SEED
-        sc.minimc(geom, "constant;wl=1.8;z=-0.05;n=200000", eng)
+        minimc_sharded(sc, geom, "constant;wl=1.8;z=-0.05;n=%d" % (world * 200000), eng, device=dev)   # warm-up
         barrier()
+        from ncrystal_b200.sharding import shard_range as _sr, merge_minimc_results
+        b0, b1 = _sr(n_src, rank, world)
         t0 = time.perf_counter()
-        res = minimc_sharded(sc, geom, src, eng, device=dev)
+        part = sc.minimc(geom, src, eng, first=b0, count=b1 - b0)
+        t_local = time.perf_counter() - t0
+        res = merge_minimc_results(part, device=dev)
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, t_local], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt, t_local = [float(x) for x in tt.tolist()]
         md = res["output"]["metadata"]
         transport = {"workload": "Al sphere r=5cm, pencil beam 1.8 Aa, %d source neutrons, tallies theta+mu" % n_src,
                      "histories_per_s": n_src / dt, "tally_records_per_s": md["tallied"]["count"] / dt,
-                     "seconds": dt, "tallied_weight_fraction": md["tallied"]["weight"] / n_src}
+                     "seconds": dt, "seconds_slice_max": t_local, "tallied_weight_fraction": md["tallied"]["weight"] / n_src}
     except Exception as e:  # noqa: BLE001
         transport = {"error": str(e)}
 

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -968,7 +969,7 @@ extern "C" {
       void*& internal = *reinterpret_cast<void**>( object );
       Scatter* s = fromInternal( internal, "ncrystal_unref" );
       if ( s->refcount.fetch_sub(1) == 1 ) {
-        { DeviceGuard dg( s->dm->device ); delete s; }
+        { DeviceGuard dg( s->dm->device ); mmcReleaseBuffers( s ); delete s; }
         internal = nullptr;
       }
     } NCBCATCH;

@@ -1,0 +1,136 @@
+"""GPU tests of the C-ABI semantics the reference's own C-API tests exercise (tests/src/app_capi, app_crng):
+special energies, ragged sizes around the pipeline chunks, repeat ordering, error state / sentinel fills,
+handle life cycle.  Reference behaviour: ncrystal_core/src/cinterface/ncrystal.cc:280-306 (error handling),
+:1089-1282 (batch entry points), :474-496 (unref)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG_KEYS_ISO
+from _mmc import cached_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _sc(cfg, seed=0):
+    import ncrystal_b200 as nc
+    return nc.Scatter(cfg, seed=seed)
+
+
+@pytest.mark.parametrize("key", CONFIG_KEYS_ISO)
+def test_special_energies_match_oracle(key, configs):
+    # below / above the tabulated grids, domain edges, subnormal, zero, infinities, NaN, negative
+    e = np.array([0.0, 5e-324, 1e-300, 1e-12, 9.999e-6, 1e-5, 0.0253, 4.99999, 5.0, 5.00001, 9.99, 10.0, 37.0, 1e3,
+                  1e9, 1e300, np.inf, np.nan, -1.0, -np.inf])
+    sc = _sc(configs[key])
+    xs = sc.crossSectionIsotropic(e)
+    o, _ = cached_oracle(key)
+    ref = o.xs_iso(e)
+    both_nan = np.isnan(xs) & np.isnan(ref)
+    fin = np.isfinite(ref) & (ref != 0)
+    assert np.all(np.abs(xs[fin] - ref[fin]) <= 1e-12 * np.abs(ref[fin]))
+    rest = ~fin & ~both_nan
+    assert np.array_equal(xs[rest], ref[rest]), (xs[rest], ref[rest])
+    # sampling at the usable extremes replays the oracle (energies where the cross section is finite and > 0)
+    es = e[fin]
+    sc.setRNGStream(21, 0, 0)
+    eo, mu = sc.sampleScatterIsotropic(es)
+    eo_r, mu_r, nd, er = o.sample_iso(es, 21, 0)
+    ok = (er == 0) & ~(np.isnan(eo) & np.isnan(eo_r))      # (E = inf gives NaN outcomes on both sides)
+    assert np.array_equal(np.isnan(eo), np.isnan(eo_r)) and np.array_equal(np.isnan(mu), np.isnan(mu_r))
+    assert np.all(np.abs(eo[ok] - eo_r[ok]) <= 1e-10 * np.maximum(np.abs(eo_r[ok]), 1e-300))
+    ok &= ~np.isnan(mu_r)
+    assert np.all(np.abs(mu[ok] - mu_r[ok]) <= 1e-10)
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, (1 << 18) - 1, (1 << 18) + 1, (1 << 20) + 777, 3 * (1 << 20) + 5])
+def test_ragged_sizes_host_pipeline_equals_device_call(n, configs):
+    # the host-pointer entry points cut the batch into chunks (256 Ki, 512 Ki, 1 Mi, ...): every size gives the
+    # same numbers as ONE device-resident launch
+    import torch
+    from _libs import loguniform_energies
+    e = loguniform_energies(n, seed=5)
+    sc = _sc(configs["CH2"], seed=2)
+    xs_h = sc.crossSectionIsotropic(e)
+    sc.setRNGStream(2, 0, 1000)
+    eo_h, mu_h = sc.sampleScatterIsotropic(e)
+    d = torch.from_numpy(e).cuda()
+    xs_d = sc.crossSectionIsotropic(d).cpu().numpy()
+    sc.setRNGStream(2, 0, 1000)
+    eo_d, mu_d = [t.cpu().numpy() for t in sc.sampleScatterIsotropic(d)]
+    assert np.array_equal(xs_h, xs_d) and np.array_equal(eo_h, eo_d) and np.array_equal(mu_h, mu_d)
+    assert sc.getRNGStream() == (2, 0, 1000 + n)
+
+
+def test_sample_repeat_ordering(configs):
+    # ncrystal_samplescatterisotropic_many: results[r*n+i]; repeat r continues the neutron-index sequence
+    from _libs import loguniform_energies
+    e = loguniform_energies(1000, seed=8)
+    sc = _sc(configs["H2O"], seed=4)
+    sc.setRNGStream(4, 0, 0)
+    eo3, mu3 = sc.sampleScatterIsotropic(e, repeat=3)
+    assert eo3.shape == (3000,)
+    sc.setRNGStream(4, 0, 0)
+    parts = [sc.sampleScatterIsotropic(e) for _ in range(3)]
+    assert np.array_equal(eo3, np.concatenate([p[0] for p in parts]))
+    assert np.array_equal(mu3, np.concatenate([p[1] for p in parts]))
+
+
+def test_error_state_and_sentinels(configs):
+    import ncrystal_b200 as nc
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    L.ncrystal_sethaltonerror(0)
+    L.ncrystal_setquietonerror(1)
+    dp = C.POINTER(C.c_double)
+    bad_p = _lib.ncrystal_process_t(None)
+    bad_s = _lib.ncrystal_scatter_t(None)
+    e = np.array([0.1, 0.2, 0.3])
+    out = np.full(3, 7.0)
+    L.ncrystal_crosssection_nonoriented_many(bad_p, e.ctypes.data_as(dp), 3, 1, out.ctypes.data_as(dp))
+    assert L.ncrystal_error() == 1 and L.ncrystal_lasterrortype() == b"LogicError"
+    assert np.all(out == -1.0)                       # ncrystal.cc:1134-1140
+    L.ncrystal_clearerror()
+    assert L.ncrystal_error() == 0
+    eo, mu = np.full(3, 7.0), np.full(3, 7.0)
+    L.ncrystal_samplescatterisotropic_many(bad_s, e.ctypes.data_as(dp), 3, 1, eo.ctypes.data_as(dp), mu.ctypes.data_as(dp))
+    assert L.ncrystal_error() == 1 and np.all(eo == -1.0) and np.all(mu == -999.0)   # ncrystal.cc:1239-1245
+    L.ncrystal_clearerror()
+    # a host random-number callback cannot be honoured on a device
+    L.ncrystal_setrandgen(C.cast(None, C.CFUNCTYPE(C.c_double)))
+    assert L.ncrystal_error() == 1
+    L.ncrystal_clearerror()
+    # unknown material
+    with pytest.raises(nc.NCException):
+        nc.Scatter("no_such_material.ncmat")
+    # oriented material through the isotropic entry point (ProcImpl::Process::crossSectionIsotropic throws LogicError)
+    ge = nc.Scatter(configs["Ge"], seed=1)
+    with pytest.raises(nc.NCLogicError):
+        ge.crossSectionIsotropic(np.array([0.01]))
+
+
+def test_handle_life_cycle(configs):
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    h = L.ncrystal_create_scatter_builtinrng(configs["Al"].encode(), 7)
+    assert L.ncrystal_valid(C.byref(h)) == 1 and L.ncrystal_refcount(C.byref(h)) == 1
+    L.ncrystal_ref(C.byref(h))
+    assert L.ncrystal_refcount(C.byref(h)) == 2
+    p = L.ncrystal_cast_scat2proc(h)
+    assert p.internal == h.internal and L.ncrystal_isnonoriented(p) == 1
+    lo, hi = C.c_double(), C.c_double()
+    L.ncrystal_domain(p, C.byref(lo), C.byref(hi))
+    assert lo.value == 0.0 and hi.value == float("inf")
+    c = L.ncrystal_clone_scatter_rngbyidx(h, 5)
+    c2 = L.ncrystal_clone_scatter_rngbyidx(h, 5)
+    e1, m1, e2, m2 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    L.ncrystal_samplescatterisotropic(c, 0.05, C.byref(e1), C.byref(m1))
+    L.ncrystal_samplescatterisotropic(c2, 0.05, C.byref(e2), C.byref(m2))
+    assert (e1.value, m1.value) == (e2.value, m2.value)      # same stream index => same sequence
+    L.ncrystal_unref(C.byref(c)); L.ncrystal_unref(C.byref(c2))
+    assert not c.internal
+    L.ncrystal_unref(C.byref(h))
+    assert h.internal and L.ncrystal_refcount(C.byref(h)) == 1
+    L.ncrystal_invalidate(C.byref(h))
+    assert L.ncrystal_valid(C.byref(h)) == 0
