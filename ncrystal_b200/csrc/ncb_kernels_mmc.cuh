@@ -17,6 +17,7 @@ namespace ncb {
 
   struct MmcState {
     double *x, *y, *z, *ux, *uy, *uz, *w, *ekin, *e0;
+    double *ux0, *uy0, *uz0;   // initial directions; null when the source direction is fixed
     int32_t *nscat, *ninel;
     uint64_t* id;
   };
@@ -67,6 +68,7 @@ namespace ncb {
         const uint32_t p = live ? pa : pm;
         T.x[p] = nt.x; T.y[p] = nt.y; T.z[p] = nt.z; T.ux[p] = nt.ux; T.uy[p] = nt.uy; T.uz[p] = nt.uz;
         T.w[p] = nt.w; T.ekin[p] = nt.ekin; T.e0[p] = nt.ekin;
+        if ( T.ux0 ) { T.ux0[p] = nt.ux; T.uy0[p] = nt.uy; T.uz0[p] = nt.uz; }
         T.nscat[p] = live ? 0 : -1;       // markAsMissedTarget, NCMMC_Baskets.cc:81
         T.ninel[p] = 0;
         T.id[p] = first_id + i;
@@ -83,9 +85,10 @@ namespace ncb {
     const uint32_t n_up = ( n + blockDim.x - 1 )/blockDim.x*blockDim.x;
     for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
       MmcStepOut o; o.survives = false;
-      double ux = 0, uy = 0, uz = 0, ekin = 0, e0 = 0; int nscat = 0, ninel = 0; uint64_t id = 0;
+      double ux = 0, uy = 0, uz = 0, ekin = 0, e0 = 0, ux0 = 0, uy0 = 0, uz0 = 0; int nscat = 0, ninel = 0; uint64_t id = 0;
       if ( i < n ) {
         id = A.id[i];
+        if ( A.ux0 ) { ux0 = A.ux0[i]; uy0 = A.uy0[i]; uz0 = A.uz0[i]; }
         ux = A.ux[i]; uy = A.uy[i]; uz = A.uz[i]; ekin = A.ekin[i]; e0 = A.e0[i];
         nscat = A.nscat[i]; ninel = A.ninel[i];
         Rng rng; rng.init( seed, id, kMmcSidBase + 2u*step );
@@ -96,6 +99,7 @@ namespace ncb {
       if ( o.survives ) {
         B.x[p] = o.x; B.y[p] = o.y; B.z[p] = o.z; B.ux[p] = ux; B.uy[p] = uy; B.uz[p] = uz;
         B.w[p] = o.w; B.ekin[p] = ekin; B.e0[p] = e0; B.nscat[p] = nscat; B.ninel[p] = ninel; B.id[p] = id;
+        if ( B.ux0 ) { B.ux0[p] = ux0; B.uy0[p] = uy0; B.uz0[p] = uz0; }
       }
     }
   }
@@ -153,7 +157,9 @@ namespace ncb {
           const double w = wt ? wt[i] : A.w[i];
           const int nscat = A.nscat[i];
           bool weighted;
-          val = mmcTallyValue( T, h.type, A.ux[i], A.uy[i], A.uz[i], A.ekin[i], w, nscat, A.e0[i], weighted );
+          double ux0 = 0, uy0 = 0, uz0 = 0;
+          if ( A.ux0 ) { ux0 = A.ux0[i]; uy0 = A.uy0[i]; uz0 = A.uz0[i]; }
+          val = mmcTallyValue( T, h.type, A.ux[i], A.uy[i], A.uz[i], A.ekin[i], w, nscat, A.e0[i], ux0, uy0, uz0, weighted );
           wgt = weighted ? w : 1.0;
           if ( wgt > 0.0 ) {
             cls = mmcClass( nscat, A.ninel[i] );

@@ -178,13 +178,15 @@ namespace ncb {
   }
 
   // ------------------------------------------------------------------ sources
-  enum { SRC_CONSTANT = 1, SRC_CIRCULAR = 2 };
-  enum { SRCE_FIXED = 0, SRCE_UNIFORM_EKIN = 1, SRCE_UNIFORM_WL = 2 };
+  enum { SRC_CONSTANT = 1, SRC_CIRCULAR = 2, SRC_ISOTROPIC = 3 };
+  enum { SRCE_FIXED = 0, SRCE_UNIFORM_EKIN = 1, SRCE_UNIFORM_WL = 2, SRCE_LOGNORMAL_EKIN = 3, SRCE_LOGNORMAL_WL = 4,
+         SRCE_MAXWELL = 5 };
   struct MmcSource {
     int kind, emode;
     double pos[3], dir[3];   // dir normalised
     double va[3], vb[3];     // circular: radius-scaled basis of the disk (NCMMC_Source.cc:664-680)
-    double w, e0, e1;        // weight; fixed energy [eV] or range (eV or Aa depending on emode)
+    double w, e0, e1;        // weight; fixed energy [eV] | range (eV or Aa) | log-normal (mu_n, sigma_n) | Maxwell (kT/2, -)
+    double minus_r;          // isotropic: start at pos + dir*minus_r (NCMMC_Source.cc:433-543)
     int may_be_outside;
   };
 
@@ -200,6 +202,26 @@ namespace ncb {
 
   struct MmcNeutron { double x, y, z, ux, uy, uz, w, ekin; };
 
+  // randNorm (ratio method), ref: src/utils/NCRandUtils.cc:113-137
+  NCB_HD double mmcRandNorm( Rng& rng )
+  {
+    double g, g2, u, v, invu;
+    while ( true ) {
+      u = rng.generate();
+      invu = 1.0/u;
+      v = rng.generate();
+      g = 1.71552776992141354 * ( v - 0.5 )*invu;
+      g2 = g*g;
+      if ( g2 <= 5.0 - 5.13610166675096558 * u )
+        break;
+      // (the reference's quick-reject test `if ( g2 >= 1.0369.../u ) continue;` sits in a do-while, where
+      //  `continue` jumps to the loop condition below -- it never changes the outcome, so it is not restated)
+      if ( !( g2 >= -4.0 * m_log( u ) ) )
+        break;
+    }
+    return g;
+  }
+
   NCB_HD MmcNeutron mmcGenerate( const MmcSource& S, Rng& rng )
   {
     MmcNeutron n;
@@ -213,9 +235,38 @@ namespace ncb {
       n.x = S.pos[0]; n.y = S.pos[1]; n.z = S.pos[2];
     }
     n.ux = S.dir[0]; n.uy = S.dir[1]; n.uz = S.dir[2];
+    if ( S.kind == SRC_ISOTROPIC ) {
+      // randIsotropicDirection (Marsaglia 1972), ref: src/utils/NCRandUtils.cc:25-49
+      double x0, x1, s;
+      do {
+        x0 = 2.0*rng.generate() - 1.0;
+        x1 = 2.0*rng.generate() - 1.0;
+        s = x0*x0 + x1*x1;
+      } while ( s >= 1.0 );
+      const double t = 2.0*sqrt( 1.0 - s );
+      n.ux = x0*t; n.uy = x1*t; n.uz = 1.0 - 2.0*s;
+    }
     n.w = S.w;
     if ( S.emode == SRCE_FIXED ) {
       n.ekin = S.e0;
+    } else if ( S.emode == SRCE_MAXWELL ) {
+      // setEnergy_Maxwell, NCMMC_Source.cc:76-101: (G1^2+G2^2+G3^2)*kT/2
+      double v = mmcRandNorm( rng );
+      v *= v;
+      const double g2 = mmcRandNorm( rng ); v += g2*g2;
+      const double g3 = mmcRandNorm( rng ); v += g3*g3;
+      n.ekin = v*S.e0;
+    } else if ( S.emode == SRCE_LOGNORMAL_EKIN || S.emode == SRCE_LOGNORMAL_WL ) {
+      // setEnergy_LogNormal, NCMMC_Source.cc:264-283
+      double v = mmcRandNorm( rng );
+      v *= S.e1; v += S.e0;
+      v = m_exp( v );
+      if ( S.emode == SRCE_LOGNORMAL_WL ) {
+        v *= v;
+        v = 1.0/dmax( 4.9406564584124654e-324, v );
+        v *= kWl2Ekin;
+      }
+      n.ekin = v;
     } else {
       // setEnergy_UniformRange, NCMMC_Source.cc:214-240 (+ convertBufWl2E :104-126)
       double v = rng.generate()*( S.e1 - S.e0 );
@@ -227,6 +278,9 @@ namespace ncb {
         v *= kWl2Ekin;
       }
       n.ekin = v;
+    }
+    if ( S.kind == SRC_ISOTROPIC && S.minus_r != 0.0 ) {
+      n.x += n.ux*S.minus_r; n.y += n.uy*S.minus_r; n.z += n.uz*S.minus_r;
     }
     return n;
   }
@@ -331,6 +385,7 @@ namespace ncb {
     MmcHist h[TALLY_NTYPES];
     double dir0[3];
     int dir0_is_z;
+    int has_dir0_fixed;       // 0: per-neutron initial directions (isotropic source)
     double e0_fixed;
     int has_e0_fixed;
   };
@@ -357,14 +412,15 @@ namespace ncb {
 
   // value of tally `type` for an exiting neutron; `weighted` tells whether the fill carries the neutron weight
   NCB_HD double mmcTallyValue( const MmcTally& T, int type, double ux, double uy, double uz, double ekin, double w,
-                               int nscat, double e_initial, bool& weighted )
+                               int nscat, double e_initial, double ux0, double uy0, double uz0, bool& weighted )
   {
     constexpr double kToDeg = 57.2957795130823208767981548141051703324054725;
     weighted = true;
     switch ( type ) {
     case TALLY_THETA: case TALLY_MU: case TALLY_Q: {
       double mu;
-      if ( T.dir0_is_z ) mu = uz;
+      if ( !T.has_dir0_fixed ) { mu = ux0*ux; mu += uy0*uy; mu += uz0*uz; }
+      else if ( T.dir0_is_z ) mu = uz;
       else { mu = T.dir0[0]*ux; mu += T.dir0[1]*uy; mu += T.dir0[2]*uz; }
       mu = dclamp( mu, -1.0, 1.0 );
       if ( type == TALLY_MU ) return mu;

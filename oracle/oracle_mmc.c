@@ -20,10 +20,11 @@
 typedef struct {
   int geom_kind;            /* 1 sphere (ga=r), 2 slab (gc=dz), 3 box (ga,gb,gc = dx,dy,dz), 4 cyl (ga=r, gb=dy or 0) */
   double ga, gb, gc;
-  int src_kind;             /* 1 constant, 2 circular */
+  int src_kind;             /* 1 constant, 2 circular, 3 isotropic (radius = signed r: start at pos - r*dir) */
   double pos[3], dir[3];    /* dir: any non-null vector */
   double radius;
-  int emode;                /* 0 fixed ekin e0, 1 uniform ekin in [e0,e1], 2 uniform wavelength in [e0,e1] */
+  int emode;                /* 0 fixed ekin e0, 1 uniform ekin in [e0,e1], 2 uniform wavelength in [e0,e1],
+                               3 log-normal ekin (mean e0, rms e1), 4 log-normal wavelength, 5 Maxwell at e0 kelvin */
   double e0, e1;
   double weight;
   double roul_psurv, roul_wthr; int roul_nscat;
@@ -166,7 +167,23 @@ enum { T_THETA, T_MU, T_NSCAT, T_NSCAT_UW, T_W, T_E, T_L, T_DE, T_Q };
 #define NCLASS 5
 #define NSTAT 5
 typedef struct { int type, nbins; double xmin, xmax, invdelta; double* g; } hist_t;
-typedef struct { int nh; hist_t h[9]; double dir0[3]; int has_e0; double e0; double tallied_w; uint64_t tallied_n; } tally_t;
+typedef struct { int nh; hist_t h[9]; double dir0[3]; int has_dir0; int has_e0; double e0; double tallied_w; uint64_t tallied_n; } tally_t;
+
+/* randNorm, ref: src/utils/NCRandUtils.cc:113-137.  (Its `continue` inside the do-while jumps to the loop condition,
+ * so the quick-reject line before it has no effect on the outcome and is left out.) */
+static double rand_norm(orc_rng* r)
+{
+  double g, g2, u, v, invu;
+  do {
+    u = orc_rand(r);
+    invu = 1.0 / u;
+    v = orc_rand(r);
+    g = 1.71552776992141354 * (v - 0.5) * invu;
+    g2 = g * g;
+    if (g2 <= 5.0 - 5.13610166675096558 * u) break;
+  } while (g2 >= -4.0 * log(u));
+  return g;
+}
 
 static int value_to_bin(const hist_t* h, double v)
 {
@@ -175,13 +192,15 @@ static int value_to_bin(const hist_t* h, double v)
   uint64_t k = (uint64_t)(h->invdelta * (v - h->xmin));
   return 1 + (int)(k < (uint64_t)h->nbins ? k : (uint64_t)h->nbins);
 }
-static void tally_record(tally_t* T, const double* u, double ekin, double w, int nscat, int ninel, double e_init)
+static void tally_record(tally_t* T, const double* u, double ekin, double w, int nscat, int ninel, double e_init,
+                         const double* u_init)
 {
   static const double kToDeg = 57.2957795130823208767981548141051703324054725;
   int cls = nscat > 1 ? (ninel ? 4 : 3) : (nscat == 1 ? (ninel ? 2 : 1) : 0);
   T->tallied_w += w; T->tallied_n += 1;
   double mu;
-  if (T->dir0[2] == 1) mu = u[2];
+  if (!T->has_dir0) { mu = u_init[0]*u[0]; mu += u_init[1]*u[1]; mu += u_init[2]*u[2]; }
+  else if (T->dir0[2] == 1) mu = u[2];
   else { mu = T->dir0[0]*u[0]; mu += T->dir0[1]*u[1]; mu += T->dir0[2]*u[2]; }
   if (mu < -1.0) mu = -1.0;
   if (mu > 1.0) mu = 1.0;
@@ -244,6 +263,14 @@ int orc_minimc_run(void* vm, const orc_mmc_cfg* c, uint64_t first, uint64_t coun
     for (int k = 0; k < 3; ++k) dir[k] = c->dir[k] * m; }
   memcpy(T.dir0, dir, sizeof(dir));
   T.has_e0 = (c->emode == 0); T.e0 = c->e0;
+  T.has_dir0 = (c->src_kind != 3);
+  /* log-normal / Maxwell parameters (NCMMC_ParseCfg.hh:414-427, :372) */
+  double mu_n = 0, sigma_n = 0, halfkT = 0;
+  if (c->emode == 3 || c->emode == 4) {
+    const double tmp = 1 + (c->e1 * c->e1) / (c->e0 * c->e0);
+    mu_n = log(c->e0 / sqrt(tmp)); sigma_n = sqrt(log(tmp));
+  }
+  if (c->emode == 5) halfkT = 8.6173303e-5 * c->e0 * 0.5;
   double va[3] = {0,0,0}, vb[3] = {0,0,0};
   if (c->src_kind == 2 && c->radius > 0.0) {
     double a[3] = {1,0,0};
@@ -256,6 +283,8 @@ int orc_minimc_run(void* vm, const orc_mmc_cfg* c, uint64_t first, uint64_t coun
     g = 1.0 / sqrt(s[0]*s[0] + s[1]*s[1] + s[2]*s[2]);
     for (int k = 0; k < 3; ++k) { vb[k] = s[k] * g * c->radius; va[k] *= c->radius; }
   }
+  const double minus_r = (c->src_kind == 3 && c->radius) ? -c->radius : 0.0;
+  /* SourceIsotropic::particlesMightBeOutside (NCMMC_Source.cc:503-506) looks at (x,y,z) only, whatever r is */
   const int may_be_outside = (c->src_kind == 2 && c->radius > 0.0) ? 1 : !point_inside(c, c->pos);
   double miss_n = 0, miss_w = 0, nsteps = 0;
   int errs = 0;
@@ -267,22 +296,42 @@ int orc_minimc_run(void* vm, const orc_mmc_cfg* c, uint64_t first, uint64_t coun
       do { a = -1.0 + orc_rand(&r) * 2.0; b = -1.0 + orc_rand(&r) * 2.0; } while (a*a + b*b > 1.0);
       for (int k = 0; k < 3; ++k) p[k] = c->pos[k] + va[k] * a + vb[k] * b;
     }
+    if (c->src_kind == 3) {
+      /* randIsotropicDirection, src/utils/NCRandUtils.cc:25-49 */
+      double x0, x1, ss;
+      do { x0 = 2.0 * orc_rand(&r) - 1.0; x1 = 2.0 * orc_rand(&r) - 1.0; ss = x0*x0 + x1*x1; } while (ss >= 1.0);
+      const double t = 2.0 * sqrt(1.0 - ss);
+      u[0] = x0 * t; u[1] = x1 * t; u[2] = 1.0 - 2.0 * ss;
+    }
     double w = c->weight, ekin;
     if (c->emode == 0) ekin = c->e0;
-    else {
+    else if (c->emode == 5) {
+      double v = rand_norm(&r); v *= v;
+      double g = rand_norm(&r); v += g * g;
+      g = rand_norm(&r); v += g * g;
+      ekin = v * halfkT;
+    } else if (c->emode == 3 || c->emode == 4) {
+      double v = rand_norm(&r);
+      v *= sigma_n; v += mu_n;
+      v = exp(v);
+      if (c->emode == 4) { v *= v; v = 1.0 / fmax(4.9406564584124654e-324, v); v *= 0.081804209605330899; }
+      ekin = v;
+    } else {
       double v = orc_rand(&r) * (c->e1 - c->e0);
       v += c->e0;
       if (v > c->e1) v = c->e1;
       if (c->emode == 2) { v *= v; v = 1.0 / fmax(4.9406564584124654e-324, v); v *= 0.081804209605330899; }
       ekin = v;
     }
+    if (minus_r != 0.0) for (int k = 0; k < 3; ++k) p[k] += u[k] * minus_r;
     const double e_init = ekin;
+    const double u_init[3] = { u[0], u[1], u[2] };
     int nscat = 0, ninel = 0;
     if (may_be_outside) {
       double d = dist_entry(c, p, u);
       if (d < 0.0) {
         miss_n += 1; miss_w += w;
-        if (!c->ignore_miss) tally_record(&T, u, ekin, w, -1, 0, e_init);
+        if (!c->ignore_miss) tally_record(&T, u, ekin, w, -1, 0, e_init, u_init);
         continue;
       }
       for (int k = 0; k < 3; ++k) p[k] += d * u[k];
@@ -306,7 +355,7 @@ int orc_minimc_run(void* vm, const orc_mmc_cfg* c, uint64_t first, uint64_t coun
       double wt = w;
       wt *= prob_transm(abs_c > 0.0, xs_a, d_exit, unb);
       wt *= ptransm;
-      tally_record(&T, u, ekin, wt, nscat, ninel, e_init);
+      tally_record(&T, u, ekin, wt, nscat, ninel, e_init, u_init);
       /* scattered part */
       if (w == 0.0 || isinf(d_scat) || !(xs_s > 0.0)) break;
       double rfact = 1.0;

@@ -46,12 +46,22 @@ class Scenario:
 
     def srccfg(self, n=None):
         kind, val = self.energy
-        if isinstance(val, tuple):
+        if kind == "thermal":
+            es = "ekin=thermal:%.17gK" % val
+        elif isinstance(val, tuple) and len(val) == 3:      # (mean, rms, "lognormal")
+            es = "%s=%.17g+-%.17g" % (kind, val[0], val[1])
+        elif isinstance(val, tuple):
             es = "%s=%.17g-%.17g" % (kind, val[0], val[1])
         else:
             es = "%s=%.17g" % (kind, val)
+        nn = self.n if n is None else int(n)
+        if self.src == "isotropic":
+            s = "isotropic;%s;x=%.17g;y=%.17g;z=%.17g;n=%d" % ((es,) + self.pos + (nn,))
+            if self.radius:
+                s += ";r=%.17g" % self.radius
+            return s
         s = "%s;%s;x=%.17g;y=%.17g;z=%.17g;ux=%.17g;uy=%.17g;uz=%.17g;n=%d" % (
-            (self.src, es) + self.pos + self.direction + (self.n if n is None else int(n),))
+            (self.src, es) + self.pos + self.direction + (nn,))
         if self.src == "circular":
             s += ";r=%.17g" % self.radius
         return s
@@ -82,13 +92,18 @@ class Scenario:
             c.ga, c.gb, c.gc = p["dx"], p["dy"], p["dz"]
         else:
             c.ga, c.gb = p["r"], p.get("dy", 0.0)
-        c.src_kind = {"constant": 1, "circular": 2}[self.src]
+        c.src_kind = {"constant": 1, "circular": 2, "isotropic": 3}[self.src]
         for k in range(3):
             c.pos[k] = self.pos[k]
             c.dir[k] = self.direction[k]
         c.radius = self.radius
         kind, val = self.energy
-        if isinstance(val, tuple):
+        if kind == "thermal":
+            c.emode, c.e0, c.e1 = 5, val, 0.0
+        elif isinstance(val, tuple) and len(val) == 3:
+            c.emode = 3 if kind == "ekin" else 4
+            c.e0, c.e1 = val[0], val[1]
+        elif isinstance(val, tuple):
             c.emode = 1 if kind == "ekin" else 2
             c.e0, c.e1 = val
         else:
@@ -250,6 +265,19 @@ def scenarios(macroxs):
     # tests/scripts/mmc_scge.py analogue on the oriented benchmark crystal (mosaic single crystal, 1 cm sphere)
     S.append(Scenario("scge", "Ge", ("sphere", {"r": 0.005}), "constant", ("wl", 3.2), 20000,
                       pos=(0, 0, -0.005 * (1 - 1e-13))))
+    # isotropic point source inside / spherical-shell source around the sample, log-normal and Maxwell spectra
+    # (tests/scripts/mmcenergy.py exercises these energy modes)
+    S.append(Scenario("iso_al", "Al", ("sphere", {"r": 0.03}), "isotropic", ("ekin", (0.025, 0.003, "lognormal")), 50000,
+                      pos=(0.005, 0.0, -0.01), tallies=(("theta", 90, 0.0, 180.0), ("mu", 100, -1.0, 1.0), ("e", 20, 0.0, 0.1))))
+    S.append(Scenario("isoshell_ch2", "CH2", ("sphere", {"r": 0.004}), "isotropic",
+                      ("wl", (1.8, 0.1, "lognormal")), 50000, pos=(0.0, 0.0, 0.0), radius=0.05,
+                      tallies=(("theta", 90, 0.0, 180.0), ("mu", 100, -1.0, 1.0))))
+    # isotropic point source OUTSIDE a box: most neutrons miss (tallied at theta = 0 w.r.t. their own direction)
+    S.append(Scenario("isopoint_box_ch2", "CH2", ("box", {"dx": 0.004, "dy": 0.006, "dz": 0.002}), "isotropic",
+                      ("wl", (1.8, 0.1, "lognormal")), 50000, pos=(0.001, 0.0, -0.006),
+                      tallies=(("theta", 90, 0.0, 180.0), ("q", 50, 0.0, 10.0))))
+    S.append(Scenario("thermal_h2o", "H2O", ("slab", {"dz": 0.001}), "constant", ("thermal", 300.0), 50000,
+                      pos=(0, 0, -0.01), tallies=(("theta", 90, 0.0, 180.0), ("e", 20, 0.0, 0.3), ("de", 20, -0.3, 0.3))))
     return {s.key: s for s in S}
 
 
@@ -281,6 +309,9 @@ def oracle_macroxs(key, ekin):
 
 def all_scenarios():
     return scenarios(oracle_macroxs)
+
+
+NO_REFERENCE = ()
 
 
 def load_golden():

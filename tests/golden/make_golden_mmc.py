@@ -13,11 +13,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from _mmc import all_scenarios, reference_minimc, hists_from_json  # noqa: E402
+from _mmc import all_scenarios, reference_minimc, hists_from_json, NO_REFERENCE  # noqa: E402
 from __graft_entry__ import CONFIGS  # noqa: E402
 
 out = {}
 for key, sc in all_scenarios().items():
+    if key in NO_REFERENCE:
+        continue
     n = 10 * sc.n
     js = reference_minimc(CONFIGS[sc.material], sc, nthreads=os.cpu_count() or 2, n=n)
     h, meta = hists_from_json(js, sc.tallies)

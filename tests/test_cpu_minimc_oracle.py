@@ -11,7 +11,8 @@ import pytest
 
 from _mmc import (all_scenarios, cached_oracle, run_oracle, load_golden, chi2_pvalue, compatible, CLASS_NAMES)
 
-SCEN = ["al_4Aa", "al_1Aa", "circ_h2o", "slab_ch2", "box_yag", "cyl_al", "cylinf_h2o", "scge"]
+SCEN = ["al_4Aa", "al_1Aa", "circ_h2o", "slab_ch2", "box_yag", "cyl_al", "cylinf_h2o", "scge", "iso_al", "isoshell_ch2",
+        "isopoint_box_ch2", "thermal_h2o"]
 PMIN = 0.001   # the reference's threshold
 
 

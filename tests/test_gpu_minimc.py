@@ -10,7 +10,8 @@ import pytest
 from _mmc import (all_scenarios, cached_oracle, run_oracle, load_golden, chi2_pvalue, compatible, hists_from_json)
 
 pytestmark = pytest.mark.gpu
-SCEN = ["al_4Aa", "al_1Aa", "circ_h2o", "slab_ch2", "box_yag", "cyl_al", "cylinf_h2o", "scge"]
+SCEN = ["al_4Aa", "al_1Aa", "circ_h2o", "slab_ch2", "box_yag", "cyl_al", "cylinf_h2o", "scge", "iso_al", "isoshell_ch2",
+        "isopoint_box_ch2", "thermal_h2o"]
 
 
 @pytest.fixture(scope="module")
@@ -91,7 +92,8 @@ def test_bad_input_is_reported_like_the_reference(handles):
     import ncrystal_b200 as nc
     s = handles("Al")
     for geom, src, eng in (("torus;r=1", "constant;ekin=1", ""), ("sphere;r=-1", "constant;ekin=1", ""),
-                           ("sphere;r=1", "isotropic;ekin=1", ""), ("sphere;r=1", "constant", ""),
+                           ("sphere;r=1", "isotropic;ekin=1;ux=1", ""), ("sphere;r=1", "laser;ekin=1", ""),
+                           ("sphere;r=1", "constant", ""), ("sphere;r=1", "constant;ekin=thermal300", ""),
                            ("sphere;r=1", "constant;ekin=1;foo=2", ""), ("sphere;r=1", "constant;ekin=1", "tally=bogus"),
                            ("sphere;r=1", "constant;ekin=1", "roulette=1.5,0.1,2")):
         with pytest.raises(nc.NCBadInput):
