@@ -360,7 +360,7 @@ def main():
         n_src = world * 10_000_000
         geom, src = "sphere;r=0.05", "constant;wl=1.8;z=-0.05;n=%d" % n_src
         eng = "tally=theta,mu;seed=%d" % SEED
-        minimc_sharded(sc, geom, "constant;wl=1.8;z=-0.05;n=%d" % (world * 200000), eng, device=dev)   # warm-up
+        minimc_sharded(sc, geom, src, eng, device=dev)   # warm-up (population buffers, NCCL)
         barrier()
         from ncrystal_b200.sharding import shard_range as _sr, merge_minimc_results
         b0, b1 = _sr(n_src, rank, world)

@@ -151,7 +151,7 @@ namespace ncb {
       }
       __syncthreads();
       for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
-        int cls = -1;
+        int cls = -1, key = -1;
         double val = 0.0, wgt = 0.0;
         if ( i < n ) {
           const double w = wt ? wt[i] : A.w[i];
@@ -163,9 +163,26 @@ namespace ncb {
           wgt = weighted ? w : 1.0;
           if ( wgt > 0.0 ) {
             cls = mmcClass( nscat, A.ninel[i] );
-            const int bin = mmcValueToBin( h, val );
-            atomicAdd( &s_cont[cls*nb2 + bin], wgt );
-            atomicAdd( &s_err[cls*nb2 + bin], wgt*wgt );
+            key = cls*nb2 + mmcValueToBin( h, val );
+          }
+        }
+        // Lanes that fill the same (class, bin) combine first: one shared-memory atomic per distinct bin and warp.
+        // (Unscattered neutrons of a pencil beam all land in ONE bin: without this the first step of a run spent
+        //  1.1 ms per 4 Mi neutrons in 32-way serialised atomics.)
+        {
+          const unsigned peers = __match_any_sync( 0xffffffffu, key );
+          const int maxcnt = __reduce_max_sync( 0xffffffffu, __popc( peers ) );
+          unsigned m = peers;
+          double s1 = 0.0, s2 = 0.0;
+          const double w1 = key >= 0 ? wgt : 0.0, w2 = w1*w1;
+          for ( int it = 0; it < maxcnt; ++it ) {
+            const int j = m ? __ffs( m ) - 1 : lane;
+            const double a = __shfl_sync( 0xffffffffu, w1, j ), b = __shfl_sync( 0xffffffffu, w2, j );
+            if ( m ) { s1 += a; s2 += b; m &= m - 1u; }
+          }
+          if ( key >= 0 && lane == __ffs( peers ) - 1 ) {
+            atomicAdd( &s_cont[key], s1 );
+            atomicAdd( &s_err[key], s2 );
           }
         }
         // running statistics (RunningStats1D): warp-reduce per class, one shared atomic per warp and class
