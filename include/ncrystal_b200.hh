@@ -79,12 +79,41 @@ namespace NCrystalB200 {
     void sampleScatterIsotropicDevice( const double* d_ekin, uint64_t n, double* d_ekin_final, double* d_mu, void* stream )
     { ncb200_samplescatterisotropic_many_dev( m_h, d_ekin, n, d_ekin_final, d_mu, stream ); checkError(); }
 
+    // device-resident transport step (NCrystal::MiniMC "mmc run" query); returns the result JSON
+    std::string minimc( const std::string& geomcfg, const std::string& srccfg, const std::string& enginecfg = "" )
+    {
+      char* js = ncb200_minimc_run( m_h, geomcfg.c_str(), srccfg.c_str(), enginecfg.c_str() );
+      checkError();
+      std::string out( js ? js : "" );
+      if ( js ) ncrystal_dealloc_string( js );
+      return out;
+    }
     void setRNGStream( uint64_t seed, uint32_t stream_id, uint64_t next_index ) { ncb200_set_rng_stream( m_h, seed, stream_id, next_index ); checkError(); }
     ncrystal_scatter_t handle() const { return m_h; }
   private:
     explicit Scatter( ncrystal_scatter_t h ) : m_h( h ) {}
     ncrystal_process_t proc() const { return ncrystal_cast_scat2proc( m_h ); }
     ncrystal_scatter_t m_h;
+  };
+
+
+  // NCrystal::Absorption (NCProc.hh): here always the 1/v process of the compiled material
+  class Absorption {
+  public:
+    explicit Absorption( const std::string& cfgstr ) : m_h( ncrystal_create_absorption( cfgstr.c_str() ) ) { checkError(); }
+    ~Absorption() { if ( m_h.internal ) ncrystal_unref( &m_h ); }
+    Absorption( const Absorption& ) = delete;
+    Absorption& operator=( const Absorption& ) = delete;
+    double crossSectionIsotropic( double ekin ) const
+    { double r; ncrystal_crosssection_nonoriented( ncrystal_cast_abs2proc( m_h ), ekin, &r ); checkError(); return r; }
+    std::vector<double> crossSectionIsotropic( const std::vector<double>& ekin ) const
+    {
+      std::vector<double> out( ekin.size() );
+      ncrystal_crosssection_nonoriented_many( ncrystal_cast_abs2proc( m_h ), ekin.data(), ekin.size(), 1, out.data() ); checkError();
+      return out;
+    }
+  private:
+    ncrystal_absorption_t m_h;
   };
 
 }
