@@ -26,7 +26,11 @@ namespace ncb {
   constexpr int kScWarps = 8;         // warps per CTA (they share the staged tables)
 
   struct ScWarpScratch {
-    double cptsq[kScMaxFam];
+    // per-family window of |normal . direction| outside which a plane cannot pass the truncation test (a superset,
+    // widened by 1e-6; the exact test of the reference is then run on the few survivors)
+    float lo[kScMaxFam];
+    float hi[kScMaxFam];
+    double cptsq[kScMaxFam];          // InteractionPars of the neutron per family, for the exact test
     double spt[kScMaxFam];
     double vals[2*kScCandCap];        // raw xs of (-normal, +normal) per candidate
     uint16_t cand[kScCandCap];
@@ -102,6 +106,7 @@ namespace ncb {
     if ( wl == 0 ) return;
     const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
     // number of active families (sorted by inv2d ascending) and their scan parameters
+    const double cta = S.cta;
     int nfam_act = 0;
     for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
       const int f = f0 + lane;
@@ -109,8 +114,16 @@ namespace ncb {
       if ( act ) {
         InteractionPars ip;
         ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+        // The truncation test of scIsCandidate, (1-x^2) cos^2(thB) > max(0, cos(tau) - x sin(thB))^2 with
+        // x = |n.d| = sin(phi), holds iff |thB - phi| < tau, i.e. x in ( sin(thB-tau), sin(thB+tau) )
+        // (no upper limit once thB+tau >= 90 deg, no lower limit once thB-tau <= 0).
+        const double spt = ip.sin_perfect_theta, cpt = sqrt( ip.cos_perfect_theta_sq );
+        const double slo = spt*cta - cpt*S.sta, shi = spt*cta + cpt*S.sta;
+        const bool open_hi = !( cpt*cta - spt*S.sta > 1e-6 );
+        ws.lo[f] = (float)( slo - 1e-6 );
+        ws.hi[f] = open_hi ? 2.0f : (float)( shi + 1e-6 );
         ws.cptsq[f] = ip.cos_perfect_theta_sq;
-        ws.spt[f] = ip.sin_perfect_theta;
+        ws.spt[f] = spt;
       }
       const uint32_t m = __ballot_sync( 0xffffffffu, act );
       nfam_act += __popc( m );
@@ -119,27 +132,44 @@ namespace ncb {
     __syncwarp();
     if ( nfam_act == 0 ) return;
     const int n_act = S.fam_first[nfam_act];
-    const double cta = S.cta;
     int count = 0;
-    for ( int base = 0; base < n_act; base += 32 ) {
-      const int in = base + lane;
-      bool is_cand = false;
-      if ( in < n_act ) {
-        const int f = fam_of[in];
-        const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
-        double sd, ds;
-        is_cand = scIsCandidate( cta, ws.cptsq[f], ws.spt[f], dot, sd, ds );
+    // two independent 32-normal slices per iteration (instruction-level parallelism: the kernel runs at
+    // 2 CTAs/SM and was latency-bound on its own dependent fp64 chain)
+    for ( int base = 0; base < n_act; base += 64 ) {
+      bool c[2];
+      int inn[2];
+#pragma unroll
+      for ( int u = 0; u < 2; ++u ) {
+        const int in = base + 32*u + lane;
+        inn[u] = in;
+        bool pre = false;
+        double dot = 0.0;
+        int f = 0;
+        if ( in < n_act ) {
+          f = fam_of[in];
+          dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
+          const double x = fabs( dot );
+          pre = ( x > (double)ws.lo[f] ) & ( x < (double)ws.hi[f] );
+        }
+        c[u] = false;
+        if ( pre ) {
+          double sd, ds;
+          c[u] = scIsCandidate( cta, ws.cptsq[f], ws.spt[f], dot, sd, ds );
+        }
       }
-      const uint32_t m = __ballot_sync( 0xffffffffu, is_cand );
-      if ( m ) {
-        if ( is_cand )
-          ws.cand[ count + __popc( m & ( ( 1u << lane ) - 1u ) ) ] = (uint16_t)in;
-        count += __popc( m );
-        __syncwarp();
-        if ( count > kScCandCap - 32 ) {
-          scFlush( S, ws, fam_of, wl, d, count, acc, mode, linear, choice );
-          count = 0;
-          if ( mode && acc.found ) return;
+#pragma unroll
+      for ( int u = 0; u < 2; ++u ) {
+        const uint32_t m = __ballot_sync( 0xffffffffu, c[u] );
+        if ( m ) {
+          if ( c[u] )
+            ws.cand[ count + __popc( m & ( ( 1u << lane ) - 1u ) ) ] = (uint16_t)inn[u];
+          count += __popc( m );
+          __syncwarp();
+          if ( count > kScCandCap - 32 ) {
+            scFlush( S, ws, fam_of, wl, d, count, acc, mode, linear, choice );
+            count = 0;
+            if ( mode && acc.found ) return;
+          }
         }
       }
     }

@@ -14,6 +14,7 @@ namespace ncb {
       throw std::runtime_error( "compiled material: degenerate SCBragg tables" );
     S.threshold_ekin = h.threshold_ekin;
     S.cta = h.gos_cta;
+    S.sta = h.gos_sta;
     S.circleint_k1 = h.gos_circleint_k1; S.circleint_k2 = h.gos_circleint_k2;
     S.numint_accuracy = h.gos_numint_accuracy;
     S.nfam = (int)nf; S.nnormals = (int)nn;

@@ -98,6 +98,7 @@ namespace ncb {
   struct ScBraggT {
     double threshold_ekin;
     double cta;                       // GaussOnSphere::m_cta
+    double sta;                       // GaussOnSphere::m_sta (only for the scan's pre-filter window)
     double circleint_k1, circleint_k2;
     double numint_accuracy;
     int nfam, nnormals;
