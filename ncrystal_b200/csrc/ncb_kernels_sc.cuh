@@ -225,6 +225,160 @@ namespace ncb {
     }
   }
 
+  // ---- two-kernel form of the scan (default): k_sc_find walks the normals with a lean register footprint
+  // (no evaluation code inlined: 6 instead of 2 CTAs per SM) and records, per neutron with at least one candidate
+  // plane, the candidate list; k_sc_eval then evaluates and accumulates them with the code of scFlush.  Neutrons
+  // with more than kScFindCap candidates are walked again by k_sc_eval with the combined scWalkWarp.
+  constexpr int kScFindCap = 32;
+#ifndef NCB_SC_FIND_WARPS
+#  define NCB_SC_FIND_WARPS 20
+#endif
+  constexpr int kScFindWarps = NCB_SC_FIND_WARPS;   // more warps per CTA share one copy of the staged tables
+  struct ScFindScratch {
+    float lo[kScMaxFam];
+    float hi[kScMaxFam];
+    double cptsq[kScMaxFam];
+    double spt[kScMaxFam];
+    uint16_t cand[kScFindCap];
+  };
+  struct ScFindArgs {
+    const double* ekin; const double* ux; const double* uy; const double* uz;
+    uint64_t n;
+    double dom_lo, dom_hi;
+    double* sc_xs; int32_t* sc_n;      // zeroed here for neutrons without candidates
+    uint32_t* work; uint32_t* work_count; uint8_t* ncand; uint16_t* cand;   // work list (bit 31: overflow)
+  };
+
+  __global__ void __launch_bounds__(32*kScFindWarps, 2)
+  k_sc_find( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+             const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    ScFindScratch& ws = reinterpret_cast<ScFindScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const int lane = threadIdx.x & 31;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kScFindWarps;
+    const double cta = S.cta;
+    for ( uint64_t i = (uint64_t)blockIdx.x * kScFindWarps + ( threadIdx.x >> 5 ); i < A.n; i += nwarps ) {
+      const double ekin_raw = A.ekin[i];
+      int count = 0;
+      bool overflow = false;
+      if ( domainContains( A.dom_lo, A.dom_hi, ekin_raw ) && !( ekin_raw <= S.threshold_ekin ) ) {
+        Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
+        vnormalise( d );
+        const double ekin = scCacheRound( ekin_raw );
+        const double wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+        if ( wl != 0 ) {
+          const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
+          int nfam_act = 0;
+          for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
+            const int f = f0 + lane;
+            const bool act = ( f < S.nfam ) && ( S.fam_inv2d[f] < inv2dcutoff );
+            if ( act ) {
+              InteractionPars ip;
+              ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+              const double spt = ip.sin_perfect_theta, cpt = sqrt( ip.cos_perfect_theta_sq );
+              const double slo = spt*cta - cpt*S.sta, shi = spt*cta + cpt*S.sta;
+              const bool open_hi = !( cpt*cta - spt*S.sta > 1e-6 );
+              ws.lo[f] = (float)( slo - 1e-6 );
+              ws.hi[f] = open_hi ? 2.0f : (float)( shi + 1e-6 );
+              ws.cptsq[f] = ip.cos_perfect_theta_sq;
+              ws.spt[f] = spt;
+            }
+            const uint32_t m = __ballot_sync( 0xffffffffu, act );
+            nfam_act += __popc( m );
+            if ( m != 0xffffffffu ) break;
+          }
+          __syncwarp();
+          const int n_act = nfam_act ? S.fam_first[nfam_act] : 0;
+          for ( int base = 0; base < n_act; base += 64 ) {
+            bool c[2]; int inn[2];
+#pragma unroll
+            for ( int u = 0; u < 2; ++u ) {
+              const int in = base + 32*u + lane;
+              inn[u] = in; c[u] = false;
+              if ( in < n_act ) {
+                const int f = fam_of[in];
+                const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
+                const double x = fabs( dot );
+                if ( ( x > (double)ws.lo[f] ) & ( x < (double)ws.hi[f] ) ) {
+                  double sd, ds;
+                  c[u] = scIsCandidate( cta, ws.cptsq[f], ws.spt[f], dot, sd, ds );
+                }
+              }
+            }
+#pragma unroll
+            for ( int u = 0; u < 2; ++u ) {
+              const uint32_t m = __ballot_sync( 0xffffffffu, c[u] );
+              if ( m ) {
+                const int pos = count + __popc( m & ( ( 1u << lane ) - 1u ) );
+                if ( c[u] && pos < kScFindCap ) ws.cand[pos] = (uint16_t)inn[u];
+                count += __popc( m );
+              }
+            }
+            if ( count > kScFindCap ) { overflow = true; break; }
+          }
+          __syncwarp();
+        }
+      }
+      if ( count == 0 ) {
+        if ( lane == 0 ) { A.sc_xs[i] = 0.0; A.sc_n[i] = 0; }
+      } else {
+        uint32_t pos = 0;
+        if ( lane == 0 ) pos = atomicAdd( A.work_count, 1u );
+        pos = __shfl_sync( 0xffffffffu, pos, 0 );
+        if ( lane == 0 ) {
+          A.work[pos] = (uint32_t)i | ( overflow ? 0x80000000u : 0u );
+          A.ncand[pos] = (uint8_t)( overflow ? 0 : count );
+        }
+        if ( !overflow && lane < count )
+          A.cand[(size_t)pos*kScFindCap + lane] = ws.cand[lane];
+      }
+      __syncwarp();
+    }
+  }
+
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_eval( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+             const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwork = *A.work_count;
+    const uint32_t nwarps = gridDim.x * kScWarps;
+    for ( uint32_t w = blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); w < nwork; w += nwarps ) {
+      const uint32_t entry = A.work[w];
+      const uint32_t i = entry & 0x7fffffffu;
+      Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
+      vnormalise( d );
+      ScAccum acc; double wl;
+      if ( entry & 0x80000000u ) {
+        scWalkWarp( S, ws, fam_of, A.ekin[i], d, wl, acc, 0, false, 0.0 );
+      } else {
+        acc.cur_fam = -1; acc.n = 0; acc.xsoffset = acc.xssum = acc.commul_last = 0.0;
+        acc.found = false; acc.chosen_in = 0; acc.chosen_sign = 1;
+        const double ekin = scCacheRound( A.ekin[i] );
+        wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+        const int count = A.ncand[w];
+        if ( lane < count ) ws.cand[lane] = A.cand[(size_t)w*kScFindCap + lane];
+        __syncwarp();
+        scFlush( S, ws, fam_of, wl, d, count, acc, 0, false, 0.0 );
+      }
+      if ( lane == 0 ) { A.sc_xs[i] = acc.commul_last; A.sc_n[i] = acc.n; }
+      __syncwarp();
+    }
+  }
+
   // ---- thread-per-neutron kernels that consume the scan result
   struct AnisoArgs {
     DirArgs D;

@@ -125,7 +125,7 @@ namespace {
     StagePlan sp_sc;         // staging plan of the warp-cooperative SCBragg kernels (SCBragg tables only)
     StagePlan sp_iso;        // hot tables of the isotropic leaves only
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
-    uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0;
+    uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0;
     std::string cfg;
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
     std::vector<SabBuildPlan> sabplans;
@@ -214,6 +214,7 @@ namespace {
       dm.sc_famof_off = o2;
       dm.sc_scratch_off = ( o2 + (uint32_t)M.sc.nnormals + 127u ) & ~127u;
       dm.sc_smem = dm.sc_scratch_off + (uint32_t)( kScWarps*sizeof(ScWarpScratch) );
+      dm.sc_find_smem = dm.sc_scratch_off + (uint32_t)( kScFindWarps*sizeof(ScFindScratch) );
     }
   }
 
@@ -303,6 +304,9 @@ namespace {
     setSmemAttr( k_classify_aniso, dm->sp_iso.total );
     setSmemAttr( k_sc_scan, dm->sc_smem );
     setSmemAttr( k_sc_sample, dm->sc_smem );
+    setSmemAttr( k_sc_eval, dm->sc_smem );
+    if ( dm->sc_find_smem <= 220u*1024u )
+      setSmemAttr( k_sc_find, dm->sc_find_smem );
     buildSabTablesOnDevice( *dm, 0 );
     return dm;
   }
@@ -362,6 +366,7 @@ namespace {
       // oriented path scratch (per neutron): SCBragg scan results, mu / stream position of the isotropic samplers
       double* sc_xs = nullptr; int32_t* sc_n = nullptr; double* mu_tmp = nullptr; uint32_t* nd_tmp = nullptr;
       uint32_t* q_sc = nullptr; size_t acap = 0;
+      uint32_t* sc_work = nullptr; uint8_t* sc_ncand = nullptr; uint16_t* sc_cand = nullptr;   // k_sc_find -> k_sc_eval
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
@@ -374,7 +379,8 @@ namespace {
       for ( auto& c : qctx ) {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
-        if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc ); }
+        if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
+                         cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); }
         if ( c.side ) cudaStreamDestroy( c.side );
         if ( c.ev_fork ) cudaEventDestroy( c.ev_fork );
         if ( c.ev_join ) cudaEventDestroy( c.ev_join );
@@ -417,6 +423,7 @@ namespace {
         if ( c.sc_xs ) {
           CUDA_OK( cudaDeviceSynchronize() );
           cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
+          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand );
         }
         c.acap = n + n/8 + 1024;
         CUDA_OK( cudaMalloc( &c.sc_xs, c.acap*sizeof(double) ) );
@@ -424,6 +431,9 @@ namespace {
         CUDA_OK( cudaMalloc( &c.mu_tmp, c.acap*sizeof(double) ) );
         CUDA_OK( cudaMalloc( &c.nd_tmp, c.acap*sizeof(uint32_t) ) );
         CUDA_OK( cudaMalloc( &c.q_sc, c.acap*sizeof(uint32_t) ) );
+        CUDA_OK( cudaMalloc( &c.sc_work, c.acap*sizeof(uint32_t) ) );
+        CUDA_OK( cudaMalloc( &c.sc_ncand, c.acap ) );
+        CUDA_OK( cudaMalloc( &c.sc_cand, c.acap*kScFindCap*sizeof(uint16_t) ) );
       }
       return c;
     }
@@ -651,7 +661,8 @@ namespace {
         Q.hist = do_sort ? qc.counts + 8 : nullptr;
         CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
         { TimedLaunch tl( "k_sample_classify", st );
-          k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
+          static const int cthreads = []{ const char* e = std::getenv( "NCB200_CLASSIFY_THREADS" ); return e ? std::atoi(e) : 256; }();
+          k_sample_classify<<< gridFor( m, cthreads, dm.device, ctas*( 256/cthreads ) ), cthreads, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
         const unsigned nsm = (unsigned)numSMs( dm.device );
         if ( do_sort ) {
           k_queue_scan<<< 1, 1024, 0, st >>>( Q.hist );
@@ -732,19 +743,41 @@ namespace {
     return -1;
   }
 
-  // SCBragg scan (one warp per neutron) -> sc_xs / sc_n
-  void launchScScan( const DeviceMaterial& dm, const double* d_ekin, const double* ux, const double* uy, const double* uz,
-                     uint64_t n, double* sc_xs, int32_t* sc_n, cudaStream_t st )
+  // SCBragg scan (one warp per neutron) -> sc_xs / sc_n.  Default: lean candidate search (k_sc_find) + evaluation of
+  // the neutrons that have candidates (k_sc_eval); NCB200_SC_ONEKERNEL=1 selects the combined k_sc_scan.
+  void launchScScan( const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
+                     const double* uy, const double* uz, uint64_t n, cudaStream_t st )
   {
+    static const bool onekernel = []{ const char* e = std::getenv( "NCB200_SC_ONEKERNEL" ); return e && std::atoi(e) != 0; }();
     const int isc = scCompIndex( dm.mat );
-    ScScanArgs SA;
-    SA.ekin = d_ekin; SA.ux = ux; SA.uy = uy; SA.uz = uz; SA.n = n; SA.sc_xs = sc_xs; SA.sc_n = sc_n;
-    SA.dom_lo = dm.mat.comp[isc].dom_lo; SA.dom_hi = dm.mat.comp[isc].dom_hi;
-    const int ctas = std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) );
     const uint64_t need = ( n + kScWarps - 1 ) / kScWarps;
-    const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)numSMs( dm.device )*std::min( ctas, 8 ) );
-    k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off );
-    ++g_launches;
+    const unsigned nsm = (unsigned)numSMs( dm.device );
+    // (small batches -- the tail of a transport run -- are launch-latency bound: one kernel instead of three launches)
+    if ( onekernel || n < 32768 || dm.sc_find_smem > 220u*1024u ) {
+      ScScanArgs SA;
+      SA.ekin = d_ekin; SA.ux = ux; SA.uy = uy; SA.uz = uz; SA.n = n; SA.sc_xs = qc.sc_xs; SA.sc_n = qc.sc_n;
+      SA.dom_lo = dm.mat.comp[isc].dom_lo; SA.dom_hi = dm.mat.comp[isc].dom_hi;
+      const int ctas = std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) );
+      const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*std::min( ctas, 8 ) );
+      k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off );
+      ++g_launches;
+      CUDA_OK( cudaGetLastError() );
+      return;
+    }
+    ScFindArgs FA;
+    FA.ekin = d_ekin; FA.ux = ux; FA.uy = uy; FA.uz = uz; FA.n = n;
+    FA.dom_lo = dm.mat.comp[isc].dom_lo; FA.dom_hi = dm.mat.comp[isc].dom_hi;
+    FA.sc_xs = qc.sc_xs; FA.sc_n = qc.sc_n;
+    FA.work = qc.sc_work; FA.work_count = qc.counts + 6; FA.ncand = qc.sc_ncand; FA.cand = qc.sc_cand;
+    CUDA_OK( cudaMemsetAsync( qc.counts + 6, 0, sizeof(uint32_t), st ) );
+    const int cf = std::min( 2, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
+    const uint64_t need_f = ( n + kScFindWarps - 1 ) / kScFindWarps;
+    const int ce = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) ) );
+    k_sc_find<<< (unsigned)std::min<uint64_t>( need_f, (uint64_t)nsm*cf ), 32*kScFindWarps, dm.sc_find_smem, st >>>(
+      dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+    k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
+      dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+    g_launches += 2;
     CUDA_OK( cudaGetLastError() );
   }
 
@@ -765,7 +798,7 @@ namespace {
     const double* sc_xs = nullptr; const int32_t* sc_n = nullptr;
     if ( has_sc ) {
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, n );
-      launchScScan( dm, d_ekin, ux, uy, uz, n, qc.sc_xs, qc.sc_n, st );
+      launchScScan( dm, qc, d_ekin, ux, uy, uz, n, st );
       sc_xs = qc.sc_xs; sc_n = qc.sc_n;
     }
     const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
@@ -805,7 +838,7 @@ namespace {
       }
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, m );
       if ( has_sc )
-        launchScScan( dm, A.ekin, D.ux, D.uy, D.uz, m, qc.sc_xs, qc.sc_n, st );
+        launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
       Q.q_sab_sorted = Q.q_fg_sorted = nullptr; Q.hist = nullptr;
