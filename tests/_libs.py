@@ -189,6 +189,9 @@ class HostSim:
             L.hostsim_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, _dp]
             L.hostsim_sab_sampler_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
             L.hostsim_sab_xscheck.argtypes = [C.c_void_p, C.c_int, _dp]
+            L.hostsim_minimc_run.restype = C.c_int
+            L.hostsim_minimc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int,
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp]
             cls._lib = L
         return cls._lib
 

@@ -356,3 +356,23 @@ def result_dict_from_layout(h, meta, tallies, provided):
               miss=dict(count=int(meta["miss_count"]), weight=float(meta["miss_weight"])),
               tallied=dict(count=int(meta["tallied_count"]), weight=float(meta["tallied_weight"])))
     return dict(output=dict(tally=out, metadata=md))
+
+
+def run_hostsim(hostsim, hdr, sc, first=0, count=None):
+    """the PRODUCT's NCB_HD transport physics compiled for the host (tests/hostsim), history by history"""
+    L = hostsim.lib()
+    count = sc.n if count is None else count
+    nt = len(sc.tallies)
+    types = (C.c_int * nt)(*[TALLY_TYPES.index(t[0]) for t in sc.tallies])
+    nbins = (C.c_int * nt)(*[t[1] for t in sc.tallies])
+    lo = (C.c_double * nt)(*[t[2] for t in sc.tallies])
+    hi = (C.c_double * nt)(*[t[3] for t in sc.tallies])
+    out = np.zeros(sum(hist_doubles(t[1]) for t in sc.tallies))
+    meta = np.zeros(5)
+    cfg = sc.orc_cfg()
+    dp = C.POINTER(C.c_double)
+    rc = L.hostsim_minimc_run(hostsim.h, C.byref(cfg), hdr["numdens"], hdr["abs_c"], first, count, nt, types, nbins, lo, hi,
+                              out.ctypes.data_as(dp), meta.ctypes.data_as(dp))
+    assert rc == 0, "hostsim transport error flags %d" % rc
+    return split_device_layout(out, sc.tallies), dict(miss_count=meta[0], miss_weight=meta[1], tallied_count=meta[2],
+                                                      tallied_weight=meta[3], steps=meta[4])

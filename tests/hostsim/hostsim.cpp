@@ -11,6 +11,7 @@
 #include "ncb_sabbuild.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
+#include "ncb_mmc.cuh"
 #include <memory>
 
 namespace ncb {
@@ -219,4 +220,144 @@ extern "C" {
       }
     return -1;
   }
+
+  // ---- transport step: the product's NCB_HD physics (ncb_mmc.cuh: source, geometry, forward step, tally values and
+  // binning) driven history by history on the host; same argument layout as oracle_mmc.c::orc_minimc_run.
+  struct hs_mmc_cfg {
+    int geom_kind; double ga, gb, gc;
+    int src_kind; double pos[3], dir[3]; double radius;
+    int emode; double e0, e1; double weight;
+    double roul_psurv, roul_wthr; int roul_nscat;
+    int nscatlimit; int ignore_miss, include_abs; uint64_t seed;
+  };
+  int hostsim_minimc_run( void* vh, const hs_mmc_cfg* c, double numdens, double abs_c_mat, uint64_t first, uint64_t count,
+                          int ntally, const int* types, const int* nbins, const double* xmin, const double* xmax,
+                          double* out, double* meta )
+  {
+    using namespace ncb;
+    auto& M = static_cast<Handle*>(vh)->mat;
+    auto& H = static_cast<Handle*>(vh)->H;
+    MmcGeom G; std::memset( &G, 0, sizeof(G) );
+    G.kind = c->geom_kind;
+    if ( G.kind == GEOM_SPHERE ) { G.a = c->ga; G.rsq = G.a*G.a; }
+    else if ( G.kind == GEOM_SLAB ) { G.c = c->gc; G.unbounded = 1; }
+    else if ( G.kind == GEOM_BOX ) { G.a = c->ga; G.b = c->gb; G.c = c->gc; }
+    else { G.a = c->ga; G.rsq = G.a*G.a; G.b = c->gb; G.unbounded = ( G.b == 0.0 ); }
+    MmcSource S; std::memset( &S, 0, sizeof(S) );
+    S.kind = c->src_kind; S.w = c->weight;
+    const double m2 = c->dir[0]*c->dir[0] + c->dir[1]*c->dir[1] + c->dir[2]*c->dir[2];
+    const double fn = 1.0/std::sqrt( m2 );
+    for ( int k = 0; k < 3; ++k ) { S.pos[k] = c->pos[k]; S.dir[k] = c->dir[k]*fn; }
+    if ( S.kind == SRC_CIRCULAR && c->radius > 0.0 ) {
+      double a[3] = { 1, 0, 0 };
+      auto dot = [&]( const double* q ) { return q[0]*S.dir[0] + q[1]*S.dir[1] + q[2]*S.dir[2]; };
+      if ( dot( a ) > 0.8 ) { a[0] = 0; a[1] = 1; a[2] = 0; }
+      if ( dot( a ) > 0.8 ) { a[0] = 0; a[1] = 0; a[2] = 1; }
+      auto cross_unit = [&]( const double* p, const double* q, double* o ) {
+        const double c0 = p[1]*q[2] - p[2]*q[1], c1 = p[2]*q[0] - p[0]*q[2], c2 = p[0]*q[1] - p[1]*q[0];
+        const double g = 1.0/std::sqrt( c0*c0 + c1*c1 + c2*c2 );
+        o[0] = c0*g; o[1] = c1*g; o[2] = c2*g;
+      };
+      double va[3], vb[3];
+      cross_unit( S.dir, a, va ); cross_unit( S.dir, va, vb );
+      for ( int k = 0; k < 3; ++k ) { S.va[k] = va[k]*c->radius; S.vb[k] = vb[k]*c->radius; }
+    }
+    if ( S.kind == SRC_ISOTROPIC ) S.minus_r = c->radius ? -c->radius : 0.0;
+    const int emap[6] = { SRCE_FIXED, SRCE_UNIFORM_EKIN, SRCE_UNIFORM_WL, SRCE_LOGNORMAL_EKIN, SRCE_LOGNORMAL_WL, SRCE_MAXWELL };
+    S.emode = emap[c->emode]; S.e0 = c->e0; S.e1 = c->e1;
+    if ( c->emode == 3 || c->emode == 4 ) {
+      const double tmp = 1 + ( c->e1*c->e1 )/( c->e0*c->e0 );
+      S.e0 = std::log( c->e0 / std::sqrt( tmp ) ); S.e1 = std::sqrt( std::log( tmp ) );
+    }
+    if ( c->emode == 5 ) { S.e0 = 0.5*kBoltzmann*c->e0; S.e1 = 0.0; }
+    auto inside = [&]() {
+      const double x = S.pos[0], y = S.pos[1], z = S.pos[2];
+      switch ( G.kind ) {
+      case GEOM_SPHERE: return x*x + y*y + z*z <= G.rsq;
+      case GEOM_SLAB: return std::fabs(z) <= G.c;
+      case GEOM_BOX: return std::fabs(x) <= G.a && std::fabs(y) <= G.b && std::fabs(z) <= G.c;
+      default: return x*x + z*z <= G.rsq && ( G.b == 0 || std::fabs(y) <= G.b );
+      }
+    };
+    S.may_be_outside = ( S.kind == SRC_CIRCULAR && c->radius > 0.0 ) ? 1 : ( inside() ? 0 : 1 );
+    MmcEngine E;
+    E.macro_factor = 100.0*numdens;
+    E.abs_c = c->include_abs ? std::max( 0.0, abs_c_mat ) : 0.0;
+    E.roulette_psurv = c->roul_psurv; E.roulette_wthr = c->roul_wthr; E.roulette_nscat = c->roul_nscat;
+    E.roulette_boost = 1.0/c->roul_psurv; E.nscatlimit = c->nscatlimit;
+    MmcTally T; std::memset( &T, 0, sizeof(T) );
+    T.nh = ntally;
+    uint32_t off = 0;
+    for ( int i = 0; i < ntally; ++i ) {
+      MmcHist& h = T.h[i];
+      h.type = types[i]; h.nbins = nbins[i]; h.xmin = xmin[i]; h.xmax = xmax[i];
+      h.invdelta = 1.0/( ( xmax[i] - xmin[i] )/nbins[i] ); h.off = off;
+      const uint32_t nd = mmcHistDoubles( nbins[i] );
+      std::fill( out + off, out + off + nd, 0.0 );
+      for ( int k = 0; k < kMmcNClass; ++k ) {
+        out[off + 2*kMmcNClass*( nbins[i] + 2 ) + k*kMmcNStat + 3] = kInf;
+        out[off + 2*kMmcNClass*( nbins[i] + 2 ) + k*kMmcNStat + 4] = -kInf;
+      }
+      off += nd;
+    }
+    for ( int k = 0; k < 3; ++k ) T.dir0[k] = S.dir[k];
+    T.dir0_is_z = ( S.dir[2] == 1.0 ); T.has_dir0_fixed = ( S.kind != SRC_ISOTROPIC );
+    T.has_e0_fixed = ( S.emode == SRCE_FIXED ); T.e0_fixed = S.e0;
+    double miss_n = 0, miss_w = 0, tall_n = 0, tall_w = 0, nsteps = 0;
+    int errs = 0;
+    auto record = [&]( double ux, double uy, double uz, double ekin, double w, int nscat, int ninel, double e_init,
+                       double ux0, double uy0, double uz0 ) {
+      tall_n += 1; tall_w += w;
+      for ( int ih = 0; ih < T.nh; ++ih ) {
+        const MmcHist& h = T.h[ih];
+        bool weighted;
+        const double v = mmcTallyValue( T, h.type, ux, uy, uz, ekin, w, nscat, e_init, ux0, uy0, uz0, weighted );
+        const double wgt = weighted ? w : 1.0;
+        if ( !( wgt > 0.0 ) ) continue;
+        const int cls = mmcClass( nscat, ninel ), nb2 = h.nbins + 2, bin = mmcValueToBin( h, v );
+        double* g = out + h.off;
+        g[cls*nb2 + bin] += wgt;
+        g[kMmcNClass*nb2 + cls*nb2 + bin] += wgt*wgt;
+        double* st = g + 2*kMmcNClass*nb2 + cls*kMmcNStat;
+        st[0] += wgt; st[1] += wgt*v; st[2] += wgt*v*v;
+        if ( v < st[3] ) st[3] = v;
+        if ( v > st[4] ) st[4] = v;
+      }
+    };
+    for ( uint64_t id = first; id < first + count; ++id ) {
+      Rng rs; rs.init( c->seed, id, kMmcSidSrc );
+      MmcNeutron nt = mmcGenerate( S, rs );
+      const double e_init = nt.ekin, ux0 = nt.ux, uy0 = nt.uy, uz0 = nt.uz;
+      if ( S.may_be_outside ) {
+        const double d = mmcDistToEntry( G, nt.x, nt.y, nt.z, nt.ux, nt.uy, nt.uz );
+        if ( d < 0.0 ) {
+          miss_n += 1; miss_w += nt.w;
+          if ( !c->ignore_miss ) record( nt.ux, nt.uy, nt.uz, nt.ekin, nt.w, -1, 0, e_init, ux0, uy0, uz0 );
+          continue;
+        }
+        nt.x += d*nt.ux; nt.y += d*nt.uy; nt.z += d*nt.uz;
+      }
+      int nscat = 0, ninel = 0;
+      for ( uint32_t step = 0; ; ++step ) {
+        nsteps += 1;
+        Rng rng; rng.init( c->seed, id, kMmcSidBase + 2u*step );
+        const double xs = matXS( M, H, nt.ekin, Vec3{ nt.ux, nt.uy, nt.uz }, nullptr, nullptr, nullptr );
+        MmcStepOut o = mmcForward( G, E, rng, nt.x, nt.y, nt.z, nt.ux, nt.uy, nt.uz, nt.w, nt.ekin, nscat, xs );
+        record( nt.ux, nt.uy, nt.uz, nt.ekin, o.wt, nscat, ninel, e_init, ux0, uy0, uz0 );
+        if ( !o.survives ) break;
+        nt.x = o.x; nt.y = o.y; nt.z = o.z; nt.w = o.w;
+        Rng rq; rq.init( c->seed, id, kMmcSidBase + 2u*step + 1u );
+        double eout; Vec3 od; int err = 0, ich;
+        matSample( M, H, nt.ekin, Vec3{ nt.ux, nt.uy, nt.uz }, rq, eout, od, err, ich );
+        errs |= err;
+        const bool was_elastic = ( nt.ekin == eout );
+        nt.ux = od.x; nt.uy = od.y; nt.uz = od.z; nt.ekin = eout;
+        ++nscat; if ( !was_elastic ) ++ninel;
+        if ( step > 100000u ) return -1;
+      }
+    }
+    meta[0] = miss_n; meta[1] = miss_w; meta[2] = tall_n; meta[3] = tall_w; meta[4] = nsteps;
+    return errs;
+  }
+
 }

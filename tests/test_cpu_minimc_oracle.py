@@ -88,3 +88,26 @@ def test_oracle_matches_reference_stored_histograms(results, key, fn):
     p, chi, k = chi2_pvalue(c, e, c_ref, e_ref)
     assert p > PMIN, "%s vs %s: chi2=%.1f dof=%d p=%.2g" % (key, fn, chi, k, p)
     assert abs(c.sum() / sc.n - ref["stats"]["integral"] / 1e5) < 5e-3
+
+
+@pytest.mark.parametrize("key", ["al_4Aa", "slab_ch2", "box_yag", "cylinf_h2o", "scge", "iso_al", "isopoint_box_ch2",
+                                 "thermal_h2o"])
+def test_product_transport_physics_on_host_equals_oracle(results, key):
+    # the product's __host__ __device__ transport code (ncb_mmc.cuh + the scatter physics), compiled by the host
+    # compiler in tests/hostsim, must reproduce the oracle restatement history by history: identical record counts
+    # and (same libm, no FMA contraction on either side) identical histogram contents
+    from _libs import HostSim
+    from _mmc import run_hostsim
+    from oracle_check import material_path
+    from __graft_entry__ import CONFIGS
+    sc, h, meta = _run(results, key)
+    o, hdr = cached_oracle(sc.material)
+    hs = HostSim(open(material_path(CONFIGS[sc.material]), "rb").read())
+    n = min(sc.n, 20000)
+    ho, mo = run_oracle(o, sc, first=0, count=n)
+    hh, mh = run_hostsim(hs, hdr, sc, first=0, count=n)
+    assert mh["tallied_count"] == mo["tallied_count"] and mh["miss_count"] == mo["miss_count"]
+    assert abs(mh["tallied_weight"] - mo["tallied_weight"]) <= 1e-12 * mo["tallied_weight"]
+    for name, *_ in sc.tallies:
+        assert np.allclose(hh[name]["content"], ho[name]["content"], rtol=1e-12, atol=1e-12), (key, name)
+        assert np.allclose(hh[name]["errsq"], ho[name]["errsq"], rtol=1e-12, atol=1e-12), (key, name)
