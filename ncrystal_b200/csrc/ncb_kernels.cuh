@@ -168,14 +168,15 @@ namespace ncb {
     uint32_t* q_sab_sorted;  // the two queues reordered by energy bin (counting sort), or null
     uint32_t* q_fg_sorted;
     uint32_t* hist;     // [2*kSortBins] per-bin counts, then turned into running cursors by k_queue_scan
+    int sort_shift = 0; // coarsen the sort key by 2^shift bins (experiments on how fine the energy classes must be)
   };
 
   // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave;
   // the SAB energy grids have ~16 points per octave, so one bin ~ one overlay sampler).
-  __device__ __forceinline__ uint32_t sortKey( double ekin )
+  __device__ __forceinline__ uint32_t sortKey( double ekin, int shift = 0 )
   {
     const int k = (int)( ( (unsigned long long)__double_as_longlong( ekin ) >> 48 ) & 0x7FFFull ) - ( 999 << 4 );
-    return (uint32_t)( k < 0 ? 0 : ( k > kSortBins-1 ? kSortBins-1 : k ) );
+    return ( (uint32_t)( k < 0 ? 0 : ( k > kSortBins-1 ? kSortBins-1 : k ) ) >> shift ) << shift;
   }
 
   __device__ __forceinline__ void warpPush( bool pred, uint32_t* q, uint32_t* counter, uint32_t entry )
@@ -269,7 +270,7 @@ namespace ncb {
           }
           entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
           if ( do_sort && cls )
-            atomicAdd( &sh_hist[ ( cls - 1 )*kSortBins + sortKey( ekin ) ], 1u );
+            atomicAdd( &sh_hist[ ( cls - 1 )*kSortBins + sortKey( ekin, Q.sort_shift ) ], 1u );
         }
         if ( A.xs_out ) A.xs_out[i] = tot;
         if ( A.component ) A.component[i] = ich;
@@ -330,7 +331,7 @@ namespace ncb {
     for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n0 + n1; j += stride ) {
       const bool fg = ( j >= n0 );
       const uint32_t entry = fg ? Q.q_fg[j - n0] : Q.q_sab[j];
-      const uint32_t key = sortKey( ekin[ entry & kQueueIdxMask ] );
+      const uint32_t key = sortKey( ekin[ entry & kQueueIdxMask ], Q.sort_shift );
       const uint32_t pos = atomicAdd( &Q.hist[ ( fg ? kSortBins : 0 ) + key ], 1u );
       ( fg ? Q.q_fg_sorted : Q.q_sab_sorted )[pos] = entry;
     }
@@ -472,6 +473,67 @@ namespace ncb {
     }
     if ( errs )
       atomicOr( A.err_flags, errs );
+  }
+
+  // Partition the free-gas queue by energy class (two octaves per class): the free-gas samplers branch on E/kT
+  // regimes, and warps -- and, for the instruction cache, whole SMs -- whose neutrons sit in one regime diverge far
+  // less (water: k_sample_fg 2.85 -> 1.8 ms per 1e7; finer classes give nothing more).  Two small kernels with
+  // block-aggregated bookkeeping: class totals per 8192-entry chunk (k_fg_hist), then every chunk reserves one run
+  // per class in the output queue with ONE global atomic per class (k_fg_partition).  The complete 1024-bin
+  // counting sort (NCB200_SORT=1) paid 1.9 ms for per-entry global atomics.
+  constexpr int kFgGroupChunk = 8192;
+  constexpr int kFgGroupClasses = 16;
+  __device__ __forceinline__ uint32_t fgClass( double ekin )
+  {
+    const uint32_t c = sortKey( ekin ) >> 5;
+    return c < (uint32_t)kFgGroupClasses ? c : (uint32_t)kFgGroupClasses - 1u;
+  }
+  // cls[0..16) class totals, cls[16..32) running cursors
+  __global__ void __launch_bounds__(256)
+  k_fg_hist( const double* __restrict__ ekin, const uint32_t* __restrict__ q_fg, const uint32_t* __restrict__ count,
+             uint32_t* __restrict__ cls )
+  {
+    __shared__ uint32_t s_cnt[kFgGroupClasses];
+    const uint32_t nq = *count;
+    if ( threadIdx.x < kFgGroupClasses ) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for ( uint32_t k = blockIdx.x*blockDim.x + threadIdx.x; k < nq; k += gridDim.x*blockDim.x )
+      atomicAdd( &s_cnt[ fgClass( ekin[ q_fg[k] & kQueueIdxMask ] ) ], 1u );
+    __syncthreads();
+    if ( threadIdx.x < kFgGroupClasses && s_cnt[threadIdx.x] )
+      atomicAdd( &cls[threadIdx.x], s_cnt[threadIdx.x] );
+  }
+  __global__ void __launch_bounds__(256)
+  k_fg_partition( const double* __restrict__ ekin, const uint32_t* __restrict__ q_fg, const uint32_t* __restrict__ count,
+                  uint32_t* __restrict__ cls, uint32_t* __restrict__ q_out )
+  {
+    __shared__ uint32_t s_in[kFgGroupChunk];
+    __shared__ uint8_t s_cls[kFgGroupChunk];
+    __shared__ uint32_t s_cnt[kFgGroupClasses], s_pos[kFgGroupClasses];
+    const uint32_t nq = *count;
+    for ( uint32_t base = blockIdx.x * kFgGroupChunk; base < nq; base += gridDim.x * kFgGroupChunk ) {
+      const uint32_t m = min( (uint32_t)kFgGroupChunk, nq - base );
+      if ( threadIdx.x < kFgGroupClasses ) s_cnt[threadIdx.x] = 0;
+      __syncthreads();
+      for ( uint32_t k = threadIdx.x; k < m; k += blockDim.x ) {
+        const uint32_t entry = q_fg[base + k];
+        s_in[k] = entry;
+        const uint32_t c = fgClass( ekin[ entry & kQueueIdxMask ] );
+        s_cls[k] = (uint8_t)c;
+        atomicAdd( &s_cnt[c], 1u );
+      }
+      __syncthreads();
+      if ( threadIdx.x < kFgGroupClasses ) {
+        uint32_t start = 0;                                   // first slot of this class in the output queue
+        for ( int c = 0; c < (int)threadIdx.x; ++c ) start += cls[c];
+        const uint32_t n = s_cnt[threadIdx.x];
+        s_pos[threadIdx.x] = start + ( n ? atomicAdd( &cls[kFgGroupClasses + threadIdx.x], n ) : 0u );
+      }
+      __syncthreads();
+      for ( uint32_t k = threadIdx.x; k < m; k += blockDim.x )
+        q_out[ atomicAdd( &s_pos[ s_cls[k] ], 1u ) ] = s_in[k];
+      __syncthreads();
+    }
   }
 
   // Free-gas samplers over q_fg: the FreeGas leaf, and for S(alpha,beta) above Emax the

@@ -125,6 +125,7 @@ namespace {
     StagePlan sp_sc;         // staging plan of the warp-cooperative SCBragg kernels (SCBragg tables only)
     StagePlan sp_iso;        // hot tables of the isotropic leaves only
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
+    bool has_fg_leaf = false; // a FreeGas leaf: its queue spans all energies (-> k_fg_group)
     uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0;
     std::string cfg;
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
@@ -292,6 +293,7 @@ namespace {
     CUDA_OK( cudaMemcpy( dm->d_arena, lm.arena.data(), dm->arena_bytes, cudaMemcpyHostToDevice ) );
     dm->mat = relocated( lm, dm->d_arena );
     dm->cfg = lm.cfg;
+    for ( int i = 0; i < lm.mat.ncomp; ++i ) if ( lm.mat.comp[i].kind == KIND_FREEGAS ) dm->has_fg_leaf = true;
     dm->numdens = lm.numdens; dm->abs_c = lm.abs_c; dm->temperature = lm.temperature;
     dm->sabplans = lm.sabplans;
     buildStagePlan( *dm );
@@ -659,6 +661,7 @@ namespace {
         Q.q_sab_sorted = do_sort ? qc.q + 4*qc.cap : nullptr;
         Q.q_fg_sorted = do_sort ? qc.q + 5*qc.cap : nullptr;
         Q.hist = do_sort ? qc.counts + 8 : nullptr;
+        { static const int sh = []{ const char* e = std::getenv( "NCB200_SORT_SHIFT" ); return e ? std::atoi(e) : 0; }(); Q.sort_shift = sh; }
         CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
         { TimedLaunch tl( "k_sample_classify", st );
           static const int cthreads = []{ const char* e = std::getenv( "NCB200_CLASSIFY_THREADS" ); return e ? std::atoi(e) : 256; }();
@@ -701,6 +704,17 @@ namespace {
             st_fg = qc.side;
           }
           auto launchFG = [&]() {
+            static const bool group = []{ const char* e = std::getenv( "NCB200_FG_GROUP" ); return !e || std::atoi(e) != 0; }();
+            if ( group && dm.has_fg_leaf && !do_sort ) {
+              TimedLaunch tl( "k_fg_partition", st_fg );
+              uint32_t* cls = qc.counts + 8;                  // [16] class totals + [16] cursors (the sort's histogram area)
+              uint32_t* q_out = qc.q + 5*qc.cap;
+              CUDA_OK( cudaMemsetAsync( cls, 0, 2*kFgGroupClasses*sizeof(uint32_t), st_fg ) );
+              k_fg_hist<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st_fg >>>( A.ekin, Q.q_fg, Q.counts + 1, cls );
+              k_fg_partition<<< gridFor( ( m + 31 )/32, 256, dm.device, 4 ), 256, 0, st_fg >>>( A.ekin, Q.q_fg, Q.counts + 1, cls, q_out );
+              g_launches += 2;
+              Q.q_fg = q_out;
+            }
             TimedLaunch tl( "k_sample_fg", st_fg );
             if ( fgminb >= 8 ) k_sample_fg<8><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
             else k_sample_fg<4><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
