@@ -625,6 +625,23 @@ namespace {
     cudaGetLastError();
   }
 
+  // Materials with a FreeGas leaf: reorder the free-gas queue by energy class (k_fg_hist / k_fg_partition);
+  // afterwards Q.q_fg points at the partitioned copy.  NCB200_FG_GROUP=0 switches it off.
+  void partitionFgQueue( const DeviceMaterial& dm, Scatter::QueueCtx& qc, QueueArgs& Q, const double* d_ekin, uint64_t m,
+                         cudaStream_t st )
+  {
+    static const bool group = []{ const char* e = std::getenv( "NCB200_FG_GROUP" ); return !e || std::atoi(e) != 0; }();
+    if ( !group || !dm.has_fg_leaf ) return;
+    TimedLaunch tl( "k_fg_partition", st );
+    uint32_t* cls = qc.counts + 8;                  // [16] class totals + [16] cursors (the sort's histogram area)
+    uint32_t* q_out = qc.q + 5*qc.cap;
+    CUDA_OK( cudaMemsetAsync( cls, 0, 2*kFgGroupClasses*sizeof(uint32_t), st ) );
+    k_fg_hist<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( d_ekin, Q.q_fg, Q.counts + 1, cls );
+    k_fg_partition<<< gridFor( ( m + 31 )/32, 256, dm.device, 4 ), 256, 0, st >>>( d_ekin, Q.q_fg, Q.counts + 1, cls, q_out );
+    g_launches += 2;
+    Q.q_fg = q_out;
+  }
+
   void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu,
                         cudaStream_t st, int ictx = kSlots )
   {
@@ -704,17 +721,7 @@ namespace {
             st_fg = qc.side;
           }
           auto launchFG = [&]() {
-            static const bool group = []{ const char* e = std::getenv( "NCB200_FG_GROUP" ); return !e || std::atoi(e) != 0; }();
-            if ( group && dm.has_fg_leaf && !do_sort ) {
-              TimedLaunch tl( "k_fg_partition", st_fg );
-              uint32_t* cls = qc.counts + 8;                  // [16] class totals + [16] cursors (the sort's histogram area)
-              uint32_t* q_out = qc.q + 5*qc.cap;
-              CUDA_OK( cudaMemsetAsync( cls, 0, 2*kFgGroupClasses*sizeof(uint32_t), st_fg ) );
-              k_fg_hist<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st_fg >>>( A.ekin, Q.q_fg, Q.counts + 1, cls );
-              k_fg_partition<<< gridFor( ( m + 31 )/32, 256, dm.device, 4 ), 256, 0, st_fg >>>( A.ekin, Q.q_fg, Q.counts + 1, cls, q_out );
-              g_launches += 2;
-              Q.q_fg = q_out;
-            }
+            if ( !do_sort ) partitionFgQueue( dm, qc, Q, A.ekin, m, st_fg );
             TimedLaunch tl( "k_sample_fg", st_fg );
             if ( fgminb >= 8 ) k_sample_fg<8><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
             else k_sample_fg<4><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
@@ -869,6 +876,7 @@ namespace {
       const unsigned gq = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
       const unsigned gf = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
       k_sample_sab_refill<false,8><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+      if ( m >= 65536 ) partitionFgQueue( dm, qc, Q, A.ekin, m, st );
       k_sample_fg<8><<< gf, 128, 0, st >>>( dm.mat, Ai, Q );
       k_sample_sab_refill<true,5><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_emax, Q.counts + 2, Q.counts + 4 );
       k_dir_from_mu<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A, Q, X );
