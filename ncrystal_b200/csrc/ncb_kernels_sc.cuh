@@ -255,10 +255,19 @@ namespace ncb {
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
+    // staged: the single-precision normals (TMA bulk copy); everything else of the crystal is read through L1
     HotTabs H;
     uint8_t* fam_of = smem + fam_of_off;
-    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
-    const ScBraggT& S = *H.sc;
+    stageHotTabs( M, sp, smem, &mbar, H );
+    const ScBraggT& S = M.sc;
+    const uint32_t nn4 = ( (uint32_t)S.nnormals + 3u ) & ~3u;
+    const float* nfx = reinterpret_cast<const float*>( smem + sp.off[kHotSlotsIso] );
+    const float* nfy = nfx + nn4;
+    const float* nfz = nfy + nn4;
+    for ( int f = threadIdx.x; f < S.nfam; f += blockDim.x )
+      for ( int in = S.fam_first[f]; in < S.fam_first[f+1]; ++in )
+        fam_of[in] = (uint8_t)f;
+    __syncthreads();
     ScFindScratch& ws = reinterpret_cast<ScFindScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
     const int lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t)gridDim.x * kScFindWarps;
@@ -284,8 +293,8 @@ namespace ncb {
               const double spt = ip.sin_perfect_theta, cpt = sqrt( ip.cos_perfect_theta_sq );
               const double slo = spt*cta - cpt*S.sta, shi = spt*cta + cpt*S.sta;
               const bool open_hi = !( cpt*cta - spt*S.sta > 1e-6 );
-              ws.lo[f] = (float)( slo - 1e-6 );
-              ws.hi[f] = open_hi ? 2.0f : (float)( shi + 1e-6 );
+              ws.lo[f] = (float)( slo - 4e-6 );               // (the window is compared with a float dot product)
+              ws.hi[f] = open_hi ? 2.0f : (float)( shi + 4e-6 );
               ws.cptsq[f] = ip.cos_perfect_theta_sq;
               ws.spt[f] = spt;
             }
@@ -295,6 +304,7 @@ namespace ncb {
           }
           __syncwarp();
           const int n_act = nfam_act ? S.fam_first[nfam_act] : 0;
+          const float dxf = (float)d.x, dyf = (float)d.y, dzf = (float)d.z;
           for ( int base = 0; base < n_act; base += 64 ) {
             bool c[2]; int inn[2];
 #pragma unroll
@@ -303,9 +313,11 @@ namespace ncb {
               inn[u] = in; c[u] = false;
               if ( in < n_act ) {
                 const int f = fam_of[in];
-                const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
-                const double x = fabs( dot );
-                if ( ( x > (double)ws.lo[f] ) & ( x < (double)ws.hi[f] ) ) {
+                // pre-filter in single precision (fused multiply-adds: it only has to be a superset) ...
+                const float xf = fabsf( __fmaf_rn( nfx[in], dxf, __fmaf_rn( nfy[in], dyf, nfz[in]*dzf ) ) );
+                if ( ( xf > ws.lo[f] ) & ( xf < ws.hi[f] ) ) {
+                  // ... the reference's test on the survivors, in double precision from the fp64 normals
+                  const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
                   double sd, ds;
                   c[u] = scIsCandidate( cta, ws.cptsq[f], ws.spt[f], dot, sd, ds );
                 }

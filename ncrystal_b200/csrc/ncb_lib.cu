@@ -123,10 +123,11 @@ namespace {
     Material mat;            // device pointers
     StagePlan sp;            // smem staging plan for the hot tables
     StagePlan sp_sc;         // staging plan of the warp-cooperative SCBragg kernels (SCBragg tables only)
+    StagePlan sp_find;       // k_sc_find: single-precision normals only
     StagePlan sp_iso;        // hot tables of the isotropic leaves only
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
     bool has_fg_leaf = false; // a FreeGas leaf: its queue spans all energies (-> k_fg_group)
-    uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0;
+    uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0, sc_find_famof_off = 0, sc_find_scratch_off = 0;
     std::string cfg;
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
     std::vector<SabBuildPlan> sabplans;
@@ -215,7 +216,18 @@ namespace {
       dm.sc_famof_off = o2;
       dm.sc_scratch_off = ( o2 + (uint32_t)M.sc.nnormals + 127u ) & ~127u;
       dm.sc_smem = dm.sc_scratch_off + (uint32_t)( kScWarps*sizeof(ScWarpScratch) );
-      dm.sc_find_smem = dm.sc_scratch_off + (uint32_t)( kScFindWarps*sizeof(ScFindScratch) );
+      // k_sc_find stages the float normals (slot of the double normals) and nothing else
+      std::memset( &dm.sp_find, 0, sizeof(StagePlan) );
+      {
+        const uint32_t nn4 = ( (uint32_t)M.sc.nnormals + 3u ) & ~3u;
+        const uint32_t nb = 3u*nn4*(uint32_t)sizeof(float);
+        dm.sp_find.src[kHotSlotsIso] = M.sc.normals_f; dm.sp_find.nbytes[kHotSlotsIso] = nb; dm.sp_find.off[kHotSlotsIso] = 0;
+        dm.sp_find.copy_bytes = nb;
+        dm.sp_find.total = ( nb + 127u ) & ~127u;
+        dm.sc_find_famof_off = dm.sp_find.total;
+        dm.sc_find_scratch_off = ( dm.sc_find_famof_off + (uint32_t)M.sc.nnormals + 127u ) & ~127u;
+        dm.sc_find_smem = dm.sc_find_scratch_off + (uint32_t)( kScFindWarps*sizeof(ScFindScratch) );
+      }
     }
   }
 
@@ -791,11 +803,11 @@ namespace {
     FA.sc_xs = qc.sc_xs; FA.sc_n = qc.sc_n;
     FA.work = qc.sc_work; FA.work_count = qc.counts + 6; FA.ncand = qc.sc_ncand; FA.cand = qc.sc_cand;
     CUDA_OK( cudaMemsetAsync( qc.counts + 6, 0, sizeof(uint32_t), st ) );
-    const int cf = std::min( 2, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
+    const int cf = std::min( 3, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
     const uint64_t need_f = ( n + kScFindWarps - 1 ) / kScFindWarps;
     const int ce = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) ) );
     k_sc_find<<< (unsigned)std::min<uint64_t>( need_f, (uint64_t)nsm*cf ), 32*kScFindWarps, dm.sc_find_smem, st >>>(
-      dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+      dm.mat, dm.sp_find, FA, dm.sc_find_famof_off, dm.sc_find_scratch_off );
     k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
       dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
     g_launches += 2;

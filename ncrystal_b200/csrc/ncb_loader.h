@@ -74,7 +74,7 @@ namespace ncb {
     }
     if ( m.sc.nfam ) {
       relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
-      relocPtr( m.sc.normals, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
+      relocPtr( m.sc.normals, base ); relocPtr( m.sc.normals_f, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
     }
     return m;
   }

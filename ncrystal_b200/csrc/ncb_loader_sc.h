@@ -25,6 +25,13 @@ namespace ncb {
     S.fam_first = offAsPtr<int>( lm.put( first.data(), (nf+1)*sizeof(int) ) );
     const double* pn = arr + 2*nf + nf + 1;
     S.normals = offAsPtr<double>( lm.put( pn, 3*nn*8 ) );
+    {
+      const size_t nn4 = ( nn + 3 ) & ~(size_t)3;          // rows padded to 16 bytes
+      std::vector<float> nf32( 3*nn4, 0.0f );
+      for ( size_t i = 0; i < nn; ++i )
+        for ( int k = 0; k < 3; ++k ) nf32[k*nn4 + i] = (float)pn[3*i+k];
+      S.normals_f = offAsPtr<float>( lm.put( nf32.data(), nf32.size()*sizeof(float) ) );
+    }
     const double* l1 = pn + 3*nn;
     const double* l2 = l1 + 2*h.lut_sofcosd_n;
     S.sofcosd.data = offAsPtr<double>( lm.put( l1, 2*h.lut_sofcosd_n*8 ) );

@@ -106,6 +106,7 @@ namespace ncb {
     const double* fam_inv2d;          // [nfam] ascending
     const int* fam_first;             // [nfam+1]
     const double* normals;            // [3*nnormals] lab frame
+    const float* normals_f;           // [3][nnormals] single-precision copy, SoA (pre-filter of k_sc_find only)
     SplineLutT sofcosd, evalcosx;
   };
 
