@@ -247,6 +247,7 @@ namespace ncb {
     double dom_lo, dom_hi;
     double* sc_xs; int32_t* sc_n;      // zeroed here for neutrons without candidates
     uint32_t* work; uint32_t* work_count; uint8_t* ncand; uint16_t* cand;   // work list (bit 31: overflow)
+    int32_t* wpos;                     // per neutron: its work-list position, -1 none, -2 overflow (for k_sc_sample)
   };
 
   __global__ void __launch_bounds__(32*kScFindWarps, 2)
@@ -338,7 +339,7 @@ namespace ncb {
         }
       }
       if ( count == 0 ) {
-        if ( lane == 0 ) { A.sc_xs[i] = 0.0; A.sc_n[i] = 0; }
+        if ( lane == 0 ) { A.sc_xs[i] = 0.0; A.sc_n[i] = 0; A.wpos[i] = -1; }
       } else {
         uint32_t pos = 0;
         if ( lane == 0 ) pos = atomicAdd( A.work_count, 1u );
@@ -346,6 +347,7 @@ namespace ncb {
         if ( lane == 0 ) {
           A.work[pos] = (uint32_t)i | ( overflow ? 0x80000000u : 0u );
           A.ncand[pos] = (uint8_t)( overflow ? 0 : count );
+          A.wpos[i] = overflow ? -2 : (int32_t)pos;
         }
         if ( !overflow && lane < count )
           A.cand[(size_t)pos*kScFindCap + lane] = ws.cand[lane];
@@ -398,6 +400,8 @@ namespace ncb {
     double* mu_tmp;                              // scratch: mu of the isotropic queue kernels
     uint32_t* nd_tmp;                            // scratch: stream position after isotropic sampling
     uint32_t* q_sc; uint32_t* q_sc_count;        // neutrons whose chosen component is SCBragg
+    // candidate lists recorded by k_sc_find (null: walk the normals again)
+    const int32_t* sc_wpos = nullptr; const uint8_t* sc_ncand = nullptr; const uint16_t* sc_cand = nullptr;
   };
 
   // total xs with precomputed SCBragg part (matXS, ncb_proc.cuh)
@@ -535,7 +539,20 @@ namespace ncb {
       double choice = -1.0; bool linear = true;
       if ( nent > 1 ) { choice = total * rng.generate(); linear = ( nent < 5 ); }
       ScAccum acc; double wl;
-      scWalkWarp( S, ws, fam_of, ekin, d, wl, acc, 1, linear, choice );
+      const int32_t wp = X.sc_wpos ? X.sc_wpos[i] : -2;
+      if ( wp >= 0 ) {
+        // the planes that can contribute were recorded by k_sc_find: select among them (same order, same values)
+        acc.cur_fam = -1; acc.n = 0; acc.xsoffset = acc.xssum = acc.commul_last = 0.0;
+        acc.found = false; acc.chosen_in = 0; acc.chosen_sign = 1;
+        const double ekr = scCacheRound( ekin );
+        wl = ekr ? sqrt( kWl2Ekin / ekr ) : kInf;
+        const int count = X.sc_ncand[wp];
+        if ( lane < count ) ws.cand[lane] = X.sc_cand[(size_t)wp*kScFindCap + lane];
+        __syncwarp();
+        scFlush( S, ws, fam_of, wl, d, count, acc, 1, linear, choice );
+      } else {
+        scWalkWarp( S, ws, fam_of, ekin, d, wl, acc, 1, linear, choice );
+      }
       const int in = acc.chosen_in;
       const double sg = acc.chosen_sign ? 1.0 : -1.0;   // vals[2k] = anti-normal, vals[2k+1] = normal
       const Vec3 pn = { sg*S.normals[3*in], sg*S.normals[3*in+1], sg*S.normals[3*in+2] };

@@ -381,6 +381,7 @@ namespace {
       double* sc_xs = nullptr; int32_t* sc_n = nullptr; double* mu_tmp = nullptr; uint32_t* nd_tmp = nullptr;
       uint32_t* q_sc = nullptr; size_t acap = 0;
       uint32_t* sc_work = nullptr; uint8_t* sc_ncand = nullptr; uint16_t* sc_cand = nullptr;   // k_sc_find -> k_sc_eval
+      int32_t* sc_wpos = nullptr; bool sc_lists_valid = false;
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
@@ -394,7 +395,7 @@ namespace {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
         if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
-                         cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); }
+                         cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); cudaFree( c.sc_wpos ); }
         if ( c.side ) cudaStreamDestroy( c.side );
         if ( c.ev_fork ) cudaEventDestroy( c.ev_fork );
         if ( c.ev_join ) cudaEventDestroy( c.ev_join );
@@ -437,7 +438,7 @@ namespace {
         if ( c.sc_xs ) {
           CUDA_OK( cudaDeviceSynchronize() );
           cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
-          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand );
+          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); cudaFree( c.sc_wpos );
         }
         c.acap = n + n/8 + 1024;
         CUDA_OK( cudaMalloc( &c.sc_xs, c.acap*sizeof(double) ) );
@@ -448,6 +449,7 @@ namespace {
         CUDA_OK( cudaMalloc( &c.sc_work, c.acap*sizeof(uint32_t) ) );
         CUDA_OK( cudaMalloc( &c.sc_ncand, c.acap ) );
         CUDA_OK( cudaMalloc( &c.sc_cand, c.acap*kScFindCap*sizeof(uint16_t) ) );
+        CUDA_OK( cudaMalloc( &c.sc_wpos, c.acap*sizeof(int32_t) ) );
       }
       return c;
     }
@@ -786,6 +788,7 @@ namespace {
     const uint64_t need = ( n + kScWarps - 1 ) / kScWarps;
     const unsigned nsm = (unsigned)numSMs( dm.device );
     // (small batches -- the tail of a transport run -- are launch-latency bound: one kernel instead of three launches)
+    qc.sc_lists_valid = false;
     if ( onekernel || n < 32768 || dm.sc_find_smem > 220u*1024u ) {
       ScScanArgs SA;
       SA.ekin = d_ekin; SA.ux = ux; SA.uy = uy; SA.uz = uz; SA.n = n; SA.sc_xs = qc.sc_xs; SA.sc_n = qc.sc_n;
@@ -802,6 +805,8 @@ namespace {
     FA.dom_lo = dm.mat.comp[isc].dom_lo; FA.dom_hi = dm.mat.comp[isc].dom_hi;
     FA.sc_xs = qc.sc_xs; FA.sc_n = qc.sc_n;
     FA.work = qc.sc_work; FA.work_count = qc.counts + 6; FA.ncand = qc.sc_ncand; FA.cand = qc.sc_cand;
+    FA.wpos = qc.sc_wpos;
+    qc.sc_lists_valid = true;
     CUDA_OK( cudaMemsetAsync( qc.counts + 6, 0, sizeof(uint32_t), st ) );
     const int cf = std::min( 3, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
     const uint64_t need_f = ( n + kScFindWarps - 1 ) / kScFindWarps;
@@ -878,6 +883,7 @@ namespace {
       AnisoArgs X;
       X.D = D; X.sc_xs = has_sc ? qc.sc_xs : nullptr; X.sc_n = has_sc ? qc.sc_n : nullptr;
       X.mu_tmp = qc.mu_tmp; X.nd_tmp = qc.nd_tmp; X.q_sc = qc.q_sc; X.q_sc_count = qc.counts + 5;
+      if ( has_sc && qc.sc_lists_valid ) { X.sc_wpos = qc.sc_wpos; X.sc_ncand = qc.sc_ncand; X.sc_cand = qc.sc_cand; }
       CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
       const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
       k_classify_aniso<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, A, Q, X );
