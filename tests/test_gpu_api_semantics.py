@@ -134,3 +134,31 @@ def test_handle_life_cycle(configs):
     assert h.internal and L.ncrystal_refcount(C.byref(h)) == 1
     L.ncrystal_invalidate(C.byref(h))
     assert L.ncrystal_valid(C.byref(h)) == 0
+
+
+def test_clones_on_concurrent_host_threads(configs):
+    # ncrystal.h:711-731: one handle per thread, clones share the immutable tables.  Four host threads, each with
+    # its own clone and its own stream indices, must reproduce what the same calls give one after the other.
+    import threading
+    from _libs import loguniform_energies
+    base = _sc(configs["CH2"], seed=11)
+    e = loguniform_energies(300001, seed=3)
+    clones = [base.clone(rng_stream_index=k) for k in range(4)]
+    ref = []
+    for c in clones:
+        st = c.getRNGStream()
+        ref.append((c.crossSectionIsotropic(e),) + tuple(c.sampleScatterIsotropic(e)))
+        c.setRNGStream(*st)
+    out = [None] * 4
+
+    def work(k):
+        c = clones[k]
+        out[k] = (c.crossSectionIsotropic(e),) + tuple(c.sampleScatterIsotropic(e))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(4):
+        for a, b in zip(out[k], ref[k]):
+            assert np.array_equal(a, b)
+    assert not np.array_equal(ref[0][2], ref[1][2])     # different stream indices => different samples
