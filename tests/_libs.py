@@ -148,6 +148,20 @@ class RefDrv:
         return eo, mu
 
 
+def _capi_sample_aniso(cls, cfg, ekin, ux, uy, uz, nthreads=None):
+    """Independent-stream oriented sampling through the reference's per-neutron C-API (ncrystal_samplescatter on
+    cloned handles, one per host thread)."""
+    ekin, ux, uy, uz = [np.ascontiguousarray(a, dtype=np.float64) for a in (ekin, ux, uy, uz)]
+    nthreads = nthreads or len(os.sched_getaffinity(0))
+    eo, ox, oy, oz = [np.empty_like(ekin) for _ in range(4)]
+    cls.lib().refdrv_bench_capi(cfg.encode(), 3, nthreads, 0, _d(ekin), _d(ux), _d(uy), _d(uz), ekin.size,
+                                _d(eo), _d(ox), _d(oy), _d(oz))
+    return eo, ox, oy, oz
+
+
+RefDrv.capi_sample_aniso = classmethod(_capi_sample_aniso)
+
+
 def _sab_dump(fn, h, c, iE, nbeta):
     x = np.zeros(nbeta + 1)
     pdf = np.zeros(nbeta + 1)

@@ -67,3 +67,38 @@ def test_mu_and_deltae_distributions(key, configs):
     ks = ks_2samp(np.concatenate(ks_mu_a), np.concatenate(ks_mu_b))
     print("%s KS(mu): D = %.2e p = %.3g" % (key, ks.statistic, ks.pvalue))
     assert ks.pvalue > P_MIN
+
+
+def test_oriented_distributions(configs):
+    """Same for the oriented single crystal: scattering-angle cosine, energy transfer and the azimuth of the outgoing
+    direction around the incoming one, against the reference's per-neutron ncrystal_samplescatter (2e7 samples)."""
+    import ncrystal_b200 as nc
+    from _libs import isotropic_directions
+    cfg = configs["Ge"]
+    n_tot = int(os.environ.get("NCB200_DIST_N_ORIENTED", "20000000"))
+    sc = nc.Scatter(cfg, seed=24680)
+    mu_edges = np.linspace(-1, 1, 201)
+    r_edges = np.concatenate([[-np.inf], np.linspace(-6, 6, 241), [np.inf]])
+    phi_edges = np.linspace(-np.pi, np.pi, 73)
+    tot = {}
+    done = 0
+    while done < n_tot:
+        m = min(5_000_000, n_tot - done)
+        e = loguniform_energies(m, seed=77 + done)
+        ux, uy, uz = isotropic_directions(m, seed=99 + done)
+        res = {"g": sc.sampleScatter(e, (ux, uy, uz)), "r": RefDrv.capi_sample_aniso(cfg, e, ux, uy, uz)}
+        for who, (eo, (ox, oy, oz)) in (("g", (res["g"][0], res["g"][1])), ("r", (res["r"][0], res["r"][1:]))):
+            mu = np.clip(ux * ox + uy * oy + uz * oz, -1, 1)
+            el = eo == e
+            with np.errstate(divide="ignore"):
+                lr = np.log10(np.maximum(eo[~el], 1e-300) / e[~el])
+            # azimuth of the outgoing direction in a frame fixed to the LAB z axis (the crystal is oriented)
+            phi = np.arctan2(oy, ox)
+            h = (np.histogram(mu, mu_edges)[0], np.concatenate([[el.sum()], np.histogram(lr, r_edges)[0]]),
+                 np.histogram(phi, phi_edges)[0])
+            tot[who] = h if who not in tot else tuple(a + b for a, b in zip(tot[who], h))
+        done += m
+    for k, name in enumerate(("mu", "de", "phi_lab")):
+        stat, dof, p = _chi2_two_sample(tot["g"][k], tot["r"][k])
+        print("Ge %s: chi2/dof = %.1f/%d  p = %.3g  (N = %d)" % (name, stat, dof, p, n_tot))
+        assert p > P_MIN, (name, stat, dof, p)
