@@ -778,6 +778,14 @@ namespace {
     return -1;
   }
 
+  // Batches below this size (the long tail of a transport run) are launch-latency bound: the all-in-one
+  // thread-per-neutron kernels (1 launch instead of 2-8) are used for them.  NCB200_SMALL_V1 overrides (0 = never).
+  uint64_t smallBatchV1()
+  {
+    static const uint64_t v = []{ const char* e = std::getenv( "NCB200_SMALL_V1" ); return e ? (uint64_t)std::atoll(e) : (uint64_t)0; }();
+    return v;
+  }
+
   // SCBragg scan (one warp per neutron) -> sc_xs / sc_n.  Default: lean candidate search (k_sc_find) + evaluation of
   // the neutrons that have candidates (k_sc_eval); NCB200_SC_ONEKERNEL=1 selects the combined k_sc_scan.
   void launchScScan( const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
@@ -825,7 +833,7 @@ namespace {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     const bool has_sc = scCompIndex( dm.mat ) >= 0;
-    if ( useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) ) {
+    if ( useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || n < smallBatchV1() ) {
       DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = D.oy = D.oz = nullptr;
       const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
       k_xs_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, D, n, d_out );
@@ -856,7 +864,7 @@ namespace {
     int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
     const bool has_sc = scCompIndex( dm.mat ) >= 0;
-    const bool v1 = useAnisoV1() || ( has_sc && !dm.sc_warp_ok );
+    const bool v1 = useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || n < smallBatchV1();
     const uint64_t maxn = v1 ? n : ( (uint64_t)1 << kQueueIdxBits );
     for ( uint64_t done = 0; done < n; done += maxn ) {
       const uint64_t m = std::min<uint64_t>( maxn, n - done );
