@@ -125,7 +125,7 @@ namespace ncb {
     Comp comp[kMaxComp];
     PowderBraggT pb[2];
     ElIncT elinc[1];
-    FreeGasT fg[2];
+    FreeGasT fg[kMaxComp];   // (gas mixtures: one free-gas leaf per element)
     SabT sab[4];
     ScBraggT sc;   // at most one SCBragg component (oriented materials only)
   };

@@ -128,10 +128,10 @@ typedef struct {
   int ncomp, oriented;
   double dom_lo, dom_hi;
   orc_comp comp[ORC_MAXCOMP];
-  orc_pb pb[2]; int npb;
-  orc_elinc elinc[1]; int nel;
-  orc_fg fg[2]; int nfg;
-  orc_sab sab[4]; int nsab;
+  orc_pb pb[ORC_MAXCOMP]; int npb;         /* (one slot per possible component of each kind) */
+  orc_elinc elinc[ORC_MAXCOMP]; int nel;
+  orc_fg fg[ORC_MAXCOMP]; int nfg;
+  orc_sab sab[ORC_MAXCOMP]; int nsab;
   orc_sc sc; int nsc;
   char err[256];
 } orc_material;

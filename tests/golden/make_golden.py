@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from _libs import RefDrv, loguniform_energies, isotropic_directions  # noqa: E402
-from __graft_entry__ import CONFIGS  # noqa: E402
+from __graft_entry__ import CONFIGS, EXTRA_CONFIGS  # noqa: E402
 
 GOLDEN_SEED = 20261017
 N = 4000
@@ -52,7 +52,10 @@ def oriented_inputs(n):
 
 
 def main():
-    for key, cfg in CONFIGS.items():
+    only = sys.argv[1:]
+    for key, cfg in list(CONFIGS.items()) + list(EXTRA_CONFIGS.items()):
+        if only and key not in only:
+            continue
         r = RefDrv(cfg)
         if RefDrv.lib().refdrv_isoriented(r.h):
             e, ux, uy, uz = oriented_inputs(N)
