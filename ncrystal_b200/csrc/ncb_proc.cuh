@@ -11,7 +11,6 @@ namespace ncb {
   // The small, hot lookup tables of the cross-section path.  The pointers are either
   // the material's global-memory arrays or their per-CTA copies staged into shared
   // memory by TMA bulk copies (ncb_kernels.cu: stageHotTabs).
-  constexpr int kMaxPB = 2, kMaxSab = 4;
   struct HotTabs {
     const double* pb_e2d[kMaxPB];
     const double* pb_fdm[kMaxPB];

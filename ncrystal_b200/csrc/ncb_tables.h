@@ -13,6 +13,7 @@ namespace ncb {
                     KIND_ABSOOV = 6 /* 1/v absorption, ref: src/absoov/NCAbsOOV.cc:33-45; not a blob kind */ };
 
   constexpr int kMaxComp = 8;
+  constexpr int kMaxPB = 4, kMaxSab = 8;   // PowderBragg / S(alpha,beta) leaves per material (multiphase mixes)
   constexpr int kMaxElIncElems = 12;
 
   // ref: NCPowderBragg.hh:91-93
@@ -123,10 +124,10 @@ namespace ncb {
     int oriented;
     double dom_lo, dom_hi;
     Comp comp[kMaxComp];
-    PowderBraggT pb[2];
+    PowderBraggT pb[kMaxPB];
     ElIncT elinc[1];
     FreeGasT fg[kMaxComp];   // (gas mixtures: one free-gas leaf per element)
-    SabT sab[4];
+    SabT sab[kMaxSab];
     ScBraggT sc;   // at most one SCBragg component (oriented materials only)
   };
 

@@ -11,7 +11,7 @@ from conftest import HERE
 from _libs import HostSim
 from _oracle_port import PortOracle
 
-EXTRA_ISO = ["Be", "D2O", "AlBe", "gas", "CH2_77K", "V"]
+EXTRA_ISO = ["Be", "D2O", "AlBe", "gas", "CH2_77K", "V", "YAGCor"]
 EXTRA_ANISO = ["Cu_sc"]
 
 

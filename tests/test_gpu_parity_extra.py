@@ -8,7 +8,7 @@ import pytest
 from conftest import HERE
 
 pytestmark = pytest.mark.gpu
-EXTRA_ISO = ["Be", "D2O", "AlBe", "gas", "CH2_77K", "V"]
+EXTRA_ISO = ["Be", "D2O", "AlBe", "gas", "CH2_77K", "V", "YAGCor"]
 EXTRA_ANISO = ["Cu_sc"]
 
 
