@@ -400,9 +400,9 @@ def main():
         dom_bytes = dom_units * BYTES_SAMPLE
     else:
         dom_units, dom_ms, ach, dom_bytes = n, ms_fused, ach_seq, n * BYTES_FUSED
-    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r1_kernels_v6_metrics.csv,
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r1_kernels_final_ncu_full.csv,
     # same command, 1e7-neutron Al batch): dram__bytes_read.sum + dram__bytes_write.sum per launch.
-    traffic = 368.6e6 if n == N_PER_GPU else None
+    traffic = 370.7e6 if n == N_PER_GPU else None
     out = {
         "metric": "neutrons/sec (xs eval + sampleScatter)", "value": value, "unit": "neutrons/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
