@@ -84,6 +84,10 @@ void ncrystal_samplescatterisotropic_many( ncrystal_scatter_t, const double * ek
 void ncrystal_samplescatter_many( ncrystal_scatter_t, double ekin, const double (*direction)[3], unsigned long repeat,
                                   double* results_ekin, double * results_dirx, double * results_diry, double * results_dirz );
 
+/* ncrystal.h:1147-1148 -- unit conversions (Aa <-> eV) */
+double ncrystal_wl2ekin( double wl );
+double ncrystal_ekin2wl( double ekin );
+
 /* ncrystal.h:1030-1045 -- error state: global, message printed unless quiet, process
  * exit(1) unless ncrystal_sethaltonerror(0); non-halting calls fill outputs with
  * -1.0 (xs, ekin) / -999 (mu) / 0-vector (direction). */

@@ -93,6 +93,8 @@ SIGNATURES = {
     "ncb200_component_scale": (C.c_double, [ncrystal_process_t, C.c_int]),
     "ncb200_kernel_launch_count": (_u64, []),
     "ncb200_table_bytes": (_u64, [ncrystal_process_t]),
+    "ncrystal_wl2ekin": (C.c_double, [C.c_double]),
+    "ncrystal_ekin2wl": (C.c_double, [C.c_double]),
     "ncrystal_cast_abs2proc": (ncrystal_process_t, [ncrystal_absorption_t]),
     "ncrystal_cast_proc2abs": (ncrystal_absorption_t, [ncrystal_process_t]),
     "ncrystal_create_absorption": (ncrystal_absorption_t, [C.c_char_p]),

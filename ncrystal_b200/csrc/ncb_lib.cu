@@ -1451,6 +1451,10 @@ extern "C" {
     } NCBCATCH;
     return -1.0;
   }
+  // ref: ncrystal.cc:1051-1059 (NCDefs.hh:834-845)
+  double ncrystal_wl2ekin( double wl ) { const double w2 = wl*wl; return w2 ? kWl2Ekin / w2 : kInf; }
+  double ncrystal_ekin2wl( double ekin ) { return ekin ? std::sqrt( kWl2Ekin / ekin ) : kInf; }
+
   uint64_t ncb200_kernel_launch_count(void) { return g_launches.load(); }
 
   void ncb200_kernel_timing( int enable )

@@ -113,3 +113,19 @@ def test_blob_layout_al(configs):
     assert h["nbytes"] == len(blob)
     egrid, xs = sab_grids(blob, 2)
     assert egrid.size == 300 and np.all(np.diff(egrid) > 0) and abs(egrid[-1] - 5.0) < 1e-9
+
+
+def _build_capi_caller(tmpdir):
+    import subprocess
+    exe = os.path.join(str(tmpdir), "capi_caller")
+    libdir = os.path.join(ROOT, "ncrystal_b200", "lib")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "capi_caller.c"), "-o", exe, "-L", libdir, "-lncrystal_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_plain_c_caller_compiles_and_links_against_the_header(tmp_path):
+    # a C99 translation unit written against include/ncrystal_b200.h only (call sequence of the reference's
+    # examples/ncrystal_example_c.c) builds warning-free and resolves every symbol from the library
+    assert os.path.exists(_build_capi_caller(tmp_path))

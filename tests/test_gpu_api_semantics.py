@@ -162,3 +162,24 @@ def test_clones_on_concurrent_host_threads(configs):
         for a, b in zip(out[k], ref[k]):
             assert np.array_equal(a, b)
     assert not np.array_equal(ref[0][2], ref[1][2])     # different stream indices => different samples
+
+
+def test_plain_c_caller_runs(tmp_path, configs):
+    # the C program of tests/capi_caller.c (the reference example's call sequence) against the library
+    import subprocess
+    from test_cpu_blob import _build_capi_caller
+    from _mmc import cached_oracle
+    exe = _build_capi_caller(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    kv = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    o, _ = cached_oracle("Al")
+    e = 0.081804209605330899 / 2.5 ** 2
+    assert abs(float(kv["al_xs_2.5Aa"][0]) - o.xs_iso(np.array([e]))[0]) <= 1e-12 * float(kv["al_xs_2.5Aa"][0])
+    ref = o.xs_iso(np.array([0.081804209605330899 / (1.0 + i) ** 2 for i in range(4)]))
+    assert np.allclose([float(x) for x in kv["al_xs_many"]], ref, rtol=1e-12, atol=0)
+    assert kv["al_refcount"] == ["1"] and kv["handles_cleared"] == ["1"] and kv["ge_isnonoriented"] == ["0"]
+    # the reference's known answers for this crystal and wavelength (_testimpl.py:253-254)
+    assert float(kv["ge_xs_dir1"][0]) == pytest.approx(591.0263476502018, rel=1e-6)
+    assert float(kv["ge_xs_dir2"][0]) == pytest.approx(1.667600586136298, rel=1e-6)
+    assert abs(float(kv["ge_outdir_norm2"][0]) - 1.0) < 1e-9
