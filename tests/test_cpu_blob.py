@@ -129,3 +129,17 @@ def test_plain_c_caller_compiles_and_links_against_the_header(tmp_path):
     # a C99 translation unit written against include/ncrystal_b200.h only (call sequence of the reference's
     # examples/ncrystal_example_c.c) builds warning-free and resolves every symbol from the library
     assert os.path.exists(_build_capi_caller(tmp_path))
+
+
+def _build_cxx_caller(tmpdir):
+    import subprocess
+    exe = os.path.join(str(tmpdir), "cxx_caller")
+    libdir = os.path.join(ROOT, "ncrystal_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cxx_caller.cc"), "-o", exe, "-L", libdir, "-lncrystal_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cxx_mirror_compiles_and_links(tmp_path):
+    assert os.path.exists(_build_cxx_caller(tmp_path))

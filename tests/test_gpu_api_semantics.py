@@ -183,3 +183,18 @@ def test_plain_c_caller_runs(tmp_path, configs):
     assert float(kv["ge_xs_dir1"][0]) == pytest.approx(591.0263476502018, rel=1e-6)
     assert float(kv["ge_xs_dir2"][0]) == pytest.approx(1.667600586136298, rel=1e-6)
     assert abs(float(kv["ge_outdir_norm2"][0]) - 1.0) < 1e-9
+
+
+def test_cxx_mirror_runs(tmp_path):
+    # include/ncrystal_b200.hh (NCrystal::Scatter / Absorption method names) from a C++17 program
+    import subprocess
+    from test_cpu_blob import _build_cxx_caller
+    from _mmc import cached_oracle
+    out = subprocess.run([_build_cxx_caller(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    kv = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    o, hdr = cached_oracle("Al")
+    assert abs(float(kv["al_xs"][0]) - o.xs_iso(np.array([0.0253]))[0]) <= 1e-12 * float(kv["al_xs"][0])
+    assert kv["al_sample_ok"] == ["1"] and kv["al_batch"] == ["1000", "1000", "1000"] and kv["clone_xs_equal"] == ["1"]
+    assert abs(float(kv["al_abs_xs_2200"][0]) - hdr["abs_c"] / np.sqrt(0.02529886)) < 1e-12
+    assert kv["minimc_json_ok"] == ["1"] and kv["bad_cfg_throws"] == ["1"]
