@@ -117,6 +117,10 @@ namespace ncb {
     const uint64_t* ids = nullptr;   // optional: random-stream index of neutron i (transport: source particle id);
                                      // default first_index + i
     NCB_HD uint64_t streamIndex( uint64_t i ) const { return ids ? ids[i] : first_index + i; }
+    // optional: the number of neutrons lives on the device (<= n); used by the transport step to run several steps
+    // without a host round trip (grids are sized for n, the kernels stop at *n_dev)
+    const uint32_t* n_dev = nullptr;
+    __device__ __forceinline__ uint64_t count() const { return n_dev ? (uint64_t)min( (uint64_t)*n_dev, n ) : n; }
   };
 
   __global__ void __launch_bounds__(128)

@@ -79,9 +79,11 @@ namespace ncb {
   __global__ void __launch_bounds__(256)
   k_mmc_forward( const __grid_constant__ MmcGeom G, const __grid_constant__ MmcEngine E, uint64_t seed, uint32_t step,
                  uint32_t n, MmcState A, const double* __restrict__ xs, double* __restrict__ wt,
-                 MmcState B, uint32_t* counter )
+                 MmcState B, uint32_t* counter, const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ n_log )
   {
     __shared__ uint32_t s_warp[8], s_base;
+    if ( n_dev ) n = min( *n_dev, n );      // population count kept on the device (several steps per host sync)
+    if ( n_log && blockIdx.x == 0 && threadIdx.x == 0 ) *n_log = n;
     const uint32_t n_up = ( n + blockDim.x - 1 )/blockDim.x*blockDim.x;
     for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n_up; i += gridDim.x*blockDim.x ) {
       MmcStepOut o; o.survives = false;
@@ -107,8 +109,9 @@ namespace ncb {
   // after the scattering kernels: SimEngine.cc:392-404
   __global__ void __launch_bounds__(256)
   k_mmc_post( uint32_t n, MmcState B, const double* __restrict__ eout, const double* __restrict__ ox,
-              const double* __restrict__ oy, const double* __restrict__ oz )
+              const double* __restrict__ oy, const double* __restrict__ oz, const uint32_t* __restrict__ n_dev )
   {
+    if ( n_dev ) n = min( *n_dev, n );
     for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x ) {
       const double e_new = eout[i];
       const bool was_elastic = ( B.ekin[i] == e_new );
@@ -130,9 +133,10 @@ namespace ncb {
   // dynamic smem: mmcHistDoubles(max nbins) doubles.
   __global__ void __launch_bounds__(256)
   k_mmc_tally( const __grid_constant__ MmcTally T, uint32_t n, MmcState A, const double* __restrict__ wt,
-               double* __restrict__ tally )
+               double* __restrict__ tally, const uint32_t* __restrict__ n_dev )
   {
     extern __shared__ __align__(16) double sh[];
+    if ( n_dev ) n = min( *n_dev, n );
     const int lane = threadIdx.x & 31;
     const uint32_t n_up = ( n + 31u ) & ~31u;
     for ( int ih = 0; ih < T.nh; ++ih ) {
@@ -229,9 +233,10 @@ namespace ncb {
 
   // sum of the tallied weights and record count (metadata "tallied"): block reduction
   __global__ void __launch_bounds__(256)
-  k_mmc_sum_weights( uint32_t n, const double* __restrict__ w, double* __restrict__ out )
+  k_mmc_sum_weights( uint32_t n, const double* __restrict__ w, double* __restrict__ out, const uint32_t* __restrict__ n_dev )
   {
     __shared__ double s[8];
+    if ( n_dev ) n = min( *n_dev, n );
     double a = 0.0;
     for ( uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x ) a += w[i];
     for ( int d = 16; d; d >>= 1 ) a += __shfl_xor_sync( 0xffffffffu, a, d );

@@ -195,6 +195,7 @@ namespace ncb {
     double* sc_xs;     // out: unscaled SCBragg xs
     int32_t* sc_n;     // out: entries of xs_commul
     double dom_lo, dom_hi;   // the SCBragg component's domain
+    const uint32_t* n_dev = nullptr;   // see SampleArgs::n_dev
   };
 
   // dynamic smem layout: [staged tables (sp.total)] [fam_of: nnormals bytes, 16-aligned] [kScWarps x ScWarpScratch]
@@ -211,7 +212,8 @@ namespace ncb {
     ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
     const int lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t)gridDim.x * kScWarps;
-    for ( uint64_t i = (uint64_t)blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); i < A.n; i += nwarps ) {
+    const uint64_t ntot = A.n_dev ? (uint64_t)min( (uint64_t)*A.n_dev, A.n ) : A.n;
+    for ( uint64_t i = (uint64_t)blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); i < ntot; i += nwarps ) {
       const double ekin = A.ekin[i];
       double xs = 0.0; int nent = 0;
       if ( domainContains( A.dom_lo, A.dom_hi, ekin ) && !( ekin <= S.threshold_ekin ) ) {
@@ -429,12 +431,13 @@ namespace ncb {
   __global__ void __launch_bounds__(256)
   k_xs_aniso_pre( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
                   const double* __restrict__ ekin, const double* __restrict__ sc_xs, const int32_t* __restrict__ sc_n,
-                  uint64_t n, double* __restrict__ out )
+                  uint64_t n, double* __restrict__ out, const uint32_t* __restrict__ n_dev )
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
+    if ( n_dev ) n = min( (uint64_t)*n_dev, n );
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride )
       out[i] = matXSPre( M, H, ekin[i], sc_xs ? sc_xs[i] : 0.0, sc_n ? sc_n[i] : 0, nullptr, nullptr );
@@ -451,11 +454,12 @@ namespace ncb {
     stageHotTabs( M, sp, smem, &mbar, H );
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     int errs = 0;
-    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < A.n; base += stride ) {
+    const uint64_t ntot = A.count();
+    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < ntot; base += stride ) {
       const uint64_t i = base + threadIdx.x;
       int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue, 3: SCBragg queue
       uint32_t entry = 0;
-      if ( i < A.n ) {
+      if ( i < ntot ) {
         const double ekin = A.ekin[i];
         const Vec3 dir = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
         double eout = ekin, tot = 0.0;

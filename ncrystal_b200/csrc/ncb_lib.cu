@@ -363,6 +363,7 @@ namespace {
     uint32_t sid = 0;
     uint64_t next_index = 0;
     int* d_err = nullptr;
+    const uint32_t* n_dev_override = nullptr; // transport: device-side neutron count for the next launches
     const uint64_t* ids_override = nullptr; // transport: device array of random-stream indices for the next sampling launch
     uint32_t* last_counts_ptr = nullptr;   // queue counters of the most recent split-path launch (diagnostics)
     uint32_t* d_diag_ndraws = nullptr;
@@ -789,7 +790,7 @@ namespace {
   // SCBragg scan (one warp per neutron) -> sc_xs / sc_n.  Default: lean candidate search (k_sc_find) + evaluation of
   // the neutrons that have candidates (k_sc_eval); NCB200_SC_ONEKERNEL=1 selects the combined k_sc_scan.
   void launchScScan( const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
-                     const double* uy, const double* uz, uint64_t n, cudaStream_t st )
+                     const double* uy, const double* uz, uint64_t n, cudaStream_t st, const uint32_t* n_dev = nullptr )
   {
     static const bool onekernel = []{ const char* e = std::getenv( "NCB200_SC_ONEKERNEL" ); return e && std::atoi(e) != 0; }();
     const int isc = scCompIndex( dm.mat );
@@ -797,10 +798,11 @@ namespace {
     const unsigned nsm = (unsigned)numSMs( dm.device );
     // (small batches -- the tail of a transport run -- are launch-latency bound: one kernel instead of three launches)
     qc.sc_lists_valid = false;
-    if ( onekernel || n < 32768 || dm.sc_find_smem > 220u*1024u ) {
+    if ( onekernel || n < 32768 || n_dev || dm.sc_find_smem > 220u*1024u ) {
       ScScanArgs SA;
       SA.ekin = d_ekin; SA.ux = ux; SA.uy = uy; SA.uz = uz; SA.n = n; SA.sc_xs = qc.sc_xs; SA.sc_n = qc.sc_n;
       SA.dom_lo = dm.mat.comp[isc].dom_lo; SA.dom_hi = dm.mat.comp[isc].dom_hi;
+      SA.n_dev = n_dev;
       const int ctas = std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) );
       const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*std::min( ctas, 8 ) );
       k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off );
@@ -844,11 +846,11 @@ namespace {
     const double* sc_xs = nullptr; const int32_t* sc_n = nullptr;
     if ( has_sc ) {
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, n );
-      launchScScan( dm, qc, d_ekin, ux, uy, uz, n, st );
+      launchScScan( dm, qc, d_ekin, ux, uy, uz, n, st, s->n_dev_override );
       sc_xs = qc.sc_xs; sc_n = qc.sc_n;
     }
     const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
-    k_xs_aniso_pre<<< gridFor( n, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, d_ekin, sc_xs, sc_n, n, d_out );
+    k_xs_aniso_pre<<< gridFor( n, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, d_ekin, sc_xs, sc_n, n, d_out, s->n_dev_override );
     ++g_launches;
     CUDA_OK( cudaGetLastError() );
   }
@@ -874,6 +876,7 @@ namespace {
       A.ndraws = diag_nd ? diag_nd + done : nullptr; A.component = diag_comp ? diag_comp + done : nullptr;
       A.err_flags = s->d_err;
       A.ids = s->ids_override ? s->ids_override + done : nullptr;
+      A.n_dev = s->n_dev_override;
       DirArgs D; D.ux = ux + done; D.uy = uy + done; D.uz = uz + done; D.ox = ox + done; D.oy = oy + done; D.oz = oz + done;
       if ( v1 ) {
         const int ctas = dm.sp.total > 56u*1024u ? 2 : 4;
@@ -884,7 +887,7 @@ namespace {
       }
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, m );
       if ( has_sc )
-        launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st );
+        launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
       Q.q_sab_sorted = Q.q_fg_sorted = nullptr; Q.hist = nullptr;
