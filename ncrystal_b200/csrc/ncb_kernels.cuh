@@ -605,6 +605,352 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
+  // Free-gas samplers as a staged pipeline over the free-gas queue.  Run neutron-per-lane (k_sample_fg above), a warp
+  // waits for its unluckiest lane twice: the beta sampler is a rejection loop with a long tail (Al above Emax: 4.2
+  // attempts on average, 15 for the worst of 32 lanes) and so is the alpha sampler (6.7 uniforms on average, 27 for the
+  // worst of 32); ncu: 9.9 of 32 lanes active.  Here each stage is a kernel in which all lanes run the same code:
+  //   k_fg_prep        per entry: everything before the beta loop -- the high-E analysis of an S(alpha,beta) leaf
+  //                    (discard / table at E=Emax / go on; <= 1 uniform) and the support [aa,bb] of the beta
+  //                    distribution (FreeGasSampler::betaSupport: erfc evaluations, no uniforms);
+  //   k_fg_beta        attempt-level: every pass of its loop runs ONE attempt of the beta rejection loop per lane; a
+  //                    lane whose beta was accepted stores it and pulls the next queue entry before the next pass;
+  //   k_fg_alpha_prep  per entry: the cheap alpha cases are finished, for the others the set-up of the alpha
+  //                    rejection loop (xsBegin) is stored;
+  //   k_fg_alpha       attempt-level, like k_fg_beta, over the alpha rejection loop (xsAttempt);
+  //   k_fg_finish      per entry: (alpha,beta) -> outcome; S(alpha,beta) leaves: accept / table at E=Emax / draw
+  //                    again (rare: finished in place with the plain nested loops).
+  // The state of a neutron between stages is a per-entry record (9 doubles + 1 word); its random stream is resumed
+  // from the number of uniforms consumed so far.  Each neutron consumes its uniforms in the reference's order
+  // (NCFreeGasUtils.cc:530-935, NCSABSampler.cc:59-156).
+  struct FgPrep {
+    double* r;        // records: slot k of entry j at r[k*cap + j]
+    uint64_t cap;
+    uint32_t* w;      // uniforms consumed so far (low 25 bits) | flags (bits 25-27) | stage (bits 28-31); kFgSkip: done
+    uint32_t* cursor; // refill cursors: [0] k_fg_beta, [1] k_fg_alpha
+    uint32_t epl;     // refill kernels: target number of entries per lane (surplus CTAs exit at once)
+    __device__ __forceinline__ double& slot( int k, uint32_t j ) const { return r[ (uint64_t)k*cap + j ]; }
+  };
+  constexpr uint32_t kFgSkip = 0xFFFFFFFFu;
+  constexpr uint32_t kFgNdMask = ( 1u << 25 ) - 1u;
+  // stages: 0..2 = FreeGasSampler::kBetaLoop/kBetaHighE/kBetaFixed (after k_fg_prep), then:
+  enum { kFgBetaDone = 3, kFgAlphaDone = 4, kFgAlphaLoop = 5, kFgXDone = 6 };
+  // record slots
+  enum { kSlotAA = 0, kSlotBB = 1, kSlotPdisc = 2, kSlotBeta = 3,               // prep / beta
+         kSlotC = 0, kSlotXm = 1, kSlotXp = 4, kSlotXmax = 5, kSlotXswitch = 6,  // alpha loop state
+         kSlotPflat = 7, kSlotAright = 8,
+         kSlotAlpha = 0,                                                         // result of the alpha stage (alpha or x)
+         kFgSlots = 9 };
+
+  __device__ __forceinline__ void fgLeafPars( const Material& M, const Comp& c, double& kT, double& mass )
+  {
+    if ( c.kind == KIND_FREEGAS ) { kT = M.fg[c.idx].kT; mass = M.fg[c.idx].mass_amu; }
+    else { kT = M.sab[c.idx].ext.kT; mass = M.sab[c.idx].ext.mass_amu; }
+  }
+
+  // paired push of (entry, stream position) to the E=Emax queue; called by all lanes of a warp
+  __device__ __forceinline__ void pushEmax( bool pred, const QueueArgs& Q, uint32_t entry, uint32_t nd )
+  {
+    const uint32_t mask = __ballot_sync( 0xffffffffu, pred );
+    if ( !mask ) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs( mask ) - 1;
+    uint32_t base = 0;
+    if ( lane == leader )
+      base = atomicAdd( Q.counts + 2, (uint32_t)__popc( mask ) );
+    base = __shfl_sync( 0xffffffffu, base, leader );
+    if ( pred ) {
+      const uint32_t pos = base + __popc( mask & ( ( 1u << lane ) - 1u ) );
+      Q.q_emax[2*pos] = entry;
+      Q.q_emax[2*pos+1] = nd;
+    }
+  }
+
+  __global__ void __launch_bounds__(128)
+  k_fg_prep( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+             const __grid_constant__ QueueArgs Q, const __grid_constant__ FgPrep P )
+  {
+    const uint32_t nq = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nq_up = ( nq + 31u ) & ~31u;   // warp-uniform trip count (full-mask ballots in pushEmax)
+    int errs = 0;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq_up; j += stride ) {
+      bool to_emax = false;
+      uint32_t entry = 0, nd = 0;
+      if ( j < nq ) {
+        entry = Q.q_fg[j];
+        const uint32_t i = entry & kQueueIdxMask;
+        const Comp& c = M.comp[ entry >> kQueueIdxBits ];
+        const double ekin = A.ekin[i];
+        nd = M.ncomp > 1 ? 1u : 0u;
+        double pdisc = 0.0;
+        int begin = kHighEGoOn;
+        if ( c.kind != KIND_FREEGAS ) {
+          Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
+          rng.seek( nd );
+          int err = 0;
+          begin = sabHighEBegin( M.sab[c.idx], ekin, rng, pdisc, err );
+          nd = rng.ndraws;
+          errs |= err;
+        }
+        if ( begin == kHighEDiscard ) {
+          A.ekin_out[i] = -1.0;
+          A.mu_out[i] = -999.0;
+          if ( A.ndraws ) A.ndraws[i] = nd;
+          P.w[j] = kFgSkip;
+        } else if ( begin == kHighEToEmax ) {
+          to_emax = true;
+          P.w[j] = kFgSkip;
+        } else {
+          double kT, mass;
+          fgLeafPars( M, c, kT, mass );
+          FreeGasSampler s( ekin, kT, mass );
+          double aa, bb;
+          const int kind = s.betaSupport( aa, bb );
+          P.slot( kSlotAA, j ) = aa; P.slot( kSlotBB, j ) = bb; P.slot( kSlotPdisc, j ) = pdisc;
+          P.w[j] = nd | ( (uint32_t)kind << 28 );
+        }
+      }
+      pushEmax( to_emax, Q, entry, nd );
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
+  // Work distribution of the two attempt-level kernels: lanes pull queue positions from a global cursor
+  // (warp-aggregated atomic).  Returns the position for this lane (>= nq: none) and whether the queue is drained.
+  __device__ __forceinline__ uint32_t fgPull( uint32_t need, bool mine, uint32_t* cursor, uint32_t nq, bool& drained )
+  {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    const int leader = __ffs( need ) - 1;
+    if ( lane == leader )
+      base = atomicAdd( cursor, (uint32_t)__popc( need ) );
+    base = __shfl_sync( 0xffffffffu, base, leader );
+    drained = ( base >= nq || nq - base <= (uint32_t)__popc( need ) );
+    return mine ? base + __popc( need & ( ( 1u << lane ) - 1u ) ) : 0xFFFFFFFFu;
+  }
+
+  template <int kMinBlocks>
+  __global__ void __launch_bounds__(128, kMinBlocks)
+  k_fg_beta( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+             const __grid_constant__ QueueArgs Q, const __grid_constant__ FgPrep P )
+  {
+    const uint32_t nq = Q.counts[1];
+    if ( (uint64_t)blockIdx.x * blockDim.x * P.epl >= nq && blockIdx.x )
+      return;
+    bool have = false, drained = false;
+    uint32_t jrec = 0;
+    FreeGasSampler s;
+    FreeGasSampler::BetaState st;
+    Rng rng; rng.init( A.seed, A.first_index, A.sid );
+    while ( true ) {
+      const uint32_t need = __ballot_sync( 0xffffffffu, !have );
+      if ( need ) {
+        const uint32_t j = fgPull( need, !have, P.cursor + 0, nq, drained );
+        if ( !have && j < nq ) {
+          const uint32_t w = P.w[j];
+          if ( w != kFgSkip ) {
+            const uint32_t entry = Q.q_fg[j];
+            const uint32_t i = entry & kQueueIdxMask;
+            double kT, mass;
+            fgLeafPars( M, M.comp[ entry >> kQueueIdxBits ], kT, mass );
+            s = FreeGasSampler( A.ekin[i], kT, mass );
+            rng.init( A.seed, A.streamIndex( i ), A.sid );
+            rng.seek( w & kFgNdMask );
+            const int kind = (int)( w >> 28 );
+            const double aa = P.slot( kSlotAA, j );
+            if ( kind != FreeGasSampler::kBetaLoop ) {
+              P.slot( kSlotBeta, j ) = s.betaDirect( kind, aa, rng );
+              P.w[j] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
+            } else {
+              s.betaBegin( st, aa, P.slot( kSlotBB, j ) );
+              jrec = j;
+              have = true;
+            }
+          }
+        }
+      }
+      if ( !__ballot_sync( 0xffffffffu, have ) ) {
+        if ( drained ) break;    // nothing in flight and nothing left to pull
+        continue;                // only finished records were met: pull again
+      }
+      if ( have ) {
+        double beta;
+        if ( s.betaAttempt( st, rng, beta ) ) {
+          P.slot( kSlotBeta, jrec ) = beta;
+          P.w[jrec] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
+          have = false;
+        }
+      }
+    }
+  }
+
+  __global__ void __launch_bounds__(128)
+  k_fg_alpha_prep( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+                   const __grid_constant__ QueueArgs Q, const __grid_constant__ FgPrep P )
+  {
+    const uint32_t nq = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
+      const uint32_t w = P.w[j];
+      if ( w == kFgSkip ) continue;
+      const uint32_t entry = Q.q_fg[j];
+      const uint32_t i = entry & kQueueIdxMask;
+      const Comp& c = M.comp[ entry >> kQueueIdxBits ];
+      const double ekin = A.ekin[i];
+      double kT, mass;
+      fgLeafPars( M, c, kT, mass );
+      FreeGasSampler s( ekin, kT, mass );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
+      rng.seek( w & kFgNdMask );
+      const double beta = P.slot( kSlotBeta, j );
+      const bool iso = muIsotropicAtBeta( beta, s.m_c );
+      if ( c.kind == KIND_FREEGAS && ( beta <= -s.m_c || iso ) ) {
+        // FreeGasSampler::sampleDeltaEMu, isotropic branch (NCFreeGasUtils.hh:163-167)
+        const double mu = rng.generate()*2.0 - 1.0;
+        A.ekin_out[i] = dmax( 0.0, ekin + beta*s.m_kT );
+        A.mu_out[i] = mu;
+        if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+        P.w[j] = kFgSkip;
+        continue;
+      }
+      double alpha;
+      int kind = FreeGasSampler::kAlphaDone;
+      XSamplerState st;
+      if ( c.kind != KIND_FREEGAS && ( beta < -s.m_c || iso ) ) {
+        // FreeGasSampler::sampleAlphaBeta, flat branch (NCFreeGasUtils.hh:149-154)
+        AlphaLimits alim = getAlphaLimits( s.m_c_real, beta );
+        const double a = alim.first + rng.generate()*(alim.second-alim.first);
+        alpha = dclamp( a, alim.first, alim.second );
+      } else {
+        kind = s.alphaBegin( beta, rng, st, alpha );
+      }
+      if ( kind == FreeGasSampler::kAlphaDone ) {
+        P.slot( kSlotAlpha, j ) = alpha;
+        P.w[j] = rng.ndraws | ( (uint32_t)kFgAlphaDone << 28 );
+      } else {
+        P.slot( kSlotC, j ) = st.c; P.slot( kSlotXm, j ) = st.xm; P.slot( kSlotXp, j ) = st.xp;
+        P.slot( kSlotXmax, j ) = st.xmax; P.slot( kSlotXswitch, j ) = st.xswitch;
+        P.slot( kSlotPflat, j ) = st.probability_flat; P.slot( kSlotAright, j ) = st.area_right;
+        const uint32_t flags = ( st.always_left ? 1u : 0u ) | ( st.always_right ? 2u : 0u ) | ( st.single_side ? 4u : 0u );
+        P.w[j] = rng.ndraws | ( flags << 25 ) | ( (uint32_t)kFgAlphaLoop << 28 );
+      }
+    }
+  }
+
+  template <int kMinBlocks>
+  __global__ void __launch_bounds__(128, kMinBlocks)
+  k_fg_alpha( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+              const __grid_constant__ QueueArgs Q, const __grid_constant__ FgPrep P )
+  {
+    const uint32_t nq = Q.counts[1];
+    if ( (uint64_t)blockIdx.x * blockDim.x * P.epl >= nq && blockIdx.x )
+      return;
+    bool have = false, drained = false;
+    uint32_t jrec = 0;
+    XSamplerState st;
+    Rng rng; rng.init( A.seed, A.first_index, A.sid );
+    while ( true ) {
+      const uint32_t need = __ballot_sync( 0xffffffffu, !have );
+      if ( need ) {
+        const uint32_t j = fgPull( need, !have, P.cursor + 1, nq, drained );
+        if ( !have && j < nq ) {
+          const uint32_t w = P.w[j];
+          if ( w != kFgSkip && ( w >> 28 ) == (uint32_t)kFgAlphaLoop ) {
+            const uint32_t i = Q.q_fg[j] & kQueueIdxMask;
+            rng.init( A.seed, A.streamIndex( i ), A.sid );
+            rng.seek( w & kFgNdMask );
+            st.c = P.slot( kSlotC, j ); st.xm = P.slot( kSlotXm, j ); st.xp = P.slot( kSlotXp, j );
+            st.xmax = P.slot( kSlotXmax, j ); st.xswitch = P.slot( kSlotXswitch, j );
+            st.probability_flat = P.slot( kSlotPflat, j ); st.area_right = P.slot( kSlotAright, j );
+            const uint32_t flags = ( w >> 25 ) & 7u;
+            st.always_left = flags & 1u; st.always_right = flags & 2u; st.single_side = flags & 4u;
+            jrec = j;
+            have = true;
+          }
+        }
+      }
+      if ( !__ballot_sync( 0xffffffffu, have ) ) {
+        if ( drained ) break;
+        continue;
+      }
+      if ( have ) {
+        double x;
+        if ( xsAttempt( st, rng, x ) ) {
+          P.slot( kSlotAlpha, jrec ) = x;
+          P.w[jrec] = rng.ndraws | ( (uint32_t)kFgXDone << 28 );
+          have = false;
+        }
+      }
+    }
+  }
+
+  __global__ void __launch_bounds__(128)
+  k_fg_finish( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
+               const __grid_constant__ QueueArgs Q, const __grid_constant__ FgPrep P )
+  {
+    const uint32_t nq = Q.counts[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nq_up = ( nq + 31u ) & ~31u;   // warp-uniform trip count (full-mask ballots in pushEmax)
+    int errs = 0;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq_up; j += stride ) {
+      bool to_emax = false;
+      uint32_t entry = 0, nd = 0;
+      const uint32_t w = j < nq ? P.w[j] : kFgSkip;
+      if ( w != kFgSkip ) {
+        entry = Q.q_fg[j];
+        const uint32_t i = entry & kQueueIdxMask;
+        const Comp& c = M.comp[ entry >> kQueueIdxBits ];
+        const double ekin = A.ekin[i];
+        double kT, mass;
+        fgLeafPars( M, c, kT, mass );
+        // FreeGasSampler ctor, the two members needed here (NCFreeGasUtils.cc:492-515)
+        const double cc = dmin( 1e14, dmax( 1e-10, ekin/kT ) );
+        const double Adiv4 = 0.25*( kInvNeutronMassAmu * mass );
+        double beta = P.slot( kSlotBeta, j );
+        double alpha = P.slot( kSlotAlpha, j );
+        if ( ( w >> 28 ) == (uint32_t)kFgXDone )
+          alpha = FreeGasSampler::alphaFromX( cc, Adiv4, beta, alpha );
+        Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
+        rng.seek( w & kFgNdMask );
+        double eout = -1.0, mu = -999.0;
+        int err = 0;
+        if ( c.kind == KIND_FREEGAS ) {
+          // tail of FreeGasSampler::sampleDeltaEMu + FreeGas::sampleScatterIsotropic (src/freegas/NCFreeGas.cc:70-75)
+          double dE;
+          alphaBetaToDeltaEMu( alpha, beta, cc*kT, kT, dE, mu, err );
+          eout = dmax( 0.0, ekin + dE );
+        } else {
+          const SabT& T = M.sab[c.idx];
+          const double pdisc = P.slot( kSlotPdisc, j );
+          int chk = sabHighECheck( T, alpha, beta, pdisc, rng );
+          if ( chk == kHighERedo ) {
+            // rare: draw (alpha,beta) again with the plain nested loops
+            FreeGasSampler s( ekin, kT, mass );
+            do {
+              s.sampleAlphaBeta( rng, alpha, beta );
+              chk = sabHighECheck( T, alpha, beta, pdisc, rng );
+            } while ( chk == kHighERedo );
+          }
+          if ( chk == kHighEAccept )
+            sabFinishScatter( T, ekin, alpha, beta, rng, eout, mu, err );
+          else
+            to_emax = true;
+        }
+        nd = rng.ndraws;
+        if ( !to_emax ) {
+          A.ekin_out[i] = eout;
+          A.mu_out[i] = mu;
+          if ( A.ndraws ) A.ndraws[i] = nd;
+        }
+        errs |= err;
+      }
+      pushEmax( to_emax, Q, entry, nd );
+    }
+    if ( errs )
+      atomicOr( A.err_flags, errs );
+  }
+
   // ------------------------------------------------------------ oriented (single crystal)
   // Per-neutron (E, direction), SoA.  One neutron per thread: the lanes of a warp walk the
   // reflection-family / demi-normal tables in lockstep (same addresses -> broadcast loads);

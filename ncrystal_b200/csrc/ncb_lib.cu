@@ -383,6 +383,7 @@ namespace {
       uint32_t* q_sc = nullptr; size_t acap = 0;
       uint32_t* sc_work = nullptr; uint8_t* sc_ncand = nullptr; uint16_t* sc_cand = nullptr;   // k_sc_find -> k_sc_eval
       int32_t* sc_wpos = nullptr; bool sc_lists_valid = false;
+      double* fg_prep = nullptr; uint32_t* fg_nd = nullptr; size_t fcap = 0;   // k_fg_prep records, one per queue slot
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
@@ -395,6 +396,7 @@ namespace {
       for ( auto& c : qctx ) {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
+        if ( c.fg_prep ) { cudaFree( c.fg_prep ); cudaFree( c.fg_nd ); }
         if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
                          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); cudaFree( c.sc_wpos ); }
         if ( c.side ) cudaStreamDestroy( c.side );
@@ -431,6 +433,15 @@ namespace {
         CUDA_OK( cudaMalloc( &c.q, 6*c.cap*sizeof(uint32_t) ) );
       }
       return c;
+    }
+    // per-entry records of the staged free-gas kernels (kFgSlots doubles + 1 word per queue slot); after ensureQueues
+    void ensureFgPrep( QueueCtx& c )
+    {
+      if ( c.fcap >= c.cap ) return;
+      if ( c.fg_prep ) { CUDA_OK( cudaDeviceSynchronize() ); cudaFree( c.fg_prep ); cudaFree( c.fg_nd ); }
+      c.fcap = c.cap;
+      CUDA_OK( cudaMalloc( &c.fg_prep, kFgSlots*c.fcap*sizeof(double) ) );
+      CUDA_OK( cudaMalloc( &c.fg_nd, c.fcap*sizeof(uint32_t) ) );
     }
     QueueCtx& ensureAnisoBuffers( int ictx, size_t n )
     {
@@ -657,6 +668,50 @@ namespace {
     Q.q_fg = q_out;
   }
 
+  // Free-gas queue: the staged pipeline k_fg_prep / k_fg_beta / k_fg_alpha_prep / k_fg_alpha / k_fg_finish (default for
+  // batches that fill the machine), or the neutron-per-lane k_sample_fg (small batches: four launches less;
+  // NCB200_FG_MODE=0 forces it).  The two refill cursors live in the (otherwise unused) sort-histogram area of the
+  // counters, zeroed with them at the start of the launch sequence.
+  void launchFgSampling( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const SampleArgs& A, const QueueArgs& Q,
+                         uint64_t m, cudaStream_t st, bool timed )
+  {
+    static const int mode = []{ const char* e = std::getenv( "NCB200_FG_MODE" ); return e ? std::atoi(e) : 1; }();
+    static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
+    static const int fgminb = []{ const char* e = std::getenv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
+    static const int epl = []{ const char* e = std::getenv( "NCB200_FG_EPL" ); return e ? std::atoi(e) : 4; }();
+    static const uint64_t minbatch = []{ const char* e = std::getenv( "NCB200_FG_STAGED_MIN" ); return e ? (uint64_t)std::atoll(e) : (uint64_t)65536; }();
+    const unsigned nsm = (unsigned)numSMs( dm.device );
+    auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
+    if ( mode == 0 || m < minbatch || Q.hist ) {
+      const unsigned g = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
+      auto tl = timer( "k_sample_fg" );
+      if ( fgminb >= 8 ) k_sample_fg<8><<< g, 128, 0, st >>>( dm.mat, A, Q );
+      else k_sample_fg<4><<< g, 128, 0, st >>>( dm.mat, A, Q );
+      ++g_launches;
+      return;
+    }
+    s->ensureFgPrep( qc );
+    FgPrep P;
+    P.r = qc.fg_prep; P.cap = qc.fcap; P.w = qc.fg_nd;
+    P.cursor = Q.counts + 8 + 48;
+    P.epl = (uint32_t)std::max( 1, epl );
+    const unsigned gflat = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
+    const unsigned grefill = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*( fgminb >= 8 ? 8 : 6 ) );
+    { auto tl = timer( "k_fg_prep" );
+      k_fg_prep<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
+    { auto tl = timer( "k_fg_beta" );
+      if ( fgminb >= 8 ) k_fg_beta<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
+      else k_fg_beta<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
+    { auto tl = timer( "k_fg_alpha_prep" );
+      k_fg_alpha_prep<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
+    { auto tl = timer( "k_fg_alpha" );
+      if ( fgminb >= 8 ) k_fg_alpha<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
+      else k_fg_alpha<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
+    { auto tl = timer( "k_fg_finish" );
+      k_fg_finish<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
+    g_launches += 5;
+  }
+
   void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu,
                         cudaStream_t st, int ictx = kSlots )
   {
@@ -737,9 +792,7 @@ namespace {
           }
           auto launchFG = [&]() {
             if ( !do_sort ) partitionFgQueue( dm, qc, Q, A.ekin, m, st_fg );
-            TimedLaunch tl( "k_sample_fg", st_fg );
-            if ( fgminb >= 8 ) k_sample_fg<8><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
-            else k_sample_fg<4><<< gfg2, 128, 0, st_fg >>>( dm.mat, A, Q );
+            launchFgSampling( s, dm, qc, A, Q, m, st_fg, true );
           };
           if ( fgfirst ) launchFG();
           { TimedLaunch tl( "k_sample_sab_refill", st );
@@ -760,7 +813,7 @@ namespace {
             CUDA_OK( cudaStreamWaitEvent( st, qc.ev_join, 0 ) );
           }
         }
-        g_launches += 4;
+        g_launches += 3;
       }
       CUDA_OK( cudaGetLastError() );
     }
@@ -906,10 +959,10 @@ namespace {
       const unsigned gf = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
       k_sample_sab_refill<false,8><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_sab, Q.counts + 0, Q.counts + 3 );
       if ( m >= 65536 ) partitionFgQueue( dm, qc, Q, A.ekin, m, st );
-      k_sample_fg<8><<< gf, 128, 0, st >>>( dm.mat, Ai, Q );
+      launchFgSampling( s, dm, qc, Ai, Q, m, st, false );
       k_sample_sab_refill<true,5><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_emax, Q.counts + 2, Q.counts + 4 );
       k_dir_from_mu<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A, Q, X );
-      g_launches += 5;
+      g_launches += 4;
       if ( has_sc ) {
         const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kScWarps - 1 )/kScWarps, (uint64_t)nsm*3 );
         k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off );

@@ -199,21 +199,26 @@ namespace ncb {
   }
 
   // randExpMInvXMCXDivSqrtX, ref: NCFreeGasUtils.cc:237-490.
-  // Sample f(x)=m_exp(-1/x-c*x)/m_sqrt(x) over [xm,xp].
-  NCB_HD_NOINLINE double randExpMInvXMCXDivSqrtX( Rng& rng, double c, double xm, double xp )
+  // Sample f(x)=m_exp(-1/x-c*x)/m_sqrt(x) over [xm,xp].  In pieces, so that the kernels can schedule the rejection
+  // loop attempt by attempt (k_fg_alpha_prep / k_fg_alpha): xsBegin is everything before the loop (no uniforms),
+  // xsAttempt is ONE pass of it; randExpMInvXMCXDivSqrtX below is their composition.
+  struct XSamplerState {
+    double c, xm, xp, xmax, xswitch, probability_flat, area_right;
+    bool always_left, always_right, single_side;
+  };
+
+  // true: the result is x_out already (the reference's early returns); false: run the loop on st.
+  NCB_HD_NOINLINE bool xsBegin( XSamplerState& st, double c, double xm, double xp, double& x_out )
   {
-    if ( xp == xm )
-      return xm;
+    if ( xp == xm ) { x_out = xm; return true; }
     const double sqrtc = m_sqrt(c);
     const double invsqrtc = 1/sqrtc;
     const double xpeak = ( c > 1e-5
                            ? ( c > 1e200 ? invsqrtc : (m_sqrt(16.0*c+1.0)-1.0)/(4.0*c) )
                            : ( 2.0-c*(8.0-c*(64.0-c*(640.0-c*7168.0))) ) );
-    if ( xpeak == 0.0 )
-      return xm > 0.0 ? xm : dmin( kDblMin, xp );
+    if ( xpeak == 0.0 ) { x_out = xm > 0.0 ? xm : dmin( kDblMin, xp ); return true; }
     const double xmax = ( xm > xpeak ? xm : dmin( xp, xpeak ) );
-    if ( !(xmax > 0.0) )
-      return xm;
+    if ( !(xmax > 0.0) ) { x_out = xm; return true; }
     double xlarge = dmax( 5.0/m_sqrt(c), 2*xpeak );
     double xsmall = dmin( 0.2/m_sqrt(c), 0.5*xpeak );
     if ( xp > xlarge )
@@ -223,8 +228,7 @@ namespace ncb {
       xm = dmax( xm, xsm / ( 1 + 30.0*xsm ) );
     }
     constexpr double fpmin = kDblMin;
-    if ( ( xm = dmax( fpmin, dmax( fpmin/xp, xm ) ) ) >= xp )
-      return xp;
+    if ( ( xm = dmax( fpmin, dmax( fpmin/xp, xm ) ) ) >= xp ) { x_out = xp; return true; }
     constexpr double fcutoff_limit = 1e-9;
     if ( xp < xpeak ) {
       while ( true ) {
@@ -263,44 +267,67 @@ namespace ncb {
       always_left = true;
       single_side = false;
     }
-    while ( true ) {
-      const bool do_flat = ( single_side ? always_left : ( rng.generate() < probability_flat ) );
-      if ( do_flat ) {
-        double dx = xswitch - xm;
-        // NB: the reference's xthr_low/xthr_up are loop-local (reset every pass,
-        // :434-441), so its cheap pre-rejection never fires; both uniforms are
-        // still consumed in this order.
-        const double xgen = xm + rng.generate()*dx;
-        const double Raccept = rng.generate();
-        constexpr double fthreshold = 0.05;
-        if ( !inInterval( xm, xswitch, xgen ) && Raccept > fthreshold )
-          continue;
-        const double fval = fgFEval( xmax, c, xgen );
-        if ( fval < fthreshold ) {
-          if ( fval < fcutoff_limit ) {
-            if ( xgen < xmax )
-              xm = xgen;
-            else
-              xswitch = xgen;
-            dx = xswitch - xm;
-            if ( !single_side ) {
-              const double area_left = dx;
-              probability_flat = area_left/(area_left+area_right);
-              always_left = ( probability_flat > 1.0-fcutoff_limit );
-              always_right = ( probability_flat < fcutoff_limit );
-              single_side = ( always_left || always_right );
-            }
-            continue;
+    st.c = c; st.xm = xm; st.xp = xp; st.xmax = xmax; st.xswitch = xswitch;
+    st.probability_flat = probability_flat; st.area_right = area_right;
+    st.always_left = always_left; st.always_right = always_right; st.single_side = single_side;
+    return false;
+  }
+
+  // ONE pass of the rejection loop (:409-489): true = accepted (x_out), false = the reference's `continue`.
+  NCB_HD_NOINLINE bool xsAttempt( XSamplerState& st, Rng& rng, double& x_out )
+  {
+    constexpr double fcutoff_limit = 1e-9;
+    const bool do_flat = ( st.single_side ? st.always_left : ( rng.generate() < st.probability_flat ) );
+    if ( do_flat ) {
+      double dx = st.xswitch - st.xm;
+      // NB: the reference's xthr_low/xthr_up are loop-local (reset every pass,
+      // :434-441), so its cheap pre-rejection never fires; both uniforms are
+      // still consumed in this order.
+      const double xgen = st.xm + rng.generate()*dx;
+      const double Raccept = rng.generate();
+      constexpr double fthreshold = 0.05;
+      if ( !inInterval( st.xm, st.xswitch, xgen ) && Raccept > fthreshold )
+        return false;
+      const double fval = fgFEval( st.xmax, st.c, xgen );
+      if ( fval < fthreshold ) {
+        if ( fval < fcutoff_limit ) {
+          if ( xgen < st.xmax )
+            st.xm = xgen;
+          else
+            st.xswitch = xgen;
+          dx = st.xswitch - st.xm;
+          if ( !st.single_side ) {
+            const double area_left = dx;
+            st.probability_flat = area_left/(area_left+st.area_right);
+            st.always_left = ( st.probability_flat > 1.0-fcutoff_limit );
+            st.always_right = ( st.probability_flat < fcutoff_limit );
+            st.single_side = ( st.always_left || st.always_right );
           }
+          return false;
         }
-        if ( Raccept <= fval )
-          return xgen;
-      } else {
-        const double xgen = randExpDivSqrt( rng, c, xswitch, xp );
-        if ( rng.generate() < m_exp( (xgen-xp)/(xgen*xp) ) )
-          return xgen;
+      }
+      if ( Raccept <= fval ) {
+        x_out = xgen;
+        return true;
+      }
+    } else {
+      const double xgen = randExpDivSqrt( rng, st.c, st.xswitch, st.xp );
+      if ( rng.generate() < m_exp( (xgen-st.xp)/(xgen*st.xp) ) ) {
+        x_out = xgen;
+        return true;
       }
     }
+    return false;
+  }
+
+  NCB_HD_NOINLINE double randExpMInvXMCXDivSqrtX( Rng& rng, double c, double xm, double xp )
+  {
+    XSamplerState st;
+    double x;
+    if ( xsBegin( st, c, xm, xp, x ) )
+      return x;
+    while ( !xsAttempt( st, rng, x ) ) {}
+    return x;
   }
 
   // FGEvalBetaDistHelper, ref: NCFreeGasUtils.cc:153-233
@@ -369,6 +396,7 @@ namespace ncb {
   struct FreeGasSampler {
     double m_c, m_kT, m_sqrtAc, m_invA, m_Adiv4, m_normfact, m_c_real;
 
+    NCB_HD FreeGasSampler() {}
     NCB_HD FreeGasSampler( double ekin, double kT, double mass_amu )
     {
       m_c = dmin( 1e14, dmax( 1e-10, ekin/kT ) );
@@ -413,8 +441,16 @@ namespace ncb {
       }
     };
 
-    NCB_HD_NOINLINE double sampleBeta( Rng& rng ) const
+    // sampleBeta, ref: NCFreeGasUtils.cc:530-849, in three pieces so that the kernels can schedule it attempt by
+    // attempt (k_fg_prep / k_sample_fg_refill); sampleBeta() below is their plain composition.
+    //
+    // (1) betaSupport: the part before the rejection loop, which consumes no random numbers (:530-680).
+    //     kBetaLoop: rejection loop over [aa,bb];  kBetaHighE: beta = aa*u (one draw; aa = -elossmax);
+    //     kBetaFixed: beta = aa.
+    enum { kBetaLoop = 0, kBetaHighE = 1, kBetaFixed = 2 };
+    NCB_HD_NOINLINE int betaSupport( double& aa, double& bb ) const
     {
+      bb = 13.815510557964274;
       if ( m_c_real > 1e4 ) {
         const double A = 1.0 / m_invA;
         const double A2 = A*A;
@@ -422,12 +458,12 @@ namespace ncb {
         if ( m_c_real > c_highe_threshold ) {
           double am1_div_ap1 = (1.0-m_invA)/(1.0+m_invA);
           double elossmax = m_c_real * (1.0-am1_div_ap1*am1_div_ap1);
-          return -elossmax*rng.generate();
+          aa = -elossmax;
+          return kBetaHighE;
         }
       }
-      constexpr double Tlim = 2.0;
       const double fcutoff_limit = 1e-6;
-      double aa( dmax( -m_c_real, -m_c ) ), bb( 13.815510557964274 );
+      aa = dmax( -m_c_real, -m_c );
       if ( m_invA <= 1.0/10.0 ) {
         if ( m_c > 10.1 ) {
           while ( true ) {
@@ -452,94 +488,137 @@ namespace ncb {
           }
         }
       }
-      if ( !(bb>aa) )
-        return aa;
-
-      Overlay ov;
-      ov.setAB( aa, bb );
-      constexpr double fthreshold = 0.1;
-      double afthreshold( ov.a ), bfthreshold( ov.b );
-
-      while ( true ) {
-        double beta, foverlay;
-        const double R_selectregion = rng.generate();
-        if ( R_selectregion < ov.prob_downscat ) {
-          beta = rng.generate()*ov.a;
-          foverlay = 1.0;
-        } else {
-          if ( R_selectregion < ov.prob_notclosetail ) {
-            if ( !ov.expsampler.isValid() )
-              ov.expsampler.set( Tlim, ov.b, 1.0 );
-            beta = ov.expsampler.sample( rng );
-            foverlay = m_exp(-beta);
-          } else {
-            const double bmax = dmin( ov.b, Tlim );
-            while ( true ) {
-              beta = rng.generate()*bmax;
-              const double Raccept0 = rng.generate();
-              constexpr double kcheap = 19./45.;
-              if ( Raccept0 > 1.0 - kcheap*beta )
-                continue;
-              constexpr double c1 = -1.;
-              constexpr double c2 = 1./2.;
-              constexpr double c3 = -1./6.;
-              constexpr double c4 = 1./24.;
-              constexpr double c5 = -1./120.;
-              constexpr double c6 = 1./720.;
-              foverlay = 1.0+beta*(c1+beta*(c2+beta*(c3+beta*(c4+beta*(c5+beta*c6)))));
-              if ( Raccept0 < foverlay )
-                break;
-            }
-          }
-        }
-        const double faccept = rng.generate()*foverlay;
-        if ( faccept > fthreshold && !inInterval( afthreshold, bfthreshold, beta ) )
-          continue;
-        FGBetaDist eval_helper( m_c, m_invA, m_sqrtAc, beta, m_normfact );
-        bool need_exact(true);
-        double fval;
-        if ( beta > 0 ) {
-          PairDD bnd = eval_helper.evalQuickBounds();
-          if ( faccept <= bnd.first )
-            return beta;
-          fval = bnd.second;
-          if ( faccept > bnd.second )
-            need_exact = false;
-        }
-        if ( need_exact ) {
-          fval = eval_helper.evalExact();
-          if ( faccept < fval )
-            return beta;
-        }
-        if ( fval < fcutoff_limit ) {
-          if ( beta < 0 )
-            ov.setAB( beta, ov.b );
-          else
-            ov.setAB( ov.a, beta );
-          continue;
-        }
-        if ( fval < fthreshold ) {
-          if ( beta < 0 )
-            afthreshold = dmax( afthreshold, beta );
-          else
-            bfthreshold = dmin( bfthreshold, beta );
-        }
-      }
+      return ( bb > aa ) ? kBetaLoop : kBetaFixed;
     }
 
-    NCB_HD_NOINLINE double sampleAlpha( double beta, Rng& rng ) const
+    // (2) state of the rejection loop: the overlay and the two thresholds that adapt while it runs (:682-720)
+    struct BetaState {
+      Overlay ov;
+      double afthreshold, bfthreshold;
+    };
+    NCB_HD void betaBegin( BetaState& st, double aa, double bb ) const
+    {
+      st.ov.setAB( aa, bb );
+      st.afthreshold = st.ov.a;
+      st.bfthreshold = st.ov.b;
+    }
+
+    // (3) ONE pass of the rejection loop (:722-849): true = beta accepted, false = the reference's `continue`.
+    NCB_HD_NOINLINE bool betaAttempt( BetaState& st, Rng& rng, double& beta_out ) const
+    {
+      constexpr double Tlim = 2.0;
+      const double fcutoff_limit = 1e-6;
+      constexpr double fthreshold = 0.1;
+      Overlay& ov = st.ov;
+      double beta, foverlay;
+      const double R_selectregion = rng.generate();
+      if ( R_selectregion < ov.prob_downscat ) {
+        beta = rng.generate()*ov.a;
+        foverlay = 1.0;
+      } else {
+        if ( R_selectregion < ov.prob_notclosetail ) {
+          if ( !ov.expsampler.isValid() )
+            ov.expsampler.set( Tlim, ov.b, 1.0 );
+          beta = ov.expsampler.sample( rng );
+          foverlay = m_exp(-beta);
+        } else {
+          const double bmax = dmin( ov.b, Tlim );
+          while ( true ) {
+            beta = rng.generate()*bmax;
+            const double Raccept0 = rng.generate();
+            constexpr double kcheap = 19./45.;
+            if ( Raccept0 > 1.0 - kcheap*beta )
+              continue;
+            constexpr double c1 = -1.;
+            constexpr double c2 = 1./2.;
+            constexpr double c3 = -1./6.;
+            constexpr double c4 = 1./24.;
+            constexpr double c5 = -1./120.;
+            constexpr double c6 = 1./720.;
+            foverlay = 1.0+beta*(c1+beta*(c2+beta*(c3+beta*(c4+beta*(c5+beta*c6)))));
+            if ( Raccept0 < foverlay )
+              break;
+          }
+        }
+      }
+      const double faccept = rng.generate()*foverlay;
+      if ( faccept > fthreshold && !inInterval( st.afthreshold, st.bfthreshold, beta ) )
+        return false;
+      FGBetaDist eval_helper( m_c, m_invA, m_sqrtAc, beta, m_normfact );
+      bool need_exact(true);
+      double fval;
+      if ( beta > 0 ) {
+        PairDD bnd = eval_helper.evalQuickBounds();
+        if ( faccept <= bnd.first ) {
+          beta_out = beta;
+          return true;
+        }
+        fval = bnd.second;
+        if ( faccept > bnd.second )
+          need_exact = false;
+      }
+      if ( need_exact ) {
+        fval = eval_helper.evalExact();
+        if ( faccept < fval ) {
+          beta_out = beta;
+          return true;
+        }
+      }
+      if ( fval < fcutoff_limit ) {
+        if ( beta < 0 )
+          ov.setAB( beta, ov.b );
+        else
+          ov.setAB( ov.a, beta );
+        return false;
+      }
+      if ( fval < fthreshold ) {
+        if ( beta < 0 )
+          st.afthreshold = dmax( st.afthreshold, beta );
+        else
+          st.bfthreshold = dmin( st.bfthreshold, beta );
+      }
+      return false;
+    }
+
+    // beta from the outcome of betaSupport when no rejection loop is needed
+    NCB_HD double betaDirect( int kind, double aa, Rng& rng ) const
+    {
+      return kind == kBetaHighE ? aa*rng.generate() : aa;
+    }
+
+    NCB_HD_NOINLINE double sampleBeta( Rng& rng ) const
+    {
+      double aa, bb;
+      const int kind = betaSupport( aa, bb );
+      if ( kind != kBetaLoop )
+        return betaDirect( kind, aa, rng );
+      BetaState st;
+      betaBegin( st, aa, bb );
+      double beta;
+      while ( !betaAttempt( st, rng, beta ) ) {}
+      return beta;
+    }
+
+    // sampleAlpha, ref: NCFreeGasUtils.cc:851-935, in pieces (see XSamplerState): alphaBegin does everything up to the
+    // rejection loop of randExpMInvXMCXDivSqrtX (the cheap cases are finished there), alphaFromX maps the loop's
+    // result back; sampleAlpha() is their composition.
+    enum { kAlphaDone = 0, kAlphaLoop = 1 };
+    NCB_HD_NOINLINE int alphaBegin( double beta, Rng& rng, XSamplerState& st, double& alpha_out ) const
     {
       if ( m_c_real < m_c || muIsotropicAtBeta( beta, m_c ) ) {
         AlphaLimits alim = getAlphaLimits( m_c_real, beta );
         double alpha = alim.first + rng.generate()*(alim.second-alim.first);
-        return dclamp( alpha, alim.first, alim.second );
+        alpha_out = dclamp( alpha, alim.first, alim.second );
+        return kAlphaDone;
       }
       beta = dmax( -m_c, beta );
       AlphaLimits alims = getAlphaLimits( m_c, beta );
       const double am = alims.first;
       const double ap = alims.second;
-      if ( am == ap )
-        return am;
+      if ( am == ap ) {
+        alpha_out = am;
+        return kAlphaDone;
+      }
       const double betasq = beta*beta;
       const double t = betasq * m_Adiv4;
       const double c = 0.0625 * betasq;
@@ -553,34 +632,59 @@ namespace ncb {
           if ( alpha < am || alpha > ap )
             continue;
           // randExp(rng) = -m_log(rng.generate()), NCRandUtils.hh:175-178
-          if ( alpha*ap*( -m_log( rng.generate() ) ) >= t*(ap-alpha) )
-            return alpha;
+          if ( alpha*ap*( -m_log( rng.generate() ) ) >= t*(ap-alpha) ) {
+            alpha_out = alpha;
+            return kAlphaDone;
+          }
         }
       } else {
         const double invt( 1.0/t );
         const double xm( am*invt ), xp( ap*invt );
-        const double x = randExpMInvXMCXDivSqrtX( rng, c, xm, xp );
-        return dclamp( x*t, am, ap );
+        double x;
+        if ( xsBegin( st, c, xm, xp, x ) ) {
+          alpha_out = dclamp( x*t, am, ap );
+          return kAlphaDone;
+        }
+        return kAlphaLoop;
       }
     }
-
-    // FreeGasSampler::sampleAlphaBeta, ref: NCFreeGasUtils.hh:146-158
-    NCB_HD void sampleAlphaBeta( Rng& rng, double& alpha, double& beta ) const
+    NCB_HD static double alphaFromX( double c_clamped, double Adiv4, double beta, double x )
     {
-      beta = sampleBeta( rng );
+      beta = dmax( -c_clamped, beta );
+      AlphaLimits alims = getAlphaLimits( c_clamped, beta );
+      const double t = ( beta*beta ) * Adiv4;
+      return dclamp( x*t, alims.first, alims.second );
+    }
+    NCB_HD_NOINLINE double sampleAlpha( double beta, Rng& rng ) const
+    {
+      XSamplerState st;
+      double alpha;
+      if ( alphaBegin( beta, rng, st, alpha ) == kAlphaDone )
+        return alpha;
+      double x;
+      while ( !xsAttempt( st, rng, x ) ) {}
+      return alphaFromX( m_c, m_Adiv4, beta, x );
+    }
+
+    // FreeGasSampler::sampleAlphaBeta, ref: NCFreeGasUtils.hh:146-158 (alphaGivenBeta: the part after sampleBeta)
+    NCB_HD double alphaGivenBeta( double beta, Rng& rng ) const
+    {
       if ( beta < -m_c || muIsotropicAtBeta( beta, m_c ) ) {
         AlphaLimits alim = getAlphaLimits( m_c_real, beta );
         const double a = alim.first + rng.generate()*(alim.second-alim.first);
-        alpha = dclamp( a, alim.first, alim.second );
-        return;
+        return dclamp( a, alim.first, alim.second );
       }
-      alpha = sampleAlpha( beta, rng );
+      return sampleAlpha( beta, rng );
+    }
+    NCB_HD void sampleAlphaBeta( Rng& rng, double& alpha, double& beta ) const
+    {
+      beta = sampleBeta( rng );
+      alpha = alphaGivenBeta( beta, rng );
     }
 
-    // FreeGasSampler::sampleDeltaEMu, ref: NCFreeGasUtils.hh:160-174
-    NCB_HD void sampleDeltaEMu( Rng& rng, double& deltaE, double& mu, int& err ) const
+    // FreeGasSampler::sampleDeltaEMu, ref: NCFreeGasUtils.hh:160-174 (deltaEMuGivenBeta: the part after sampleBeta)
+    NCB_HD void deltaEMuGivenBeta( double beta, Rng& rng, double& deltaE, double& mu, int& err ) const
     {
-      const double beta = sampleBeta( rng );
       if ( beta <= -m_c || muIsotropicAtBeta( beta, m_c ) ) {
         deltaE = beta*m_kT;
         mu = rng.generate()*2.0 - 1.0;
@@ -588,6 +692,11 @@ namespace ncb {
       }
       const double alpha = sampleAlpha( beta, rng );
       alphaBetaToDeltaEMu( alpha, beta, m_c*m_kT, m_kT, deltaE, mu, err );
+    }
+    NCB_HD void sampleDeltaEMu( Rng& rng, double& deltaE, double& mu, int& err ) const
+    {
+      const double beta = sampleBeta( rng );
+      deltaEMuGivenBeta( beta, rng, deltaE, mu, err );
     }
   };
 

@@ -239,38 +239,64 @@ namespace ncb {
     return iu;
   }
 
-  // SABSampler::sampleHighE, ref: NCSABSampler.cc:59-156.  Returns true if (alpha,beta)
-  // was sampled with the free-gas extender; false => sample the table at E=Emax.
-  NCB_HD bool sabSampleHighE( const SabT& T, double ekin, Rng& rng, double& alpha, double& beta, int& err )
+  // SABSampler::sampleHighE, ref: NCSABSampler.cc:59-156, in two pieces (the kernels schedule the free-gas sampling
+  // between them attempt by attempt); sabSampleHighE below is their composition.
+  enum { kHighEGoOn = 0, kHighEDiscard = 1, kHighEToEmax = 2, kHighEAccept = 3, kHighERedo = 4 };
+
+  // Before the free-gas loop (:59-120): kHighEDiscard (error raised), kHighEToEmax (sample the table at E=Emax;
+  // one uniform consumed) or kHighEGoOn (0 or 1 uniforms consumed).
+  NCB_HD int sabHighEBegin( const SabT& T, double ekin, Rng& rng, double& P_discardinside, int& err )
   {
-    const double emax = T.egrid[T.negrid-1];
     const double extenderXSMultE = ekin * fgXS( T.ext, ekin );
     const double P_inside = T.k1 / ( (T.k1-T.k2) + extenderXSMultE );
     const double P_extender_inside = T.k2 / extenderXSMultE;
-    const double P_discardinside = ( P_extender_inside >= P_inside ? (1.0-P_inside/P_extender_inside) : 0.0 );
+    P_discardinside = ( P_extender_inside >= P_inside ? (1.0-P_inside/P_extender_inside) : 0.0 );
     if ( P_discardinside > 0.95 ) {
       err |= ERR_SAB_DISCARD;
-      alpha = -1.0; beta = 0.0;
-      return true;
+      return kHighEDiscard;
     }
     if ( P_extender_inside < P_inside ) {
       const double aa = 1.0 - P_extender_inside;
       const double P_extrainside = aa > 1e-10 ? (P_inside-P_extender_inside)/aa : 1.0;
       if ( rng.generate() < P_extrainside )
-        return false;
+        return kHighEToEmax;
     }
-    const double emax_div_kt = emax / T.kT;
+    return kHighEGoOn;
+  }
+
+  // After one free-gas (alpha,beta) (:122-155): accept it, draw again, or sample the table at E=Emax.
+  NCB_HD int sabHighECheck( const SabT& T, double alpha, double beta, double P_discardinside, Rng& rng )
+  {
+    const double emax_div_kt = T.egrid[T.negrid-1] / T.kT;
+    if ( beta <= -emax_div_kt )
+      return kHighEAccept;
+    AlphaLimits alims = getAlphaLimits( emax_div_kt, beta );
+    if ( !inInterval( alims.first, alims.second, alpha ) )
+      return kHighEAccept;
+    if ( P_discardinside && rng.generate() < P_discardinside )
+      return kHighERedo;
+    return kHighEToEmax;
+  }
+
+  // Returns true if (alpha,beta) was sampled with the free-gas extender; false => sample the table at E=Emax.
+  NCB_HD bool sabSampleHighE( const SabT& T, double ekin, Rng& rng, double& alpha, double& beta, int& err )
+  {
+    double P_discardinside;
+    const int b = sabHighEBegin( T, ekin, rng, P_discardinside, err );
+    if ( b == kHighEDiscard ) {
+      alpha = -1.0; beta = 0.0;
+      return true;
+    }
+    if ( b == kHighEToEmax )
+      return false;
     FreeGasSampler fgs( ekin, T.ext.kT, T.ext.mass_amu );
     while ( true ) {
       fgs.sampleAlphaBeta( rng, alpha, beta );
-      if ( beta <= -emax_div_kt )
+      const int c = sabHighECheck( T, alpha, beta, P_discardinside, rng );
+      if ( c == kHighEAccept )
         return true;
-      AlphaLimits alims = getAlphaLimits( emax_div_kt, beta );
-      if ( !inInterval( alims.first, alims.second, alpha ) )
-        return true;
-      if ( P_discardinside && rng.generate() < P_discardinside )
-        continue;
-      return false;
+      if ( c == kHighEToEmax )
+        return false;
     }
   }
 
