@@ -74,6 +74,15 @@ void ncrystal_samplescatterisotropic( ncrystal_scatter_t, double ekin, double* e
 void ncrystal_samplescatter( ncrystal_scatter_t, double ekin, const double (*direction)[3],
                              double* ekin_final, double (*direction_final)[3] );
 
+/* ncrystal.h:792 -- caller-supplied generator rngfct(rngstate): two numbers are drawn from it per call and key the
+ * neutron's device stream (a host callback cannot run on the device; see ncrystal_b200_virtapi.hh) */
+void ncrystal_samplescatter_rs( double (*rngfct)(void*), void* rngstate, ncrystal_scatter_t, double ekin,
+                                const double (*direction)[3], double* ekin_final, double (*direction_final)[3] );
+
+/* NCVirtAPIFactory.hh:45-52 -- OpenMC's boundary; C++ class layout in ncrystal_b200_virtapi.hh.  Returns the address
+ * of a static std::shared_ptr<const VirtAPI_Type1_v1> for interface_id 1001, else NULL. */
+void * ncrystal_access_virtual_api( unsigned interface_id );
+
 /* ncrystal.h:1305 -- results[r*n_ekin+i] */
 void ncrystal_crosssection_nonoriented_many( ncrystal_process_t, const double * ekin, unsigned long n_ekin,
                                              unsigned long repeat, double* results );

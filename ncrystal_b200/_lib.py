@@ -52,6 +52,11 @@ SIGNATURES = {
     "ncrystal_samplescatterisotropic": (None, [ncrystal_scatter_t, C.c_double, _dblp, _dblp]),
     "ncrystal_samplescatter": (None, [ncrystal_scatter_t, C.c_double, C.POINTER(C.c_double * 3), _dblp,
                                       C.POINTER(C.c_double * 3)]),
+    # caller-supplied generator double(*)(void*) + its state (ncrystal.h:792)
+    "ncrystal_samplescatter_rs": (None, [C.CFUNCTYPE(C.c_double, C.c_void_p), C.c_void_p, ncrystal_scatter_t, C.c_double,
+                                         C.POINTER(C.c_double * 3), _dblp, C.POINTER(C.c_double * 3)]),
+    # OpenMC's C++ boundary (include/ncrystal_b200_virtapi.hh); listed so that the export is checked
+    "ncrystal_access_virtual_api": (C.c_void_p, [C.c_uint]),
     "ncrystal_crosssection_nonoriented_many": (None, [ncrystal_process_t, _dblp, _ulong, _ulong, _dblp]),
     "ncrystal_samplescatterisotropic_many": (None, [ncrystal_scatter_t, _dblp, _ulong, _ulong, _dblp, _dblp]),
     "ncrystal_samplescatter_many": (None, [ncrystal_scatter_t, C.c_double, C.POINTER(C.c_double * 3), _ulong,

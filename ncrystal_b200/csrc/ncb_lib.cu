@@ -1632,3 +1632,6 @@ extern "C" {
 #undef NCB_MMC_CAPI
 
 }
+
+// ---- per-neutron boundaries with a caller-supplied generator (OpenMC virtual API, ncrystal_samplescatter_rs)
+#include "ncb_lib_virtapi.inc"

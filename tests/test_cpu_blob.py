@@ -143,3 +143,30 @@ def _build_cxx_caller(tmpdir):
 
 def test_cxx_mirror_compiles_and_links(tmp_path):
     assert os.path.exists(_build_cxx_caller(tmp_path))
+
+
+def _build_virtapi_caller(tmpdir):
+    import subprocess
+    exe = os.path.join(str(tmpdir), "virtapi_caller")
+    libdir = os.path.join(ROOT, "ncrystal_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "virtapi_caller.cc"), "-o", exe, "-L", libdir, "-lncrystal_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_virtual_api_client_compiles_and_links(tmp_path):
+    # a client of the OpenMC boundary (ncrystal_access_virtual_api, VirtAPI_Type1_v1) builds against the header
+    assert os.path.exists(_build_virtapi_caller(tmp_path))
+
+
+def test_virtual_api_vtable_layout_matches_reference_header():
+    # the abstract class must declare the same virtual methods in the same order as the reference's header
+    # (include/NCrystal/virtualapi/NCVirtAPI_Type1_v1.hh:79-91): that order IS the binary interface
+    import re
+    src = open(os.path.join(ROOT, "include", "ncrystal_b200_virtapi.hh")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    names = re.findall(r"virtual\s+[^;(]*?(~?\w+)\s*\(", src)
+    assert names == ["createScatter", "cloneScatter", "deallocateScatter", "crossSectionUncached",
+                     "sampleScatterUncached", "~VirtAPI_Type1_v1"]
+    assert "interface_id = 1001" in src
