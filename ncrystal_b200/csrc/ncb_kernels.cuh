@@ -628,6 +628,7 @@ namespace ncb {
     uint32_t* w;      // uniforms consumed so far (low 25 bits) | flags (bits 25-27) | stage (bits 28-31); kFgSkip: done
     uint32_t* cursor; // refill cursors: [0] k_fg_beta, [1] k_fg_alpha
     uint32_t epl;     // refill kernels: target number of entries per lane (surplus CTAs exit at once)
+    uint32_t batch;   // k_fg_beta: lanes waiting for the exact evaluation before it is run
     __device__ __forceinline__ double& slot( int k, uint32_t j ) const { return r[ (uint64_t)k*cap + j ]; }
   };
   constexpr uint32_t kFgSkip = 0xFFFFFFFFu;
@@ -738,45 +739,70 @@ namespace ncb {
     const uint32_t nq = Q.counts[1];
     if ( (uint64_t)blockIdx.x * blockDim.x * P.epl >= nq && blockIdx.x )
       return;
-    bool have = false, drained = false;
+    // An attempt has a cheap half (candidate + erfc bounds from the lookup table) and an expensive one (exact erfc
+    // evaluation, needed by roughly every second candidate).  Lanes that need the exact evaluation wait while the
+    // others go on with cheap halves (and refills), until P.batch lanes are waiting or nobody else can move: the
+    // expensive code then runs with most lanes active instead of about a third of them.
+    bool have = false, wait_exact = false, drained = false;
     uint32_t jrec = 0;
+    double beta = 0.0, faccept = 0.0;
     FreeGasSampler s;
     FreeGasSampler::BetaState st;
     Rng rng; rng.init( A.seed, A.first_index, A.sid );
     while ( true ) {
-      const uint32_t need = __ballot_sync( 0xffffffffu, !have );
-      if ( need ) {
-        const uint32_t j = fgPull( need, !have, P.cursor + 0, nq, drained );
-        if ( !have && j < nq ) {
-          const uint32_t w = P.w[j];
-          if ( w != kFgSkip ) {
-            const uint32_t entry = Q.q_fg[j];
-            const uint32_t i = entry & kQueueIdxMask;
-            double kT, mass;
-            fgLeafPars( M, M.comp[ entry >> kQueueIdxBits ], kT, mass );
-            s = FreeGasSampler( A.ekin[i], kT, mass );
-            rng.init( A.seed, A.streamIndex( i ), A.sid );
-            rng.seek( w & kFgNdMask );
-            const int kind = (int)( w >> 28 );
-            const double aa = P.slot( kSlotAA, j );
-            if ( kind != FreeGasSampler::kBetaLoop ) {
-              P.slot( kSlotBeta, j ) = s.betaDirect( kind, aa, rng );
-              P.w[j] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
-            } else {
-              s.betaBegin( st, aa, P.slot( kSlotBB, j ) );
-              jrec = j;
-              have = true;
+      while ( true ) {
+        const uint32_t need = __ballot_sync( 0xffffffffu, !have );
+        if ( need && !drained ) {
+          const uint32_t j = fgPull( need, !have, P.cursor + 0, nq, drained );
+          if ( !have && j < nq ) {
+            const uint32_t w = P.w[j];
+            if ( w != kFgSkip ) {
+              const uint32_t entry = Q.q_fg[j];
+              const uint32_t i = entry & kQueueIdxMask;
+              double kT, mass;
+              fgLeafPars( M, M.comp[ entry >> kQueueIdxBits ], kT, mass );
+              s = FreeGasSampler( A.ekin[i], kT, mass );
+              rng.init( A.seed, A.streamIndex( i ), A.sid );
+              rng.seek( w & kFgNdMask );
+              const int kind = (int)( w >> 28 );
+              const double aa = P.slot( kSlotAA, j );
+              if ( kind != FreeGasSampler::kBetaLoop ) {
+                P.slot( kSlotBeta, j ) = s.betaDirect( kind, aa, rng );
+                P.w[j] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
+              } else {
+                s.betaBegin( st, aa, P.slot( kSlotBB, j ) );
+                jrec = j;
+                have = true;
+                wait_exact = false;
+              }
             }
           }
         }
+        const bool run = have && !wait_exact;
+        const uint32_t running = __ballot_sync( 0xffffffffu, run );
+        if ( !running ) {
+          // nobody can do a cheap half: leave unless lanes are idle only because they met finished records
+          if ( drained || !__ballot_sync( 0xffffffffu, !have ) ) break;
+          continue;
+        }
+        if ( run ) {
+          const int q = s.betaAttemptQuick( st, rng, beta, faccept );
+          if ( q == FreeGasSampler::kBetaAccept ) {
+            P.slot( kSlotBeta, jrec ) = beta;
+            P.w[jrec] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
+            have = false;
+          } else if ( q == FreeGasSampler::kBetaNeedExact ) {
+            wait_exact = true;
+          }
+        }
+        if ( (uint32_t)__popc( __ballot_sync( 0xffffffffu, have && wait_exact ) ) >= P.batch )
+          break;
       }
-      if ( !__ballot_sync( 0xffffffffu, have ) ) {
-        if ( drained ) break;    // nothing in flight and nothing left to pull
-        continue;                // only finished records were met: pull again
-      }
-      if ( have ) {
-        double beta;
-        if ( s.betaAttempt( st, rng, beta ) ) {
+      if ( !__ballot_sync( 0xffffffffu, have ) )
+        break;      // the inner loop ends with nothing in flight only when the queue is drained
+      if ( have && wait_exact ) {
+        wait_exact = false;
+        if ( s.betaAttemptExact( st, beta, faccept ) ) {
           P.slot( kSlotBeta, jrec ) = beta;
           P.w[jrec] = rng.ndraws | ( (uint32_t)kFgBetaDone << 28 );
           have = false;

@@ -695,6 +695,8 @@ namespace {
     P.r = qc.fg_prep; P.cap = qc.fcap; P.w = qc.fg_nd;
     P.cursor = Q.counts + 8 + 48;
     P.epl = (uint32_t)std::max( 1, epl );
+    static const int batch = []{ const char* e = std::getenv( "NCB200_FG_BATCH" ); return e ? std::atoi(e) : 20; }();
+    P.batch = (uint32_t)std::min( 32, std::max( 1, batch ) );
     const unsigned gflat = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
     const unsigned grefill = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*( fgminb >= 8 ? 8 : 6 ) );
     { auto tl = timer( "k_fg_prep" );

@@ -503,11 +503,32 @@ namespace ncb {
       st.bfthreshold = st.ov.b;
     }
 
-    // (3) ONE pass of the rejection loop (:722-849): true = beta accepted, false = the reference's `continue`.
-    NCB_HD_NOINLINE bool betaAttempt( BetaState& st, Rng& rng, double& beta_out ) const
+    // (3) ONE pass of the rejection loop (:722-849), itself in two halves so that the kernel can run the expensive
+    //     exact evaluation for many lanes at once: betaAttemptQuick draws the candidate and decides what the cheap
+    //     erfc bounds can decide; betaAttemptExact is the exact evaluation for candidates they could not decide.
+    enum { kBetaReject = 0, kBetaAccept = 1, kBetaNeedExact = 2 };
+    // after a candidate was not accepted (:822-848): shrink the overlay / tighten the thresholds
+    NCB_HD void betaNotAccepted( BetaState& st, double beta, double fval ) const
+    {
+      const double fcutoff_limit = 1e-6;
+      constexpr double fthreshold = 0.1;
+      if ( fval < fcutoff_limit ) {
+        if ( beta < 0 )
+          st.ov.setAB( beta, st.ov.b );
+        else
+          st.ov.setAB( st.ov.a, beta );
+        return;
+      }
+      if ( fval < fthreshold ) {
+        if ( beta < 0 )
+          st.afthreshold = dmax( st.afthreshold, beta );
+        else
+          st.bfthreshold = dmin( st.bfthreshold, beta );
+      }
+    }
+    NCB_HD_NOINLINE int betaAttemptQuick( BetaState& st, Rng& rng, double& beta_out, double& faccept_out ) const
     {
       constexpr double Tlim = 2.0;
-      const double fcutoff_limit = 1e-6;
       constexpr double fthreshold = 0.1;
       Overlay& ov = st.ov;
       double beta, foverlay;
@@ -543,41 +564,37 @@ namespace ncb {
       }
       const double faccept = rng.generate()*foverlay;
       if ( faccept > fthreshold && !inInterval( st.afthreshold, st.bfthreshold, beta ) )
-        return false;
-      FGBetaDist eval_helper( m_c, m_invA, m_sqrtAc, beta, m_normfact );
-      bool need_exact(true);
-      double fval;
+        return kBetaReject;
+      beta_out = beta;
+      faccept_out = faccept;
       if ( beta > 0 ) {
+        FGBetaDist eval_helper( m_c, m_invA, m_sqrtAc, beta, m_normfact );
         PairDD bnd = eval_helper.evalQuickBounds();
-        if ( faccept <= bnd.first ) {
-          beta_out = beta;
-          return true;
-        }
-        fval = bnd.second;
-        if ( faccept > bnd.second )
-          need_exact = false;
-      }
-      if ( need_exact ) {
-        fval = eval_helper.evalExact();
-        if ( faccept < fval ) {
-          beta_out = beta;
-          return true;
+        if ( faccept <= bnd.first )
+          return kBetaAccept;
+        if ( faccept > bnd.second ) {
+          betaNotAccepted( st, beta, bnd.second );
+          return kBetaReject;
         }
       }
-      if ( fval < fcutoff_limit ) {
-        if ( beta < 0 )
-          ov.setAB( beta, ov.b );
-        else
-          ov.setAB( ov.a, beta );
-        return false;
-      }
-      if ( fval < fthreshold ) {
-        if ( beta < 0 )
-          st.afthreshold = dmax( st.afthreshold, beta );
-        else
-          st.bfthreshold = dmin( st.bfthreshold, beta );
-      }
+      return kBetaNeedExact;
+    }
+    NCB_HD_NOINLINE bool betaAttemptExact( BetaState& st, double beta, double faccept ) const
+    {
+      const double fval = FGBetaDist( m_c, m_invA, m_sqrtAc, beta, m_normfact ).evalExact();
+      if ( faccept < fval )
+        return true;
+      betaNotAccepted( st, beta, fval );
       return false;
+    }
+    // true = beta accepted, false = the reference's `continue`
+    NCB_HD bool betaAttempt( BetaState& st, Rng& rng, double& beta_out ) const
+    {
+      double faccept;
+      const int q = betaAttemptQuick( st, rng, beta_out, faccept );
+      if ( q != kBetaNeedExact )
+        return q == kBetaAccept;
+      return betaAttemptExact( st, beta_out, faccept );
     }
 
     // beta from the outcome of betaSupport when no rejection loop is needed
