@@ -205,6 +205,9 @@ void     ncb200_material_bulk( ncrystal_process_t, double* numdens, double* abs_
  * recording; the report is a JSON object {"kernel": {"launches": n, "ms_avg": t}, ...} (returns its length). */
 void     ncb200_kernel_timing( int enable );
 int      ncb200_kernel_timing_report( char* buf, int buflen );
+/* Batches of at least nmin neutrons sample their free-gas queue with the staged kernels (k_fg_prep ... k_fg_finish),
+ * smaller ones with the single neutron-per-lane kernel; identical results.  Default 4e6 ($NCB200_FG_STAGED_MIN). */
+void     ncb200_set_fg_staged_min( uint64_t nmin );
 /* sizes of the work queues of the most recent isotropic sampling launch: table path, free-gas path, table at Emax */
 int      ncb200_last_queue_counts( ncrystal_scatter_t, uint32_t* out3 );
 const char* ncb200_version(void);

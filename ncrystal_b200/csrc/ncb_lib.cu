@@ -668,10 +668,13 @@ namespace {
     Q.q_fg = q_out;
   }
 
-  // Free-gas queue: the staged pipeline k_fg_prep / k_fg_beta / k_fg_alpha_prep / k_fg_alpha / k_fg_finish (default for
-  // batches that fill the machine), or the neutron-per-lane k_sample_fg (small batches: four launches less;
-  // NCB200_FG_MODE=0 forces it).  The two refill cursors live in the (otherwise unused) sort-histogram area of the
+  // Free-gas queue: the staged pipeline k_fg_prep / k_fg_beta / k_fg_alpha_prep / k_fg_alpha / k_fg_finish for large
+  // batches (>= NCB200_FG_STAGED_MIN neutrons, default 4e6), or the neutron-per-lane k_sample_fg (four launches and
+  // two kernel tails less: measured better for the 1 Mi-neutron chunks of the host-pointer pipeline and for the
+  // shrinking populations of a transport run; NCB200_FG_MODE=0 forces it).  The two refill cursors live in the (otherwise unused) sort-histogram area of the
   // counters, zeroed with them at the start of the launch sequence.
+  std::atomic<uint64_t> g_fg_staged_min{ []{ const char* e = std::getenv( "NCB200_FG_STAGED_MIN" );
+                                             return e ? (uint64_t)std::atoll(e) : (uint64_t)4000000; }() };
   void launchFgSampling( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const SampleArgs& A, const QueueArgs& Q,
                          uint64_t m, cudaStream_t st, bool timed )
   {
@@ -679,7 +682,7 @@ namespace {
     static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
     static const int fgminb = []{ const char* e = std::getenv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
     static const int epl = []{ const char* e = std::getenv( "NCB200_FG_EPL" ); return e ? std::atoi(e) : 4; }();
-    static const uint64_t minbatch = []{ const char* e = std::getenv( "NCB200_FG_STAGED_MIN" ); return e ? (uint64_t)std::atoll(e) : (uint64_t)65536; }();
+    const uint64_t minbatch = g_fg_staged_min.load();
     const unsigned nsm = (unsigned)numSMs( dm.device );
     auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
     if ( mode == 0 || m < minbatch || Q.hist ) {
@@ -1407,6 +1410,7 @@ extern "C" {
       s->seed = seed; s->sid = stream_id; s->next_index = next_index;
     } NCBCATCH;
   }
+  void ncb200_set_fg_staged_min( uint64_t nmin ) { g_fg_staged_min.store( nmin ); }
   void ncb200_get_rng_stream( ncrystal_scatter_t o, uint64_t* seed, uint32_t* stream_id, uint64_t* next_index )
   {
     try {

@@ -48,6 +48,28 @@ def test_extra_isotropic(key):
     assert (~ok & ~flips).sum() == 0 and ok.mean() >= 0.999
 
 
+@pytest.mark.parametrize("key", ["D2O", "gas", "CH2_77K", "YAGCor"])
+def test_extra_isotropic_staged_free_gas(key):
+    # the staged free-gas kernels (used for batches >= 4e6 neutrons) forced on a small batch: same golden vectors
+    import torch
+    g = np.load(os.path.join(HERE, "golden", "iso_%s.npz" % key))
+    seed = int(g["seed"])
+    sc = _scatter(key, seed)
+    d_e = torch.from_numpy(g["ekin"]).cuda()
+    nd = torch.zeros(d_e.numel(), dtype=torch.int32, device="cuda")
+    sc._L.ncb200_set_fg_staged_min(1)
+    try:
+        sc.setRNGStream(seed, 0, 0)
+        sc._L.ncb200_set_diagnostics_dev(sc._h, nd.data_ptr(), None)
+        eo, mu = [t.cpu().numpy() for t in sc.sampleScatterIsotropic(d_e)]
+        sc.checkDeviceErrors()
+    finally:
+        sc._L.ncb200_set_fg_staged_min(4000000)
+    ok = (np.abs(eo - g["ekin_out"]) <= 1e-10 * np.maximum(np.abs(g["ekin_out"]), 1e-300)) & (np.abs(mu - g["mu"]) <= 1e-10)
+    flips = nd.cpu().numpy().astype(np.uint32) != g["ndraws"]
+    assert (~ok & ~flips).sum() == 0 and ok.mean() >= 0.999
+
+
 @pytest.mark.parametrize("key", EXTRA_ANISO)
 def test_extra_oriented(key):
     import torch
