@@ -105,6 +105,35 @@ namespace ncb {
     return i;
   }
 
+  // Loads from the immutable material tables in global memory: ld.global.nc instead of the generic-address loads the
+  // compiler emits for pointers it only knows from a by-value struct (ncu: LD.E + two R2UR per search step).
+  template <class T>
+  NCB_HD T ldTable( const T* p )
+  {
+#if defined(__CUDA_ARCH__)
+    return __ldg( p );
+#else
+    return *p;
+#endif
+  }
+  // upperBound / lowerBound over a table in global memory
+  NCB_HD int upperBoundTable( const double* a, int lo, int hi, double v )
+  {
+    while ( lo < hi ) {
+      int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( !( v < ldTable( a + mid ) ) ) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+  NCB_HD int lowerBoundTable( const double* a, int lo, int hi, double v )
+  {
+    while ( lo < hi ) {
+      int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( ldTable( a + mid ) < v ) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+
   template <class Ptr>
   NCB_HD int lowerBound( Ptr a, int lo, int hi, double v )
   {

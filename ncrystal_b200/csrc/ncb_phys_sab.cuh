@@ -46,21 +46,22 @@ namespace ncb {
   {
     if ( p == 1. ) {
       idx = n-2;
-      return x[n-1];
+      return ldTable( x + n-1 );
     }
     int i;
     if ( guide ) {
       const int b = (int)( p * (double)kSabGB );
-      i = lowerBound( cdf, (int)guide[b], (int)guide[b+1], p );
+      i = lowerBoundTable( cdf, (int)ldTable( guide + b ), (int)ldTable( guide + b+1 ), p );
     } else {
-      i = lowerBound( cdf, 0, n, p );
+      i = lowerBoundTable( cdf, 0, n, p );
     }
     i = i < n-1 ? i : n-1;
     i = i > 1 ? i : 1;
-    const double dx = x[i] - x[i-1];
-    const double c = ( p - cdf[i-1] );
-    const double a = y[i-1];
-    const double d = y[i] - a;
+    const double x0 = ldTable( x + i-1 ), x1 = ldTable( x + i );
+    const double dx = x1 - x0;
+    const double c = ( p - ldTable( cdf + i-1 ) );
+    const double a = ldTable( y + i-1 );
+    const double d = ldTable( y + i ) - a;
     double zdx;
     if ( !a ) {
       zdx = d > 0.0 ? sqrt( ( 2.0 * c * dx ) / d ) : 0.5*dx;
@@ -72,7 +73,7 @@ namespace ncb {
         zdx = ( 1 + 0.5 * e * ( e - 1.0 ) ) * c / a;
     }
     idx = i-1;
-    return dclamp( x[i-1] + zdx, x[i-1], x[i] );
+    return dclamp( x0 + zdx, x0, x1 );
   }
 
   // SABSamplerAtE_Alg1::sampleAlpha, ref: NCSABSamplerModels.cc:157-233.
@@ -82,62 +83,65 @@ namespace ncb {
   // log/exp sequence once instead of up to three times.  Same arithmetic, same results.
   NCB_HD_NOINLINE double sabSampleAlpha( const SabT& T, const SabEPoint& ep, int ibeta, double rand_percentile )
   {
-    const SabAlphaInfo& info = T.ainfo[ ep.off_i + ( ibeta - ep.ibeta_off ) ];
+    const SabAlphaInfo* info = &T.ainfo[ ep.off_i + ( ibeta - ep.ibeta_off ) ];
     const int nalpha = T.nalpha;
     const double* cumul  = T.cumul  + (size_t)ibeta*nalpha;
     const double* sab    = T.sab    + (size_t)ibeta*nalpha;
     const double* logsab = T.logsab + (size_t)ibeta*nalpha;
     const double* agrid  = T.alpha;
     double a, fa, b, fb, r, la, lb;
-    const double prob_front = info.prob_front, prob_notback = info.prob_notback;
+    const double prob_front = ldTable( &info->prob_front ), prob_notback = ldTable( &info->prob_notback );
 
     if ( rand_percentile <= prob_front ) {
+      const double f_alpha = ldTable( &info->f_alpha );
       if ( prob_front == 2.0 ) {
-        const double da = info.b_alpha - info.f_alpha;
-        return info.f_alpha + rand_percentile*da;
+        const double da = ldTable( &info->b_alpha ) - f_alpha;
+        return f_alpha + rand_percentile*da;
       } else if ( prob_front == 1.0 ) {
-        a = info.f_alpha; fa = info.f_sval; b = info.b_alpha; fb = info.b_sval;
-        r = rand_percentile; la = info.f_logsval; lb = info.b_logsval;
+        a = f_alpha; fa = ldTable( &info->f_sval ); b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
+        r = rand_percentile; la = ldTable( &info->f_logsval ); lb = ldTable( &info->b_logsval );
       } else {
-        const int fi = info.f_idx;
-        a = info.f_alpha; fa = info.f_sval; b = agrid[fi]; fb = sab[fi];
+        const int fi = ldTable( &info->f_idx );
+        a = f_alpha; fa = ldTable( &info->f_sval ); b = ldTable( agrid + fi ); fb = ldTable( sab + fi );
         r = dclamp( rand_percentile / prob_front, kDblMin, 1.0 );
-        la = info.f_logsval; lb = logsab[fi];
+        la = ldTable( &info->f_logsval ); lb = ldTable( logsab + fi );
       }
     } else if ( rand_percentile <= prob_notback ) {
       const double percentile2 = dclamp( ( rand_percentile - prob_front ) / ( prob_notback - prob_front ), 0.0, 1.0 );
-      const int ilow = info.f_idx, iupp = info.b_idx;
-      const double clow = cumul[ilow], cupp = cumul[iupp];
+      const int ilow = ldTable( &info->f_idx ), iupp = ldTable( &info->b_idx );
+      const double clow = ldTable( cumul + ilow ), cupp = ldTable( cumul + iupp );
       const double selectedArea = clow + percentile2 * ( cupp - clow );
       int isel_upp;
       {
         // upper_bound( cumul[ilow..iupp], selectedArea ) = clamp( upper_bound over the whole row ) to that
         // range; the whole-row position is bracketed by the row's guide table and verified (the bucket
         // index involves a rounded product), with a full search as fall-back.
-        const double sc = T.ascale[ibeta];
-        int b = (int)( selectedArea * sc );
-        b = b < 0 ? 0 : ( b > kSabGA-1 ? kSabGA-1 : b );
-        const uint16_t* g = T.aguide + (size_t)ibeta*( kSabGA+1 ) + b;
-        int r0 = upperBound( cumul, (int)g[0], (int)g[1], selectedArea );
-        const bool ok = ( r0 == 0 || !( selectedArea < cumul[r0-1] ) ) && ( r0 == nalpha || selectedArea < cumul[r0] );
+        const double sc = ldTable( T.ascale + ibeta );
+        int bk = (int)( selectedArea * sc );
+        bk = bk < 0 ? 0 : ( bk > kSabGA-1 ? kSabGA-1 : bk );
+        const uint16_t* g = T.aguide + (size_t)ibeta*( kSabGA+1 ) + bk;
+        int r0 = upperBoundTable( cumul, (int)ldTable( g ), (int)ldTable( g + 1 ), selectedArea );
+        const bool ok = ( r0 == 0 || !( selectedArea < ldTable( cumul + r0-1 ) ) ) && ( r0 == nalpha || selectedArea < ldTable( cumul + r0 ) );
         if ( !ok )
-          r0 = upperBound( cumul, 0, nalpha, selectedArea );
+          r0 = upperBoundTable( cumul, 0, nalpha, selectedArea );
         isel_upp = r0 < ilow ? ilow : ( r0 > iupp+1 ? iupp+1 : r0 );
       }
       if ( isel_upp > iupp )
-        return agrid[iupp];
+        return ldTable( agrid + iupp );
       if ( isel_upp <= ilow )
-        return agrid[ilow];
+        return ldTable( agrid + ilow );
       const int a0 = isel_upp - 1;
       const int a1 = isel_upp;
-      const double c0 = cumul[a0], c1 = cumul[a1];
+      const double c0 = ldTable( cumul + a0 ), c1 = ldTable( cumul + a1 );
       const double binArea = c1 - c0;
       r = dclamp( ( selectedArea - c0 ) / binArea, kDblMin, 1.0 );
-      a = agrid[a0]; fa = sab[a0]; b = agrid[a1]; fb = sab[a1]; la = logsab[a0]; lb = logsab[a1];
+      a = ldTable( agrid + a0 ); fa = ldTable( sab + a0 ); b = ldTable( agrid + a1 ); fb = ldTable( sab + a1 );
+      la = ldTable( logsab + a0 ); lb = ldTable( logsab + a1 );
     } else {
-      const int bi = info.b_idx;
+      const int bi = ldTable( &info->b_idx );
       r = dclamp( ( rand_percentile - prob_notback ) / ( 1.0 - prob_notback ), kDblMin, 1.0 );
-      a = agrid[bi]; fa = sab[bi]; b = info.b_alpha; fb = info.b_sval; la = logsab[bi]; lb = info.b_logsval;
+      a = ldTable( agrid + bi ); fa = ldTable( sab + bi ); b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
+      la = ldTable( logsab + bi ); lb = ldTable( &info->b_logsval );
     }
     return sampleLogLinDistFast( a, fa, b, fb, r, la, lb );
   }
