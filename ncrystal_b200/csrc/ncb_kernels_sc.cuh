@@ -98,6 +98,7 @@ namespace ncb {
                                               int mode, bool linear, double choice )
   {
     const int lane = threadIdx.x & 31;
+    __syncwarp();   // the scratch is reused from the previous neutron of this warp: its last reads come first
     acc.cur_fam = -1; acc.n = 0; acc.xsoffset = acc.xssum = acc.commul_last = 0.0;
     acc.found = false; acc.chosen_in = 0; acc.chosen_sign = 1;
     const double ekin = scCacheRound( ekin_raw );
