@@ -93,6 +93,29 @@ void ncrystal_samplescatterisotropic_many( ncrystal_scatter_t, const double * ek
 void ncrystal_samplescatter_many( ncrystal_scatter_t, double ekin, const double (*direction)[3], unsigned long repeat,
                                   double* results_ekin, double * results_dirx, double * results_diry, double * results_dirz );
 
+/* ncrystal.h:1340-1368 -- the reference's obsolete "genscatter" entry points (older McStas / Geant4 bindings):
+ * the same sampling reported as (scattering angle [rad], energy transfer) / (direction, energy transfer) */
+void ncrystal_genscatter_nonoriented( ncrystal_scatter_t, double ekin, double* result_angle, double* result_dekin );
+void ncrystal_genscatter_nonoriented_many( ncrystal_scatter_t, const double * ekin, unsigned long n_ekin, unsigned long repeat,
+                                           double* results_angle, double* results_dekin );
+void ncrystal_genscatter( ncrystal_scatter_t, double ekin, const double (*direction)[3],
+                          double (*result_direction)[3], double* result_deltaekin );
+void ncrystal_genscatter_many( ncrystal_scatter_t, double ekin, const double (*direction)[3], unsigned long repeat,
+                               double * results_dirx, double * results_diry, double * results_dirz, double * results_dekin );
+
+/* ncrystal.h:719 */
+ncrystal_absorption_t ncrystal_clone_absorption( ncrystal_absorption_t );
+/* ncrystal.h:1164 -- id of the underlying immutable process (same for clones); free with ncrystal_dealloc_string */
+char * ncrystal_process_uid( ncrystal_process_t );
+/* ncrystal.h:1229-1234 -- version of the NCrystal release whose hot path this library restates (4.4.2) */
+int ncrystal_version(void);
+const char * ncrystal_version_str(void);
+const char * ncrystal_namespace(void);
+/* ncrystal.h:1220, :1389 (obsolete in the reference too: raises an error) */
+void ncrystal_dealloc_doubleptr( double* );
+void ncrystal_runmmcsim_stdengine( unsigned, unsigned, const char *, const char *, const char *, char **, unsigned *,
+                                   double **, double ** );
+
 /* ncrystal.h:1147-1148 -- unit conversions (Aa <-> eV) */
 double ncrystal_wl2ekin( double wl );
 double ncrystal_ekin2wl( double ekin );
@@ -109,11 +132,13 @@ int  ncrystal_sethaltonerror( int );
 void ncrystal_seterrhandler( void (*handler)(char*,char*) );
 
 /* ncrystal.h:1067-1087 -- RNG control.  Host callbacks cannot be honoured on the
- * device: ncrystal_setrandgen raises an error.  State strings serialise
+ * device: ncrystal_setrandgen raises an error.  The ncrystal_setbuiltinrandgen* calls set the seed (and restart the
+ * stream numbering) of the scatter handles that ncrystal_create_scatter makes afterwards.  State strings serialise
  * (seed, stream id, next neutron index). */
 void ncrystal_setrandgen( double (*rg)(void) );
 void ncrystal_setbuiltinrandgen(void);
 void ncrystal_setbuiltinrandgen_withseed( unsigned long seed );
+void ncrystal_setbuiltinrandgen_withstate( const char* state );   /* a string from ncrystal_getrngstate_ofscatter */
 int  ncrystal_rngsupportsstatemanip_ofscatter( ncrystal_scatter_t );
 char* ncrystal_getrngstate_ofscatter( ncrystal_scatter_t );  /* free with ncrystal_dealloc_string */
 void ncrystal_setrngstate_ofscatter( ncrystal_scatter_t, const char* );

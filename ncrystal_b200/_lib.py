@@ -52,6 +52,20 @@ SIGNATURES = {
     "ncrystal_samplescatterisotropic": (None, [ncrystal_scatter_t, C.c_double, _dblp, _dblp]),
     "ncrystal_samplescatter": (None, [ncrystal_scatter_t, C.c_double, C.POINTER(C.c_double * 3), _dblp,
                                       C.POINTER(C.c_double * 3)]),
+    "ncrystal_genscatter_nonoriented": (None, [ncrystal_scatter_t, C.c_double, _dblp, _dblp]),
+    "ncrystal_genscatter_nonoriented_many": (None, [ncrystal_scatter_t, _dblp, _ulong, _ulong, _dblp, _dblp]),
+    "ncrystal_genscatter": (None, [ncrystal_scatter_t, C.c_double, C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 3), _dblp]),
+    "ncrystal_genscatter_many": (None, [ncrystal_scatter_t, C.c_double, C.POINTER(C.c_double * 3), _ulong,
+                                        _dblp, _dblp, _dblp, _dblp]),
+    "ncrystal_clone_absorption": (ncrystal_absorption_t, [ncrystal_absorption_t]),
+    "ncrystal_process_uid": (C.c_void_p, [ncrystal_process_t]),
+    "ncrystal_version": (C.c_int, []),
+    "ncrystal_version_str": (C.c_char_p, []),
+    "ncrystal_namespace": (C.c_char_p, []),
+    "ncrystal_dealloc_doubleptr": (None, [_dblp]),
+    "ncrystal_runmmcsim_stdengine": (None, [C.c_uint, C.c_uint, C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
+    "ncrystal_setbuiltinrandgen_withstate": (None, [C.c_char_p]),
     # caller-supplied generator double(*)(void*) + its state (ncrystal.h:792)
     "ncrystal_samplescatter_rs": (None, [C.CFUNCTYPE(C.c_double, C.c_void_p), C.c_void_p, ncrystal_scatter_t, C.c_double,
                                          C.POINTER(C.c_double * 3), _dblp, C.POINTER(C.c_double * 3)]),

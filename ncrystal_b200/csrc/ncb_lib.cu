@@ -116,6 +116,7 @@ namespace {
   };
 
   // ------------------------------------------------------------------ material on device
+  std::atomic<uint64_t> g_material_uid_counter{0};
   struct DeviceMaterial {
     int device = 0;
     void* d_arena = nullptr;
@@ -132,6 +133,7 @@ namespace {
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
     std::vector<SabBuildPlan> sabplans;
     std::atomic<uint32_t> clone_counter{0};
+    uint64_t uid = 0;        // ncrystal_process_uid
     ~DeviceMaterial() { if ( d_arena ) cudaFree( d_arena ); }
   };
 
@@ -298,6 +300,7 @@ namespace {
       throw Err( "BadInput", e.what() );
     }
     auto dm = std::make_shared<DeviceMaterial>();
+    dm->uid = ++g_material_uid_counter;
     CUDA_OK( cudaGetDevice( &dm->device ) );
     ensureErfcLut( dm->device );
     dm->arena_bytes = lm.arena.size();
@@ -513,6 +516,7 @@ namespace {
 
   std::atomic<uint32_t> g_default_stream_counter{0};
   constexpr uint64_t kDefaultSeed = 0x4e4372797374616cULL; // "NCrystal"
+  std::atomic<uint64_t> g_default_seed{ kDefaultSeed };    // ncrystal_setbuiltinrandgen[_withseed|_withstate]
 
   ncrystal_scatter_t newHandle( std::shared_ptr<DeviceMaterial> dm, uint64_t seed, uint32_t sid )
   {
@@ -1174,6 +1178,7 @@ extern "C" {
       if ( hdr.magic != NCB_MAGIC || hdr.version != NCB_VERSION ) throw Err( "BadInput", "compiled material: bad magic or version" );
       if ( hdr.abs_c < 0.0 ) throw Err( "BadInput", "the material's absorption process is not of the 1/v type" );
       auto dm = std::make_shared<DeviceMaterial>();
+      dm->uid = ++g_material_uid_counter;
       CUDA_OK( cudaGetDevice( &dm->device ) );
       std::memset( &dm->mat, 0, sizeof(dm->mat) );
       std::memset( &dm->sp, 0, sizeof(dm->sp) ); std::memset( &dm->sp_sc, 0, sizeof(dm->sp_sc) ); std::memset( &dm->sp_iso, 0, sizeof(dm->sp_iso) );
@@ -1210,6 +1215,44 @@ extern "C" {
     return { nullptr };
   }
 
+  // ref: ncrystal.cc:1518-1525 -- absorption handles carry no state: the clone shares the material
+  ncrystal_absorption_t ncrystal_clone_absorption( ncrystal_absorption_t a )
+  {
+    try {
+      Scatter* s = fromInternal( a.internal, "ncrystal_clone_absorption" );
+      if ( s->fp.tag != kAbsorptionTag ) throw Err( "LogicError", "ncrystal_clone_absorption: not an absorption handle" );
+      ncrystal_scatter_t h = newHandle( s->dm, 0, 0 );
+      static_cast<FingerPrint*>( h.internal )->tag = kAbsorptionTag;
+      return { h.internal };
+    } NCBCATCH;
+    return { nullptr };
+  }
+  // ref: ncrystal.cc:2287-2295 -- id of the underlying (shared, immutable) process: equal for a handle and its clones
+  char* ncrystal_process_uid( ncrystal_process_t p )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncrystal_process_uid" );
+      const std::string u = std::to_string( s->dm->uid );
+      char* out = static_cast<char*>( std::malloc( u.size()+1 ) );
+      std::strcpy( out, u.c_str() );
+      return out;
+    } NCBCATCH;
+    return nullptr;
+  }
+  // ref: ncrystal.h:1229-1234 -- the NCrystal release whose hot path this library restates
+  int ncrystal_version(void) { return 4004002; }
+  const char* ncrystal_version_str(void) { return "4.4.2"; }
+  const char* ncrystal_namespace(void) { return ""; }
+  void ncrystal_dealloc_doubleptr( double* p ) { std::free( p ); }
+  // ref: ncrystal.h:1387-1393 -- obsolete in the reference as well ("Calling it will result in an error")
+  void ncrystal_runmmcsim_stdengine( unsigned, unsigned, const char*, const char*, const char*, char**, unsigned*, double**, double** )
+  {
+    try {
+      throw Err( "LogicError", "The ncrystal_runmmcsim_stdengine function is obsolete; use ncb200_minimc_run "
+                 "(the [\"mmc\",\"run\",...] query of ncrystal_jsonquery)." );
+    } NCBCATCH;
+  }
+
   // ---- creation
   ncrystal_scatter_t ncb200_create_scatter_from_blob( const void* blob, size_t nbytes, unsigned long seed )
   {
@@ -1242,7 +1285,7 @@ extern "C" {
       auto d = findCompiledMaterial( cfgstr );
       // every handle created without explicit seed gets its own stream, like the reference's
       // default RNG producer (NCFact.cc:28-35)
-      return newHandle( uploadMaterial( d.data(), d.size() ), kDefaultSeed, 0x10000000u + g_default_stream_counter++ );
+      return newHandle( uploadMaterial( d.data(), d.size() ), g_default_seed.load(), 0x10000000u + g_default_stream_counter++ );
     } NCBCATCH;
     return { nullptr };
   }
@@ -1427,8 +1470,21 @@ extern "C" {
                  "ncrystal_b200 uses per-neutron counter-based streams (see ncb200_set_rng_stream)" );
     } NCBCATCH;
   }
-  void ncrystal_setbuiltinrandgen(void) {}
-  void ncrystal_setbuiltinrandgen_withseed( unsigned long ) {}
+  // ref: ncrystal.cc:1996-2025.  The "default generator" is the seed (and stream numbering) that scatter handles
+  // created afterwards by ncrystal_create_scatter start from: re-seeding makes their outcomes reproducible.
+  void ncrystal_setbuiltinrandgen(void) { g_default_seed.store( kDefaultSeed ); g_default_stream_counter.store( 0 ); }
+  void ncrystal_setbuiltinrandgen_withseed( unsigned long seed ) { g_default_seed.store( seed ); g_default_stream_counter.store( 0 ); }
+  void ncrystal_setbuiltinrandgen_withstate( const char* st )
+  {
+    try {
+      unsigned long long seed, idx; unsigned sid;
+      if ( !st || std::strlen(st) != 48 || std::strcmp( st+40, "b2005eed" ) != 0
+           || std::sscanf( st, "%16llx%8x%16llx", &seed, &sid, &idx ) != 3 )
+        throw Err( "BadInput", std::string("ncrystal_setbuiltinrandgen_withstate got state which is not from this library's RNG: ")
+                   + ( st ? st : "<null>" ) );
+      g_default_seed.store( seed ); g_default_stream_counter.store( 0 );
+    } NCBCATCH;
+  }
   int ncrystal_rngsupportsstatemanip_ofscatter( ncrystal_scatter_t ) { return 1; }
   char* ncrystal_getrngstate_ofscatter( ncrystal_scatter_t o )
   {

@@ -261,3 +261,107 @@ def test_samplescatter_rs_uses_the_callers_generator(configs):
     assert a == b and a != c
     assert abs(sum(x * x for x in a[1]) - 1.0) < 1e-12 and a[0] > 0
     assert sc.getRNGStream() == before
+
+
+def test_obsolete_genscatter_entry_points(configs):
+    # ncrystal.h:1340-1368 / ncrystal.cc:1284-1373: the same sampling reported as (angle, dE) or (direction, dE);
+    # with the stream rewound they must restate the current entry points exactly
+    import ctypes as C
+    from ncrystal_b200 import _lib
+    import ncrystal_b200 as nc
+    L = _lib.lib()
+    dp = C.POINTER(C.c_double)
+    sc = nc.Scatter(configs["Al"], seed=9)
+    e = 10.0 ** np.random.default_rng(3).uniform(-4, 0.5, 5000)
+    sc.setRNGStream(9, 0, 0)
+    eo, mu = sc.sampleScatterIsotropic(e, repeat=2)
+    ang, de = np.empty(2 * e.size), np.empty(2 * e.size)
+    sc.setRNGStream(9, 0, 0)
+    L.ncrystal_genscatter_nonoriented_many(sc._h, e.ctypes.data_as(dp), e.size, 2, ang.ctypes.data_as(dp), de.ctypes.data_as(dp))
+    assert np.array_equal(de, eo - np.tile(e, 2))
+    assert np.max(np.abs(ang - np.arccos(mu))) <= 4e-16 * np.pi     # libm acos vs numpy's: last-bit differences only
+    sc.setRNGStream(9, 0, 0)
+    a1, d1 = C.c_double(), C.c_double()
+    L.ncrystal_genscatter_nonoriented(sc._h, float(e[0]), C.byref(a1), C.byref(d1))
+    assert a1.value == ang[0] and d1.value == de[0]
+    # oriented flavour on the single crystal
+    ge = nc.Scatter(configs["Ge"], seed=4)
+    ekin = 0.081804209605330899 / 1.54 ** 2
+    d_in = (C.c_double * 3)(0.0, 1.0, 1.0)
+    ge.setRNGStream(4, 0, 0)
+    ef, d_out = C.c_double(), (C.c_double * 3)()
+    L.ncrystal_samplescatter(ge._h, ekin, C.byref(d_in), C.byref(ef), C.byref(d_out))
+    ge.setRNGStream(4, 0, 0)
+    dek, g_out = C.c_double(), (C.c_double * 3)()
+    L.ncrystal_genscatter(ge._h, ekin, C.byref(d_in), C.byref(g_out), C.byref(dek))
+    assert tuple(g_out) == tuple(d_out) and dek.value == ef.value - ekin
+    n = 64
+    ge.setRNGStream(4, 0, 0)
+    re_, rx, ry, rz = (np.empty(n) for _ in range(4))
+    L.ncrystal_samplescatter_many(ge._h, ekin, C.byref(d_in), n, *[a.ctypes.data_as(dp) for a in (re_, rx, ry, rz)])
+    ge.setRNGStream(4, 0, 0)
+    gx, gy, gz, gde = (np.empty(n) for _ in range(4))
+    L.ncrystal_genscatter_many(ge._h, ekin, C.byref(d_in), n, *[a.ctypes.data_as(dp) for a in (gx, gy, gz, gde)])
+    assert np.array_equal(gx, rx) and np.array_equal(gy, ry) and np.array_equal(gz, rz) and np.array_equal(gde, re_ - ekin)
+
+
+def test_version_uid_absorption_clone_and_default_seeding(configs):
+    import ctypes as C
+    from ncrystal_b200 import _lib
+    import ncrystal_b200 as nc
+    L = _lib.lib()
+    assert L.ncrystal_version() == 4004002 and L.ncrystal_version_str() == b"4.4.2" and L.ncrystal_namespace() == b""
+
+    def uid(proc):
+        p = L.ncrystal_process_uid(proc)
+        v = C.cast(p, C.c_char_p).value
+        L.ncrystal_dealloc_string(p)
+        return v
+
+    a, b = nc.Scatter(configs["Al"], seed=1), nc.Scatter(configs["CH2"], seed=1)
+    c = a.clone()
+    assert uid(a._p) == uid(c._p) and uid(a._p) != uid(b._p)
+    # absorption clone: same 1/v cross section (ncrystal.h:719)
+    ab = L.ncrystal_create_absorption(configs["Al"].encode())
+    ab2 = L.ncrystal_clone_absorption(ab)
+    x1, x2 = C.c_double(), C.c_double()
+    L.ncrystal_crosssection_nonoriented(L.ncrystal_cast_abs2proc(ab), 0.0253, C.byref(x1))
+    L.ncrystal_crosssection_nonoriented(L.ncrystal_cast_abs2proc(ab2), 0.0253, C.byref(x2))
+    assert x1.value == x2.value > 0
+    for h in (ab, ab2):
+        L.ncrystal_unref(C.byref(h))
+    # seeding the default generator makes handles from ncrystal_create_scatter reproducible (ncrystal.h:1071-1073)
+    e = np.full(2000, 0.0253)
+    dp = C.POINTER(C.c_double)
+
+    def run():
+        h = L.ncrystal_create_scatter(configs["Al"].encode())
+        eo, mu = np.empty(e.size), np.empty(e.size)
+        L.ncrystal_samplescatterisotropic_many(h, e.ctypes.data_as(dp), e.size, 1, eo.ctypes.data_as(dp), mu.ctypes.data_as(dp))
+        p = L.ncrystal_getrngstate_ofscatter(h)
+        st = C.cast(p, C.c_char_p).value
+        L.ncrystal_dealloc_string(p)
+        L.ncrystal_unref(C.byref(h))
+        return mu, st
+
+    try:
+        L.ncrystal_setbuiltinrandgen_withseed(4242)
+        m1, st1 = run()
+        m_next, _ = run()                      # the next handle gets its own stream
+        L.ncrystal_setbuiltinrandgen_withseed(4242)
+        m2, _ = run()
+        L.ncrystal_setbuiltinrandgen_withseed(4243)
+        m3, _ = run()
+        assert np.array_equal(m1, m2) and not np.array_equal(m1, m_next) and not np.array_equal(m1, m3)
+        # a state string seeds the default generator as well; garbage raises (non-halting here: error state)
+        L.ncrystal_setbuiltinrandgen_withstate(st1)
+        m4, _ = run()
+        assert np.array_equal(m4, m1)
+        old = L.ncrystal_sethaltonerror(0); L.ncrystal_setquietonerror(1); L.ncrystal_clearerror()
+        L.ncrystal_setbuiltinrandgen_withstate(b"not-a-state")
+        assert L.ncrystal_error() == 1
+        L.ncrystal_runmmcsim_stdengine(0, 0, b"", b"", b"", None, None, None, None)
+        assert L.ncrystal_error() == 1 and b"obsolete" in L.ncrystal_lasterror()
+        L.ncrystal_clearerror(); L.ncrystal_sethaltonerror(old); L.ncrystal_setquietonerror(0)
+    finally:
+        L.ncrystal_setbuiltinrandgen()
