@@ -46,6 +46,14 @@ namespace NCrystalB200 {
     const char* name() const { return ncrystal_name( proc() ); }
     bool isOriented() const { return !ncrystal_isnonoriented( proc() ); }
     std::pair<double,double> domain() const { double a, b; ncrystal_domain( proc(), &a, &b ); return { a, b }; }
+    // ProcImpl::Process::isNull / getUniqueID (NCProc.hh:86-92): id of the shared immutable process, equal for clones
+    bool isNull() const { auto d = domain(); return !( d.first < d.second ); }
+    unsigned long long getUniqueID() const
+    {
+      char* u = ncrystal_process_uid( proc() ); checkError();
+      const unsigned long long v = std::stoull( u ); ncrystal_dealloc_string( u );
+      return v;
+    }
 
     // single-neutron calls (ref: NCProc.hh:65-66,112-113)
     double crossSectionIsotropic( double ekin ) const { double r; ncrystal_crosssection_nonoriented( proc(), ekin, &r ); checkError(); return r; }
@@ -71,6 +79,16 @@ namespace NCrystalB200 {
       std::vector<double> out( ekin.size() );
       ncb200_crosssection_many( proc(), ekin.data(), ux.data(), uy.data(), uz.data(), ekin.size(), out.data() ); checkError();
       return out;
+    }
+    // per-neutron (E, direction) batch, SoA in and out
+    void sampleScatter( const std::vector<double>& ekin, const std::vector<double>& ux, const std::vector<double>& uy,
+                        const std::vector<double>& uz, std::vector<double>& ekin_final, std::vector<double>& ox,
+                        std::vector<double>& oy, std::vector<double>& oz )
+    {
+      const size_t n = ekin.size();
+      ekin_final.resize( n ); ox.resize( n ); oy.resize( n ); oz.resize( n );
+      ncb200_samplescatter_manydir( m_h, ekin.data(), ux.data(), uy.data(), uz.data(), n, ekin_final.data(),
+                                    ox.data(), oy.data(), oz.data() ); checkError();
     }
 
     // device-resident batches (caller's stream; asynchronous)
@@ -104,6 +122,8 @@ namespace NCrystalB200 {
     ~Absorption() { if ( m_h.internal ) ncrystal_unref( &m_h ); }
     Absorption( const Absorption& ) = delete;
     Absorption& operator=( const Absorption& ) = delete;
+    Absorption( Absorption&& o ) noexcept : m_h( o.m_h ) { o.m_h.internal = nullptr; }
+    Absorption clone() const { Absorption a( ncrystal_clone_absorption( m_h ) ); checkError(); return a; }
     double crossSectionIsotropic( double ekin ) const
     { double r; ncrystal_crosssection_nonoriented( ncrystal_cast_abs2proc( m_h ), ekin, &r ); checkError(); return r; }
     std::vector<double> crossSectionIsotropic( const std::vector<double>& ekin ) const
@@ -113,6 +133,7 @@ namespace NCrystalB200 {
       return out;
     }
   private:
+    explicit Absorption( ncrystal_absorption_t h ) : m_h( h ) {}
     ncrystal_absorption_t m_h;
   };
 

@@ -100,6 +100,25 @@ class Process:
         return n.decode()
 
     getCalcName = getName
+    name = property(getName)
+
+    def getUniqueID(self):
+        """ref: core.py:1245 -- UID of the underlying (shared, immutable) process: equal for a handle and its clones"""
+        p = self._L.ncrystal_process_uid(self._p)
+        _check_error()
+        v = int(C.cast(p, C.c_char_p).value)
+        self._L.ncrystal_dealloc_string(p)
+        return v
+    uid = property(getUniqueID)
+
+    def isNull(self):
+        """ref: core.py:1261 -- a null process vanishes everywhere (domain with elow >= ehigh or elow = inf)"""
+        elow, ehigh = self.domain()
+        return elow == float("inf") or elow >= ehigh
+
+    def crossSectionNonOriented(self, ekin, repeat=None):
+        """ref: core.py:1289 -- deprecated alias of crossSectionIsotropic"""
+        return self.crossSectionIsotropic(ekin, repeat)
 
     def domain(self):
         a, b = C.c_double(), C.c_double()
@@ -354,6 +373,47 @@ class Scatter(Process):
             _check_error()
         return eo, (ox, oy, oz)
 
+    def generateScatteringNonOriented(self, ekin, repeat=None):
+        """ref: core.py:1523 (deprecated spelling); C: ncrystal_genscatter_nonoriented[_many].
+        Returns (scatter_angle [rad], delta_ekin)."""
+        if repeat is None and not hasattr(ekin, "__len__"):
+            a, b = C.c_double(), C.c_double()
+            self._L.ncrystal_genscatter_nonoriented(self._h, float(ekin), C.byref(a), C.byref(b))
+            _check_error()
+            return a.value, b.value
+        e = _np_d(ekin if hasattr(ekin, "__len__") else [ekin])
+        rep = 1 if repeat is None else int(repeat)
+        ang, de = np.empty(e.size * rep), np.empty(e.size * rep)
+        if ang.size:
+            self._L.ncrystal_genscatter_nonoriented_many(self._h, e.ctypes.data_as(_dblp), e.size, rep,
+                                                         ang.ctypes.data_as(_dblp), de.ctypes.data_as(_dblp))
+            _check_error()
+        return ang, de
+
+    def generateScattering(self, ekin, direction, repeat=None):
+        """ref: core.py:1506 (deprecated spelling); C: ncrystal_genscatter[_many].
+        Returns ((ux,uy,uz), delta_ekin) for one fixed (ekin, direction)."""
+        d = (C.c_double * 3)(*[float(x) for x in direction])
+        if repeat is None:
+            de, do = C.c_double(), (C.c_double * 3)()
+            self._L.ncrystal_genscatter(self._h, float(ekin), C.byref(d), C.byref(do), C.byref(de))
+            _check_error()
+            return (do[0], do[1], do[2]), de.value
+        rep = int(repeat)
+        ox, oy, oz, de = [np.empty(rep) for _ in range(4)]
+        if rep:
+            self._L.ncrystal_genscatter_many(self._h, float(ekin), C.byref(d), rep, ox.ctypes.data_as(_dblp),
+                                             oy.ctypes.data_as(_dblp), oz.ctypes.data_as(_dblp), de.ctypes.data_as(_dblp))
+            _check_error()
+        return (ox, oy, oz), de
+
+    def genscat(self, ekin=None, direction=None, wl=None, repeat=None):
+        """ref: core.py:1554 (deprecated spelling of scatter)"""
+        ekin = _parse_ekin(ekin, wl)
+        if direction is None:
+            return self.generateScatteringNonOriented(ekin, repeat)
+        return self.generateScattering(ekin, direction, repeat)
+
     def scatter(self, ekin=None, direction=None, wl=None, repeat=None):
         """ref: core.py:1543"""
         ekin = _parse_ekin(ekin, wl)
@@ -410,6 +470,12 @@ class Absorption(Process):
         h = _lib.lib().ncb200_create_absorption_from_blob(blob, len(blob))
         _check_error()
         return cls(_handle=h)
+
+    def clone(self):
+        """ref: core.py:1410; C: ncrystal_clone_absorption"""
+        h = self._L.ncrystal_clone_absorption(self._h)
+        _check_error()
+        return Absorption(_handle=h)
 
 
 def createAbsorption(cfgstr):

@@ -22,7 +22,19 @@ int main()
     std::printf( "al_batch %zu %zu %zu\n", xs.size(), ef.size(), mu.size() );
     NB::Scatter c = al.clone();
     std::printf( "clone_xs_equal %d\n", c.crossSectionIsotropic( ekin ) == al.crossSectionIsotropic( ekin ) ? 1 : 0 );
+    std::printf( "clone_uid_equal %d\n", ( c.getUniqueID() == al.getUniqueID() && !al.isNull() ) ? 1 : 0 );
+    {
+      std::vector<double> ux( e.size(), 0.0 ), uy( e.size(), 0.0 ), uz( e.size(), 1.0 ), ox, oy, oz;
+      al.sampleScatter( e, ux, uy, uz, ef, ox, oy, oz );
+      double worst = 0.0;
+      for ( size_t i = 0; i < e.size(); ++i ) {
+        const double n2 = ox[i]*ox[i] + oy[i]*oy[i] + oz[i]*oz[i] - 1.0;
+        worst = n2 < 0 ? ( -n2 > worst ? -n2 : worst ) : ( n2 > worst ? n2 : worst );
+      }
+      std::printf( "al_dir_batch_ok %d\n", worst < 1e-12 ? 1 : 0 );
+    }
     NB::Absorption ab( "Al_sg225.ncmat;temp=293.15K" );
+    std::printf( "abs_clone_equal %d\n", ab.clone().crossSectionIsotropic( 0.0253 ) == ab.crossSectionIsotropic( 0.0253 ) ? 1 : 0 );
     std::printf( "al_abs_xs_2200 %.17g\n", ab.crossSectionIsotropic( 0.02529886 ) );
     const std::string js = al.minimc( "sphere;r=0.01", "constant;ekin=0.0253;z=-0.01;n=10000", "tally=mu" );
     std::printf( "minimc_json_ok %d\n", js.find( "NCrystalMiniMCResults_v1" ) != std::string::npos ? 1 : 0 );

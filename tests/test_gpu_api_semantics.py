@@ -198,6 +198,7 @@ def test_cxx_mirror_runs(tmp_path):
     assert kv["al_sample_ok"] == ["1"] and kv["al_batch"] == ["1000", "1000", "1000"] and kv["clone_xs_equal"] == ["1"]
     assert abs(float(kv["al_abs_xs_2200"][0]) - hdr["abs_c"] / np.sqrt(0.02529886)) < 1e-12
     assert kv["minimc_json_ok"] == ["1"] and kv["bad_cfg_throws"] == ["1"]
+    assert kv["clone_uid_equal"] == ["1"] and kv["al_dir_batch_ok"] == ["1"] and kv["abs_clone_equal"] == ["1"]
 
 
 def test_virtual_api_client_runs(tmp_path):
@@ -365,3 +366,22 @@ def test_version_uid_absorption_clone_and_default_seeding(configs):
         L.ncrystal_clearerror(); L.ncrystal_sethaltonerror(old); L.ncrystal_setquietonerror(0)
     finally:
         L.ncrystal_setbuiltinrandgen()
+
+
+def test_python_mirror_deprecated_spellings(configs):
+    # NCrystal.Scatter's deprecated method names (core.py:1506-1570) and Process.uid / isNull / Absorption.clone
+    import ncrystal_b200 as nc
+    sc = nc.Scatter(configs["Al"], seed=21)
+    e = np.full(300, 0.0253)
+    sc.setRNGStream(21, 0, 0)
+    eo, mu = sc.sampleScatterIsotropic(e)
+    sc.setRNGStream(21, 0, 0)
+    ang, de = sc.genscat(ekin=e)
+    assert np.array_equal(de, eo - e) and np.max(np.abs(np.cos(ang) - mu)) < 1e-15
+    sc.setRNGStream(21, 0, 0)
+    (ox, oy, oz), de2 = sc.generateScattering(0.0253, (0, 0, 1), repeat=50)
+    assert np.allclose(ox * ox + oy * oy + oz * oz, 1.0, atol=1e-12) and de2.shape == (50,)
+    assert sc.uid == sc.clone().uid and not sc.isNull() and sc.name == sc.getName()
+    assert np.array_equal(sc.crossSectionNonOriented(e), sc.crossSectionIsotropic(e))
+    ab = nc.Absorption(configs["Al"])
+    assert ab.clone().crossSectionIsotropic(0.0253) == ab.crossSectionIsotropic(0.0253)
