@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <dirent.h>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
@@ -571,6 +572,22 @@ namespace {
     return d;
   }
 
+  // Order- and prefix-insensitive key of a cfg string / file stem: "stdlib::" dropped, parameters (after the data
+  // name) sorted.  The reference normalises cfg strings completely (units, defaults: ncrystal_normalisecfg); material
+  // setup is not restated here, so only these spelling variants of one cfg find the same compiled material.
+  std::string looseCfgKey( std::string stem )
+  {
+    if ( stem.rfind( "stdlib__", 0 ) == 0 ) stem = stem.substr( 8 );
+    std::vector<std::string> parts;
+    std::stringstream ss( stem );
+    std::string item;
+    while ( std::getline( ss, item, '+' ) ) if ( !item.empty() ) parts.push_back( item );
+    if ( parts.size() > 2 ) std::sort( parts.begin() + 1, parts.end() );
+    std::string out;
+    for ( auto& q : parts ) { if ( !out.empty() ) out += '+'; out += q; }
+    return out;
+  }
+
   std::vector<unsigned char> findCompiledMaterial( const char* cfg )
   {
     std::vector<std::string> dirs;
@@ -591,6 +608,25 @@ namespace {
       auto data = readFile( path );
       if ( !data.empty() ) return data;
       tried += " " + path;
+    }
+    // second chance: same cfg spelled with another parameter order or the "stdlib::" prefix
+    const std::string key = looseCfgKey( stem );
+    for ( auto& d : dirs ) {
+      DIR* dir = opendir( d.c_str() );
+      if ( !dir ) continue;
+      std::string hit;
+      while ( dirent* ent = readdir( dir ) ) {
+        const std::string fn = ent->d_name;
+        if ( fn.size() > 4 && fn.compare( fn.size()-4, 4, ".ncb" ) == 0 && looseCfgKey( fn.substr( 0, fn.size()-4 ) ) == key ) {
+          hit = d + "/" + fn;
+          break;
+        }
+      }
+      closedir( dir );
+      if ( !hit.empty() ) {
+        auto data = readFile( hit );
+        if ( !data.empty() ) return data;
+      }
     }
     throw Err( "FileNotFound", std::string("No compiled material for cfg \"")+cfg+"\" (looked for:"+tried
                +"). Material setup is done by the NCrystal reference: compile it with oracle/_ref/bin/ncb200_matcompile"

@@ -170,3 +170,32 @@ def test_virtual_api_vtable_layout_matches_reference_header():
     assert names == ["createScatter", "cloneScatter", "deallocateScatter", "crossSectionUncached",
                      "sampleScatterUncached", "~VirtAPI_Type1_v1"]
     assert "interface_id = 1001" in src
+
+
+def test_cfg_spelling_variants_find_the_same_compiled_material(configs):
+    # "stdlib::" prefix and another parameter order resolve to the same .ncb file; an unknown material does not.
+    # Without a GPU the call then stops at the device (LogicError / CUDA message), never at FileNotFound.
+    from ncrystal_b200 import _lib
+    from oracle_check import material_path
+    if not os.path.exists(material_path(configs["Ge"])):
+        pytest.skip("compiled materials not built")
+    L = _lib.lib()
+    old = L.ncrystal_sethaltonerror(0)
+    L.ncrystal_setquietonerror(1)
+    try:
+        variants = ["stdlib::" + configs["Al"],
+                    "Ge_sg227.ncmat;dir2=@crys_hkl:0,-1,1@lab:0,1,0;mos=40arcsec;dir1=@crys_hkl:5,1,1@lab:0,0,1"]
+        for cfg in variants + ["no_such_material.ncmat;temp=5K"]:
+            L.ncrystal_clearerror()
+            h = L.ncrystal_create_scatter(cfg.encode())
+            typ = L.ncrystal_lasterrortype() if L.ncrystal_error() else b""
+            if h.internal:
+                L.ncrystal_unref(C.byref(h))
+            if cfg in variants:
+                assert typ != b"FileNotFound", (cfg, L.ncrystal_lasterror())
+            else:
+                assert typ == b"FileNotFound"
+    finally:
+        L.ncrystal_clearerror()
+        L.ncrystal_sethaltonerror(old)
+        L.ncrystal_setquietonerror(0)

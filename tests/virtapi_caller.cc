@@ -14,7 +14,7 @@ int main()
   if ( !api ) { std::printf( "error no_api\n" ); return 1; }
   std::printf( "bad_id_null %d\n", ncrystal_access_virtual_api( 999 ) == nullptr ? 1 : 0 );
   try {
-    auto al = api->createScatter( "Al_sg225.ncmat;temp=293.15K" );
+    auto al = api->createScatter( "stdlib::Al_sg225.ncmat;temp=293.15K" );   // prefix as in the reference test
     auto ge = api->createScatter( "Ge_sg227.ncmat;mos=40arcsec;dir1=@crys_hkl:5,1,1@lab:0,0,1;dir2=@crys_hkl:0,-1,1@lab:0,1,0" );
     auto al2 = api->cloneScatter( al );
     auto wl2ekin = []( double wl ) { return 0.081804209605330899 / ( wl*wl ); };
