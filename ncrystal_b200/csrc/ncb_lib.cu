@@ -770,7 +770,13 @@ namespace {
     uint32_t* diag_nd = s->d_diag_ndraws;
     int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
-    const uint64_t maxn = useSampleV1() ? n : ( (uint64_t)1 << kQueueIdxBits );
+    // Sub-launches of at most 2^26 neutrons (queue entries hold 28 index bits): bounds the scratch (index queues
+    // 24 B and free-gas stage records 76 B per neutron of a sub-launch, ~7 GB) however large the batch is; results do
+    // not depend on the split (streams are keyed by the global neutron index).  NCB200_SUBLAUNCH overrides (tests).
+    static const uint64_t sub = []{ const char* e = std::getenv( "NCB200_SUBLAUNCH" );
+                                    const uint64_t v = e ? (uint64_t)std::atoll(e) : ( (uint64_t)1 << 26 );
+                                    return std::min<uint64_t>( std::max<uint64_t>( v, 1024 ), (uint64_t)1 << kQueueIdxBits ); }();
+    const uint64_t maxn = useSampleV1() ? n : sub;
     for ( uint64_t done = 0; done < n; done += maxn ) {
       const uint64_t m = std::min<uint64_t>( maxn, n - done );
       SampleArgs A;
