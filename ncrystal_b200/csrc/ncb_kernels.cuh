@@ -878,7 +878,7 @@ namespace ncb {
     Rng rng; rng.init( A.seed, A.first_index, A.sid );
     while ( true ) {
       const uint32_t need = __ballot_sync( 0xffffffffu, !have );
-      if ( need ) {
+      if ( need && !drained ) {
         const uint32_t j = fgPull( need, !have, P.cursor + 1, nq, drained );
         if ( !have && j < nq ) {
           const uint32_t w = P.w[j];
