@@ -29,3 +29,17 @@ torch.cuda.synchronize(); print("H2D 80MB: %.1f GB/s" % (5 * 8 * n / (time.perf_
 t0 = time.perf_counter()
 for _ in range(5): h_xs.copy_(d, non_blocking=True)
 torch.cuda.synchronize(); print("D2H 80MB: %.1f GB/s" % (5 * 8 * n / (time.perf_counter() - t0) / 1e9))
+# both directions at once in 8 MB pieces on two streams: what the link gives a 1:2 (in:out) pipeline such as the sampling call
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+d2 = torch.empty(2 * n, dtype=torch.float64, device="cuda")
+h_out = torch.empty(2 * n, dtype=torch.float64).pin_memory()
+piece = 1 << 20
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    for k in range(0, n, piece):
+        with torch.cuda.stream(s1):
+            d[k:k + piece].copy_(h_e[k:k + piece], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out[2 * k:2 * (k + piece)].copy_(d2[2 * k:2 * (k + piece)], non_blocking=True)
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+print("80 MB in + 160 MB out concurrently: %.3f ms (%.1f GB/s in total)" % (dt * 1e3, 24 * n / dt / 1e9))
