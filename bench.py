@@ -352,6 +352,23 @@ def main():
     e2e_val = world * n * e2e_steps / e2e_s
     mean_mu = float(h_mu.mean())
 
+    # ---- for information: the same result through ONE fused host-pointer call (the reference's experimental batch
+    # ABI has such an entry, NCABIUtils.hh:78-100; its C-API does not): 8 B in + 24 B out per neutron over the bus
+    def e2e_fused_step():
+        L.ncb200_xs_and_samplescatterisotropic_many(sc._h, C.cast(h_e.data_ptr(), dp), n, C.cast(h_xs.data_ptr(), dp),
+                                                    C.cast(h_eo.data_ptr(), dp), C.cast(h_mu.data_ptr(), dp))
+    e2e_fused_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_fused_step()
+    barrier()
+    tf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    nc.core._check_error()
+    e2e_fused_val = world * n * e2e_steps / float(tf.item())
+
     # ---- secondary figure: the device-resident transport step (ncb200_minimc_run) on the same
     # material: 1e7 source neutrons per GPU through a 10 cm Al sphere, tallies all-reduced over the ranks (NCCL)
     transport = None
@@ -420,7 +437,9 @@ def main():
             "transport_step": transport,
         },
         "e2e": {"value": e2e_val, "unit": "neutrons/s", "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n,
-                "steps": e2e_steps, "api": "ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many"},
+                "steps": e2e_steps, "api": "ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many",
+                "fused_call": {"value": e2e_fused_val, "api": "ncb200_xs_and_samplescatterisotropic_many (extension)",
+                               "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 3 * 8 * n}},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "k_sample_sab_refill",

@@ -176,6 +176,11 @@ void ncb200_samplescatterisotropic_many_dev( ncrystal_scatter_t, const double* d
 void ncb200_xs_and_samplescatterisotropic_many_dev( ncrystal_scatter_t, const double* d_ekin, uint64_t n,
                                                     double* d_xs, double* d_ekin_final, double* d_mu, void* stream );
 
+/* the fused call on HOST arrays: one pass, 8 B in + 24 B out per neutron over the bus (the two separate *_many calls
+ * move 16 B in + 24 B out); same results as those two calls */
+void ncb200_xs_and_samplescatterisotropic_many( ncrystal_scatter_t, const double* ekin, uint64_t n,
+                                                double* results_xs, double* results_ekin, double* results_cos_scat_angle );
+
 /* Batched oriented calls, per-neutron (E,dir), SoA (host pointers / device pointers). */
 void ncb200_crosssection_many( ncrystal_process_t, const double* ekin, const double* ux, const double* uy, const double* uz,
                                uint64_t n, double* results );

@@ -324,6 +324,17 @@ class Scatter(Process):
             return a.value, b.value
         e = _np_d(ekin if hasattr(ekin, "__len__") else [ekin])
         rep = 1 if repeat is None else int(repeat)
+        if with_xs:
+            # fused host-pointer call (one pass over the bus); repeat is not supported here
+            if rep != 1:
+                raise NCBadInput("with_xs=True does not take repeat")
+            xs, eo, mu = np.empty(e.size), np.empty(e.size), np.empty(e.size)
+            if e.size:
+                self._L.ncb200_xs_and_samplescatterisotropic_many(self._h, e.ctypes.data_as(_dblp), e.size,
+                                                                  xs.ctypes.data_as(_dblp), eo.ctypes.data_as(_dblp),
+                                                                  mu.ctypes.data_as(_dblp))
+                _check_error()
+            return xs, eo, mu
         eo = np.empty(e.size * rep)
         mu = np.empty(e.size * rep)
         if eo.size:

@@ -89,3 +89,18 @@ def test_batch_larger_than_one_sublaunch(configs):
     del a, b
     xs = sc.crossSectionIsotropic(e)
     assert bool(torch.isfinite(xs).all()) and float(xs.min()) > 0.0
+
+
+def test_fused_host_call_equals_the_two_reference_calls(configs):
+    """ncb200_xs_and_samplescatterisotropic_many (host arrays, one pass over the bus) returns what
+    ncrystal_crosssection_nonoriented_many + ncrystal_samplescatterisotropic_many return."""
+    import ncrystal_b200 as nc
+    from _libs import loguniform_energies
+    sc = nc.Scatter(configs["Al"], seed=13)
+    e = loguniform_energies(2_500_003, seed=8)
+    xs = sc.crossSectionIsotropic(e)
+    sc.setRNGStream(13, 0, 0)
+    eo, mu = sc.sampleScatterIsotropic(e)
+    sc.setRNGStream(13, 0, 0)
+    xs2, eo2, mu2 = sc.sampleScatterIsotropic(e, with_xs=True)
+    assert np.array_equal(xs, xs2) and np.array_equal(eo, eo2) and np.array_equal(mu, mu2)
