@@ -45,3 +45,17 @@ def test_extra_oriented_vs_golden(key, impl):
     assert np.array_equal(nd, g["ndraws"])
     for a, b in ((eo, g["ekin_out"]), (ox, g["ox"]), (oy, g["oy"]), (oz, g["oz"])):
         assert np.array_equal(a, b)
+
+
+def test_material_compiler_refuses_leaves_outside_the_scope():
+    # a layered crystal (LCBragg leaf) is outside the restated path: the reference-side material compiler says so
+    # instead of producing tables the kernels would misread
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "ncb200_matcompile")
+    if not os.path.exists(exe):
+        pytest.skip("reference not built here")
+    cfg = ("C_sg194_pyrolytic_graphite.ncmat;mos=1deg;dir1=@crys_hkl:0,0,1@lab:0,0,1;"
+           "dir2=@crys_hkl:1,0,0@lab:1,0,0;lcaxis=0,0,1")
+    out = subprocess.run([exe, cfg, os.devnull], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "unsupported leaf process type: LCBragg" in (out.stdout + out.stderr)
