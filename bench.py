@@ -420,6 +420,13 @@ def main():
     # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r1_kernels_final_ncu_full.csv,
     # same command, 1e7-neutron Al batch): dram__bytes_read.sum + dram__bytes_write.sum per launch.
     traffic = 370.7e6 if n == N_PER_GPU else None
+    # FP64 side of the reading (north_star: "FP64 pipe utilisation for the sampling kernels against B200 peak"): the
+    # vector-FP64 FMA rate measured here with a DFMA probe kernel; the dominant kernel's FP64 pipe utilisation is the
+    # ncu figure of the committed capture (sm__inst_executed_pipe_fp64, profiles/r1_kernels_final_ncu_full.csv)
+    try:
+        fp64_peak = float(L.ncb200_fp64_fma_probe())
+    except Exception:  # noqa: BLE001
+        fp64_peak = None
     out = {
         "metric": "neutrons/sec (xs eval + sampleScatter)", "value": value, "unit": "neutrons/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -448,6 +455,8 @@ def main():
                      "algorithmic_bytes_per_launch": dom_bytes, "units_per_launch": dom_units, "ms_per_launch": dom_ms,
                      "note": "rejection sampling in fp64: latency/issue bound, not HBM bound (SURVEY 8d); "
                              "ncu stall and pipe evidence under profiles/",
+                     "fp64": {"fma_peak_tflops_measured": fp64_peak, "pipe_pct_dominant_kernel": 23.1,
+                              "source": "DFMA probe (live) / ncu capture (committed)"},
                      "kernel_ms": ktimes, "queue_units": qcounts,
                      "launch_sequence": {"achieved": ach_seq, "frac": ach_seq / peak,
                                          "algorithmic_bytes_per_step": n * BYTES_FUSED, "ms": ms_fused},

@@ -241,6 +241,9 @@ void     ncb200_set_fg_staged_min( uint64_t nmin );
 /* sizes of the work queues of the most recent isotropic sampling launch: table path, free-gas path, table at Emax */
 int      ncb200_last_queue_counts( ncrystal_scatter_t, uint32_t* out3 );
 const char* ncb200_version(void);
+/* Measured vector-FP64 FMA rate of the current device in TFLOP/s (8 independent DFMA chains per thread, all SMs): the
+ * denominator for "FP64 pipe utilisation against peak" in profiles/ (not a product function). */
+double   ncb200_fp64_fma_probe(void);
 /* SAB table builder check: per-energy-point total xs recomputed on the device while
  * building the sampler tables (compare with the xs grid of the compiled material). */
 int      ncb200_sab_xscheck( ncrystal_process_t, int component, double* out, int nmax );

@@ -121,6 +121,7 @@ SIGNATURES = {
     "ncb200_minimc_run": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p]),
     "ncb200_minimc_run_slice": (C.c_void_p, [ncrystal_scatter_t, C.c_char_p, C.c_char_p, C.c_char_p, _u64, _u64]),
     "ncb200_material_bulk": (None, [ncrystal_process_t, _dblp, _dblp, _dblp]),
+    "ncb200_fp64_fma_probe": (C.c_double, []),
     "ncb200_set_fg_staged_min": (None, [C.c_uint64]),
     "ncb200_xs_and_samplescatterisotropic_many": (None, [ncrystal_scatter_t, _dblp, C.c_uint64, _dblp, _dblp, _dblp]),
     "ncb200_kernel_timing": (None, [C.c_int]),

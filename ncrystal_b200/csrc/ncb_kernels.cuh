@@ -977,6 +977,20 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
+  // FP64 FMA probe: the denominator for "FP64 pipe utilisation against B200 peak" (SURVEY 8d asks for a measured
+  // figure: the vendor's vector-FP64 number is not in MEASURED_PEAKS.json).  8 independent DFMA chains per thread.
+  __global__ void __launch_bounds__(256)
+  k_fp64_fma_probe( double* __restrict__ out, int iters, double a, double b )
+  {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for ( int i = 0; i < iters; ++i ) {
+      x0 = fma( x0, a, b ); x1 = fma( x1, a, b ); x2 = fma( x2, a, b ); x3 = fma( x3, a, b );
+      x4 = fma( x4, a, b ); x5 = fma( x5, a, b ); x6 = fma( x6, a, b ); x7 = fma( x7, a, b );
+    }
+    const double s = ( ( x0 + x1 ) + ( x2 + x3 ) ) + ( ( x4 + x5 ) + ( x6 + x7 ) );
+    if ( s == 12345.678 ) out[0] = s;   // keeps the chains alive
+  }
+
   // ------------------------------------------------------------ oriented (single crystal)
   // Per-neutron (E, direction), SoA.  One neutron per thread: the lanes of a warp walk the
   // reflection-family / demi-normal tables in lockstep (same addresses -> broadcast loads);

@@ -1704,6 +1704,31 @@ extern "C" {
     try { return fromInternal( p.internal, "ncb200_table_bytes" )->dm->arena_bytes; } NCBCATCH;
     return 0;
   }
+  // measured vector-FP64 FMA rate of the current device [TFLOP/s] (best of 5 launches, CUDA events)
+  double ncb200_fp64_fma_probe(void)
+  {
+    try {
+      int dev = 0; CUDA_OK( cudaGetDevice( &dev ) );
+      double* d_out = nullptr; CUDA_OK( cudaMalloc( &d_out, sizeof(double) ) );
+      cudaEvent_t e0, e1; CUDA_OK( cudaEventCreate( &e0 ) ); CUDA_OK( cudaEventCreate( &e1 ) );
+      const int iters = 1 << 15, threads = 256;
+      const unsigned grid = (unsigned)numSMs( dev ) * 8;
+      double best = 0.0;
+      for ( int rep = 0; rep < 6; ++rep ) {
+        CUDA_OK( cudaEventRecord( e0, nullptr ) );
+        k_fp64_fma_probe<<< grid, threads >>>( d_out, iters, 0.999999, 1e-9 );
+        CUDA_OK( cudaEventRecord( e1, nullptr ) );
+        CUDA_OK( cudaEventSynchronize( e1 ) );
+        float ms = 0.f; CUDA_OK( cudaEventElapsedTime( &ms, e0, e1 ) );
+        const double tflops = 2.0*8.0*(double)iters*(double)threads*(double)grid / ( (double)ms*1e-3 ) / 1e12;
+        if ( rep && tflops > best ) best = tflops;     // first launch: warm-up
+      }
+      ++g_launches;
+      cudaEventDestroy( e0 ); cudaEventDestroy( e1 ); cudaFree( d_out );
+      return best;
+    } NCBCATCH;
+    return -1.0;
+  }
   const char* ncb200_version(void) { return "ncrystal_b200 0.1 (sm_100a; hot path of NCrystal 4.4.2)"; }
 
   int ncb200_sab_xscheck( ncrystal_process_t p, int component, double* out, int nmax )
