@@ -409,7 +409,7 @@ def main():
     ach_seq = n * BYTES_FUSED / (ms_fused * 1e-3) / 1e9
     # dominant kernel: k_sample_sab_refill (S(alpha,beta)-table sampling of the neutrons queued for it):
     # algorithmic bytes per unit = BYTES_SAMPLE (8 B energy in, 16 B (E', mu) out), units = its queue length.
-    dom = ktimes.get("k_sample_sab_refill")
+    dom = ktimes.get("k_sab_classes") or ktimes.get("k_sample_sab_refill")
     if dom and qcounts:
         dom_units = qcounts[0]
         dom_ms = dom["ms_avg"]

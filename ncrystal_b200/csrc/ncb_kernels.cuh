@@ -123,60 +123,32 @@ namespace ncb {
     __device__ __forceinline__ uint64_t count() const { return n_dev ? (uint64_t)min( (uint64_t)*n_dev, n ) : n; }
   };
 
-  __global__ void __launch_bounds__(128)
-  k_sample_iso( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
-                const __grid_constant__ SampleArgs A )
-  {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t mbar;
-    HotTabs H;
-    stageHotTabs( M, sp, smem, &mbar, H );
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    int errs = 0;
-    for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += stride ) {
-      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
-      double eout, mu;
-      int err = 0, ich;
-      const double xs = matSampleIso( M, H, A.ekin[i], rng, eout, mu, err, ich );
-      A.ekin_out[i] = eout;
-      A.mu_out[i] = mu;
-      if ( A.xs_out ) A.xs_out[i] = xs;
-      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
-      if ( A.component ) A.component[i] = ich;
-      errs |= err;
-    }
-    if ( errs )
-      atomicOr( A.err_flags, errs );
-  }
-
-  // ------------------------------------------------------- sampling (isotropic), v2
-  // Three launches per batch instead of one divergent kernel:
-  //   k_sample_classify  xs + component pick; the cheap elastic leaves (PowderBragg, ElInc) are
-  //                      sampled in place; S(alpha,beta) table neutrons and free-gas neutrons
-  //                      (FreeGas leaf, SAB above Emax) are appended to two index queues with
-  //                      warp-aggregated atomics
-  //   k_sample_sab       the S(alpha,beta) table path (Alg. 1) over its queue
-  //   k_sample_fg        the free-gas rejection samplers over their queue
-  // Each queue holds homogeneous work, so warps no longer serialise over unrelated code paths.
-  // Because the random streams are counter based, a later kernel resumes a neutron's stream
-  // simply by re-deriving block 0 (no RNG state is stored).
+  // ------------------------------------------------------- sampling (isotropic)
+  // A batch is sampled by a sequence of launches instead of one divergent kernel:
+  //   k_sample_classify  xs + component pick; the cheap elastic leaves (PowderBragg, ElInc) are sampled in place;
+  //                      S(alpha,beta) table neutrons and free-gas neutrons (FreeGas leaf, SAB above Emax) are
+  //                      appended to two index queues
+  //   S(alpha,beta) table queue: large batches are partitioned by overlay sampler ("class") and sampled by
+  //                      k_sab_classes with the class's tables staged in shared memory (ncb_kernels_cls.cuh);
+  //                      small ones go through k_sample_sab_refill directly
+  //   free-gas queue:    k_fg_* staged pipeline / k_sample_fg
+  // Each queue holds homogeneous work, so warps do not serialise over unrelated code paths.  Because the random
+  // streams are counter based, a later kernel resumes a neutron's stream by re-deriving one block (no RNG state
+  // is stored).
   constexpr uint32_t kQueueIdxBits = 28;
   constexpr uint32_t kQueueIdxMask = ( 1u << kQueueIdxBits ) - 1u;   // <= 2^28 neutrons per launch
 
-  constexpr int kSortBins = 1024;   // energy-sort keys: 16 bins per octave from 2^-24 eV upwards
+  constexpr int kSortBins = 1024;   // size of the scratch area behind the queue counters (class totals, cursors)
   struct QueueArgs {
     uint32_t* q_sab;    // S(alpha,beta) table path, E < Emax
     uint32_t* q_fg;     // free-gas leaf and S(alpha,beta) above Emax
     uint32_t* q_emax;   // pairs (entry, draws consumed): table sampling at E=Emax requested by the high-E analysis
     uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs), [3],[4] refill cursors
-    uint32_t* q_sab_sorted;  // the two queues reordered by energy bin (counting sort), or null
-    uint32_t* q_fg_sorted;
-    uint32_t* hist;     // [2*kSortBins] per-bin counts, then turned into running cursors by k_queue_scan
-    int sort_shift = 0; // coarsen the sort key by 2^shift bins (experiments on how fine the energy classes must be)
+    uint16_t* q_cls = nullptr;   // class (overlay sampler) of every q_sab entry, or null: no class partition
+    uint32_t cls_base[kMaxSab+1] = {};   // class id of energy point 0 of S(alpha,beta) leaf k
   };
 
-  // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave;
-  // the SAB energy grids have ~16 points per octave, so one bin ~ one overlay sampler).
+  // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave).
   __device__ __forceinline__ uint32_t sortKey( double ekin, int shift = 0 )
   {
     const int k = (int)( ( (unsigned long long)__double_as_longlong( ekin ) >> 48 ) & 0x7FFFull ) - ( 999 << 4 );
@@ -197,27 +169,27 @@ namespace ncb {
       q[ base + __popc( mask & ( ( 1u << lane ) - 1u ) ) ] = entry;
   }
 
-  // Block-aggregated variant for two queues at once: one global atomic per queue per CTA iteration
-  // (per-warp atomics on the two hot counters were ~8% of k_sample_classify's stall samples).
-  // Must be called by all threads of the CTA (contains __syncthreads).
-  __device__ __forceinline__ void blockPush2( int cls, uint32_t entry, uint32_t* q1, uint32_t* q2, uint32_t* counts,
-                                              uint32_t (*s_cnt)[2], uint32_t* s_base )
+  // Queue pushes of k_sample_classify: every warp collects its entries in a private shared-memory buffer and
+  // writes them out in runs (one global atomic and a coalesced copy per ~100 entries).  No CTA barrier on the
+  // path (r1: three __syncthreads per CTA iteration, `barrier` was the top stall reason of the kernel).
+  constexpr int kWarpBuf = 128;            // entries per warp and queue; flushed when fewer than 32 slots are left
+  struct WarpQueueBuf {
+    uint32_t e[2][kWarpBuf];
+    uint16_t c[kWarpBuf];
+  };
+  __device__ __forceinline__ void warpBufFlush( const uint32_t* buf, const uint16_t* bcls, uint32_t n, uint32_t* q, uint16_t* qc,
+                                                uint32_t* counter )
   {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const uint32_t m1 = __ballot_sync( 0xffffffffu, cls == 1 );
-    const uint32_t m2 = __ballot_sync( 0xffffffffu, cls == 2 );
-    if ( lane == 0 ) { s_cnt[w][0] = __popc( m1 ); s_cnt[w][1] = __popc( m2 ); }
-    __syncthreads();
-    if ( threadIdx.x < 2 ) {
-      uint32_t tot = 0;
-      for ( int k = 0; k < nw; ++k ) { const uint32_t c = s_cnt[k][threadIdx.x]; s_cnt[k][threadIdx.x] = tot; tot += c; }
-      s_base[threadIdx.x] = tot ? atomicAdd( counts + threadIdx.x, tot ) : 0u;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    uint32_t base = 0;
+    if ( lane == 0 ) base = atomicAdd( counter, n );
+    base = __shfl_sync( 0xffffffffu, base, 0 );
+    for ( uint32_t k = lane; k < n; k += 32 ) {
+      q[base + k] = buf[k];
+      if ( qc ) qc[base + k] = bcls[k];
     }
-    __syncthreads();
-    const uint32_t lt = ( 1u << lane ) - 1u;
-    if ( cls == 1 ) q1[ s_base[0] + s_cnt[w][0] + __popc( m1 & lt ) ] = entry;
-    if ( cls == 2 ) q2[ s_base[1] + s_cnt[w][1] + __popc( m2 & lt ) ] = entry;
-    __syncthreads();   // s_cnt / s_base are reused by the next iteration
+    __syncwarp();
   }
 
   __global__ void __launch_bounds__(256)
@@ -226,23 +198,19 @@ namespace ncb {
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
-    __shared__ uint32_t sh_hist[2*kSortBins];
-    __shared__ uint32_t s_cnt[8][2];
-    __shared__ uint32_t s_base[2];
+    __shared__ WarpQueueBuf s_wq[8];
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
-    const bool do_sort = ( Q.hist != nullptr );
-    if ( do_sort ) {
-      for ( int b = threadIdx.x; b < 2*kSortBins; b += blockDim.x ) sh_hist[b] = 0;
-      __syncthreads();
-    }
+    const int lane = threadIdx.x & 31;
+    WarpQueueBuf& wq = s_wq[threadIdx.x >> 5];
+    uint32_t c1 = 0, c2 = 0;                 // entries in the warp's two buffers (warp-uniform)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    int errs = 0;
-    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < A.n; base += stride ) {
+    const uint64_t n = A.n;
+    for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride ) {
       const uint64_t i = base + threadIdx.x;
       int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue
-      uint32_t entry = 0;
-      if ( i < A.n ) {
+      uint32_t entry = 0, key = 0;
+      if ( i < n ) {
         const double ekin = A.ekin[i];
         double eout = ekin, mu = 1.0, tot = 0.0;
         int ich = -1;
@@ -257,7 +225,13 @@ namespace ncb {
           if ( c.kind == KIND_SAB ) {
             const SabT& T = M.sab[c.idx];
             // upper_bound(egrid,E)==end  <=>  !(E < egrid.back())  (NCSABSampler.cc:166-171)
-            cls = ( ekin < H.sab_egrid[c.idx][T.negrid-1] ) ? 1 : 2;
+            int iu = aux[ich];
+            if ( iu < 0 ) iu = upperBound( H.sab_egrid[c.idx], 0, T.negrid, ekin );   // (E outside the leaf's domain)
+            cls = ( iu < T.negrid ) ? 1 : 2;
+            if ( cls == 1 && Q.q_cls ) {
+              bool ultra;
+              key = Q.cls_base[c.idx] + (uint32_t)sabPickSamplerFrom( T, H.sab_egrid[c.idx], ekin, iu, ultra );
+            }
           } else if ( c.kind == KIND_FREEGAS ) {
             cls = 2;
           } else if ( c.kind == KIND_POWDERBRAGG ) {
@@ -273,8 +247,6 @@ namespace ncb {
             nd = rng.ndraws;
           }
           entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
-          if ( do_sort && cls )
-            atomicAdd( &sh_hist[ ( cls - 1 )*kSortBins + sortKey( ekin, Q.sort_shift ) ], 1u );
         }
         if ( A.xs_out ) A.xs_out[i] = tot;
         if ( A.component ) A.component[i] = ich;
@@ -284,94 +256,17 @@ namespace ncb {
           if ( A.ndraws ) A.ndraws[i] = nd;
         }
       }
-      blockPush2( cls, entry, Q.q_sab, Q.q_fg, Q.counts, s_cnt, s_base );
+      const uint32_t m1 = __ballot_sync( 0xffffffffu, cls == 1 );
+      const uint32_t m2 = __ballot_sync( 0xffffffffu, cls == 2 );
+      const uint32_t lt = ( 1u << lane ) - 1u;
+      if ( cls == 1 ) { const uint32_t k = c1 + __popc( m1 & lt ); wq.e[0][k] = entry; wq.c[k] = (uint16_t)key; }
+      if ( cls == 2 ) wq.e[1][ c2 + __popc( m2 & lt ) ] = entry;
+      c1 += __popc( m1 ); c2 += __popc( m2 );
+      if ( c1 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[0], wq.c, c1, Q.q_sab, Q.q_cls, Q.counts + 0 ); c1 = 0; }
+      if ( c2 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[1], nullptr, c2, Q.q_fg, nullptr, Q.counts + 1 ); c2 = 0; }
     }
-    if ( do_sort ) {
-      __syncthreads();
-      for ( int b = threadIdx.x; b < 2*kSortBins; b += blockDim.x )
-        if ( sh_hist[b] ) atomicAdd( &Q.hist[b], sh_hist[b] );
-    }
-    if ( errs )
-      atomicOr( A.err_flags, errs );
-  }
-
-  // Counting sort of the two queues by energy bin, so that neighbouring lanes of the sampling
-  // kernels work on the same overlay sampler (same beta-CDF rows -> L1 hits, same search
-  // lengths -> converged warps).  k_queue_scan: per-queue exclusive prefix sum of the bin
-  // histogram (one CTA, 1024 threads); k_queue_scatter: entry -> its bin's running cursor.
-  __global__ void __launch_bounds__(1024)
-  k_queue_scan( uint32_t* __restrict__ hist )
-  {
-    __shared__ uint32_t warp_tot[32];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    for ( int q = 0; q < 2; ++q ) {
-      const uint32_t v = hist[q*kSortBins + t];
-      uint32_t incl = v;
-      for ( int d = 1; d < 32; d <<= 1 ) {
-        const uint32_t o = __shfl_up_sync( 0xffffffffu, incl, d );
-        if ( lane >= d ) incl += o;
-      }
-      if ( lane == 31 ) warp_tot[w] = incl;
-      __syncthreads();
-      if ( w == 0 ) {
-        uint32_t x = warp_tot[lane];
-        for ( int d = 1; d < 32; d <<= 1 ) {
-          const uint32_t o = __shfl_up_sync( 0xffffffffu, x, d );
-          if ( lane >= d ) x += o;
-        }
-        warp_tot[lane] = x;
-      }
-      __syncthreads();
-      hist[q*kSortBins + t] = incl - v + ( w ? warp_tot[w-1] : 0u );
-      __syncthreads();
-    }
-  }
-
-  __global__ void __launch_bounds__(256)
-  k_queue_scatter( const double* __restrict__ ekin, const __grid_constant__ QueueArgs Q )
-  {
-    const uint32_t n0 = Q.counts[0], n1 = Q.counts[1];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n0 + n1; j += stride ) {
-      const bool fg = ( j >= n0 );
-      const uint32_t entry = fg ? Q.q_fg[j - n0] : Q.q_sab[j];
-      const uint32_t key = sortKey( ekin[ entry & kQueueIdxMask ], Q.sort_shift );
-      const uint32_t pos = atomicAdd( &Q.hist[ ( fg ? kSortBins : 0 ) + key ], 1u );
-      ( fg ? Q.q_fg_sorted : Q.q_sab_sorted )[pos] = entry;
-    }
-  }
-
-  // S(alpha,beta) table path over a queue.  kAtEmax=false: entries of q_sab (E < Emax, stream
-  // resumes after the component pick); kAtEmax=true: (entry, ndraws) pairs of q_emax.
-  template <bool kAtEmax>
-  __global__ void __launch_bounds__(128)
-  k_sample_sab( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A,
-                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ count )
-  {
-    const uint32_t nq = *count;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    int errs = 0;
-    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
-      const uint32_t entry = kAtEmax ? queue[2*j] : queue[j];
-      const uint32_t i = entry & kQueueIdxMask;
-      const int ich = (int)( entry >> kQueueIdxBits );
-      const double ekin = A.ekin[i];
-      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
-      rng.seek( kAtEmax ? queue[2*j+1] : ( M.ncomp > 1 ? 1u : 0u ) );
-      const SabT& T = M.sab[M.comp[ich].idx];
-      double eout, mu;
-      int err = 0;
-      if ( kAtEmax )
-        sabSampleScatterAtEmax( T, ekin, rng, eout, mu, err );
-      else
-        sabSampleScatter<false>( T, ekin, rng, eout, mu, err );
-      A.ekin_out[i] = eout;
-      A.mu_out[i] = mu;
-      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
-      errs |= err;
-    }
-    if ( errs )
-      atomicOr( A.err_flags, errs );
+    if ( c1 ) warpBufFlush( wq.e[0], wq.c, c1, Q.q_sab, Q.q_cls, Q.counts + 0 );
+    if ( c2 ) warpBufFlush( wq.e[1], nullptr, c2, Q.q_fg, nullptr, Q.counts + 1 );
   }
 
   // S(alpha,beta) table path, attempt-level scheduling ("lane refill").  The reference's
@@ -1078,7 +973,7 @@ namespace ncb {
   {
     const int ie = blockIdx.x * blockDim.x + threadIdx.x;
     if ( ie >= T.negrid ) return;
-    const uint32_t off_b = (uint32_t)( (size_t)ie*( T.nbeta+1 ) );
+    const uint32_t off_b = (uint32_t)( (size_t)ie*(size_t)T.bstride );
     int err = 0;
     SabEPoint e;
     xscheck[ie] = sabAssembleEPoint( T.beta, T.nbeta, T.kT, T.bound_xs, T.egrid[ie], rows + (size_t)ie*T.nbeta,
@@ -1095,7 +990,7 @@ namespace ncb {
     if ( y < T.negrid ) {
       const SabEPoint e = ep[y];
       const double* cdf = T.bcdf + e.off_b;
-      uint16_t* g = bguide + (size_t)y*( kSabGB+1 );
+      uint16_t* g = bguide + (size_t)y*kSabGBStride;
       for ( int b = blockIdx.x*blockDim.x + threadIdx.x; b <= kSabGB; b += gridDim.x*blockDim.x )
         g[b] = sabBetaGuideEntry( cdf, e.npts, b );
       if ( blockIdx.x == 0 && threadIdx.x == 0 )
@@ -1109,6 +1004,20 @@ namespace ncb {
         g[b] = sabAlphaGuideEntry( row, T.nalpha, sc, b );
       if ( blockIdx.x == 0 && threadIdx.x == 0 )
         ascale[ib] = sc;
+    }
+  }
+
+  // stage 4: blockIdx.y = 0: heads (one thread per (energy point, beta row)); 1: points (one per (beta row, alpha))
+  __global__ void k_sab_gather_tabs( SabT T, SabHead* __restrict__ heads, SabPoint* __restrict__ pts )
+  {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ( blockIdx.y == 0 ) {
+      if ( k < (size_t)T.negrid*T.nbeta ) {
+        const int ib = (int)( k % (size_t)T.nbeta );
+        heads[k] = sabMakeHead( T.ainfo[k], T.cumul + (size_t)ib*T.nalpha, T.ascale[ib] );
+      }
+    } else if ( k < (size_t)T.nbeta*T.nalpha ) {
+      pts[k] = sabMakePoint( T.alpha, T.sab, T.logsab, T.cumul, T.nalpha, k );
     }
   }
 

@@ -9,6 +9,7 @@
 // There is NO CPU fallback: every compute entry point launches CUDA kernels and
 // raises an error when no usable device is present.
 #include "ncb_kernels.cuh"
+#include "ncb_kernels_cls.cuh"
 #include "ncb_kernels_sc.cuh"
 #include "ncb_kernels_mmc.cuh"
 #include "ncb_loader.h"
@@ -129,6 +130,11 @@ namespace {
     StagePlan sp_iso;        // hot tables of the isotropic leaves only
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
     bool has_fg_leaf = false; // a FreeGas leaf: its queue spans all energies (-> k_fg_group)
+    // class-staged S(alpha,beta) sampling (ncb_kernels_cls.cuh): shared-memory plan, classes per leaf
+    ClassSmem cls_smem = {};
+    uint32_t cls_base[kMaxSab+1] = {};
+    uint32_t ncls = 0;        // 0: the class path is not available for this material
+    int cls_ctas = 0;         // resident CTAs per SM of k_sab_classes
     uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0, sc_find_famof_off = 0, sc_find_scratch_off = 0;
     std::string cfg;
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
@@ -200,6 +206,30 @@ namespace {
       }
     }
     sp.total = off;
+    // class-staged sampling plan
+    {
+      int nbmax = 0, bsmax = 0;
+      uint32_t nc = 0;
+      for ( int i = 0; i < nsab; ++i ) {
+        dm.cls_base[i] = nc;
+        nc += (uint32_t)M.sab[i].negrid;
+        nbmax = std::max( nbmax, M.sab[i].nbeta );
+        bsmax = std::max( bsmax, M.sab[i].bstride );
+      }
+      for ( int i = nsab; i <= kMaxSab; ++i ) dm.cls_base[i] = nc;
+      auto al = []( size_t b ) { return (uint32_t)( ( b + 127 ) & ~(size_t)127 ); };
+      ClassSmem& S = dm.cls_smem;
+      uint32_t o = 0;
+      S.off_bx = o; o += al( (size_t)bsmax*8 );
+      S.off_bpdf = o; o += al( (size_t)bsmax*8 );
+      S.off_bcdf = o; o += al( (size_t)bsmax*8 );
+      S.off_guide = o; o += al( (size_t)kSabGBStride*2 );
+      S.off_heads = o; o += al( (size_t)nbmax*sizeof(SabHead) );
+      S.off_beta = o; o += al( (size_t)nbmax*8 + 16 );
+      S.total = o;
+      dm.cls_ctas = nsab ? std::min( 4, (int)( ( 226u*1024u ) / ( S.total + 1024u ) ) ) : 0;
+      dm.ncls = ( nsab && nc <= (uint32_t)kClsMax && dm.cls_ctas >= 1 ) ? nc : 0;
+    }
     // derived plans
     dm.sp_iso = sp; dm.sp_sc = sp;
     std::memset( &dm.sp_sc, 0, sizeof(StagePlan) );
@@ -234,12 +264,19 @@ namespace {
     }
   }
 
+  // The dynamic shared-memory limit is an attribute of the KERNEL (per device), not of a material: it is raised once
+  // per device to the opt-in maximum for every kernel that stages tables, so that handles of several materials can
+  // be alive together whatever order they were created in (r1 set it to the size of the material loaded last).
+  constexpr int kSmemOptIn = 227*1024;
   template <class K>
-  void setSmemAttr( K kernel, uint32_t bytes )
+  void setSmemAttr( K kernel )
   {
-    if ( bytes > 48u*1024u )
-      CUDA_OK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes ) );
+    cudaFuncAttributes fa;
+    CUDA_OK( cudaFuncGetAttributes( &fa, kernel ) );   // static shared memory counts against the same per-CTA limit
+    const int dyn = kSmemOptIn - (int)( ( fa.sharedSizeBytes + 1023 ) & ~(size_t)1023 );
+    CUDA_OK( cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn ) );
   }
+  void ensureKernelAttrs( int device );   // after the kernels' declarations, below
 
   int numSMs( int device )
   {
@@ -276,7 +313,12 @@ namespace {
       k_sab_guides<<< dim3( 4, ne + nb ), 256, 0, st >>>( T, ep, reinterpret_cast<uint16_t*>( base + pl.off_bguide ),
                                                        reinterpret_cast<uint16_t*>( base + pl.off_aguide ),
                                                        reinterpret_cast<double*>( base + pl.off_ascale ) );
-      g_launches += 5;
+      {
+        const size_t nmax = std::max( (size_t)ne*nb, ntot );
+        k_sab_gather_tabs<<< dim3( (unsigned)( ( nmax + 255 )/256 ), 2 ), 256, 0, st >>>(
+          T, reinterpret_cast<SabHead*>( base + pl.off_heads ), reinterpret_cast<SabPoint*>( base + pl.off_pts ) );
+      }
+      g_launches += 6;
       CUDA_OK( cudaGetLastError() );
       std::vector<int> herrs( ne );
       CUDA_OK( cudaMemcpyAsync( herrs.data(), errs, (size_t)ne*4, cudaMemcpyDeviceToHost, st ) );
@@ -313,20 +355,32 @@ namespace {
     dm->numdens = lm.numdens; dm->abs_c = lm.abs_c; dm->temperature = lm.temperature;
     dm->sabplans = lm.sabplans;
     buildStagePlan( *dm );
-    setSmemAttr( k_xs_iso, dm->sp.total );
-    setSmemAttr( k_sample_iso, dm->sp.total );
-    setSmemAttr( k_sample_classify, dm->sp.total );
-    setSmemAttr( k_xs_aniso, dm->sp.total );
-    setSmemAttr( k_sample_aniso, dm->sp.total );
-    setSmemAttr( k_xs_aniso_pre, dm->sp_iso.total );
-    setSmemAttr( k_classify_aniso, dm->sp_iso.total );
-    setSmemAttr( k_sc_scan, dm->sc_smem );
-    setSmemAttr( k_sc_sample, dm->sc_smem );
-    setSmemAttr( k_sc_eval, dm->sc_smem );
-    if ( dm->sc_find_smem <= 220u*1024u )
-      setSmemAttr( k_sc_find, dm->sc_find_smem );
+    ensureKernelAttrs( dm->device );
     buildSabTablesOnDevice( *dm, 0 );
     return dm;
+  }
+
+  void ensureKernelAttrs( int device )
+  {
+    static std::mutex m; static std::vector<int> done;
+    std::lock_guard<std::mutex> g( m );
+    for ( int d : done ) if ( d == device ) return;
+    setSmemAttr( k_xs_iso );
+    setSmemAttr( k_sample_classify );
+    setSmemAttr( k_xs_aniso );
+    setSmemAttr( k_sample_aniso );
+    setSmemAttr( k_xs_aniso_pre );
+    setSmemAttr( k_classify_aniso );
+    setSmemAttr( k_sc_scan );
+    setSmemAttr( k_sc_sample );
+    setSmemAttr( k_sc_eval );
+    setSmemAttr( k_sc_find );
+    setSmemAttr( k_tally_hist );
+    setSmemAttr( k_sab_classes<256,4> );
+    setSmemAttr( k_sab_classes<320,3> );
+    setSmemAttr( k_sab_classes<512,2> );
+    setSmemAttr( k_sab_classes<1024,1> );
+    done.push_back( device );
   }
 
   // ------------------------------------------------------------------ handles
@@ -391,6 +445,8 @@ namespace {
       uint32_t* sc_work = nullptr; uint8_t* sc_ncand = nullptr; uint16_t* sc_cand = nullptr;   // k_sc_find -> k_sc_eval
       int32_t* sc_wpos = nullptr; bool sc_lists_valid = false;
       double* fg_prep = nullptr; uint32_t* fg_nd = nullptr; size_t fcap = 0;   // k_fg_prep records, one per queue slot
+      uint16_t* q_cls = nullptr; size_t ccap = 0;       // class of every q_sab entry
+      uint32_t* cls_words = nullptr;                    // hist | start | fill | cursor | nticket(2) | tickets (uint16)
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
@@ -404,6 +460,8 @@ namespace {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
         if ( c.fg_prep ) { cudaFree( c.fg_prep ); cudaFree( c.fg_nd ); }
+        if ( c.q_cls ) cudaFree( c.q_cls );
+        if ( c.cls_words ) cudaFree( c.cls_words );
         if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
                          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); cudaFree( c.sc_wpos ); }
         if ( c.side ) cudaStreamDestroy( c.side );
@@ -440,6 +498,16 @@ namespace {
         CUDA_OK( cudaMalloc( &c.q, 6*c.cap*sizeof(uint32_t) ) );
       }
       return c;
+    }
+    // scratch of the class partition (after ensureQueues)
+    void ensureClassScratch( QueueCtx& c )
+    {
+      if ( !c.cls_words )
+        CUDA_OK( cudaMalloc( &c.cls_words, ( 4*( kClsMax + 1 ) + 2 )*sizeof(uint32_t) + kClsTicketsMax*sizeof(uint16_t) ) );
+      if ( c.ccap >= c.cap ) return;
+      if ( c.q_cls ) { CUDA_OK( cudaDeviceSynchronize() ); cudaFree( c.q_cls ); }
+      c.ccap = c.cap;
+      CUDA_OK( cudaMalloc( &c.q_cls, c.ccap*sizeof(uint16_t) ) );
     }
     // per-entry records of the staged free-gas kernels (kFgSlots doubles + 1 word per queue slot); after ensureQueues
     void ensureFgPrep( QueueCtx& c )
@@ -658,42 +726,6 @@ namespace {
     CUDA_OK( cudaGetLastError() );
   }
 
-  bool useSampleV1()
-  {
-    static const bool v1 = []{ const char* e = std::getenv( "NCB200_SAMPLE_V1" ); return e && *e && *e != '0'; }();
-    return v1;
-  }
-
-  // Keep the material tables resident in L2 while the sampling kernels stream neutron arrays through it
-  // (ncu: 36 MB of S(alpha,beta) tables were re-read from DRAM ~4x per launch, L2 hit rate 88%): the stream gets
-  // an access-policy window over the arena with "persisting" hits; streaming data around it stays "streaming".
-  // Measured: no gain (2.36 vs 2.34 ms per 1e7) -- the gathers are latency-bound whether they hit L2 or not --
-  // so it is OFF by default; NCB200_L2PERSIST=1 turns it on.
-  void pinTablesInL2( const DeviceMaterial& dm, cudaStream_t st )
-  {
-    static const bool on = []{ const char* e = std::getenv( "NCB200_L2PERSIST" ); return e && std::atoi( e ) != 0; }();
-    if ( !on || !dm.d_arena || !dm.arena_bytes ) return;
-    static std::mutex mtx;
-    static std::map<std::pair<cudaStream_t,const void*>,bool> done;
-    std::lock_guard<std::mutex> g( mtx );
-    auto key = std::make_pair( st, (const void*)dm.d_arena );
-    if ( done.count( key ) ) return;
-    done[key] = true;
-    cudaDeviceProp prop;
-    if ( cudaGetDeviceProperties( &prop, dm.device ) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 ) return;
-    const size_t want = std::min<size_t>( (size_t)prop.persistingL2CacheMaxSize, std::max<size_t>( dm.arena_bytes, (size_t)1 << 20 ) );
-    cudaDeviceSetLimit( cudaLimitPersistingL2CacheSize, want );
-    cudaStreamAttrValue attr;
-    std::memset( &attr, 0, sizeof(attr) );
-    attr.accessPolicyWindow.base_ptr = dm.d_arena;
-    attr.accessPolicyWindow.num_bytes = std::min<size_t>( dm.arena_bytes, (size_t)prop.accessPolicyMaxWindowSize );
-    attr.accessPolicyWindow.hitRatio = (float)std::min( 1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes );
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute( st, cudaStreamAttributeAccessPolicyWindow, &attr );
-    cudaGetLastError();
-  }
-
   // Materials with a FreeGas leaf: reorder the free-gas queue by energy class (k_fg_hist / k_fg_partition);
   // afterwards Q.q_fg points at the partitioned copy.  NCB200_FG_GROUP=0 switches it off.
   void partitionFgQueue( const DeviceMaterial& dm, Scatter::QueueCtx& qc, QueueArgs& Q, const double* d_ekin, uint64_t m,
@@ -728,7 +760,7 @@ namespace {
     const uint64_t minbatch = g_fg_staged_min.load();
     const unsigned nsm = (unsigned)numSMs( dm.device );
     auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
-    if ( mode == 0 || m < minbatch || Q.hist ) {
+    if ( mode == 0 || m < minbatch ) {
       const unsigned g = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
       auto tl = timer( "k_sample_fg" );
       if ( fgminb >= 8 ) k_sample_fg<8><<< g, 128, 0, st >>>( dm.mat, A, Q );
@@ -760,13 +792,63 @@ namespace {
     g_launches += 5;
   }
 
+  // S(alpha,beta) table queue of a launch sequence.  Large batches: partition by overlay sampler and sample class
+  // by class with the class tables staged in shared memory (ncb_kernels_cls.cuh); small batches (the chunks of a
+  // short host call, transport steps, materials whose tables do not fit the plan): the lane-refill kernel on the
+  // queue in arrival order.  NCB200_CLS_MIN overrides the threshold (0 = never use the class path).
+  std::atomic<uint64_t> g_cls_min{ []{ const char* e = std::getenv( "NCB200_CLS_MIN" );
+                                       return e ? (uint64_t)std::atoll(e) : (uint64_t)( 1u << 19 ); }() };
+  bool useClassPath( const DeviceMaterial& dm, uint64_t m )
+  {
+    const uint64_t mn = g_cls_min.load();
+    return dm.ncls && mn && m >= mn;
+  }
+  void launchSabQueue( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const SampleArgs& A, const QueueArgs& Q,
+                       uint64_t m, cudaStream_t st, bool timed )
+  {
+    const unsigned nsm = (unsigned)numSMs( dm.device );
+    auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
+    if ( !Q.q_cls ) {
+      const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
+      auto tl = timer( "k_sample_sab_refill" );
+      k_sample_sab_refill<false,8><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+      ++g_launches;
+      return;
+    }
+    ClassArgs K;
+    uint32_t* w = qc.cls_words;
+    K.q_in = Q.q_sab; K.q_cls = Q.q_cls; K.count = Q.counts + 0; K.q_out = qc.q + 4*qc.cap;
+    K.hist = w; K.start = w + kClsMax; K.fill = w + 2*kClsMax + 1; K.cursor = w + 3*kClsMax + 1;
+    K.nticket = w + 4*kClsMax + 1;
+    K.tickets = reinterpret_cast<uint16_t*>( w + 4*( kClsMax + 1 ) + 2 );
+    K.ncls = dm.ncls;
+    static const int tmul = []{ const char* e = std::getenv( "NCB200_CLS_TICKETS" ); return e ? std::atoi(e) : 5; }();   // tickets per 2 resident CTAs
+    static const int umin = []{ const char* e = std::getenv( "NCB200_CLS_UNIT" ); return e ? std::atoi(e) : 2048; }();
+    K.tickets_target = std::max( 1u, nsm*(unsigned)dm.cls_ctas*(unsigned)tmul/2u );
+    K.unit_min = (uint32_t)std::max( 256, umin );
+    CUDA_OK( cudaMemsetAsync( K.hist, 0, dm.ncls*sizeof(uint32_t), st ) );
+    { auto tl = timer( "k_cls_partition" );
+      k_cls_hist<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( K );
+      k_cls_scan<<< 1, 1024, 0, st >>>( K );
+      k_cls_partition<<< gridFor( ( m + 15 )/16, 256, dm.device, 4 ), 256, 0, st >>>( K ); }
+    { auto tl = timer( "k_sab_classes" );
+      const unsigned grid = nsm*(unsigned)dm.cls_ctas;
+      const uint32_t sm = dm.cls_smem.total;
+      switch ( dm.cls_ctas ) {
+      case 4: k_sab_classes<256,4><<< grid, 256, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
+      case 3: k_sab_classes<320,3><<< grid, 320, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
+      case 2: k_sab_classes<512,2><<< grid, 512, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
+      default: k_sab_classes<1024,1><<< grid, 1024, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
+      } }
+    g_launches += 4;
+  }
+
   void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu,
                         cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
     requireScatter( s->fp, "sampleScatterIsotropic" );
     const DeviceMaterial& dm = *s->dm;
-    pinTablesInL2( dm, st );
     if ( dm.mat.oriented )
       throw Err( "LogicError", "Process::sampleScatterIsotropic can only be called for isotropic materials." );
     s->ensureErrWord();
@@ -774,14 +856,13 @@ namespace {
     int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
     // Sub-launches of at most 2^26 neutrons (queue entries hold 28 index bits): bounds the scratch (index queues
-    // 24 B and free-gas stage records 76 B per neutron of a sub-launch, ~7 GB) however large the batch is; results do
+    // 26 B and free-gas stage records 76 B per neutron of a sub-launch, ~7 GB) however large the batch is; results do
     // not depend on the split (streams are keyed by the global neutron index).  NCB200_SUBLAUNCH overrides (tests).
     static const uint64_t sub = []{ const char* e = std::getenv( "NCB200_SUBLAUNCH" );
                                     const uint64_t v = e ? (uint64_t)std::atoll(e) : ( (uint64_t)1 << 26 );
                                     return std::min<uint64_t>( std::max<uint64_t>( v, 1024 ), (uint64_t)1 << kQueueIdxBits ); }();
-    const uint64_t maxn = useSampleV1() ? n : sub;
-    for ( uint64_t done = 0; done < n; done += maxn ) {
-      const uint64_t m = std::min<uint64_t>( maxn, n - done );
+    for ( uint64_t done = 0; done < n; done += sub ) {
+      const uint64_t m = std::min<uint64_t>( sub, n - done );
       SampleArgs A;
       A.ekin = d_ekin + done; A.n = m; A.seed = s->seed; A.first_index = s->next_index + done; A.sid = s->sid;
       A.xs_out = d_xs ? d_xs + done : nullptr; A.ekin_out = d_eout + done; A.mu_out = d_mu + done;
@@ -789,86 +870,26 @@ namespace {
       A.err_flags = s->d_err;
       A.ids = s->ids_override ? s->ids_override + done : nullptr;
       const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
-      if ( useSampleV1() ) {
-        k_sample_iso<<< gridFor( m, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, A );
-        ++g_launches;
-      } else {
-        Scatter::QueueCtx& qc = s->ensureQueues( ictx, m );
-        QueueArgs Q;
-        // energy-sorting the queues was measured to cost more (scatter pass) than it saves in the
-        // sampling kernels (L1 hit rate 54% -> 70%, -0.1 ms); off by default, kept for experiments
-        static const bool do_sort = []{ const char* e = std::getenv( "NCB200_SORT" ); return e ? std::atoi(e) != 0 : false; }();
-        Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
-        Q.q_sab_sorted = do_sort ? qc.q + 4*qc.cap : nullptr;
-        Q.q_fg_sorted = do_sort ? qc.q + 5*qc.cap : nullptr;
-        Q.hist = do_sort ? qc.counts + 8 : nullptr;
-        { static const int sh = []{ const char* e = std::getenv( "NCB200_SORT_SHIFT" ); return e ? std::atoi(e) : 0; }(); Q.sort_shift = sh; }
-        CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
-        { TimedLaunch tl( "k_sample_classify", st );
-          static const int cthreads = []{ const char* e = std::getenv( "NCB200_CLASSIFY_THREADS" ); return e ? std::atoi(e) : 256; }();
-          k_sample_classify<<< gridFor( m, cthreads, dm.device, ctas*( 256/cthreads ) ), cthreads, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
-        const unsigned nsm = (unsigned)numSMs( dm.device );
-        if ( do_sort ) {
-          k_queue_scan<<< 1, 1024, 0, st >>>( Q.hist );
-          k_queue_scatter<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A.ekin, Q );
-          g_launches += 2;
-          Q.q_sab = Q.q_sab_sorted; Q.q_fg = Q.q_fg_sorted;   // the sampling kernels read the sorted queues
-        }
-        const unsigned gsab = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
-        const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*4 );
-        static const int sabmode = []{ const char* e = std::getenv( "NCB200_SAB_MODE" ); return e ? std::atoi(e) : 1; }();
-        static const int sabctas = []{ const char* e = std::getenv( "NCB200_SAB_CTAS" ); return e ? std::atoi(e) : 0; }();
-        static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
-        // running the free-gas kernels on a side stream concurrently with the table kernel was measured
-        // to be no faster (each kernel alone already fills the SMs); off by default
-        static const bool overlap = []{ const char* e = std::getenv( "NCB200_FG_OVERLAP" ); return e ? std::atoi(e) != 0 : false; }();
-        const unsigned gfg2 = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
-        if ( sabmode == 0 ) {
-          k_sample_sab<false><<< gsab, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0 );
-          k_sample_fg<4><<< gfg2, 128, 0, st >>>( dm.mat, A, Q );
-          k_sample_sab<true><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2 );
-        } else {
-          // counts[3] / counts[4] : cursors of the refill kernels
-          static const int sabminb = []{ const char* e = std::getenv( "NCB200_SAB_MINB" ); return e ? std::atoi(e) : 8; }();
-          const int ctas_eff = sabctas > 0 ? sabctas : sabminb;
-          const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*ctas_eff );
-          auto launchRefill = [&]( auto kern, unsigned grid, const uint32_t* q, const uint32_t* cnt, uint32_t* cur, cudaStream_t s2 ) {
-            kern<<< grid, 128, 0, s2 >>>( dm.mat, A, q, cnt, cur );
-          };
-          static const int fgminb = []{ const char* e = std::getenv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
-          static const bool fgfirst = []{ const char* e = std::getenv( "NCB200_FG_FIRST" ); return e ? std::atoi(e) != 0 : false; }();
-          cudaStream_t st_fg = st;
-          if ( overlap ) {
-            // fork: free-gas queue (+ its E=Emax follow-up) on the side stream, S(alpha,beta) table queue on `st`
-            CUDA_OK( cudaEventRecord( qc.ev_fork, st ) );
-            CUDA_OK( cudaStreamWaitEvent( qc.side, qc.ev_fork, 0 ) );
-            st_fg = qc.side;
-          }
-          auto launchFG = [&]() {
-            if ( !do_sort ) partitionFgQueue( dm, qc, Q, A.ekin, m, st_fg );
-            launchFgSampling( s, dm, qc, A, Q, m, st_fg, true );
-          };
-          if ( fgfirst ) launchFG();
-          { TimedLaunch tl( "k_sample_sab_refill", st );
-          switch ( sabminb ) {
-          case 4: launchRefill( k_sample_sab_refill<false,4>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          case 6: launchRefill( k_sample_sab_refill<false,6>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          case 8: launchRefill( k_sample_sab_refill<false,8>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          case 10: launchRefill( k_sample_sab_refill<false,10>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          case 12: launchRefill( k_sample_sab_refill<false,12>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          default: launchRefill( k_sample_sab_refill<false,5>, gr, Q.q_sab, Q.counts + 0, Q.counts + 3, st ); break;
-          } }
-          if ( !fgfirst ) launchFG();
-          { TimedLaunch tl( "k_sample_sab_refill_emax", st_fg );
-            launchRefill( k_sample_sab_refill<true,5>, gfg, Q.q_emax, Q.counts + 2, Q.counts + 4, st_fg ); }
-          s->last_counts_ptr = Q.counts;
-          if ( overlap ) {
-            CUDA_OK( cudaEventRecord( qc.ev_join, qc.side ) );
-            CUDA_OK( cudaStreamWaitEvent( st, qc.ev_join, 0 ) );
-          }
-        }
-        g_launches += 3;
+      Scatter::QueueCtx& qc = s->ensureQueues( ictx, m );
+      QueueArgs Q;
+      Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
+      if ( useClassPath( dm, m ) ) {
+        s->ensureClassScratch( qc );
+        Q.q_cls = qc.q_cls;
+        for ( int k = 0; k <= kMaxSab; ++k ) Q.cls_base[k] = dm.cls_base[k];
       }
+      CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
+      { TimedLaunch tl( "k_sample_classify", st );
+        k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
+      ++g_launches;
+      launchSabQueue( s, dm, qc, A, Q, m, st, true );
+      partitionFgQueue( dm, qc, Q, A.ekin, m, st );
+      launchFgSampling( s, dm, qc, A, Q, m, st, true );
+      { TimedLaunch tl( "k_sample_sab_refill_emax", st );
+        const unsigned gfg = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)numSMs( dm.device )*4 );
+        k_sample_sab_refill<true,5><<< gfg, 128, 0, st >>>( dm.mat, A, Q.q_emax, Q.counts + 2, Q.counts + 4 ); }
+      ++g_launches;
+      s->last_counts_ptr = Q.counts;
       CUDA_OK( cudaGetLastError() );
     }
     s->next_index += n;
@@ -912,7 +933,8 @@ namespace {
       SA.n_dev = n_dev;
       const int ctas = std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) );
       const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*std::min( ctas, 8 ) );
-      k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off );
+      { TimedLaunch tl( "k_sc_scan", st );
+        k_sc_scan<<< grid, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, SA, dm.sc_famof_off, dm.sc_scratch_off ); }
       ++g_launches;
       CUDA_OK( cudaGetLastError() );
       return;
@@ -928,10 +950,12 @@ namespace {
     const int cf = std::min( 3, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
     const uint64_t need_f = ( n + kScFindWarps - 1 ) / kScFindWarps;
     const int ce = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) ) );
-    k_sc_find<<< (unsigned)std::min<uint64_t>( need_f, (uint64_t)nsm*cf ), 32*kScFindWarps, dm.sc_find_smem, st >>>(
-      dm.mat, dm.sp_find, FA, dm.sc_find_famof_off, dm.sc_find_scratch_off );
-    k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
-      dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+    { TimedLaunch tl( "k_sc_find", st );
+      k_sc_find<<< (unsigned)std::min<uint64_t>( need_f, (uint64_t)nsm*cf ), 32*kScFindWarps, dm.sc_find_smem, st >>>(
+        dm.mat, dm.sp_find, FA, dm.sc_find_famof_off, dm.sc_find_scratch_off ); }
+    { TimedLaunch tl( "k_sc_eval", st );
+      k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
+        dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off ); }
     g_launches += 2;
     CUDA_OK( cudaGetLastError() );
   }
@@ -957,7 +981,8 @@ namespace {
       sc_xs = qc.sc_xs; sc_n = qc.sc_n;
     }
     const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
-    k_xs_aniso_pre<<< gridFor( n, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, d_ekin, sc_xs, sc_n, n, d_out, s->n_dev_override );
+    { TimedLaunch tl( "k_xs_aniso_pre", st );
+      k_xs_aniso_pre<<< gridFor( n, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, d_ekin, sc_xs, sc_n, n, d_out, s->n_dev_override ); }
     ++g_launches;
     CUDA_OK( cudaGetLastError() );
   }
@@ -997,29 +1022,31 @@ namespace {
         launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
-      Q.q_sab_sorted = Q.q_fg_sorted = nullptr; Q.hist = nullptr;
       AnisoArgs X;
       X.D = D; X.sc_xs = has_sc ? qc.sc_xs : nullptr; X.sc_n = has_sc ? qc.sc_n : nullptr;
       X.mu_tmp = qc.mu_tmp; X.nd_tmp = qc.nd_tmp; X.q_sc = qc.q_sc; X.q_sc_count = qc.counts + 5;
       if ( has_sc && qc.sc_lists_valid ) { X.sc_wpos = qc.sc_wpos; X.sc_ncand = qc.sc_ncand; X.sc_cand = qc.sc_cand; }
       CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
       const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
-      k_classify_aniso<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, A, Q, X );
+      { TimedLaunch tl( "k_classify_aniso", st );
+        k_classify_aniso<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp_iso.total, st >>>( dm.mat, dm.sp_iso, A, Q, X ); }
       // isotropic leaves: same queue kernels as the isotropic path; they leave (E', mu, stream position)
       SampleArgs Ai = A;
       Ai.mu_out = qc.mu_tmp; Ai.ndraws = qc.nd_tmp; Ai.component = nullptr;
       const unsigned nsm = (unsigned)numSMs( dm.device );
       const unsigned gq = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
-      const unsigned gf = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
-      k_sample_sab_refill<false,8><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+      launchSabQueue( s, dm, qc, Ai, Q, m, st, true );
       if ( m >= 65536 ) partitionFgQueue( dm, qc, Q, A.ekin, m, st );
-      launchFgSampling( s, dm, qc, Ai, Q, m, st, false );
-      k_sample_sab_refill<true,5><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_emax, Q.counts + 2, Q.counts + 4 );
-      k_dir_from_mu<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A, Q, X );
-      g_launches += 4;
+      launchFgSampling( s, dm, qc, Ai, Q, m, st, true );
+      { TimedLaunch tl( "k_sample_sab_refill_emax", st );
+        k_sample_sab_refill<true,5><<< gq, 128, 0, st >>>( dm.mat, Ai, Q.q_emax, Q.counts + 2, Q.counts + 4 ); }
+      { TimedLaunch tl( "k_dir_from_mu", st );
+        k_dir_from_mu<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( A, Q, X ); }
+      g_launches += 3;
       if ( has_sc ) {
         const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kScWarps - 1 )/kScWarps, (uint64_t)nsm*3 );
-        k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off );
+        { TimedLaunch tl( "k_sc_sample", st );
+          k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off ); }
         ++g_launches;
       }
       CUDA_OK( cudaGetLastError() );
@@ -1065,6 +1092,17 @@ namespace {
     const uint64_t W = std::min<uint64_t>( n, kWindowMax );
     s->ensurePipeline( (size_t)W * (size_t)( nin + nout ) );
     const PipeSchedule ps = pipeSchedule();
+    // A failure while work is queued must not return to the caller (who then fills the output arrays with the
+    // error sentinels) before the copies already queued into those arrays have drained.
+    struct Drain {
+      Scatter* s; bool armed = true;
+      ~Drain() {
+        if ( !armed ) return;
+        cudaStreamSynchronize( s->st_h2d );
+        for ( int c = 0; c < kSlots; ++c ) cudaStreamSynchronize( s->streams[c] );
+        cudaStreamSynchronize( s->st_d2h );
+      }
+    } drain{ s };
     for ( uint64_t w0 = 0; w0 < n; w0 += W ) {
       const uint64_t wn = std::min<uint64_t>( W, n - w0 );
       uint64_t done = 0;
@@ -1100,6 +1138,7 @@ namespace {
       for ( int c = 0; c < kSlots; ++c )
         CUDA_OK( cudaStreamSynchronize( s->streams[c] ) );
     }
+    drain.armed = false;
   }
 
   void xsIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* results )
@@ -1238,6 +1277,7 @@ extern "C" {
       if ( nbytes < sizeof(ncb_header_t) ) throw Err( "BadInput", "compiled material: buffer too small" );
       ncb_header_t hdr; std::memcpy( &hdr, blob, sizeof(hdr) );
       if ( hdr.magic != NCB_MAGIC || hdr.version != NCB_VERSION ) throw Err( "BadInput", "compiled material: bad magic or version" );
+      if ( hdr.nbytes > nbytes ) throw Err( "BadInput", "compiled material: inconsistent header" );
       if ( hdr.abs_c < 0.0 ) throw Err( "BadInput", "the material's absorption process is not of the 1/v type" );
       auto dm = std::make_shared<DeviceMaterial>();
       dm->uid = ++g_material_uid_counter;
@@ -1611,7 +1651,7 @@ extern "C" {
         throw Err( "BadInput", "ncb200_tally_hist_dev: need hi>lo and 1<=nbins<=12000" );
       int dev = 0; CUDA_OK( cudaGetDevice( &dev ) );
       const uint32_t smem = ( nbins + 2 ) * 8u * ( d_sumw2 ? 2u : 1u );
-      setSmemAttr( k_tally_hist, smem );
+      ensureKernelAttrs( dev );
       k_tally_hist<<< gridFor( n, 256, dev, 4 ), 256, smem, static_cast<cudaStream_t>( stream ) >>>(
         d_values, d_weights, n, lo, (double)nbins/( hi - lo ), nbins, d_hist, d_sumw2 );
       ++g_launches;

@@ -10,6 +10,7 @@
 #include "ncb_blob.h"
 #include "ncb_tables.h"
 #include <cstring>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -19,7 +20,7 @@ namespace ncb {
   struct SabBuildPlan {       // what the build stages need for one SAB leaf
     int sab_index;            // index into Material::sab
     size_t off_logsab, off_cumul, off_ep, off_bx, off_bpdf, off_bcdf, off_ainfo, off_rows, off_xscheck;
-    size_t off_bguide, off_aguide, off_ascale;
+    size_t off_bguide, off_aguide, off_ascale, off_heads, off_pts;
   };
 
   struct LoadedMaterial {
@@ -71,6 +72,7 @@ namespace ncb {
       relocPtr( s.ep, base ); relocPtr( s.bx, base ); relocPtr( s.bpdf, base ); relocPtr( s.bcdf, base );
       relocPtr( s.ainfo, base );
       relocPtr( s.bguide, base ); relocPtr( s.aguide, base ); relocPtr( s.ascale, base );
+      relocPtr( s.heads, base ); relocPtr( s.pts, base );
     }
     if ( m.sc.nfam ) {
       relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
@@ -80,6 +82,20 @@ namespace ncb {
   }
 
   void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
+
+  // Payload validation: the array counts inside a component payload come from the (untrusted) buffer; before any
+  // copy the payload must hold its header plus `ndoubles` fp64 values.  Counts are bounded first so that the sums
+  // and products below cannot wrap.
+  constexpr uint64_t kMaxBlobCount = (uint64_t)1 << 31;
+  inline void checkPayload( const ncb_comp_t& c, size_t header_bytes, std::initializer_list<uint64_t> counts,
+                            uint64_t ndoubles, const char* what )
+  {
+    for ( uint64_t n : counts )
+      if ( n > kMaxBlobCount )
+        throw std::runtime_error( std::string("compiled material: implausible array length in ")+what+" payload" );
+    if ( ndoubles > ( (uint64_t)1 << 40 ) || c.nbytes < header_bytes || ( c.nbytes - header_bytes ) / 8 < ndoubles )
+      throw std::runtime_error( std::string("compiled material: truncated ")+what+" payload" );
+  }
 
   inline void loadBlob( const void* blob_, size_t nbytes, LoadedMaterial& lm )
   {
@@ -107,8 +123,10 @@ namespace ncb {
     int npb = 0, nel = 0, nfg = 0, nsab = 0;
     for ( int i = 0; i < m.ncomp; ++i ) {
       const ncb_comp_t& c = hdr.comp[i];
-      if ( c.off + c.nbytes > hdr.nbytes )
+      if ( c.off > hdr.nbytes || c.nbytes > hdr.nbytes - c.off || c.off < sizeof(ncb_header_t) )
         throw std::runtime_error( "compiled material: component out of bounds" );
+      if ( c.off % 8 != 0 )
+        throw std::runtime_error( "compiled material: misaligned component payload" );
       Comp& k = m.comp[i];
       k.kind = (int)c.kind;
       k.scale = c.scale;
@@ -118,7 +136,10 @@ namespace ncb {
       switch ( c.kind ) {
       case NCB_KIND_POWDERBRAGG: {
         if ( npb >= (int)( sizeof(m.pb)/sizeof(m.pb[0]) ) ) throw std::runtime_error( "too many PowderBragg components" );
+        checkPayload( c, sizeof(ncb_powderbragg_t), {}, 0, "PowderBragg" );
         ncb_powderbragg_t h; std::memcpy( &h, p, sizeof(h) );
+        checkPayload( c, sizeof(h), { h.nplanes }, 2*h.nplanes, "PowderBragg" );
+        if ( h.nplanes == 0 ) throw std::runtime_error( "compiled material: PowderBragg without planes" );
         const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
         PowderBraggT& T = m.pb[npb];
         T.n = (int)h.nplanes;
@@ -130,8 +151,10 @@ namespace ncb {
       }
       case NCB_KIND_ELINC: {
         if ( nel >= 1 ) throw std::runtime_error( "too many ElIncScatter components" );
+        checkPayload( c, sizeof(ncb_elinc_t), {}, 0, "ElIncScatter" );
         ncb_elinc_t h; std::memcpy( &h, p, sizeof(h) );
         if ( h.nelem > (uint64_t)kMaxElIncElems ) throw std::runtime_error( "too many ElInc elements" );
+        checkPayload( c, sizeof(h), { h.nelem }, 2*h.nelem, "ElIncScatter" );
         const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
         ElIncT& T = m.elinc[nel];
         T.n = (int)h.nelem;
@@ -141,6 +164,7 @@ namespace ncb {
       }
       case NCB_KIND_FREEGAS: {
         if ( nfg >= (int)( sizeof(m.fg)/sizeof(m.fg[0]) ) ) throw std::runtime_error( "too many FreeGas components" );
+        checkPayload( c, sizeof(ncb_freegas_t), {}, 0, "FreeGas" );
         ncb_freegas_t h; std::memcpy( &h, p, sizeof(h) );
         FreeGasT& T = m.fg[nfg];
         T.sigma_free = h.sigma_free;
@@ -152,7 +176,12 @@ namespace ncb {
       }
       case NCB_KIND_SAB: {
         if ( nsab >= (int)( sizeof(m.sab)/sizeof(m.sab[0]) ) ) throw std::runtime_error( "too many SABScatter components" );
+        checkPayload( c, sizeof(ncb_sab_t), {}, 0, "SABScatter" );
         ncb_sab_t h; std::memcpy( &h, p, sizeof(h) );
+        if ( h.negrid < 2 || h.nalpha < 2 || h.nbeta < 2 ) throw std::runtime_error( "compiled material: degenerate SAB grids" );
+        if ( h.nbeta + 1 > 65535 || h.nalpha > 65535 || h.negrid > 65535 )
+          throw std::runtime_error( "compiled material: SAB grids too large for 16-bit guide tables" );
+        checkPayload( c, sizeof(h), { h.negrid, h.nalpha, h.nbeta }, 2*h.negrid + h.nalpha + h.nbeta + h.nalpha*h.nbeta, "SABScatter" );
         const double* arr = reinterpret_cast<const double*>( p + sizeof(h) );
         SabT& T = m.sab[nsab];
         T.scale = h.scale;
@@ -173,7 +202,6 @@ namespace ncb {
         T.ext.mass_amu = h.ext_mass_amu;
         T.negrid = (int)h.negrid; T.nalpha = (int)h.nalpha; T.nbeta = (int)h.nbeta;
         const size_t ne = h.negrid, na = h.nalpha, nb = h.nbeta;
-        if ( ne < 2 || na < 2 || nb < 2 ) throw std::runtime_error( "compiled material: degenerate SAB grids" );
         T.egrid = offAsPtr<double>( lm.put( arr, ne*8 ) );
         T.xs    = offAsPtr<double>( lm.put( arr + ne, ne*8 ) );
         T.alpha = offAsPtr<double>( lm.put( arr + 2*ne, na*8 ) );
@@ -184,16 +212,19 @@ namespace ncb {
         pl.off_logsab = lm.reserve( na*nb*8 );
         pl.off_cumul  = lm.reserve( na*nb*8 );
         pl.off_ep     = lm.reserve( ne*sizeof(SabEPoint) );
-        pl.off_bx     = lm.reserve( ne*(nb+1)*8 );
-        pl.off_bpdf   = lm.reserve( ne*(nb+1)*8 );
-        pl.off_bcdf   = lm.reserve( ne*(nb+1)*8 );
+        T.bstride = sabBStride( (int)nb );
+        const size_t bst = (size_t)T.bstride;
+        pl.off_bx     = lm.reserve( ne*bst*8 );
+        pl.off_bpdf   = lm.reserve( ne*bst*8 );
+        pl.off_bcdf   = lm.reserve( ne*bst*8 );
         pl.off_ainfo  = lm.reserve( ne*nb*sizeof(SabAlphaInfo) );
         pl.off_rows   = lm.reserve( ne*nb*16 );
         pl.off_xscheck= lm.reserve( ne*8 + ne*4 );
-        pl.off_bguide = lm.reserve( ne*( kSabGB+1 )*sizeof(uint16_t) );
+        pl.off_bguide = lm.reserve( ne*(size_t)kSabGBStride*sizeof(uint16_t) );
         pl.off_aguide = lm.reserve( nb*( kSabGA+1 )*sizeof(uint16_t) );
         pl.off_ascale = lm.reserve( nb*8 );
-        if ( nb + 1 > 65535 || na > 65535 ) throw std::runtime_error( "compiled material: SAB grids too large for 16-bit guide tables" );
+        pl.off_heads  = lm.reserve( ne*nb*sizeof(SabHead) );
+        pl.off_pts    = lm.reserve( na*nb*sizeof(SabPoint) );
         T.logsab = offAsPtr<double>( pl.off_logsab );
         T.cumul  = offAsPtr<double>( pl.off_cumul );
         T.ep     = offAsPtr<SabEPoint>( pl.off_ep );
@@ -204,6 +235,8 @@ namespace ncb {
         T.bguide = offAsPtr<uint16_t>( pl.off_bguide );
         T.aguide = offAsPtr<uint16_t>( pl.off_aguide );
         T.ascale = offAsPtr<double>( pl.off_ascale );
+        T.heads  = offAsPtr<SabHead>( pl.off_heads );
+        T.pts    = offAsPtr<SabPoint>( pl.off_pts );
         lm.sabplans.push_back( pl );
         k.idx = nsab++;
         break;

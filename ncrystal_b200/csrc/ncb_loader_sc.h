@@ -4,7 +4,10 @@
 namespace ncb {
   inline void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c )
   {
+    checkPayload( c, sizeof(ncb_scbragg_t), {}, 0, "SCBragg" );
     ncb_scbragg_t h; std::memcpy( &h, blob + c.off, sizeof(h) );
+    checkPayload( c, sizeof(h), { h.nfam, h.nnormals, h.lut_sofcosd_n, h.lut_evalcosx_n },
+                  3*h.nfam + 1 + 3*h.nnormals + 2*h.lut_sofcosd_n + 2*h.lut_evalcosx_n, "SCBragg" );
     const double* arr = reinterpret_cast<const double*>( blob + c.off + sizeof(h) );
     ScBraggT& S = lm.mat.sc;
     if ( S.nfam != 0 )
@@ -21,7 +24,14 @@ namespace ncb {
     S.fam_xsfact = offAsPtr<double>( lm.put( arr, nf*8 ) );
     S.fam_inv2d = offAsPtr<double>( lm.put( arr + nf, nf*8 ) );
     std::vector<int> first( nf+1 );
-    for ( size_t i = 0; i <= nf; ++i ) first[i] = (int)arr[2*nf+i];
+    for ( size_t i = 0; i <= nf; ++i ) {
+      const double v = arr[2*nf+i];
+      if ( !( v >= 0.0 && v <= (double)nn ) || ( i && (int)v < first[i-1] ) )
+        throw std::runtime_error( "compiled material: inconsistent SCBragg family index" );
+      first[i] = (int)v;
+    }
+    if ( first[nf] != (int)nn )
+      throw std::runtime_error( "compiled material: inconsistent SCBragg family index" );
     S.fam_first = offAsPtr<int>( lm.put( first.data(), (nf+1)*sizeof(int) ) );
     const double* pn = arr + 2*nf + nf + 1;
     S.normals = offAsPtr<double>( lm.put( pn, 3*nn*8 ) );

@@ -134,11 +134,13 @@ namespace ncb {
   // --------------------------------------------------------------- SAB xs
   // SABXSProvider::crossSection, ref: src/sab/NCSABXSProvider.cc:54-95, times
   // SABScatter::m_scale (src/sabscatter/NCSABScatter.cc:87-90).
+  // `iu_out` (optional) receives upper_bound(egrid, E), which the sampler's choice of overlay starts from.
   template <class Ptr>
-  NCB_HD double sabXS( const SabT& T, Ptr egrid, Ptr xsv, double ekin )
+  NCB_HD double sabXS( const SabT& T, Ptr egrid, Ptr xsv, double ekin, int* iu_out = nullptr )
   {
     const int n = T.negrid;
     const int iu = upperBound( egrid, 0, n, ekin );
+    if ( iu_out ) *iu_out = iu;
     double xs;
     if ( iu == n ) {
       xs = T.k_extension / ekin + fgXS( T.ext, ekin );

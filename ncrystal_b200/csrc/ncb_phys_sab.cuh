@@ -208,6 +208,189 @@ namespace ncb {
     return false;
   }
 
+  // ---------------------------------------------------------------------------------------------------------
+  // Class-staged variants: the same arithmetic as pwdPercentileWithIndex / sabSampleAlpha / sabAttemptAtE above, for
+  // a kernel whose CTA works on ONE overlay sampler (energy point) at a time.  That sampler's beta distribution
+  // (x, pdf, cdf), its beta guide and its SabHead entries sit in shared memory (`SabClassTabs`, plain loads);
+  // what is gathered from global memory per alpha sample is the row's alpha guide and SabPoint records.
+  struct SabClassTabs {
+    const double* bx; const double* bpdf; const double* bcdf;   // [npts]
+    const uint16_t* guide;                                       // [kSabGB+1]
+    const SabHead* heads;                                        // indexed by beta row; rows max(ibeta_off-1,0) ... nbeta-1 are present
+    const double* beta;                                          // the kernel's beta grid [nbeta]
+    const SabAlphaInfo* ainfo;                                   // (global) this energy point's entry for beta row 0
+    int npts, ibeta_off;
+    double first_bin_endpoint;
+  };
+
+  NCB_HD SabPoint ldPoint( const SabPoint* p )
+  {
+#if defined(__CUDA_ARCH__)
+    const double2 a = __ldg( reinterpret_cast<const double2*>( p ) );
+    const double2 b = __ldg( reinterpret_cast<const double2*>( p ) + 1 );
+    return SabPoint{ a.x, a.y, b.x, b.y };
+#else
+    return *p;
+#endif
+  }
+  NCB_HD int upperBoundPts( const SabPoint* a, int lo, int hi, double v )
+  {
+    while ( lo < hi ) {
+      int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( !( v < ldTable( &a[mid].cumul ) ) ) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+
+#if !defined(__CUDA_ARCH__) && defined(NCB_HOST_TRACE)
+  inline void (*g_alpha_trace)( int, double, int, int, int, int, int, double ) = nullptr;   // tests/hostsim only
+#endif
+
+  // PointwiseDist::percentileWithIndex over staged rows (ref: NCPointwiseDist.cc:76-105)
+  NCB_HD double pwdPercentileStaged( const SabClassTabs& C, double p, int& idx )
+  {
+    const int n = C.npts;
+    if ( p == 1. ) {
+      idx = n-2;
+      return C.bx[n-1];
+    }
+    const int b = (int)( p * (double)kSabGB );
+    int i = lowerBound( C.bcdf, (int)C.guide[b], (int)C.guide[b+1], p );
+    i = i < n-1 ? i : n-1;
+    i = i > 1 ? i : 1;
+    const double x0 = C.bx[i-1], x1 = C.bx[i];
+    const double dx = x1 - x0;
+    const double c = ( p - C.bcdf[i-1] );
+    const double a = C.bpdf[i-1];
+    const double d = C.bpdf[i] - a;
+    double zdx;
+    if ( !a ) {
+      zdx = d > 0.0 ? sqrt( ( 2.0 * c * dx ) / d ) : 0.5*dx;
+    } else {
+      const double e = d * c / ( dx * a * a );
+      if ( fabs(e) > 1e-7 )
+        zdx = ( sqrt( 1.0 + 2.0 * e ) - 1.0 ) * dx * a / d;
+      else
+        zdx = ( 1 + 0.5 * e * ( e - 1.0 ) ) * c / a;
+    }
+    idx = i-1;
+    return dclamp( x0 + zdx, x0, x1 );
+  }
+
+  // SABSamplerAtE_Alg1::sampleAlpha (ref: NCSABSamplerModels.cc:157-233), staged head + point records
+  NCB_HD_NOINLINE double sabSampleAlphaStaged( const SabT& T, const SabClassTabs& C, int ibeta, double rand_percentile )
+  {
+    const SabHead& h = C.heads[ibeta];
+    const SabPoint* P = T.pts + (size_t)ibeta*T.nalpha;
+    double a, fa, b, fb, r, la, lb;
+    const double prob_front = h.prob_front, prob_notback = h.prob_notback;
+    if ( rand_percentile <= prob_front ) {
+      const SabAlphaInfo* info = C.ainfo + ibeta;
+      const double f_alpha = ldTable( &info->f_alpha );
+      if ( prob_front == 2.0 ) {
+        const double da = ldTable( &info->b_alpha ) - f_alpha;
+        return f_alpha + rand_percentile*da;
+      } else if ( prob_front == 1.0 ) {
+        a = f_alpha; fa = ldTable( &info->f_sval ); b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
+        r = rand_percentile; la = ldTable( &info->f_logsval ); lb = ldTable( &info->b_logsval );
+      } else {
+        const SabPoint q = ldPoint( P + h.f_idx );
+        a = f_alpha; fa = ldTable( &info->f_sval ); b = q.alpha; fb = q.sab;
+        r = dclamp( rand_percentile / prob_front, kDblMin, 1.0 );
+        la = ldTable( &info->f_logsval ); lb = q.logsab;
+      }
+    } else if ( rand_percentile <= prob_notback ) {
+      const double percentile2 = dclamp( ( rand_percentile - prob_front ) / ( prob_notback - prob_front ), 0.0, 1.0 );
+      const int ilow = (int)h.f_idx, iupp = (int)h.b_idx, nalpha = T.nalpha;
+      const double clow = h.clow, cupp = h.cupp;
+      const double selectedArea = clow + percentile2 * ( cupp - clow );
+      int bk = (int)( selectedArea * h.ascale );
+      bk = bk < 0 ? 0 : ( bk > kSabGA-1 ? kSabGA-1 : bk );
+      const uint16_t* g = T.aguide + (size_t)ibeta*( kSabGA+1 ) + bk;
+      int r0 = upperBoundPts( P, (int)ldTable( g ), (int)ldTable( g + 1 ), selectedArea );
+      const bool ok = ( r0 == 0 || !( selectedArea < ldTable( &P[r0-1].cumul ) ) ) && ( r0 == nalpha || selectedArea < ldTable( &P[r0].cumul ) );
+#if !defined(__CUDA_ARCH__) && defined(NCB_HOST_TRACE)
+      if ( g_alpha_trace ) g_alpha_trace( ibeta, selectedArea, ilow, iupp, (int)g[0], (int)g[1], r0, percentile2 );
+#endif
+      if ( !ok )
+        r0 = upperBoundPts( P, 0, nalpha, selectedArea );
+      const int isel_upp = r0 < ilow ? ilow : ( r0 > iupp+1 ? iupp+1 : r0 );
+      if ( isel_upp > iupp )
+        return ldTable( &P[iupp].alpha );
+      if ( isel_upp <= ilow )
+        return ldTable( &P[ilow].alpha );
+      const SabPoint p0 = ldPoint( P + isel_upp - 1 ), p1 = ldPoint( P + isel_upp );
+      const double binArea = p1.cumul - p0.cumul;
+      r = dclamp( ( selectedArea - p0.cumul ) / binArea, kDblMin, 1.0 );
+      a = p0.alpha; fa = p0.sab; b = p1.alpha; fb = p1.sab; la = p0.logsab; lb = p1.logsab;
+    } else {
+      const SabAlphaInfo* info = C.ainfo + ibeta;
+      const SabPoint q = ldPoint( P + h.b_idx );
+      r = dclamp( ( rand_percentile - prob_notback ) / ( 1.0 - prob_notback ), kDblMin, 1.0 );
+      a = q.alpha; fa = q.sab; b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
+      la = q.logsab; lb = ldTable( &info->b_logsval );
+    }
+    return sampleLogLinDistFast( a, fa, b, fb, r, la, lb );
+  }
+
+  // One pass of the rejection loop of SABSamplerAtE_Alg1::sampleAlphaBeta (ref: NCSABSamplerModels.cc:62-148), staged
+  NCB_HD bool sabAttemptStaged( const SabT& T, const SabClassTabs& C, double ekin_div_kT, Rng& rng,
+                                double& alpha_out, double& beta_out, int& err )
+  {
+    const double firstBin = C.first_bin_endpoint;
+    int ibetaSampled;
+    double beta = pwdPercentileStaged( C, rng.generate(), ibetaSampled );
+
+    if ( ibetaSampled == 0 && firstBin <= 0.0 ) {
+      const double b0 = firstBin;
+      const double b1 = C.bx[1];
+      if ( b1 < -ekin_div_kT )
+        return false;
+      const double delta_beta = b1 - b0;
+      double alphaval = 0.0;
+      constexpr int nsampletries = 30;
+      for ( int iii = 0; iii < nsampletries; ++iii ) {
+        beta = dmax( firstBin, b0 + delta_beta*rng.generate() );
+        if ( beta < -ekin_div_kT )
+          break;
+        alphaval = sabSampleAlphaStaged( T, C, C.ibeta_off, rng.generate() );
+        AlphaLimits alims = getAlphaLimits( -firstBin, beta );
+        if ( inInterval( alims.first, alims.second, alphaval ) )
+          break;
+        if ( iii == nsampletries-1 ) {
+          err |= ERR_SAB_ISOFALLBACK;
+          alphaval = 0.5*( alims.first + alims.second );
+          break;
+        }
+      }
+      if ( beta < -ekin_div_kT )
+        return false;
+      AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+      if ( inInterval( alimits.first, alimits.second, alphaval ) ) {
+        alpha_out = alphaval; beta_out = beta;
+        return true;
+      }
+      return false;
+    }
+
+    if ( beta <= dmax( -ekin_div_kT, C.beta[0] ) )
+      return false;
+
+    const double rand_percentile = rng.generate();
+    const int ibeta = C.ibeta_off + ibetaSampled;
+    const double bl = C.beta[ibeta-1];
+    const double alphal = sabSampleAlphaStaged( T, C, ibeta-1, rand_percentile );
+    const double bh = C.beta[ibeta];
+    const double alphah = sabSampleAlphaStaged( T, C, ibeta, rand_percentile );
+    const double alpha = alphal + (alphah-alphal) * (beta-bl)/(bh-bl);
+    AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
+    if ( inInterval( alimits.first, alimits.second, alpha ) ) {
+      alpha_out = alpha; beta_out = beta;
+      return true;
+    }
+    return false;
+  }
+
   // SABSamplerAtE_Alg1::sampleAlphaBeta, ref: NCSABSamplerModels.cc:48-155
   // (npts==0 is SABSamplerAtE_NoScatter: returns (0,0), NCSABSamplerModels.hh:86)
   NCB_HD void sabSampleAtE( const SabT& T, const SabEPoint& ep, double ekin_div_kT, Rng& rng,
@@ -226,6 +409,22 @@ namespace ncb {
 
   // Choice of the overlay sampler for an in-grid or below-grid energy
   // (SABSampler::sampleAlphaBeta, ref: NCSABSampler.cc:166-192; E < Emax only).
+  // Same, starting from iu = upper_bound(egrid,E) when the caller already has it (the cross-section pass does).
+  template <class Ptr>
+  NCB_HD int sabPickSamplerFrom( const SabT& T, Ptr egrid, double ekin, int iu, bool& ultra_small_ekin_mode )
+  {
+    const int n = T.negrid;
+    ultra_small_ekin_mode = false;
+    if ( iu == 0 ) {
+      ultra_small_ekin_mode = ( ekin < egrid[0] );
+      return 0;
+    }
+    if ( T.egrid_margin > 1.0 ) {
+      while ( iu+1 != n && ekin*T.egrid_margin > egrid[iu] )
+        ++iu;
+    }
+    return iu;
+  }
   NCB_HD int sabPickSampler( const SabT& T, const double* egrid, double ekin, bool& ultra_small_ekin_mode )
   {
     const int n = T.negrid;
@@ -367,6 +566,60 @@ namespace ncb {
       }
     }
     ekin_out = dmax( 0.0, ekin + deltaE );
+  }
+
+  // The class tables of energy point `ie` addressed in place (no staging): used by the host build of these
+  // functions (tests/hostsim) -- the kernel builds the same struct with shared-memory pointers.
+  NCB_HD SabClassTabs sabClassTabsInPlace( const SabT& T, int ie )
+  {
+    const SabEPoint& ep = T.ep[ie];
+    SabClassTabs C;
+    C.bx = T.bx + ep.off_b; C.bpdf = T.bpdf + ep.off_b; C.bcdf = T.bcdf + ep.off_b;
+    C.guide = T.bguide + (size_t)ie*kSabGBStride;
+    C.heads = T.heads + (size_t)ie*T.nbeta;
+    C.ainfo = T.ainfo + (size_t)ie*T.nbeta;
+    C.beta = T.beta;
+    C.npts = ep.npts; C.ibeta_off = ep.ibeta_off; C.first_bin_endpoint = ep.first_bin_endpoint;
+    return C;
+  }
+
+  // Table path (E < Emax) of SABScatter::sampleScatterIsotropic through the staged functions: the sequence of
+  // attempts the class kernel runs for one neutron (k_sab_classes), as one loop.
+  NCB_HD void sabSampleScatterStaged( const SabT& T, double ekin, Rng& rng, double& ekin_out, double& mu, int& err )
+  {
+    bool ultra = false;
+    const int ie = sabPickSampler( T, T.egrid, ekin, ultra );
+    const SabClassTabs C = sabClassTabsInPlace( T, ie );
+    const double ekin_div_kT = ekin / T.kT;
+    const double sampling_ediv = ultra ? T.egrid[0] / T.kT : ekin_div_kT;
+    int inner = 0, outer = 0;
+    ekin_out = -1.0; mu = -999.0;
+    while ( true ) {
+      double alpha = 0.0, beta = 0.0;
+      bool inner_ok = true;
+      if ( C.npts != 0 )
+        inner_ok = sabAttemptStaged( T, C, sampling_ediv, rng, alpha, beta, err );
+      if ( !inner_ok ) {
+        if ( ++inner == 100 ) { err |= ERR_SAB_LOOP_INNER; return; }
+        continue;
+      }
+      inner = 0;
+      bool acc = false;
+      if ( !( beta < -ekin_div_kT ) ) {
+        AlphaLimits al = getAlphaLimits( ekin_div_kT, beta );
+        if ( inInterval( al.first, al.second, alpha ) ) {
+          acc = true;
+        } else if ( ultra ) {
+          alpha = al.first + rng.generate()*( al.second - al.first );
+          acc = true;
+        }
+      }
+      if ( acc ) {
+        sabFinishScatter( T, ekin, alpha, beta, rng, ekin_out, mu, err );
+        return;
+      }
+      if ( ++outer == 100 ) { err |= ERR_SAB_LOOP_OUTER; return; }
+    }
   }
 
   // Table sampling for a neutron above Emax whose high-E analysis (sabSampleHighE) asked for

@@ -26,7 +26,8 @@ namespace ncb {
     H.sc = &M.sc;
   }
 
-  // Unscaled isotropic xs of component i.  aux receives the PowderBragg plane index.
+  // Unscaled isotropic xs of component i.  aux receives the PowderBragg plane index / the S(alpha,beta) energy-grid
+  // position upper_bound(egrid,E).
   NCB_HD double compXSIso( const Material& M, const HotTabs& H, int i, double ekin, int& aux )
   {
     const Comp& c = M.comp[i];
@@ -39,7 +40,7 @@ namespace ncb {
       return elincXS( M.elinc[c.idx], ekin, nullptr );
     case KIND_SAB: {
       const SabT& T = M.sab[c.idx];
-      return sabXS( T, H.sab_egrid[c.idx], H.sab_xs[c.idx], ekin );
+      return sabXS( T, H.sab_egrid[c.idx], H.sab_xs[c.idx], ekin, &aux );
     }
     case KIND_FREEGAS:
       return fgXS( M.fg[c.idx], ekin );

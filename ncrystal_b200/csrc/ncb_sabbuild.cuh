@@ -281,4 +281,21 @@ namespace ncb {
     return (uint16_t)upperBound( cumul_row, 0, nalpha, (double)b / scale );
   }
 
+  // ---- stage 4: gather-friendly copies for the class-staged sampling kernel (layout only, same values)
+  NCB_HD SabHead sabMakeHead( const SabAlphaInfo& info, const double* cumul_row, double ascale_row )
+  {
+    SabHead h;
+    h.prob_front = info.prob_front; h.prob_notback = info.prob_notback;
+    h.f_idx = (uint32_t)info.f_idx; h.b_idx = (uint32_t)info.b_idx;
+    h.clow = cumul_row[info.f_idx]; h.cupp = cumul_row[info.b_idx];
+    h.ascale = ascale_row;
+    return h;
+  }
+  NCB_HD SabPoint sabMakePoint( const double* agrid, const double* sab, const double* logsab, const double* cumul, int nalpha, size_t k )
+  {
+    SabPoint p;
+    p.alpha = agrid[k % (size_t)nalpha]; p.sab = sab[k]; p.logsab = logsab[k]; p.cumul = cumul[k];
+    return p;
+  }
+
 }

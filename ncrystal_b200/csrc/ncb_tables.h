@@ -58,6 +58,19 @@ namespace ncb {
     double pad;                         // 80 bytes
   };
 
+  // Per (energy point, beta row): what SABSamplerAtE_Alg1::sampleAlpha needs to choose its case and to run the
+  // "whole bins" case, packed so that one overlay sampler's entries can be staged in shared memory (48 B, a
+  // multiple of 16 for the bulk copy).  clow/cupp/ascale are copies of cumul[row][f_idx], cumul[row][b_idx] and
+  // ascale[row]: they take two dependent gathers out of every alpha sample.
+  struct SabHead {
+    double prob_front, prob_notback;
+    double clow, cupp;
+    double ascale;
+    uint32_t f_idx, b_idx;
+  };
+  // Per (beta row, alpha grid point): everything sampleAlpha gathers at one grid point, in one 32-byte sector.
+  struct SabPoint { double alpha, sab, logsab, cumul; };
+
   struct SabT {
     // SABScatter / SABXSProvider / SABSampler scalars
     double scale;          // SABScatter::m_scale
@@ -83,10 +96,15 @@ namespace ncb {
     const SabAlphaInfo* ainfo; // packed
     // Guide tables (inverse-CDF bucket index -> first candidate position) that replace most steps of the
     // two binary searches of a sampling attempt; the search result is unchanged (see ncb_phys_sab.cuh).
-    const uint16_t* bguide;    // [negrid][kSabGB+1]  over each energy point's beta CDF
+    const uint16_t* bguide;    // [negrid][kSabGBStride] (kSabGB+1 used) over each energy point's beta CDF
     const uint16_t* aguide;    // [nbeta][kSabGA+1]   over each beta row of the cumulative alpha integrals
     const double* ascale;      // [nbeta]  kSabGA / cumul[row][nalpha-1]  (0 for an all-zero row)
+    const SabHead* heads;      // [negrid*nbeta], indexed like ainfo
+    const SabPoint* pts;       // [nbeta*nalpha]
+    int bstride;               // doubles between the beta-sampler rows of consecutive energy points (even: 16-byte rows)
   };
+  constexpr int kSabGBStride = 1032;   // uint16 entries between the beta guides of consecutive energy points (16-byte rows)
+  inline int sabBStride( int nbeta ) { return ( nbeta + 2 ) & ~1; }
   constexpr int kSabGB = 1024;
   constexpr int kSabGA = 256;
 

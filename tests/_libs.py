@@ -192,11 +192,13 @@ class HostSim:
             L.hostsim_free.argtypes = [C.c_void_p]
             L.hostsim_lasterror.restype = C.c_char_p
             L.hostsim_ncomp.argtypes = [C.c_void_p]
+            L.hostsim_component_kind.argtypes = [C.c_void_p, C.c_int]
             L.hostsim_xs_iso.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp]
             L.hostsim_xs_iso_components.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp]
             L.hostsim_sample_iso.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, C.c_uint64, _dp, _dp, _u32p, _i32p]
             L.hostsim_sample_iso_leaf.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, _dp, C.c_uint64, _dp, _dp,
                                                   _u32p, _i32p]
+            L.hostsim_sample_sab_staged.argtypes = L.hostsim_sample_iso_leaf.argtypes
             L.hostsim_xs.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_uint64, _dp]
             L.hostsim_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, C.c_uint64,
                                          _dp, _dp, _dp, _dp, _u32p, _i32p]
@@ -224,6 +226,9 @@ class HostSim:
     def ncomp(self):
         return self.lib().hostsim_ncomp(self.h)
 
+    def component_kind(self, c):
+        return self.lib().hostsim_component_kind(self.h, c)
+
     def xs_iso(self, ekin):
         ekin = np.ascontiguousarray(ekin, dtype=np.float64)
         out = np.empty_like(ekin)
@@ -248,6 +253,16 @@ class HostSim:
         else:
             self.lib().hostsim_sample_iso_leaf(self.h, leaf, seed, first_index, _d(ekin), ekin.size, _d(eo), _d(mu),
                                                nd.ctypes.data_as(_u32p), er.ctypes.data_as(_i32p))
+        return eo, mu, nd, er
+
+    def sample_sab_staged(self, ekin, leaf, seed=1, first_index=0):
+        ekin = np.ascontiguousarray(ekin, dtype=np.float64)
+        eo = np.empty_like(ekin)
+        mu = np.empty_like(ekin)
+        nd = np.zeros(ekin.size, dtype=np.uint32)
+        er = np.zeros(ekin.size, dtype=np.int32)
+        self.lib().hostsim_sample_sab_staged(self.h, leaf, seed, first_index, _d(ekin), ekin.size, _d(eo), _d(mu),
+                                             nd.ctypes.data_as(_u32p), er.ctypes.data_as(_i32p))
         return eo, mu, nd, er
 
     def xs(self, ekin, ux, uy, uz):

@@ -7,6 +7,7 @@
 // (pytest -m "not gpu").  It is NOT part of the product: the package never loads
 // this library and has no CPU fallback (ncrystal_b200/_lib.py fails loudly when
 // the CUDA library is missing).
+#define NCB_HOST_TRACE 1
 #include "ncb_proc.cuh"
 #include "ncb_sabbuild.cuh"
 #include "ncb_loader.h"
@@ -52,7 +53,7 @@ namespace {
         for ( int ib = 0; ib < nb; ++ib )
           rows[(size_t)ie*nb+ib] = sabAnalyseRow( T.alpha, na, T.beta, T.sab, logsab, cumul, ekin_div_kT, ib, ainfo[(size_t)ie*nb+ib] );
         int err = 0;
-        const uint32_t off_b = (uint32_t)( (size_t)ie*(nb+1) );
+        const uint32_t off_b = (uint32_t)( (size_t)ie*(size_t)T.bstride );
         xscheck[ie] = sabAssembleEPoint( T.beta, nb, T.kT, T.bound_xs, T.egrid[ie], rows + (size_t)ie*nb,
                                          off_b, (uint32_t)( (size_t)ie*nb ), ep[ie], bx + off_b, bpdf + off_b, bcdf + off_b, err );
         if ( err )
@@ -63,7 +64,7 @@ namespace {
       uint16_t* aguide = reinterpret_cast<uint16_t*>( base + pl.off_aguide );
       double* ascale = reinterpret_cast<double*>( base + pl.off_ascale );
       for ( int ie = 0; ie < ne; ++ie ) {
-        uint16_t* g = bguide + (size_t)ie*( kSabGB+1 );
+        uint16_t* g = bguide + (size_t)ie*kSabGBStride;
         for ( int b = 0; b <= kSabGB; ++b )
           g[b] = sabBetaGuideEntry( bcdf + ep[ie].off_b, ep[ie].npts, b );
         ep[ie].guide = ep[ie].npts > 0 ? g : nullptr;
@@ -74,6 +75,13 @@ namespace {
         for ( int b = 0; b <= kSabGA; ++b )
           aguide[(size_t)ib*( kSabGA+1 ) + b] = sabAlphaGuideEntry( row, na, ascale[ib], b );
       }
+      // stage 4: gather-friendly copies
+      SabHead* heads = reinterpret_cast<SabHead*>( base + pl.off_heads );
+      SabPoint* pts = reinterpret_cast<SabPoint*>( base + pl.off_pts );
+      for ( size_t k = 0; k < (size_t)ne*nb; ++k )
+        heads[k] = sabMakeHead( ainfo[k], cumul + ( k % (size_t)nb )*na, ascale[k % (size_t)nb] );
+      for ( size_t k = 0; k < (size_t)nb*na; ++k )
+        pts[k] = sabMakePoint( T.alpha, T.sab, logsab, cumul, na, k );
     }
   }
 }
@@ -99,6 +107,7 @@ extern "C" {
   void hostsim_free( void* h ) { delete static_cast<Handle*>(h); }
 
   int hostsim_ncomp( void* vh ) { return static_cast<Handle*>(vh)->mat.ncomp; }
+  int hostsim_component_kind( void* vh, int c ) { return static_cast<Handle*>(vh)->mat.comp[c].kind; }
 
   void hostsim_xs_iso( void* vh, const double* ekin, uint64_t n, double* out )
   {
@@ -147,6 +156,49 @@ extern "C" {
       if ( errs ) errs[i] = err;
     }
   }
+
+  // S(alpha,beta) leaf `c` through the class-staged variants of the table sampler (E below the table's Emax; above
+  // it the plain path): must reproduce hostsim_sample_iso_leaf bit for bit
+  void hostsim_sample_sab_staged( void* vh, int c, uint64_t seed, uint64_t first_index, const double* ekin, uint64_t n,
+                                  double* ekin_out, double* mu_out, uint32_t* ndraws, int32_t* errs )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    const ncb::SabT& T = M.sab[M.comp[c].idx];
+    for ( uint64_t i = 0; i < n; ++i ) {
+      ncb::Rng rng; rng.init( seed, first_index + i );
+      int err = 0;
+      if ( ekin[i] < T.egrid[T.negrid-1] )
+        ncb::sabSampleScatterStaged( T, ekin[i], rng, ekin_out[i], mu_out[i], err );
+      else
+        ncb::sabSampleScatter( T, ekin[i], rng, ekin_out[i], mu_out[i], err );
+      if ( ndraws ) ndraws[i] = rng.ndraws;
+      if ( errs ) errs[i] = err;
+    }
+  }
+
+  // design aid: trace of the "whole bins" alpha searches of the staged sampler (rows: ibeta, area, ilow, iupp, ga, gb, r0, pct)
+  static std::vector<double>* s_trace = nullptr;
+  static void traceHook( int ibeta, double area, int ilow, int iupp, int ga, int gb, int r0, double pct )
+  {
+    if ( s_trace ) { double v[8] = { (double)ibeta, area, (double)ilow, (double)iupp, (double)ga, (double)gb, (double)r0, pct }; s_trace->insert( s_trace->end(), v, v+8 ); }
+  }
+  uint64_t hostsim_alpha_trace( void* vh, int c, uint64_t seed, const double* ekin, uint64_t n, double* out, uint64_t maxrows )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    const ncb::SabT& T = M.sab[M.comp[c].idx];
+    std::vector<double> tr; s_trace = &tr; ncb::g_alpha_trace = traceHook;
+    for ( uint64_t i = 0; i < n; ++i ) {
+      ncb::Rng rng; rng.init( seed, i );
+      int err = 0; double eo, mu;
+      if ( ekin[i] < T.egrid[T.negrid-1] ) ncb::sabSampleScatterStaged( T, ekin[i], rng, eo, mu, err );
+    }
+    ncb::g_alpha_trace = nullptr; s_trace = nullptr;
+    const uint64_t rows = std::min<uint64_t>( tr.size()/8, maxrows );
+    std::memcpy( out, tr.data(), rows*8*sizeof(double) );
+    return rows;
+  }
+  void hostsim_sab_dims( void* vh, int c, int* dims ) { auto& M = static_cast<Handle*>(vh)->mat; const ncb::SabT& T = M.sab[M.comp[c].idx]; dims[0]=T.negrid; dims[1]=T.nalpha; dims[2]=T.nbeta; }
+  void hostsim_sab_cumul( void* vh, int c, double* out ) { auto& M = static_cast<Handle*>(vh)->mat; const ncb::SabT& T = M.sab[M.comp[c].idx]; std::memcpy( out, T.cumul, (size_t)T.nalpha*T.nbeta*8 ); }
 
   void hostsim_xs( void* vh, const double* ekin, const double* ux, const double* uy, const double* uz, uint64_t n, double* out )
   {

@@ -199,3 +199,61 @@ def test_cfg_spelling_variants_find_the_same_compiled_material(configs):
         L.ncrystal_clearerror()
         L.ncrystal_sethaltonerror(old)
         L.ncrystal_setquietonerror(0)
+
+
+# ---- untrusted buffers: the loader (shared by the product and the host build) must reject truncated or corrupt
+# compiled materials before copying anything (counts inside the payloads were trusted)
+def _patched(blob, off, fmt, *vals):
+    b = bytearray(blob)
+    struct.pack_into(fmt, b, off, *vals)
+    return bytes(b)
+
+
+@pytest.mark.parametrize("key", ["Al", "Ge", "H2O"])
+def test_loader_rejects_corrupt_blobs(configs, key):
+    from oracle_check import material_path
+    from _libs import HostSim
+    p = material_path(configs[key])
+    if not os.path.exists(p):
+        pytest.skip("compiled material not built")
+    blob = open(p, "rb").read()
+    h = parse_header(blob)
+    L = HostSim.lib()
+    nbytes_off = struct.calcsize("<QIIII")
+    comp0 = struct.calcsize(HDR_FMT)
+    csz = struct.calcsize(COMP_FMT)
+    bad = []
+    # (a) truncated buffer: header claims more than is there, or a component reaches past the end
+    bad.append(("short buffer", blob[: len(blob) // 2]))
+    for i, c in enumerate(h["comps"]):
+        cut = c["off"] + c["nbytes"] // 2
+        bad.append(("comp %d truncated" % i, _patched(blob[:cut], nbytes_off, "<Q", cut)))
+        # (b) component offset/size fields: out of bounds, wrapping, misaligned
+        o = comp0 + i * csz + struct.calcsize("<IIddd")
+        bad.append(("comp %d off past end" % i, _patched(blob, o, "<Q", len(blob) + 16)))
+        bad.append(("comp %d off+nbytes wraps" % i, _patched(blob, o, "<QQ", 2**64 - 8, 64)))
+        bad.append(("comp %d misaligned" % i, _patched(blob, o, "<Q", c["off"] + 4)))
+        bad.append(("comp %d inside header" % i, _patched(blob, o, "<Q", 8)))
+        # (c) array counts inside the payload larger than the payload
+        if c["kind"] == 1:
+            bad.append(("nplanes huge", _patched(blob, c["off"], "<Q", 2**40)))
+            bad.append(("nplanes +1", _patched(blob, c["off"], "<Q", (c["nbytes"] - 16) // 16 + 1)))
+        if c["kind"] == 2:
+            bad.append(("nelem 13", _patched(blob, c["off"], "<Q", 13)))
+        if c["kind"] == 3:
+            g = c["off"] + 14 * 8
+            ne, na, nb = struct.unpack_from("<3Q", blob, g)
+            bad.append(("negrid 0", _patched(blob, g, "<Q", 0)))
+            bad.append(("nalpha huge", _patched(blob, g + 8, "<Q", 2**33)))
+            bad.append(("nbeta x2", _patched(blob, g + 16, "<Q", 2 * nb)))
+            bad.append(("product wraps", _patched(blob, g + 8, "<QQ", 2**32, 2**32)))
+        if c["kind"] == 5:
+            g = c["off"] + 20 * 8
+            nf, nn = struct.unpack_from("<2Q", blob, g)
+            bad.append(("nnormals x4", _patched(blob, g + 8, "<Q", 4 * nn)))
+            bad.append(("nfam huge", _patched(blob, g, "<Q", 2**50)))
+            bad.append(("family index beyond normals", _patched(blob, c["off"] + 24 * 8 + 8 * (2 * nf + 1), "<d", 1e9)))
+    for what, b in bad:
+        hnd = L.hostsim_load(b, len(b))
+        assert not hnd, "%s: %s was accepted" % (key, what)
+        assert b"compiled material" in L.hostsim_lasterror() or b"too many" in L.hostsim_lasterror(), what

@@ -188,3 +188,22 @@ def test_edge_energies_vs_reference(configs):
     a = r.sample_iso(e, seed=99)
     b = h.sample_iso(e, seed=99)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("key", ["Al", "CH2", "H2O", "YAG"])
+def test_class_staged_sampler_equals_plain_sampler(key, configs):
+    """The class-staged variants of the S(alpha,beta) table sampler (SabHead / SabPoint gather records, the layout
+    k_sab_classes stages per overlay sampler) consume the same uniforms and give bit-identical outcomes as the plain
+    restatement, which the goldens pin against the reference -- for every S(alpha,beta) leaf of the material."""
+    h = HostSim(_blob(configs[key]))
+    ekin = np.concatenate([loguniform_energies(30000, seed=5), [1e-9, 1e-7, 4.99999, 5.0, 7.5]])
+    nleaf = 0
+    for c in range(h.ncomp):
+        if h.component_kind(c) != 3:
+            continue
+        nleaf += 1
+        a = h.sample_iso(ekin, seed=77, leaf=c)
+        b = h.sample_sab_staged(ekin, c, seed=77)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert nleaf >= 1
