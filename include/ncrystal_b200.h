@@ -214,6 +214,29 @@ void ncb200_generate_source_dev( uint64_t seed, uint64_t first_index, uint64_t n
 void ncb200_tally_hist_dev( const double* d_values, const double* d_weights, uint64_t n,
                             double lo, double hi, uint32_t nbins, double* d_hist, double* d_sumw2, void* stream );
 
+/* Host buffers.  The *_many entry points take caller-owned host arrays.  Page-locked arrays are copied directly;
+ * pageable (malloc'd) arrays of calls with >= 2^16 neutrons go through a pinned bounce ring filled / drained by a
+ * small pool of host threads (bounded by the host's memcpy bandwidth: measured 1.0e9 neutrons/s against 1.6e9 from
+ * pinned arrays).  A caller that reuses its arrays can page-lock them once with ncb200_pin_host_buffer (about 20 ms
+ * per 80 MB) and unpin them before freeing.  0 on success, -1 on error. */
+int      ncb200_pin_host_buffer( void* p, uint64_t nbytes );
+int      ncb200_unpin_host_buffer( void* p );
+
+/* Several GPUs from ONE process (the single-process shape of an OpenMC / McStas caller).  After
+ * ncb200_set_devices(n) (0 = all visible devices; 1 = off) the host-pointer batch entry points (ncrystal_*_many,
+ * ncb200_crosssection_many, ncb200_samplescatter_manydir, ncb200_xs_and_samplescatterisotropic_many) split a batch
+ * of at least ncb200_set_fanout_min() neutrons (default 2^20) into contiguous slices, one per device: tables are
+ * replicated per device, streams are keyed by the global neutron index, results are bit-identical to the one-device
+ * result.  ncb200_tally_hist_many histograms host arrays on the devices and merges with ncclAllReduce(sum, fp64) --
+ * the analogue of the reference's worker threads + Tally::merge (src/minimc/NCMMC_SimMgr.cc:167-263,
+ * NCMMC_Tally.hh:40-62).  hist[nbins+2] (underflow, bins, overflow) and sumw2 (may be null) are ADDED to.
+ * Returns the number of devices now in use, -1 on error. */
+int      ncb200_set_devices( int n );
+int      ncb200_get_devices( void );
+void     ncb200_set_fanout_min( uint64_t n );
+void     ncb200_tally_hist_many( const double* values, const double* weights, uint64_t n,
+                                 double lo, double hi, uint32_t nbins, double* hist, double* sumw2 );
+
 /* Introspection */
 int      ncb200_ncomponents( ncrystal_process_t );
 int      ncb200_component_kind( ncrystal_process_t, int i ); /* enum ncb_kind */
@@ -250,6 +273,9 @@ int      ncb200_sab_xscheck( ncrystal_process_t, int component, double* out, int
 /* Copy of built sampler tables for one energy point (layout as oracle refdrv_sab_sampler_dump) */
 int      ncb200_sab_sampler_dump( ncrystal_process_t, int component, int iE, double* x, double* pdf, double* cdf,
                                   double* infos, double* meta );
+/* Consistency of the gather-friendly copies of the sampler tables and of the log guide with the tables they were
+ * derived from, all read back from the device: number of violations (0 = consistent), -1 on error. */
+long     ncb200_sab_selfcheck( ncrystal_process_t, int component );
 
 #ifdef __cplusplus
 }

@@ -130,6 +130,13 @@ SIGNATURES = {
     "ncb200_version": (C.c_char_p, []),
     "ncb200_sab_xscheck": (C.c_int, [ncrystal_process_t, C.c_int, _dblp, C.c_int]),
     "ncb200_sab_sampler_dump": (C.c_int, [ncrystal_process_t, C.c_int, C.c_int, _dblp, _dblp, _dblp, _dblp, _dblp]),
+    "ncb200_sab_selfcheck": (C.c_long, [ncrystal_process_t, C.c_int]),
+    "ncb200_pin_host_buffer": (C.c_int, [_vp, _u64]),
+    "ncb200_unpin_host_buffer": (C.c_int, [_vp]),
+    "ncb200_set_devices": (C.c_int, [C.c_int]),
+    "ncb200_get_devices": (C.c_int, []),
+    "ncb200_set_fanout_min": (None, [_u64]),
+    "ncb200_tally_hist_many": (None, [_dblp, _dblp, _u64, C.c_double, C.c_double, C.c_uint32, _dblp, _dblp]),
 }
 
 _lib = None

@@ -105,6 +105,34 @@ namespace ncb {
     return i;
   }
 
+  // Energy-key lookup table over an ascending fp64 table a[0..n): key(v) = bits(v) >> shift (exponent and the top
+  // 52-shift mantissa bits: a monotone function of v for v >= 0), lut[k] = number of table entries whose key is
+  // below key0 + k.  For a value with (clamped) key k, upper_bound(a, v) lies in [lut[k], lut[k+1]]: entries with
+  // a smaller key are < v, entries with a larger key are > v.  The search inside that range gives the exact
+  // std::upper_bound for every input (negative, inf, NaN included: they land in the first / last bucket, whose
+  // range ends at 0 / n).  Replaces the 8-13 step whole-table bisections of the cross-section path by 0-2 steps.
+  struct KeyLut {
+    const uint16_t* lut;   // nk+1 entries, or null: plain bisection
+    int key0, shift, nk;
+  };
+  NCB_HD long long doubleBits( double v )
+  {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong( v );
+#else
+    long long b; __builtin_memcpy( &b, &v, sizeof(b) ); return b;
+#endif
+  }
+  template <class Ptr>
+  NCB_HD int upperBoundKeyed( Ptr a, int n, double v, const uint16_t* lut, int key0, int shift, int nk )
+  {
+    if ( !lut )
+      return upperBound( a, 0, n, v );
+    long long k = ( doubleBits( v ) >> shift ) - (long long)key0;
+    k = k < 0 ? 0 : ( k > (long long)( nk-1 ) ? (long long)( nk-1 ) : k );
+    return upperBound( a, (int)lut[k], (int)lut[k+1], v );
+  }
+
   // Loads from the immutable material tables in global memory: ld.global.nc instead of the generic-address loads the
   // compiler emits for pointers it only knows from a by-value struct (ncu: LD.E + two R2UR per search step).
   template <class T>

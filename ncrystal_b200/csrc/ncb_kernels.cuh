@@ -17,7 +17,8 @@
 
 namespace ncb {
 
-  constexpr int kHotSlotsIso = 2*kMaxPB + 2*kMaxSab;
+  // slots: PowderBragg 2dE | cumulative tables | SAB energy grids | xs grids | PowderBragg key luts | SAB key luts
+  constexpr int kHotSlotsIso = 3*kMaxPB + 3*kMaxSab;
   // + SCBragg: demi-normals, family xsfact / inv2d / first-index arrays, the two spline LUTs
   constexpr int kHotSlots = kHotSlotsIso + 6;
 
@@ -69,7 +70,9 @@ namespace ncb {
       if ( s < kMaxPB ) H.pb_e2d[s] = p;
       else if ( s < 2*kMaxPB ) H.pb_fdm[s-kMaxPB] = p;
       else if ( s < 2*kMaxPB+kMaxSab ) H.sab_egrid[s-2*kMaxPB] = p;
-      else H.sab_xs[s-2*kMaxPB-kMaxSab] = p;
+      else if ( s < 2*kMaxPB+2*kMaxSab ) H.sab_xs[s-2*kMaxPB-kMaxSab] = p;
+      else if ( s < 3*kMaxPB+2*kMaxSab ) H.pb_lut[s-2*kMaxPB-2*kMaxSab] = reinterpret_cast<const uint16_t*>( p );
+      else H.sab_elut[s-3*kMaxPB-2*kMaxSab] = reinterpret_cast<const uint16_t*>( p );
     }
     if ( sp.nbytes[kHotSlotsIso] ) {   // SCBragg tables are staged all-or-nothing
       H.scv = M.sc;
@@ -87,7 +90,10 @@ namespace ncb {
   // One neutron per thread per grid-stride step.  ekin is read / xs written fully
   // coalesced (8 B per lane).  n_in: length of ekin (outputs index idx use ekin[idx % n_in]
   // only through the host wrapper's repeat handling; here n_in == n).
-  __global__ void __launch_bounds__(256)
+  // (register caps measured on B200, r2: 5 CTAs/SM (48 registers) is the best trade for the cross-section kernel --
+  // Al 4.25e10 -> 4.44e10 xs/s against 4 CTAs, 3.9e10 at 6 --, 8 CTAs/SM (32 registers, 80 B of spills) for the
+  // classify kernel)
+  __global__ void __launch_bounds__(256, 5)
   k_xs_iso( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
             const double* __restrict__ ekin, uint64_t n, double* __restrict__ out )
   {
@@ -96,8 +102,15 @@ namespace ncb {
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride )
-      out[i] = matXSIso( M, H, ekin[i], nullptr, nullptr );
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double e = i < n ? ekin[i] : 0.0;
+    while ( i < n ) {
+      // the next step's energy is requested before this step's arithmetic (the load latency was the top stall)
+      const uint64_t inext = i + stride;
+      const double enext = inext < n ? ekin[inext] : 0.0;
+      out[i] = matXSIso( M, H, e, nullptr, nullptr );
+      e = enext; i = inext;
+    }
   }
 
   // ------------------------------------------------------- sampling (isotropic), v1
@@ -128,9 +141,7 @@ namespace ncb {
   //   k_sample_classify  xs + component pick; the cheap elastic leaves (PowderBragg, ElInc) are sampled in place;
   //                      S(alpha,beta) table neutrons and free-gas neutrons (FreeGas leaf, SAB above Emax) are
   //                      appended to two index queues
-  //   S(alpha,beta) table queue: large batches are partitioned by overlay sampler ("class") and sampled by
-  //                      k_sab_classes with the class's tables staged in shared memory (ncb_kernels_cls.cuh);
-  //                      small ones go through k_sample_sab_refill directly
+  //   S(alpha,beta) table queue: k_sample_sab_refill (attempt-level lane refill, short-chain table lookups)
   //   free-gas queue:    k_fg_* staged pipeline / k_sample_fg
   // Each queue holds homogeneous work, so warps do not serialise over unrelated code paths.  Because the random
   // streams are counter based, a later kernel resumes a neutron's stream by re-deriving one block (no RNG state
@@ -144,8 +155,6 @@ namespace ncb {
     uint32_t* q_fg;     // free-gas leaf and S(alpha,beta) above Emax
     uint32_t* q_emax;   // pairs (entry, draws consumed): table sampling at E=Emax requested by the high-E analysis
     uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs), [3],[4] refill cursors
-    uint16_t* q_cls = nullptr;   // class (overlay sampler) of every q_sab entry, or null: no class partition
-    uint32_t cls_base[kMaxSab+1] = {};   // class id of energy point 0 of S(alpha,beta) leaf k
   };
 
   // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave).
@@ -175,24 +184,20 @@ namespace ncb {
   constexpr int kWarpBuf = 128;            // entries per warp and queue; flushed when fewer than 32 slots are left
   struct WarpQueueBuf {
     uint32_t e[2][kWarpBuf];
-    uint16_t c[kWarpBuf];
   };
-  __device__ __forceinline__ void warpBufFlush( const uint32_t* buf, const uint16_t* bcls, uint32_t n, uint32_t* q, uint16_t* qc,
-                                                uint32_t* counter )
+  __device__ __forceinline__ void warpBufFlush( const uint32_t* buf, uint32_t n, uint32_t* q, uint32_t* counter )
   {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     uint32_t base = 0;
     if ( lane == 0 ) base = atomicAdd( counter, n );
     base = __shfl_sync( 0xffffffffu, base, 0 );
-    for ( uint32_t k = lane; k < n; k += 32 ) {
+    for ( uint32_t k = lane; k < n; k += 32 )
       q[base + k] = buf[k];
-      if ( qc ) qc[base + k] = bcls[k];
-    }
     __syncwarp();
   }
 
-  __global__ void __launch_bounds__(256)
+  __global__ void __launch_bounds__(256, 8)
   k_sample_classify( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
                      const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q )
   {
@@ -206,12 +211,14 @@ namespace ncb {
     uint32_t c1 = 0, c2 = 0;                 // entries in the warp's two buffers (warp-uniform)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n = A.n;
+    double enext = ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x < n ) ? A.ekin[ (uint64_t)blockIdx.x * blockDim.x + threadIdx.x ] : 0.0;
     for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride ) {
       const uint64_t i = base + threadIdx.x;
       int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue
-      uint32_t entry = 0, key = 0;
+      uint32_t entry = 0;
+      const double ekin = enext;
+      enext = ( i + stride < n ) ? A.ekin[i + stride] : 0.0;     // requested one step ahead
       if ( i < n ) {
-        const double ekin = A.ekin[i];
         double eout = ekin, mu = 1.0, tot = 0.0;
         int ich = -1;
         uint32_t nd = 0;
@@ -228,17 +235,13 @@ namespace ncb {
             int iu = aux[ich];
             if ( iu < 0 ) iu = upperBound( H.sab_egrid[c.idx], 0, T.negrid, ekin );   // (E outside the leaf's domain)
             cls = ( iu < T.negrid ) ? 1 : 2;
-            if ( cls == 1 && Q.q_cls ) {
-              bool ultra;
-              key = Q.cls_base[c.idx] + (uint32_t)sabPickSamplerFrom( T, H.sab_egrid[c.idx], ekin, iu, ultra );
-            }
           } else if ( c.kind == KIND_FREEGAS ) {
             cls = 2;
           } else if ( c.kind == KIND_POWDERBRAGG ) {
             // PowderBragg::sampleScatterIsotropic, ref: NCPowderBragg.cc:202-216
             const PowderBraggT& T = M.pb[c.idx];
             if ( !( ekin < T.threshold || !isFinite(ekin) ) ) {
-              const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+              const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
               mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
             }
             nd = rng.ndraws;
@@ -259,14 +262,14 @@ namespace ncb {
       const uint32_t m1 = __ballot_sync( 0xffffffffu, cls == 1 );
       const uint32_t m2 = __ballot_sync( 0xffffffffu, cls == 2 );
       const uint32_t lt = ( 1u << lane ) - 1u;
-      if ( cls == 1 ) { const uint32_t k = c1 + __popc( m1 & lt ); wq.e[0][k] = entry; wq.c[k] = (uint16_t)key; }
+      if ( cls == 1 ) wq.e[0][ c1 + __popc( m1 & lt ) ] = entry;
       if ( cls == 2 ) wq.e[1][ c2 + __popc( m2 & lt ) ] = entry;
       c1 += __popc( m1 ); c2 += __popc( m2 );
-      if ( c1 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[0], wq.c, c1, Q.q_sab, Q.q_cls, Q.counts + 0 ); c1 = 0; }
-      if ( c2 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[1], nullptr, c2, Q.q_fg, nullptr, Q.counts + 1 ); c2 = 0; }
+      if ( c1 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[0], c1, Q.q_sab, Q.counts + 0 ); c1 = 0; }
+      if ( c2 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[1], c2, Q.q_fg, Q.counts + 1 ); c2 = 0; }
     }
-    if ( c1 ) warpBufFlush( wq.e[0], wq.c, c1, Q.q_sab, Q.q_cls, Q.counts + 0 );
-    if ( c2 ) warpBufFlush( wq.e[1], nullptr, c2, Q.q_fg, nullptr, Q.counts + 1 );
+    if ( c1 ) warpBufFlush( wq.e[0], c1, Q.q_sab, Q.counts + 0 );
+    if ( c2 ) warpBufFlush( wq.e[1], c2, Q.q_fg, Q.counts + 1 );
   }
 
   // S(alpha,beta) table path, attempt-level scheduling ("lane refill").  The reference's
@@ -339,7 +342,7 @@ namespace ncb {
         bool done = false, failed = false;
         bool inner_ok = true;
         if ( ep.npts != 0 )
-          inner_ok = sabAttemptAtE( T, ep, sampling_ediv, rng, alpha, beta, err );
+          inner_ok = sabAttemptFast( T, isampler, ep, sampling_ediv, rng, alpha, beta, err );
         if ( !inner_ok ) {
           if ( ++inner == 100 ) { err |= ERR_SAB_LOOP_INNER; failed = true; }
         } else {
@@ -1007,17 +1010,34 @@ namespace ncb {
     }
   }
 
-  // stage 4: blockIdx.y = 0: heads (one thread per (energy point, beta row)); 1: points (one per (beta row, alpha))
-  __global__ void k_sab_gather_tabs( SabT T, SabHead* __restrict__ heads, SabPoint* __restrict__ pts )
+  // stage 4: gather-friendly copies.  blockIdx.y = 0: heads + tails (one thread per (energy point, beta row));
+  // 1: points (one per (beta row, alpha)); 2: beta-distribution points (one per (energy point, point));
+  // 3: log guide (one thread per (beta row, key))
+  __global__ void k_sab_gather_tabs( SabT T, SabHead* __restrict__ heads, SabTail* __restrict__ tails,
+                                     SabPoint* __restrict__ pts, SabBPoint* __restrict__ bpts, uint16_t* __restrict__ lguide )
   {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ( blockIdx.y == 0 ) {
       if ( k < (size_t)T.negrid*T.nbeta ) {
         const int ib = (int)( k % (size_t)T.nbeta );
-        heads[k] = sabMakeHead( T.ainfo[k], T.cumul + (size_t)ib*T.nalpha, T.ascale[ib] );
+        const SabAlphaInfo info = T.ainfo[k];
+        heads[k] = sabMakeHead( info, T.cumul + (size_t)ib*T.nalpha, T.nalpha );
+        sabMakeTails( info, tails + 2*k );
       }
-    } else if ( k < (size_t)T.nbeta*T.nalpha ) {
-      pts[k] = sabMakePoint( T.alpha, T.sab, T.logsab, T.cumul, T.nalpha, k );
+    } else if ( blockIdx.y == 1 ) {
+      if ( k < (size_t)T.nbeta*T.nalpha )
+        pts[k] = sabMakePoint( T.alpha, T.sab, T.logsab, T.cumul, T.nalpha, k );
+    } else if ( blockIdx.y == 2 ) {
+      if ( k < (size_t)T.negrid*T.bstride ) {
+        SabBPoint b; b.x = T.bx[k]; b.pdf = T.bpdf[k]; b.cdf = T.bcdf[k]; b.pad = 0.0;
+        bpts[k] = b;
+      }
+    } else if ( k < (size_t)T.nbeta*( kSabGL + 1 ) ) {
+      const int ib = (int)( k / (size_t)( kSabGL + 1 ) ), key = (int)( k % (size_t)( kSabGL + 1 ) );
+      const double* row = T.cumul + (size_t)ib*T.nalpha;
+      const double tot = row[T.nalpha-1];
+      const double inv = ( tot > 0.0 && isFinite( 1.0/tot ) ) ? 1.0/tot : 0.0;
+      lguide[(size_t)ib*kSabGLStride + key] = sabLogGuideEntry( row, T.nalpha, inv, key );
     }
   }
 

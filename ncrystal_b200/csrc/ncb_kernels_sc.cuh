@@ -488,7 +488,7 @@ namespace ncb {
             if ( c.kind == KIND_POWDERBRAGG ) {
               const PowderBraggT& T = M.pb[c.idx];
               if ( !( ekin < T.threshold || !isFinite(ekin) ) ) {
-                const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+                const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
                 mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
               }
             } else if ( c.kind == KIND_ELINC ) {

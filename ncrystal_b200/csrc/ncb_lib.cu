@@ -9,7 +9,6 @@
 // There is NO CPU fallback: every compute entry point launches CUDA kernels and
 // raises an error when no usable device is present.
 #include "ncb_kernels.cuh"
-#include "ncb_kernels_cls.cuh"
 #include "ncb_kernels_sc.cuh"
 #include "ncb_kernels_mmc.cuh"
 #include "ncb_loader.h"
@@ -17,6 +16,8 @@
 #include "../../include/ncrystal_b200.h"
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <dirent.h>
 #include <cstdlib>
@@ -130,17 +131,16 @@ namespace {
     StagePlan sp_iso;        // hot tables of the isotropic leaves only
     bool sc_warp_ok = false; // SCBragg tables fit the warp-cooperative kernels
     bool has_fg_leaf = false; // a FreeGas leaf: its queue spans all energies (-> k_fg_group)
-    // class-staged S(alpha,beta) sampling (ncb_kernels_cls.cuh): shared-memory plan, classes per leaf
-    ClassSmem cls_smem = {};
-    uint32_t cls_base[kMaxSab+1] = {};
-    uint32_t ncls = 0;        // 0: the class path is not available for this material
-    int cls_ctas = 0;         // resident CTAs per SM of k_sab_classes
     uint32_t sc_famof_off = 0, sc_scratch_off = 0, sc_smem = 0, sc_find_smem = 0, sc_find_famof_off = 0, sc_find_scratch_off = 0;
     std::string cfg;
     double numdens = 0.0, abs_c = 0.0, temperature = -1.0;
     std::vector<SabBuildPlan> sabplans;
     std::atomic<uint32_t> clone_counter{0};
     uint64_t uid = 0;        // ncrystal_process_uid
+    // multi-device fan-out (ncb_lib_multigpu.inc): the compiled material it was made from, its copies on other devices
+    std::shared_ptr<const std::vector<unsigned char>> blob;
+    std::map<int, std::shared_ptr<DeviceMaterial>> peers;
+    std::mutex peers_mtx;
     ~DeviceMaterial() { if ( d_arena ) cudaFree( d_arena ); }
   };
 
@@ -162,8 +162,11 @@ namespace {
     StagePlan& sp = dm.sp;
     std::memset( &sp, 0, sizeof(sp) );
     const Material& M = dm.mat;
-    // Budget: keep >= 2 CTAs/SM worth of shared memory (227 KB per SM usable).
-    const uint32_t budget = 100u*1024u;
+    // Budget: what still lets 8 CTAs of 256 threads share an SM (227 KB usable, the classify kernel has 8 KB of
+    // its own).  With the energy-key luts a search touches 0-2 table entries, so large Bragg tables (YAG: 2 x 48 KB)
+    // are better left to L1/L2 than staged at the price of occupancy (measured, YAG cross sections: 1.6e10/s with
+    // the tables in global memory and 8 CTAs/SM, 1.25e10/s with 2dE staged and 2 CTAs/SM).
+    uint32_t budget = 20u*1024u;
     uint32_t off = 0;
     auto add = [&]( int slot, const void* p, int n, int elem = 8 ) {
       if ( !p || n <= 0 ) return;
@@ -178,20 +181,20 @@ namespace {
       if ( M.comp[i].kind == KIND_POWDERBRAGG ) ++npb;
       if ( M.comp[i].kind == KIND_SAB ) ++nsab;
     }
-    // small SAB grids first, then the (possibly large) Bragg tables
+    // small tables first (SAB grids, the energy-key luts), then the Bragg tables: 2dE (searched) before the
+    // cumulative table (one or two reads per neutron); whatever does not fit is read through L1
     for ( int i = 0; i < nsab; ++i ) {
       add( 2*kMaxPB + i, M.sab[i].egrid, M.sab[i].negrid );
       add( 2*kMaxPB + kMaxSab + i, M.sab[i].xs, M.sab[i].negrid );
+      if ( M.sab[i].elut ) add( 3*kMaxPB + 2*kMaxSab + i, M.sab[i].elut, M.sab[i].elut_nk + 1, 2 );
     }
-    for ( int i = 0; i < npb; ++i ) {
-      // both or none, so a lookup never mixes memory spaces
-      const uint32_t need = 2u*( ( (uint32_t)M.pb[i].n*8u + 127u ) & ~127u );
-      if ( off + need <= budget ) {
-        add( i, M.pb[i].e2d, M.pb[i].n );
-        add( kMaxPB + i, M.pb[i].fdm, M.pb[i].n );
-      }
-    }
+    for ( int i = 0; i < npb; ++i )
+      if ( M.pb[i].lut ) add( 2*kMaxPB + 2*kMaxSab + i, M.pb[i].lut, M.pb[i].lut_nk + 1, 2 );
+    for ( int i = 0; i < npb; ++i ) add( i, M.pb[i].e2d, M.pb[i].n );
+    for ( int i = 0; i < npb; ++i ) add( kMaxPB + i, M.pb[i].fdm, M.pb[i].n );
     if ( M.sc.nfam ) {
+      // single-crystal tables: staged whole by the warp-per-neutron kernels (their own plans below, 1-3 CTAs/SM)
+      budget = off + 100u*1024u;
       const ScBraggT& S = M.sc;
       auto al = []( size_t b ) { return (uint32_t)( ( b + 127 ) & ~(size_t)127 ); };
       const uint32_t need = al( (size_t)S.nnormals*24 ) + 2*al( (size_t)S.nfam*8 ) + al( (size_t)( S.nfam+1 )*4 )
@@ -206,30 +209,6 @@ namespace {
       }
     }
     sp.total = off;
-    // class-staged sampling plan
-    {
-      int nbmax = 0, bsmax = 0;
-      uint32_t nc = 0;
-      for ( int i = 0; i < nsab; ++i ) {
-        dm.cls_base[i] = nc;
-        nc += (uint32_t)M.sab[i].negrid;
-        nbmax = std::max( nbmax, M.sab[i].nbeta );
-        bsmax = std::max( bsmax, M.sab[i].bstride );
-      }
-      for ( int i = nsab; i <= kMaxSab; ++i ) dm.cls_base[i] = nc;
-      auto al = []( size_t b ) { return (uint32_t)( ( b + 127 ) & ~(size_t)127 ); };
-      ClassSmem& S = dm.cls_smem;
-      uint32_t o = 0;
-      S.off_bx = o; o += al( (size_t)bsmax*8 );
-      S.off_bpdf = o; o += al( (size_t)bsmax*8 );
-      S.off_bcdf = o; o += al( (size_t)bsmax*8 );
-      S.off_guide = o; o += al( (size_t)kSabGBStride*2 );
-      S.off_heads = o; o += al( (size_t)nbmax*sizeof(SabHead) );
-      S.off_beta = o; o += al( (size_t)nbmax*8 + 16 );
-      S.total = o;
-      dm.cls_ctas = nsab ? std::min( 4, (int)( ( 226u*1024u ) / ( S.total + 1024u ) ) ) : 0;
-      dm.ncls = ( nsab && nc <= (uint32_t)kClsMax && dm.cls_ctas >= 1 ) ? nc : 0;
-    }
     // derived plans
     dm.sp_iso = sp; dm.sp_sc = sp;
     std::memset( &dm.sp_sc, 0, sizeof(StagePlan) );
@@ -314,9 +293,11 @@ namespace {
                                                        reinterpret_cast<uint16_t*>( base + pl.off_aguide ),
                                                        reinterpret_cast<double*>( base + pl.off_ascale ) );
       {
-        const size_t nmax = std::max( (size_t)ne*nb, ntot );
-        k_sab_gather_tabs<<< dim3( (unsigned)( ( nmax + 255 )/256 ), 2 ), 256, 0, st >>>(
-          T, reinterpret_cast<SabHead*>( base + pl.off_heads ), reinterpret_cast<SabPoint*>( base + pl.off_pts ) );
+        const size_t nmax = std::max( std::max( (size_t)ne*nb, ntot ), std::max( (size_t)ne*T.bstride, (size_t)nb*( kSabGL + 1 ) ) );
+        k_sab_gather_tabs<<< dim3( (unsigned)( ( nmax + 255 )/256 ), 4 ), 256, 0, st >>>(
+          T, reinterpret_cast<SabHead*>( base + pl.off_heads ), reinterpret_cast<SabTail*>( base + pl.off_tails ),
+          reinterpret_cast<SabPoint*>( base + pl.off_pts ), reinterpret_cast<SabBPoint*>( base + pl.off_bpts ),
+          reinterpret_cast<uint16_t*>( base + pl.off_lguide ) );
       }
       g_launches += 6;
       CUDA_OK( cudaGetLastError() );
@@ -354,6 +335,8 @@ namespace {
     for ( int i = 0; i < lm.mat.ncomp; ++i ) if ( lm.mat.comp[i].kind == KIND_FREEGAS ) dm->has_fg_leaf = true;
     dm->numdens = lm.numdens; dm->abs_c = lm.abs_c; dm->temperature = lm.temperature;
     dm->sabplans = lm.sabplans;
+    dm->blob = std::make_shared<const std::vector<unsigned char>>( static_cast<const unsigned char*>( blob ),
+                                                                   static_cast<const unsigned char*>( blob ) + nbytes );
     buildStagePlan( *dm );
     ensureKernelAttrs( dm->device );
     buildSabTablesOnDevice( *dm, 0 );
@@ -376,10 +359,6 @@ namespace {
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_find );
     setSmemAttr( k_tally_hist );
-    setSmemAttr( k_sab_classes<256,4> );
-    setSmemAttr( k_sab_classes<320,3> );
-    setSmemAttr( k_sab_classes<512,2> );
-    setSmemAttr( k_sab_classes<1024,1> );
     done.push_back( device );
   }
 
@@ -398,7 +377,7 @@ namespace {
   }
   constexpr int kSlots = 3;
   constexpr uint64_t kWindowMax = (uint64_t)1 << 24;   // neutrons staged on the device per window of the host-pointer path
-  struct PipeSchedule { uint64_t first, max; double growth; double tail; };
+  struct PipeSchedule { uint64_t first, max; double growth; };
   PipeSchedule pipeSchedule()
   {
     static const PipeSchedule ps = []{
@@ -408,9 +387,6 @@ namespace {
       p.max = chunkSize();
       p.first = std::min<uint64_t>( p.max, std::max<uint64_t>( 4096, e0 ? (uint64_t)std::atoll(e0) : ( (uint64_t)1 << 18 ) ) );
       p.growth = std::max( 1.0, eg ? std::atof(eg) : 2.0 );
-      // ramp-down: a chunk is at most this fraction of what is left (0 = off), so the last copies out are short
-      const char* et = std::getenv( "NCB200_CHUNK_TAIL" );
-      p.tail = std::min( 1.0, std::max( 0.0, et ? std::atof(et) : 0.0 ) );   // measured: no gain (4.11 vs 4.15 ms per 1e7 samples) -> off
       return p;
     }();
     return ps;
@@ -434,7 +410,8 @@ namespace {
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
     double* d_win = nullptr;                // staging window: (nin+nout) arrays of win_doubles/(nin+nout) neutrons
     size_t win_doubles = 0;
-    std::vector<cudaEvent_t> ev_h, ev_c;    // per chunk: copy-in done, kernels done
+    std::vector<cudaEvent_t> ev_h, ev_c, ev_d;   // per chunk: copy-in done, kernels done, copy-out done
+    double* h_ring = nullptr; size_t ring_doubles = 0;   // pinned bounce ring for pageable caller arrays
     // work queues of the split sampling path: one context per pipeline slot + one for the
     // device-pointer entry points (a handle has at most one launch sequence in flight per context)
     struct QueueCtx {
@@ -445,12 +422,11 @@ namespace {
       uint32_t* sc_work = nullptr; uint8_t* sc_ncand = nullptr; uint16_t* sc_cand = nullptr;   // k_sc_find -> k_sc_eval
       int32_t* sc_wpos = nullptr; bool sc_lists_valid = false;
       double* fg_prep = nullptr; uint32_t* fg_nd = nullptr; size_t fcap = 0;   // k_fg_prep records, one per queue slot
-      uint16_t* q_cls = nullptr; size_t ccap = 0;       // class of every q_sab entry
-      uint32_t* cls_words = nullptr;                    // hist | start | fill | cursor | nticket(2) | tickets (uint16)
       cudaStream_t side = nullptr;              // free-gas kernels run here, concurrently with the table kernel
       cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     };
     QueueCtx qctx[kSlots+1];
+    std::vector<std::unique_ptr<Scatter>> peer_handles;   // this handle's twins on other devices (multi-device fan-out)
 
     Scatter() { fp.tag = kScatterTag; fp.self = this; }
     ~Scatter()
@@ -460,8 +436,6 @@ namespace {
         if ( c.q ) cudaFree( c.q );
         if ( c.counts ) cudaFree( c.counts );
         if ( c.fg_prep ) { cudaFree( c.fg_prep ); cudaFree( c.fg_nd ); }
-        if ( c.q_cls ) cudaFree( c.q_cls );
-        if ( c.cls_words ) cudaFree( c.cls_words );
         if ( c.sc_xs ) { cudaFree( c.sc_xs ); cudaFree( c.sc_n ); cudaFree( c.mu_tmp ); cudaFree( c.nd_tmp ); cudaFree( c.q_sc );
                          cudaFree( c.sc_work ); cudaFree( c.sc_ncand ); cudaFree( c.sc_cand ); cudaFree( c.sc_wpos ); }
         if ( c.side ) cudaStreamDestroy( c.side );
@@ -475,6 +449,8 @@ namespace {
       if ( d_win ) cudaFree( d_win );
       for ( auto e : ev_h ) cudaEventDestroy( e );
       for ( auto e : ev_c ) cudaEventDestroy( e );
+      for ( auto e : ev_d ) cudaEventDestroy( e );
+      if ( h_ring ) cudaFreeHost( h_ring );
     }
     void ensureErrWord()
     {
@@ -498,16 +474,6 @@ namespace {
         CUDA_OK( cudaMalloc( &c.q, 6*c.cap*sizeof(uint32_t) ) );
       }
       return c;
-    }
-    // scratch of the class partition (after ensureQueues)
-    void ensureClassScratch( QueueCtx& c )
-    {
-      if ( !c.cls_words )
-        CUDA_OK( cudaMalloc( &c.cls_words, ( 4*( kClsMax + 1 ) + 2 )*sizeof(uint32_t) + kClsTicketsMax*sizeof(uint16_t) ) );
-      if ( c.ccap >= c.cap ) return;
-      if ( c.q_cls ) { CUDA_OK( cudaDeviceSynchronize() ); cudaFree( c.q_cls ); }
-      c.ccap = c.cap;
-      CUDA_OK( cudaMalloc( &c.q_cls, c.ccap*sizeof(uint16_t) ) );
     }
     // per-entry records of the staged free-gas kernels (kFgSlots doubles + 1 word per queue slot); after ensureQueues
     void ensureFgPrep( QueueCtx& c )
@@ -556,11 +522,19 @@ namespace {
     void ensureChunkEvents( size_t k )
     {
       while ( ev_h.size() < k ) {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, c;
         CUDA_OK( cudaEventCreateWithFlags( &a, cudaEventDisableTiming ) );
         CUDA_OK( cudaEventCreateWithFlags( &b, cudaEventDisableTiming ) );
-        ev_h.push_back( a ); ev_c.push_back( b );
+        CUDA_OK( cudaEventCreateWithFlags( &c, cudaEventDisableTiming ) );
+        ev_h.push_back( a ); ev_c.push_back( b ); ev_d.push_back( c );
       }
+    }
+    void ensureBounce( size_t ndoubles )
+    {
+      if ( ndoubles <= ring_doubles ) return;
+      if ( h_ring ) { CUDA_OK( cudaDeviceSynchronize() ); cudaFreeHost( h_ring ); h_ring = nullptr; }
+      CUDA_OK( cudaHostAlloc( (void**)&h_ring, ndoubles*sizeof(double), cudaHostAllocDefault ) );
+      ring_doubles = ndoubles;
     }
   };
 
@@ -792,55 +766,21 @@ namespace {
     g_launches += 5;
   }
 
-  // S(alpha,beta) table queue of a launch sequence.  Large batches: partition by overlay sampler and sample class
-  // by class with the class tables staged in shared memory (ncb_kernels_cls.cuh); small batches (the chunks of a
-  // short host call, transport steps, materials whose tables do not fit the plan): the lane-refill kernel on the
-  // queue in arrival order.  NCB200_CLS_MIN overrides the threshold (0 = never use the class path).
-  std::atomic<uint64_t> g_cls_min{ []{ const char* e = std::getenv( "NCB200_CLS_MIN" );
-                                       return e ? (uint64_t)std::atoll(e) : (uint64_t)( 1u << 19 ); }() };
-  bool useClassPath( const DeviceMaterial& dm, uint64_t m )
-  {
-    const uint64_t mn = g_cls_min.load();
-    return dm.ncls && mn && m >= mn;
-  }
+  // S(alpha,beta) table queue of a launch sequence: attempt-level lane refill over the queue in arrival order.
+  // (r2 experiment, dropped: partitioning the queue by overlay sampler and staging each sampler's beta tables in
+  // shared memory with TMA -- the un-sorted reads/writes of the neutron arrays cost more DRAM traffic (986 MB vs
+  // 371 MB per 1e7 batch) and the per-class CTA tails more time than the staged lookups saved; see DESIGN.md.)
   void launchSabQueue( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const SampleArgs& A, const QueueArgs& Q,
                        uint64_t m, cudaStream_t st, bool timed )
   {
     const unsigned nsm = (unsigned)numSMs( dm.device );
-    auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
-    if ( !Q.q_cls ) {
-      const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*8 );
-      auto tl = timer( "k_sample_sab_refill" );
-      k_sample_sab_refill<false,8><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
-      ++g_launches;
-      return;
-    }
-    ClassArgs K;
-    uint32_t* w = qc.cls_words;
-    K.q_in = Q.q_sab; K.q_cls = Q.q_cls; K.count = Q.counts + 0; K.q_out = qc.q + 4*qc.cap;
-    K.hist = w; K.start = w + kClsMax; K.fill = w + 2*kClsMax + 1; K.cursor = w + 3*kClsMax + 1;
-    K.nticket = w + 4*kClsMax + 1;
-    K.tickets = reinterpret_cast<uint16_t*>( w + 4*( kClsMax + 1 ) + 2 );
-    K.ncls = dm.ncls;
-    static const int tmul = []{ const char* e = std::getenv( "NCB200_CLS_TICKETS" ); return e ? std::atoi(e) : 5; }();   // tickets per 2 resident CTAs
-    static const int umin = []{ const char* e = std::getenv( "NCB200_CLS_UNIT" ); return e ? std::atoi(e) : 2048; }();
-    K.tickets_target = std::max( 1u, nsm*(unsigned)dm.cls_ctas*(unsigned)tmul/2u );
-    K.unit_min = (uint32_t)std::max( 256, umin );
-    CUDA_OK( cudaMemsetAsync( K.hist, 0, dm.ncls*sizeof(uint32_t), st ) );
-    { auto tl = timer( "k_cls_partition" );
-      k_cls_hist<<< gridFor( m, 256, dm.device, 8 ), 256, 0, st >>>( K );
-      k_cls_scan<<< 1, 1024, 0, st >>>( K );
-      k_cls_partition<<< gridFor( ( m + 15 )/16, 256, dm.device, 4 ), 256, 0, st >>>( K ); }
-    { auto tl = timer( "k_sab_classes" );
-      const unsigned grid = nsm*(unsigned)dm.cls_ctas;
-      const uint32_t sm = dm.cls_smem.total;
-      switch ( dm.cls_ctas ) {
-      case 4: k_sab_classes<256,4><<< grid, 256, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
-      case 3: k_sab_classes<320,3><<< grid, 320, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
-      case 2: k_sab_classes<512,2><<< grid, 512, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
-      default: k_sab_classes<1024,1><<< grid, 1024, sm, st >>>( dm.mat, A, K, Q, dm.cls_smem ); break;
-      } }
-    g_launches += 4;
+    static const int minb = []{ const char* e = std::getenv( "NCB200_SAB_MINB" ); return e ? std::atoi(e) : 8; }();
+    const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*minb );
+    std::unique_ptr<TimedLaunch> tl( timed ? new TimedLaunch( "k_sample_sab_refill", st ) : nullptr );
+    if ( minb == 6 ) k_sample_sab_refill<false,6><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+    else if ( minb == 7 ) k_sample_sab_refill<false,7><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+    else k_sample_sab_refill<false,8><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+    ++g_launches;
   }
 
   void launchSampleIso( Scatter* s, const double* d_ekin, uint64_t n, double* d_xs, double* d_eout, double* d_mu,
@@ -873,11 +813,6 @@ namespace {
       Scatter::QueueCtx& qc = s->ensureQueues( ictx, m );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
-      if ( useClassPath( dm, m ) ) {
-        s->ensureClassScratch( qc );
-        Q.q_cls = qc.q_cls;
-        for ( int k = 0; k <= kMaxSab; ++k ) Q.cls_base[k] = dm.cls_base[k];
-      }
       CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
       { TimedLaunch tl( "k_sample_classify", st );
         k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
@@ -1078,12 +1013,97 @@ namespace {
       throw Err( "CalcError", "convertAlphaBetaToDeltaEMu invalid for beta=-E/kT" );
   }
 
+  // ---- pageable caller buffers.  Real callers of the *_many entry points (OpenMC, McStas, the reference's Python
+  // layer) pass malloc'd arrays; cudaMemcpyAsync from pageable memory is staged by the driver on one thread and
+  // serialises the pipeline (r1: measured 0.33e9 neutrons/s against 1.6e9 from pinned buffers).  Arrays that are
+  // not page-locked therefore go through a pinned bounce ring of this handle: a small pool of host threads copies
+  // chunk k+1 into the ring while chunk k is on the bus, and a drain thread copies finished chunks out.
+  class CopyPool {
+  public:
+    static CopyPool& instance() { static CopyPool p; return p; }
+    // copy with all pool threads + the caller; returns when done
+    void copy( void* dst, const void* src, size_t bytes )
+    {
+      const size_t piece = (size_t)1 << 20;
+      if ( bytes <= piece || workers_.empty() ) { std::memcpy( dst, src, bytes ); return; }
+      const size_t nparts = std::min<size_t>( workers_.size() + 1, ( bytes + piece - 1 )/piece );
+      const size_t per = ( ( bytes + nparts - 1 )/nparts + 63 ) & ~(size_t)63;
+      Batch bt; bt.left = 0;
+      {
+        std::lock_guard<std::mutex> g( m_ );
+        for ( size_t o = per; o < bytes; o += per ) {
+          tasks_.push_back( Task{ static_cast<char*>( dst ) + o, static_cast<const char*>( src ) + o, std::min( per, bytes - o ), &bt } );
+          ++bt.left;
+        }
+      }
+      cv_.notify_all();
+      std::memcpy( dst, src, std::min( per, bytes ) );
+      std::unique_lock<std::mutex> lk( m_ );
+      while ( bt.left ) {
+        if ( !tasks_.empty() ) {            // help instead of waiting
+          Task t = tasks_.front(); tasks_.pop_front();
+          lk.unlock(); std::memcpy( t.dst, t.src, t.n ); lk.lock();
+          if ( --t.batch->left == 0 ) done_.notify_all();
+        } else {
+          done_.wait( lk );
+        }
+      }
+    }
+  private:
+    struct Batch { size_t left; };
+    struct Task { char* dst; const char* src; size_t n; Batch* batch; };
+    CopyPool()
+    {
+      unsigned hw = std::thread::hardware_concurrency();
+      if ( const char* e = std::getenv( "NCB200_COPY_THREADS" ) ) hw = (unsigned)std::max( 0, std::atoi( e ) ) + 2u;
+      // measured on the 16-core GPU box: memcpy pageable->pinned 14.5 GB/s with 1 thread, 46 with 8, 50 with 16 (the
+      // ceiling of the path); end to end 7.7e8 / 1.0e9 / 8.1e8 neutrons/s with 3 / 7 / 15 pool threads
+      const unsigned nw = std::min( 7u, hw > 3 ? hw/2 - 1 : 0u );
+      for ( unsigned i = 0; i < nw; ++i )
+        workers_.emplace_back( [this]{ run(); } );
+    }
+    ~CopyPool()
+    {
+      { std::lock_guard<std::mutex> g( m_ ); stop_ = true; }
+      cv_.notify_all();
+      for ( auto& t : workers_ ) t.join();
+    }
+    void run()
+    {
+      std::unique_lock<std::mutex> lk( m_ );
+      while ( true ) {
+        cv_.wait( lk, [this]{ return stop_ || !tasks_.empty(); } );
+        if ( stop_ ) return;
+        Task t = tasks_.front(); tasks_.pop_front();
+        lk.unlock(); std::memcpy( t.dst, t.src, t.n ); lk.lock();
+        if ( --t.batch->left == 0 ) done_.notify_all();
+      }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<Task> tasks_;
+    std::vector<std::thread> workers_;
+    bool stop_ = false;
+  };
+
+  bool isPageLocked( const void* p, size_t bytes )
+  {
+    auto one = []( const void* q ) {
+      cudaPointerAttributes a;
+      if ( cudaPointerGetAttributes( &a, q ) != cudaSuccess ) { cudaGetLastError(); return false; }
+      return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    };
+    return one( p ) && one( static_cast<const char*>( p ) + ( bytes ? bytes - 1 : 0 ) );
+  }
+  constexpr uint64_t kBounceMin = (uint64_t)1 << 16;   // shorter calls: the driver's own staging is as good
+  constexpr int kRingSlots = 6;                        // bounce-ring depth (chunks): the host copies run ahead of / behind the bus
+
   // Host-pointer pipeline.  The call's arrays are staged in one device window (<= kWindowMax neutrons; longer
   // calls run window after window).  Three kinds of streams: one for H2D copies, kSlots for the kernels
   // (round robin, so the tail of one chunk's rejection kernels overlaps the next chunk), one for D2H copies;
-  // events order chunk k's copy-in -> kernels -> copy-out, the host only blocks at the end of a window.
-  // Chunks start small (the first D2H starts early) and grow geometrically up to chunkSize() (launch efficiency);
-  // optionally (NCB200_CHUNK_TAIL) they shrink again towards the end of the call.
+  // events order chunk k's copy-in -> kernels -> copy-out, the host only blocks at the end of a window (and, for
+  // pageable arrays, on the bounce ring).  Chunks start small (the first D2H starts early) and grow geometrically
+  // up to chunkSize() (launch efficiency).
   // `launch(chunk_n, in_dev[], out_dev[], stream, slot)` enqueues the kernel(s).
   void runHostPipeline( Scatter* s, uint64_t n, int nin, const double* const* in, int nout, double* const* out,
                         const std::function<void(uint64_t,double* const*,double* const*,cudaStream_t,int)>& launch )
@@ -1092,17 +1112,63 @@ namespace {
     const uint64_t W = std::min<uint64_t>( n, kWindowMax );
     s->ensurePipeline( (size_t)W * (size_t)( nin + nout ) );
     const PipeSchedule ps = pipeSchedule();
+    // which arrays need the bounce ring
+    bool bin[4] = {}, bout[4] = {};
+    bool any_in = false, any_out = false;
+    if ( n >= kBounceMin ) {
+      for ( int a = 0; a < nin; ++a ) { bin[a] = !isPageLocked( in[a], n*sizeof(double) ); any_in |= bin[a]; }
+      for ( int a = 0; a < nout; ++a ) { bout[a] = !isPageLocked( out[a], n*sizeof(double) ); any_out |= bout[a]; }
+    }
+    const size_t cmax = (size_t)ps.max;
+    if ( any_in || any_out ) s->ensureBounce( (size_t)kRingSlots*( nin + nout )*cmax );
+    auto ringIn = [&]( int slot, int a ) { return s->h_ring + ( (size_t)slot*( nin + nout ) + a )*cmax; };
+    auto ringOut = [&]( int slot, int a ) { return s->h_ring + ( (size_t)slot*( nin + nout ) + nin + a )*cmax; };
+
+    // drain thread: chunk by chunk, waits for the D2H copies into the ring and copies them out to the caller
+    struct OutJob { size_t k; int slot; uint64_t off, m; };
+    std::mutex dm; std::condition_variable dcv;
+    std::deque<OutJob> djobs; bool dstop = false; size_t ddone = 0;   // ddone: chunks copied out so far
+    std::thread drainer;
+    const int device = s->dm->device;
+    if ( any_out )
+      drainer = std::thread( [&]{
+        cudaSetDevice( device );
+        while ( true ) {
+          OutJob j;
+          {
+            std::unique_lock<std::mutex> lk( dm );
+            dcv.wait( lk, [&]{ return dstop || !djobs.empty(); } );
+            if ( djobs.empty() ) return;
+            j = djobs.front(); djobs.pop_front();
+          }
+          cudaEventSynchronize( s->ev_d[j.k] );
+          for ( int a = 0; a < nout; ++a )
+            if ( bout[a] ) CopyPool::instance().copy( out[a] + j.off, ringOut( j.slot, a ), j.m*sizeof(double) );
+          { std::lock_guard<std::mutex> g( dm ); ddone = j.k + 1; }
+          dcv.notify_all();
+        }
+      } );
     // A failure while work is queued must not return to the caller (who then fills the output arrays with the
     // error sentinels) before the copies already queued into those arrays have drained.
     struct Drain {
-      Scatter* s; bool armed = true;
-      ~Drain() {
-        if ( !armed ) return;
-        cudaStreamSynchronize( s->st_h2d );
-        for ( int c = 0; c < kSlots; ++c ) cudaStreamSynchronize( s->streams[c] );
-        cudaStreamSynchronize( s->st_d2h );
+      Scatter* s; std::thread* t; std::mutex* m; std::condition_variable* cv; bool* stop; bool armed = true;
+      void finish()
+      {
+        if ( t->joinable() ) {
+          { std::lock_guard<std::mutex> g( *m ); *stop = true; }
+          cv->notify_all();
+          t->join();
+        }
       }
-    } drain{ s };
+      ~Drain() {
+        if ( armed ) {
+          cudaStreamSynchronize( s->st_h2d );
+          for ( int c = 0; c < kSlots; ++c ) cudaStreamSynchronize( s->streams[c] );
+          cudaStreamSynchronize( s->st_d2h );
+        }
+        finish();
+      }
+    } drain{ s, &drainer, &dm, &dcv, &dstop };
     for ( uint64_t w0 = 0; w0 < n; w0 += W ) {
       const uint64_t wn = std::min<uint64_t>( W, n - w0 );
       uint64_t done = 0;
@@ -1110,17 +1176,23 @@ namespace {
       double chunk = (double)ps.first;
       while ( done < wn ) {
         uint64_t m = std::min<uint64_t>( (uint64_t)chunk, wn - done );
-        if ( ps.tail > 0.0 && w0 + wn == n )                    // (last window only)
-          m = std::min<uint64_t>( m, std::max<uint64_t>( ps.first/2, (uint64_t)( ps.tail*(double)( wn - done ) ) ) );
-        if ( wn - done - m < ps.first/4 ) m = wn - done;      // no tiny last chunk
+        if ( wn - done - m < ps.first/4 && wn - done <= cmax ) m = wn - done;      // no tiny last chunk
         chunk = std::min<double>( chunk*ps.growth, (double)ps.max );
         s->ensureChunkEvents( k + 1 );
         const int slot = (int)( k % kSlots );
+        const int rslot = (int)( k % kRingSlots );
         cudaStream_t cs = s->streams[slot];
         double* din[4]; double* dout[4];
+        if ( k >= (size_t)kRingSlots ) {
+          // ring slot reuse: its previous H2D must be done, its previous chunk copied out
+          if ( any_in ) CUDA_OK( cudaEventSynchronize( s->ev_h[k - kRingSlots] ) );
+          if ( any_out ) { std::unique_lock<std::mutex> lk( dm ); dcv.wait( lk, [&]{ return ddone >= k - kRingSlots + 1; } ); }
+        }
         for ( int a = 0; a < nin; ++a ) {
           din[a] = s->d_win + (size_t)a*W + done;
-          CUDA_OK( cudaMemcpyAsync( din[a], in[a] + w0 + done, m*sizeof(double), cudaMemcpyHostToDevice, s->st_h2d ) );
+          const double* src = in[a] + w0 + done;
+          if ( bin[a] ) { CopyPool::instance().copy( ringIn( rslot, a ), src, m*sizeof(double) ); src = ringIn( rslot, a ); }
+          CUDA_OK( cudaMemcpyAsync( din[a], src, m*sizeof(double), cudaMemcpyHostToDevice, s->st_h2d ) );
         }
         CUDA_OK( cudaEventRecord( s->ev_h[k], s->st_h2d ) );
         for ( int a = 0; a < nout; ++a )
@@ -1130,20 +1202,40 @@ namespace {
         CUDA_OK( cudaEventRecord( s->ev_c[k], cs ) );
         CUDA_OK( cudaStreamWaitEvent( s->st_d2h, s->ev_c[k], 0 ) );
         for ( int a = 0; a < nout; ++a )
-          CUDA_OK( cudaMemcpyAsync( out[a] + w0 + done, dout[a], m*sizeof(double), cudaMemcpyDeviceToHost, s->st_d2h ) );
+          CUDA_OK( cudaMemcpyAsync( bout[a] ? ringOut( rslot, a ) : out[a] + w0 + done, dout[a], m*sizeof(double),
+                                    cudaMemcpyDeviceToHost, s->st_d2h ) );
+        if ( any_out ) {
+          CUDA_OK( cudaEventRecord( s->ev_d[k], s->st_d2h ) );
+          { std::lock_guard<std::mutex> g( dm ); djobs.push_back( OutJob{ k, rslot, w0 + done, m } ); }
+          dcv.notify_all();
+        }
         done += m;
         ++k;
       }
       CUDA_OK( cudaStreamSynchronize( s->st_d2h ) );
       for ( int c = 0; c < kSlots; ++c )
         CUDA_OK( cudaStreamSynchronize( s->streams[c] ) );
+      if ( any_out ) {
+        std::unique_lock<std::mutex> lk( dm );
+        dcv.wait( lk, [&]{ return ddone >= k; } );
+        ddone = 0;      // chunk numbering restarts with the next window
+      }
     }
     drain.armed = false;
   }
 
+#include "ncb_lib_multigpu.inc"
+
   void xsIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* results )
   {
     if ( !n || !repeat ) return;
+    const auto devs = fanDevices( s, n );
+    if ( !devs.empty() ) {
+      fanOut( s, devs, n, false, [&]( Scatter* h, uint64_t b, uint64_t m ) { xsIsoHost( h, ekin + b, m, 1, results + b ); } );
+      for ( uint64_t r = 1; r < repeat; ++r )
+        std::memcpy( results + r*n, results, n*sizeof(double) );
+      return;
+    }
     DeviceGuard dg( s->dm->device );
     const double* in[1] = { ekin };
     double* out[1] = { results };
@@ -1158,6 +1250,12 @@ namespace {
   void sampleIsoHost( Scatter* s, const double* ekin, uint64_t n, uint64_t repeat, double* eout, double* mu )
   {
     if ( !n || !repeat ) return;
+    const auto devs = fanDevices( s, n );
+    if ( !devs.empty() ) {
+      for ( uint64_t r = 0; r < repeat; ++r )
+        fanOut( s, devs, n, true, [&]( Scatter* h, uint64_t b, uint64_t m ) { sampleIsoHost( h, ekin + b, m, 1, eout + r*n + b, mu + r*n + b ); } );
+      return;
+    }
     DeviceGuard dg( s->dm->device );
     for ( uint64_t r = 0; r < repeat; ++r ) {
       const double* in[1] = { ekin };
@@ -1174,6 +1272,11 @@ namespace {
   void xsAndSampleIsoHost( Scatter* s, const double* ekin, uint64_t n, double* xs, double* eout, double* mu )
   {
     if ( !n ) return;
+    const auto devs = fanDevices( s, n );
+    if ( !devs.empty() ) {
+      fanOut( s, devs, n, true, [&]( Scatter* h, uint64_t b, uint64_t m ) { xsAndSampleIsoHost( h, ekin + b, m, xs + b, eout + b, mu + b ); } );
+      return;
+    }
     DeviceGuard dg( s->dm->device );
     const double* in[1] = { ekin };
     double* out[3] = { xs, eout, mu };
@@ -1187,6 +1290,11 @@ namespace {
                     uint64_t n, double* results )
   {
     if ( !n ) return;
+    const auto devs = fanDevices( s, n );
+    if ( !devs.empty() ) {
+      fanOut( s, devs, n, false, [&]( Scatter* h, uint64_t b, uint64_t m ) { xsAnisoHost( h, ekin + b, ux + b, uy + b, uz + b, m, results + b ); } );
+      return;
+    }
     DeviceGuard dg( s->dm->device );
     const double* in[4] = { ekin, ux, uy, uz };
     double* out[1] = { results };
@@ -1199,6 +1307,12 @@ namespace {
                         uint64_t n, double* eout, double* ox, double* oy, double* oz )
   {
     if ( !n ) return;
+    const auto devs = fanDevices( s, n );
+    if ( !devs.empty() ) {
+      fanOut( s, devs, n, true, [&]( Scatter* h, uint64_t b, uint64_t m ) {
+        sampleAnisoHost( h, ekin + b, ux + b, uy + b, uz + b, m, eout + b, ox + b, oy + b, oz + b ); } );
+      return;
+    }
     DeviceGuard dg( s->dm->device );
     const double* in[4] = { ekin, ux, uy, uz };
     double* out[4] = { eout, ox, oy, oz };
@@ -1659,6 +1773,42 @@ extern "C" {
     } NCBCATCH;
   }
 
+  // ---- page-locking of caller buffers: a caller that reuses its arrays pins them once (about 20 ms per 80 MB) and
+  // every later *_many call on them runs at the pinned-buffer rate instead of through the bounce ring
+  int ncb200_pin_host_buffer( void* p, uint64_t nbytes )
+  {
+    try { CUDA_OK( cudaHostRegister( p, nbytes, cudaHostRegisterPortable ) ); return 0; } NCBCATCH;
+    return -1;
+  }
+  int ncb200_unpin_host_buffer( void* p )
+  {
+    try { CUDA_OK( cudaHostUnregister( p ) ); return 0; } NCBCATCH;
+    return -1;
+  }
+
+  // ---- several devices from one process (ncb_lib_multigpu.inc)
+  int ncb200_set_devices( int n )
+  {
+    try {
+      int ndev = 0;
+      CUDA_OK( cudaGetDeviceCount( &ndev ) );
+      if ( n < 0 || n > ndev ) throw Err( "BadInput", "ncb200_set_devices: "+std::to_string(n)+" devices requested, "+std::to_string(ndev)+" visible" );
+      if ( n == 0 ) n = ndev;
+      std::lock_guard<std::mutex> g( g_dev_mtx );
+      g_devices.clear();
+      if ( n > 1 ) for ( int d = 0; d < n; ++d ) g_devices.push_back( d );
+      return n;
+    } NCBCATCH;
+    return -1;
+  }
+  int ncb200_get_devices(void) { std::lock_guard<std::mutex> g( g_dev_mtx ); return g_devices.empty() ? 1 : (int)g_devices.size(); }
+  void ncb200_set_fanout_min( uint64_t n ) { std::lock_guard<std::mutex> g( g_dev_mtx ); g_fanout_min = n ? n : 1; }
+  void ncb200_tally_hist_many( const double* values, const double* weights, uint64_t n, double lo, double hi, uint32_t nbins,
+                               double* hist, double* sumw2 )
+  {
+    try { if ( n ) tallyHistHost( values, weights, n, lo, hi, nbins, hist, sumw2 ); } NCBCATCH;
+  }
+
   // ---- introspection
   int ncb200_ncomponents( ncrystal_process_t p )
   {
@@ -1820,6 +1970,69 @@ extern "C" {
       }
       if ( meta ) { meta[0] = ep.ibeta_off; meta[1] = ep.first_bin_endpoint; }
       return n;
+    } NCBCATCH;
+    return -1;
+  }
+
+  // Consistency of the gather-friendly table copies and guides with the sampler tables they were derived from, all
+  // read back from the device: heads / tails against AlphaSampleInfo + cumulative rows, points against the alpha /
+  // S / log S / cumulative arrays, beta points against the (x,pdf,cdf) rows, and for every row and key of the log
+  // guide the bracketing property the sampler relies on.  Returns the number of violations (0 = consistent), -1 on error.
+  long ncb200_sab_selfcheck( ncrystal_process_t p, int component )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_sab_selfcheck" );
+      const Material& M = s->dm->mat;
+      if ( component < 0 || component >= M.ncomp || M.comp[component].kind != KIND_SAB ) return -1;
+      const SabT& T = M.sab[M.comp[component].idx];
+      DeviceGuard dg( s->dm->device );
+      CUDA_OK( cudaDeviceSynchronize() );
+      const size_t ne = T.negrid, na = T.nalpha, nb = T.nbeta, bst = T.bstride;
+      auto fetch = [&]( auto* dst, const void* src, size_t count ) {
+        CUDA_OK( cudaMemcpy( dst, src, count*sizeof(*dst), cudaMemcpyDeviceToHost ) );
+      };
+      std::vector<double> alpha( na ), sab( na*nb ), logsab( na*nb ), cumul( na*nb ), bx( ne*bst ), bpdf( ne*bst ), bcdf( ne*bst );
+      std::vector<SabAlphaInfo> ainfo( ne*nb );
+      std::vector<SabHead> heads( ne*nb );
+      std::vector<SabTail> tails( 2*ne*nb );
+      std::vector<SabPoint> pts( na*nb );
+      std::vector<SabBPoint> bpts( ne*bst );
+      std::vector<uint16_t> lg( nb*(size_t)kSabGLStride );
+      std::vector<SabEPoint> ep( ne );
+      fetch( alpha.data(), T.alpha, na ); fetch( sab.data(), T.sab, na*nb ); fetch( logsab.data(), T.logsab, na*nb );
+      fetch( cumul.data(), T.cumul, na*nb ); fetch( bx.data(), T.bx, ne*bst ); fetch( bpdf.data(), T.bpdf, ne*bst );
+      fetch( bcdf.data(), T.bcdf, ne*bst ); fetch( ainfo.data(), T.ainfo, ne*nb ); fetch( heads.data(), T.heads, ne*nb );
+      fetch( tails.data(), T.tails, 2*ne*nb ); fetch( pts.data(), T.pts, na*nb ); fetch( bpts.data(), T.bpts, ne*bst );
+      fetch( lg.data(), T.lguide, nb*(size_t)kSabGLStride ); fetch( ep.data(), T.ep, ne );
+      auto same = []( double a, double b ) { return std::memcmp( &a, &b, sizeof(double) ) == 0; };
+      long bad = 0;
+      for ( size_t k = 0; k < ne*nb; ++k ) {
+        const SabAlphaInfo& f = ainfo[k]; const SabHead& h = heads[k];
+        const double* row = cumul.data() + ( k % nb )*na;
+        bad += !( same( h.prob_front, f.prob_front ) && same( h.prob_notback, f.prob_notback ) && (int)h.f_idx == f.f_idx
+                  && (int)h.b_idx == f.b_idx && same( h.clow, row[f.f_idx] ) && same( h.cupp, row[f.b_idx] ) );
+        bad += !( same( tails[2*k].alpha, f.f_alpha ) && same( tails[2*k].sval, f.f_sval ) && same( tails[2*k].logsval, f.f_logsval )
+                  && same( tails[2*k+1].alpha, f.b_alpha ) && same( tails[2*k+1].sval, f.b_sval ) && same( tails[2*k+1].logsval, f.b_logsval ) );
+      }
+      for ( size_t k = 0; k < na*nb; ++k )
+        bad += !( same( pts[k].alpha, alpha[k % na] ) && same( pts[k].sab, sab[k] ) && same( pts[k].logsab, logsab[k] ) && same( pts[k].cumul, cumul[k] ) );
+      for ( size_t ie = 0; ie < ne; ++ie )
+        for ( int j = 0; j < ep[ie].npts; ++j ) {
+          const size_t k = ep[ie].off_b + j;
+          bad += !( same( bpts[k].x, bx[k] ) && same( bpts[k].pdf, bpdf[k] ) && same( bpts[k].cdf, bcdf[k] ) );
+        }
+      for ( size_t ib = 0; ib < nb; ++ib ) {
+        const double* row = cumul.data() + ib*na;
+        const uint16_t* g = lg.data() + ib*(size_t)kSabGLStride;
+        const double inv = heads[ib].inv_total;
+        bad += !( g[0] == 0 && g[kSabGL] == (uint16_t)na );
+        for ( int key = 0; key < kSabGL; ++key ) {
+          bad += !( g[key] <= g[key+1] );
+          // every point in [g[key], g[key+1]) has exactly this key; the points before / after have a smaller / larger one
+          for ( int i = g[key]; i < g[key+1]; ++i ) bad += ( sabLogKey( row[i]*inv ) != key );
+        }
+      }
+      return bad;
     } NCBCATCH;
     return -1;
   }

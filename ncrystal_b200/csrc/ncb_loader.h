@@ -9,6 +9,7 @@
 #pragma once
 #include "ncb_blob.h"
 #include "ncb_tables.h"
+#include <algorithm>
 #include <cstring>
 #include <initializer_list>
 #include <stdexcept>
@@ -20,7 +21,7 @@ namespace ncb {
   struct SabBuildPlan {       // what the build stages need for one SAB leaf
     int sab_index;            // index into Material::sab
     size_t off_logsab, off_cumul, off_ep, off_bx, off_bpdf, off_bcdf, off_ainfo, off_rows, off_xscheck;
-    size_t off_bguide, off_aguide, off_ascale, off_heads, off_pts;
+    size_t off_bguide, off_aguide, off_ascale, off_heads, off_pts, off_tails, off_bpts, off_lguide;
   };
 
   struct LoadedMaterial {
@@ -64,21 +65,51 @@ namespace ncb {
     for ( int i = 0; i < npb; ++i ) {
       relocPtr( m.pb[i].e2d, base );
       relocPtr( m.pb[i].fdm, base );
+      if ( m.pb[i].lut ) relocPtr( m.pb[i].lut, base );
     }
     for ( int i = 0; i < nsab; ++i ) {
       SabT& s = m.sab[i];
+      if ( s.elut ) relocPtr( s.elut, base );
       relocPtr( s.egrid, base ); relocPtr( s.xs, base ); relocPtr( s.alpha, base ); relocPtr( s.beta, base );
       relocPtr( s.sab, base ); relocPtr( s.logsab, base ); relocPtr( s.cumul, base );
       relocPtr( s.ep, base ); relocPtr( s.bx, base ); relocPtr( s.bpdf, base ); relocPtr( s.bcdf, base );
       relocPtr( s.ainfo, base );
       relocPtr( s.bguide, base ); relocPtr( s.aguide, base ); relocPtr( s.ascale, base );
-      relocPtr( s.heads, base ); relocPtr( s.pts, base );
+      relocPtr( s.heads, base ); relocPtr( s.pts, base ); relocPtr( s.tails, base ); relocPtr( s.bpts, base ); relocPtr( s.lguide, base );
     }
     if ( m.sc.nfam ) {
       relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
       relocPtr( m.sc.normals, base ); relocPtr( m.sc.normals_f, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
     }
     return m;
+  }
+
+  // Energy-key table (KeyLut) over an ascending table of positive energies; appended to the arena.  The number of
+  // mantissa bits in the key is the largest (<= 8) that keeps the table within ~2 entries per point and 4096 entries.
+  inline size_t buildKeyLut( LoadedMaterial& lm, const double* a, size_t n, int& key0, int& shift, int& nk )
+  {
+    key0 = shift = nk = 0;
+    if ( n < 8 || !( a[0] > 0.0 ) || n > 65535 )
+      return 0;
+    auto bits = []( double v ) { long long b; std::memcpy( &b, &v, sizeof(b) ); return b; };
+    int m = 8;
+    long long span = 0;
+    for ( ; m >= 0; --m ) {
+      span = ( bits( a[n-1] ) >> ( 52 - m ) ) - ( bits( a[0] ) >> ( 52 - m ) ) + 1;
+      if ( span + 1 <= 4096 && span <= (long long)std::max<size_t>( 2*n, 64 ) ) break;
+    }
+    if ( m < 0 )
+      return 0;
+    shift = 52 - m;
+    key0 = (int)( bits( a[0] ) >> shift );
+    nk = (int)span;
+    std::vector<uint16_t> lut( (size_t)nk + 1 );
+    size_t i = 0;
+    for ( int k = 0; k <= nk; ++k ) {
+      while ( i < n && ( bits( a[i] ) >> shift ) - key0 < k ) ++i;
+      lut[k] = (uint16_t)i;
+    }
+    return lm.put( lut.data(), lut.size()*sizeof(uint16_t) );
   }
 
   void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
@@ -146,6 +177,7 @@ namespace ncb {
         T.threshold = h.threshold;
         T.e2d = offAsPtr<double>( lm.put( arr, h.nplanes*8 ) );
         T.fdm = offAsPtr<double>( lm.put( arr + h.nplanes, h.nplanes*8 ) );
+        T.lut = offAsPtr<uint16_t>( buildKeyLut( lm, arr, h.nplanes, T.lut_key0, T.lut_shift, T.lut_nk ) );
         k.idx = npb++;
         break;
       }
@@ -204,6 +236,7 @@ namespace ncb {
         const size_t ne = h.negrid, na = h.nalpha, nb = h.nbeta;
         T.egrid = offAsPtr<double>( lm.put( arr, ne*8 ) );
         T.xs    = offAsPtr<double>( lm.put( arr + ne, ne*8 ) );
+        T.elut  = offAsPtr<uint16_t>( buildKeyLut( lm, arr, ne, T.elut_key0, T.elut_shift, T.elut_nk ) );
         T.alpha = offAsPtr<double>( lm.put( arr + 2*ne, na*8 ) );
         T.beta  = offAsPtr<double>( lm.put( arr + 2*ne + na, nb*8 ) );
         T.sab   = offAsPtr<double>( lm.put( arr + 2*ne + na + nb, na*nb*8 ) );
@@ -225,6 +258,9 @@ namespace ncb {
         pl.off_ascale = lm.reserve( nb*8 );
         pl.off_heads  = lm.reserve( ne*nb*sizeof(SabHead) );
         pl.off_pts    = lm.reserve( na*nb*sizeof(SabPoint) );
+        pl.off_tails  = lm.reserve( ne*nb*2*sizeof(SabTail) );
+        pl.off_bpts   = lm.reserve( ne*bst*sizeof(SabBPoint) );
+        pl.off_lguide = lm.reserve( nb*(size_t)kSabGLStride*sizeof(uint16_t) );
         T.logsab = offAsPtr<double>( pl.off_logsab );
         T.cumul  = offAsPtr<double>( pl.off_cumul );
         T.ep     = offAsPtr<SabEPoint>( pl.off_ep );
@@ -237,6 +273,9 @@ namespace ncb {
         T.ascale = offAsPtr<double>( pl.off_ascale );
         T.heads  = offAsPtr<SabHead>( pl.off_heads );
         T.pts    = offAsPtr<SabPoint>( pl.off_pts );
+        T.tails  = offAsPtr<SabTail>( pl.off_tails );
+        T.bpts   = offAsPtr<SabBPoint>( pl.off_bpts );
+        T.lguide = offAsPtr<uint16_t>( pl.off_lguide );
         lm.sabplans.push_back( pl );
         k.idx = nsab++;
         break;

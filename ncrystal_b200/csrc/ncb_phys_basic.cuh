@@ -16,16 +16,23 @@ namespace ncb {
   {
     return upperBound( e2d, 1, n, ekin ) - 1;
   }
+  // same through the table's energy-key lut (`lut`: the table's, possibly staged; may be null)
+  template <class Ptr>
+  NCB_HD int pbLastValidPlane( const PowderBraggT& T, Ptr e2d, const uint16_t* lut, double ekin )
+  {
+    const int u = upperBoundKeyed( e2d, T.n, ekin, lut, T.lut_key0, T.lut_shift, T.lut_nk );   // over [0,n)
+    return ( u > 1 ? u : 1 ) - 1;                                                               // = upper_bound over [1,n) - 1
+  }
 
   // crossSectionIsotropic, ref: NCPowderBragg.cc:166-176 (+ cache update :42-50: inv_ekin = 1/E)
   // `idx_out` receives the last valid plane (or -1).
   template <class Ptr>
-  NCB_HD double pbXS( Ptr e2d, Ptr fdm, int n, double threshold, double ekin, int& idx_out )
+  NCB_HD double pbXS( const PowderBraggT& T, Ptr e2d, Ptr fdm, const uint16_t* lut, double ekin, int& idx_out )
   {
     idx_out = -1;
-    if ( ekin < threshold || !isFinite(ekin) )
+    if ( ekin < T.threshold || !isFinite(ekin) )
       return 0.0;
-    const int idx = pbLastValidPlane( e2d, n, ekin );
+    const int idx = pbLastValidPlane( T, e2d, lut, ekin );
     idx_out = idx;
     const double inv_ekin = 1.0 / ekin;
     return fdm[idx] * inv_ekin;
@@ -136,10 +143,10 @@ namespace ncb {
   // SABScatter::m_scale (src/sabscatter/NCSABScatter.cc:87-90).
   // `iu_out` (optional) receives upper_bound(egrid, E), which the sampler's choice of overlay starts from.
   template <class Ptr>
-  NCB_HD double sabXS( const SabT& T, Ptr egrid, Ptr xsv, double ekin, int* iu_out = nullptr )
+  NCB_HD double sabXS( const SabT& T, Ptr egrid, Ptr xsv, const uint16_t* elut, double ekin, int* iu_out = nullptr )
   {
     const int n = T.negrid;
-    const int iu = upperBound( egrid, 0, n, ekin );
+    const int iu = upperBoundKeyed( egrid, n, ekin, elut, T.elut_key0, T.elut_shift, T.elut_nk );
     if ( iu_out ) *iu_out = iu;
     double xs;
     if ( iu == n ) {

@@ -209,20 +209,16 @@ namespace ncb {
   }
 
   // ---------------------------------------------------------------------------------------------------------
-  // Class-staged variants: the same arithmetic as pwdPercentileWithIndex / sabSampleAlpha / sabAttemptAtE above, for
-  // a kernel whose CTA works on ONE overlay sampler (energy point) at a time.  That sampler's beta distribution
-  // (x, pdf, cdf), its beta guide and its SabHead entries sit in shared memory (`SabClassTabs`, plain loads);
-  // what is gathered from global memory per alpha sample is the row's alpha guide and SabPoint records.
-  struct SabClassTabs {
-    const double* bx; const double* bpdf; const double* bcdf;   // [npts]
-    const uint16_t* guide;                                       // [kSabGB+1]
-    const SabHead* heads;                                        // indexed by beta row; rows max(ibeta_off-1,0) ... nbeta-1 are present
-    const double* beta;                                          // the kernel's beta grid [nbeta]
-    const SabAlphaInfo* ainfo;                                   // (global) this energy point's entry for beta row 0
-    int npts, ibeta_off;
-    double first_bin_endpoint;
-  };
-
+  // Short-chain variants: the same arithmetic as pwdPercentileWithIndex / sabSampleAlpha / sabAttemptAtE above on
+  // the gather-friendly copies of the tables (SabBPoint / SabHead / SabTail / SabPoint, ncb_tables.h).  A table
+  // attempt is latency-bound on its chain of DEPENDENT gathers; here the chain is
+  //     beta guide -> beta points | heads of both rows -> log guide -> alpha points        (~6 round trips)
+  // instead of r1's ~20 (energy-point record, guide, CDF search, x/pdf/cdf rows; per row: info, cumul[ilow]/[iupp]
+  // and scale, linear guide, a 5.8-step search for heavy scatterers, alpha/sab/logsab rows).
+  // Measured and dropped (r2, Al 1e7: this version 0.873 ms): four independent probes instead of the bisection
+  // behind the log guide (0.900), two for the beta CDF (0.882), both rows' chains run side by side (0.983: the
+  // inlined double bookkeeping costs instruction-cache misses and issue slots) -- extra loads and code cost more
+  // than the shorter chain saves once the chain is this short.
   NCB_HD SabPoint ldPoint( const SabPoint* p )
   {
 #if defined(__CUDA_ARCH__)
@@ -231,6 +227,28 @@ namespace ncb {
     return SabPoint{ a.x, a.y, b.x, b.y };
 #else
     return *p;
+#endif
+  }
+  NCB_HD SabHead ldHead( const SabHead* p )
+  {
+#if defined(__CUDA_ARCH__)
+    const double2 a = __ldg( reinterpret_cast<const double2*>( p ) );
+    const double2 b = __ldg( reinterpret_cast<const double2*>( p ) + 1 );
+    const uint4 c = __ldg( reinterpret_cast<const uint4*>( p ) + 2 );
+    SabHead h;
+    h.prob_front = a.x; h.prob_notback = a.y; h.clow = b.x; h.cupp = b.y;
+    h.inv_total = __hiloint2double( (int)c.y, (int)c.x ); h.f_idx = c.z; h.b_idx = c.w;
+    return h;
+#else
+    return *p;
+#endif
+  }
+  NCB_HD void prefetchL1( const void* p )
+  {
+#if defined(__CUDA_ARCH__)
+    asm volatile( "prefetch.global.L1 [%0];" :: "l"(p) );
+#else
+    (void)p;
 #endif
   }
   NCB_HD int upperBoundPts( const SabPoint* a, int lo, int hi, double v )
@@ -246,23 +264,32 @@ namespace ncb {
   inline void (*g_alpha_trace)( int, double, int, int, int, int, int, double ) = nullptr;   // tests/hostsim only
 #endif
 
-  // PointwiseDist::percentileWithIndex over staged rows (ref: NCPointwiseDist.cc:76-105)
-  NCB_HD double pwdPercentileStaged( const SabClassTabs& C, double p, int& idx )
+  // PointwiseDist::percentileWithIndex (ref: NCPointwiseDist.cc:76-105) over SabBPoint records
+  NCB_HD double pwdPercentileFast( const SabBPoint* B, const uint16_t* guide, int n, double p, int& idx )
   {
-    const int n = C.npts;
     if ( p == 1. ) {
       idx = n-2;
-      return C.bx[n-1];
+      return ldTable( &B[n-1].x );
     }
     const int b = (int)( p * (double)kSabGB );
-    int i = lowerBound( C.bcdf, (int)C.guide[b], (int)C.guide[b+1], p );
-    i = i < n-1 ? i : n-1;
+    int lo = (int)ldTable( guide + b ), hi = (int)ldTable( guide + b+1 );
+    while ( lo < hi ) {
+      const int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( ldTable( &B[mid].cdf ) < p ) lo = mid + 1; else hi = mid;
+    }
+    int i = lo < n-1 ? lo : n-1;
     i = i > 1 ? i : 1;
-    const double x0 = C.bx[i-1], x1 = C.bx[i];
+#if defined(__CUDA_ARCH__)
+    const double2 q0 = __ldg( reinterpret_cast<const double2*>( B + i-1 ) );
+    const double cdf0 = __ldg( &B[i-1].cdf );
+    const double2 q1 = __ldg( reinterpret_cast<const double2*>( B + i ) );
+    const double x0 = q0.x, a = q0.y, x1 = q1.x, y1 = q1.y;
+#else
+    const double x0 = B[i-1].x, a = B[i-1].pdf, cdf0 = B[i-1].cdf, x1 = B[i].x, y1 = B[i].pdf;
+#endif
     const double dx = x1 - x0;
-    const double c = ( p - C.bcdf[i-1] );
-    const double a = C.bpdf[i-1];
-    const double d = C.bpdf[i] - a;
+    const double c = ( p - cdf0 );
+    const double d = y1 - a;
     double zdx;
     if ( !a ) {
       zdx = d > 0.0 ? sqrt( ( 2.0 * c * dx ) / d ) : 0.5*dx;
@@ -277,43 +304,37 @@ namespace ncb {
     return dclamp( x0 + zdx, x0, x1 );
   }
 
-  // SABSamplerAtE_Alg1::sampleAlpha (ref: NCSABSamplerModels.cc:157-233), staged head + point records
-  NCB_HD_NOINLINE double sabSampleAlphaStaged( const SabT& T, const SabClassTabs& C, int ibeta, double rand_percentile )
+  // SABSamplerAtE_Alg1::sampleAlpha (ref: NCSABSamplerModels.cc:157-233).  `hr` = ie*nbeta + ibeta.
+  // The reference's three cases each rescale the percentile with one division; the operands are selected first and
+  // ONE division serves all lanes of a warp (same operands per case -> same quotient).
+  NCB_HD_NOINLINE double sabSampleAlphaFast( const SabT& T, size_t hr, int ibeta, double rand_percentile )
   {
-    const SabHead& h = C.heads[ibeta];
+    const SabHead h = ldHead( T.heads + hr );
     const SabPoint* P = T.pts + (size_t)ibeta*T.nalpha;
-    double a, fa, b, fb, r, la, lb;
     const double prob_front = h.prob_front, prob_notback = h.prob_notback;
-    if ( rand_percentile <= prob_front ) {
-      const SabAlphaInfo* info = C.ainfo + ibeta;
-      const double f_alpha = ldTable( &info->f_alpha );
-      if ( prob_front == 2.0 ) {
-        const double da = ldTable( &info->b_alpha ) - f_alpha;
-        return f_alpha + rand_percentile*da;
-      } else if ( prob_front == 1.0 ) {
-        a = f_alpha; fa = ldTable( &info->f_sval ); b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
-        r = rand_percentile; la = ldTable( &info->f_logsval ); lb = ldTable( &info->b_logsval );
-      } else {
-        const SabPoint q = ldPoint( P + h.f_idx );
-        a = f_alpha; fa = ldTable( &info->f_sval ); b = q.alpha; fb = q.sab;
-        r = dclamp( rand_percentile / prob_front, kDblMin, 1.0 );
-        la = ldTable( &info->f_logsval ); lb = q.logsab;
-      }
-    } else if ( rand_percentile <= prob_notback ) {
-      const double percentile2 = dclamp( ( rand_percentile - prob_front ) / ( prob_notback - prob_front ), 0.0, 1.0 );
-      const int ilow = (int)h.f_idx, iupp = (int)h.b_idx, nalpha = T.nalpha;
-      const double clow = h.clow, cupp = h.cupp;
-      const double selectedArea = clow + percentile2 * ( cupp - clow );
-      int bk = (int)( selectedArea * h.ascale );
-      bk = bk < 0 ? 0 : ( bk > kSabGA-1 ? kSabGA-1 : bk );
-      const uint16_t* g = T.aguide + (size_t)ibeta*( kSabGA+1 ) + bk;
-      int r0 = upperBoundPts( P, (int)ldTable( g ), (int)ldTable( g + 1 ), selectedArea );
-      const bool ok = ( r0 == 0 || !( selectedArea < ldTable( &P[r0-1].cumul ) ) ) && ( r0 == nalpha || selectedArea < ldTable( &P[r0].cumul ) );
+    const bool front = ( rand_percentile <= prob_front );
+    const bool middle = !front && ( rand_percentile <= prob_notback );
+    if ( front && prob_front == 2.0 ) {
+      const double f_alpha = ldTable( &T.tails[2*hr].alpha );
+      const double da = ldTable( &T.tails[2*hr+1].alpha ) - f_alpha;
+      return f_alpha + rand_percentile*da;
+    }
+    // (prob_front == 1.0, the single-bin case, uses the percentile as it is: x/1.0 == x)
+    const double num = front ? rand_percentile : ( middle ? rand_percentile - prob_front : rand_percentile - prob_notback );
+    const double den = front ? ( prob_front == 1.0 ? 1.0 : prob_front ) : ( middle ? prob_notback - prob_front : 1.0 - prob_notback );
+    const double q = num / den;
+    double a, fa, b, fb, r, la, lb;
+    if ( middle ) {
+      const double percentile2 = dclamp( q, 0.0, 1.0 );
+      const int ilow = (int)h.f_idx, iupp = (int)h.b_idx;
+      const double selectedArea = h.clow + percentile2 * ( h.cupp - h.clow );
+      const uint16_t* g = T.lguide + (size_t)ibeta*kSabGLStride + sabLogKey( selectedArea * h.inv_total );
+      // upper_bound( cumul[ilow..iupp], selectedArea ) = clamp( upper_bound over the whole row ) to that range; the
+      // whole-row position lies in [g[0], g[1]] (sabLogGuideEntry)
+      const int r0 = upperBoundPts( P, (int)ldTable( g ), (int)ldTable( g + 1 ), selectedArea );
 #if !defined(__CUDA_ARCH__) && defined(NCB_HOST_TRACE)
       if ( g_alpha_trace ) g_alpha_trace( ibeta, selectedArea, ilow, iupp, (int)g[0], (int)g[1], r0, percentile2 );
 #endif
-      if ( !ok )
-        r0 = upperBoundPts( P, 0, nalpha, selectedArea );
       const int isel_upp = r0 < ilow ? ilow : ( r0 > iupp+1 ? iupp+1 : r0 );
       if ( isel_upp > iupp )
         return ldTable( &P[iupp].alpha );
@@ -323,27 +344,41 @@ namespace ncb {
       const double binArea = p1.cumul - p0.cumul;
       r = dclamp( ( selectedArea - p0.cumul ) / binArea, kDblMin, 1.0 );
       a = p0.alpha; fa = p0.sab; b = p1.alpha; fb = p1.sab; la = p0.logsab; lb = p1.logsab;
+    } else if ( front ) {
+      const SabTail* t = T.tails + 2*hr;
+      a = ldTable( &t[0].alpha ); fa = ldTable( &t[0].sval ); la = ldTable( &t[0].logsval );
+      if ( prob_front == 1.0 ) {
+        b = ldTable( &t[1].alpha ); fb = ldTable( &t[1].sval ); lb = ldTable( &t[1].logsval );
+        r = rand_percentile;
+      } else {
+        const SabPoint p = ldPoint( P + h.f_idx );
+        b = p.alpha; fb = p.sab; lb = p.logsab;
+        r = dclamp( q, kDblMin, 1.0 );
+      }
     } else {
-      const SabAlphaInfo* info = C.ainfo + ibeta;
-      const SabPoint q = ldPoint( P + h.b_idx );
-      r = dclamp( ( rand_percentile - prob_notback ) / ( 1.0 - prob_notback ), kDblMin, 1.0 );
-      a = q.alpha; fa = q.sab; b = ldTable( &info->b_alpha ); fb = ldTable( &info->b_sval );
-      la = q.logsab; lb = ldTable( &info->b_logsval );
+      const SabTail* t = T.tails + 2*hr + 1;
+      const SabPoint p = ldPoint( P + h.b_idx );
+      a = p.alpha; fa = p.sab; la = p.logsab;
+      b = ldTable( &t->alpha ); fb = ldTable( &t->sval ); lb = ldTable( &t->logsval );
+      r = dclamp( q, kDblMin, 1.0 );
     }
     return sampleLogLinDistFast( a, fa, b, fb, r, la, lb );
   }
 
-  // One pass of the rejection loop of SABSamplerAtE_Alg1::sampleAlphaBeta (ref: NCSABSamplerModels.cc:62-148), staged
-  NCB_HD bool sabAttemptStaged( const SabT& T, const SabClassTabs& C, double ekin_div_kT, Rng& rng,
-                                double& alpha_out, double& beta_out, int& err )
+  // One pass of the rejection loop of SABSamplerAtE_Alg1::sampleAlphaBeta (ref: NCSABSamplerModels.cc:62-148) for
+  // energy point `ie` (requires ep.npts>0).  true: a point was accepted, false where the reference `continue`s.
+  NCB_HD bool sabAttemptFast( const SabT& T, int ie, const SabEPoint& ep, double ekin_div_kT, Rng& rng,
+                              double& alpha_out, double& beta_out, int& err )
   {
-    const double firstBin = C.first_bin_endpoint;
+    const SabBPoint* B = T.bpts + ep.off_b;
+    const double firstBin = ep.first_bin_endpoint;
+    const size_t hr0 = (size_t)ie*T.nbeta;
     int ibetaSampled;
-    double beta = pwdPercentileStaged( C, rng.generate(), ibetaSampled );
+    double beta = pwdPercentileFast( B, T.bguide + (size_t)ie*kSabGBStride, ep.npts, rng.generate(), ibetaSampled );
 
     if ( ibetaSampled == 0 && firstBin <= 0.0 ) {
       const double b0 = firstBin;
-      const double b1 = C.bx[1];
+      const double b1 = ldTable( &B[1].x );
       if ( b1 < -ekin_div_kT )
         return false;
       const double delta_beta = b1 - b0;
@@ -353,7 +388,7 @@ namespace ncb {
         beta = dmax( firstBin, b0 + delta_beta*rng.generate() );
         if ( beta < -ekin_div_kT )
           break;
-        alphaval = sabSampleAlphaStaged( T, C, C.ibeta_off, rng.generate() );
+        alphaval = sabSampleAlphaFast( T, hr0 + ep.ibeta_off, ep.ibeta_off, rng.generate() );
         AlphaLimits alims = getAlphaLimits( -firstBin, beta );
         if ( inInterval( alims.first, alims.second, alphaval ) )
           break;
@@ -373,15 +408,16 @@ namespace ncb {
       return false;
     }
 
-    if ( beta <= dmax( -ekin_div_kT, C.beta[0] ) )
+    if ( beta <= dmax( -ekin_div_kT, ldTable( T.beta ) ) )
       return false;
 
+    const int ibeta = ep.ibeta_off + ibetaSampled;
     const double rand_percentile = rng.generate();
-    const int ibeta = C.ibeta_off + ibetaSampled;
-    const double bl = C.beta[ibeta-1];
-    const double alphal = sabSampleAlphaStaged( T, C, ibeta-1, rand_percentile );
-    const double bh = C.beta[ibeta];
-    const double alphah = sabSampleAlphaStaged( T, C, ibeta, rand_percentile );
+    const double bl = ldTable( T.beta + ibeta-1 );
+    const double bh = ldTable( T.beta + ibeta );
+    prefetchL1( T.heads + hr0 + ibeta );               // the second row's head, while the first row is processed
+    const double alphal = sabSampleAlphaFast( T, hr0 + ibeta-1, ibeta-1, rand_percentile );
+    const double alphah = sabSampleAlphaFast( T, hr0 + ibeta, ibeta, rand_percentile );
     const double alpha = alphal + (alphah-alphal) * (beta-bl)/(bh-bl);
     AlphaLimits alimits = getAlphaLimits( ekin_div_kT, beta );
     if ( inInterval( alimits.first, alimits.second, alpha ) ) {
@@ -568,28 +604,13 @@ namespace ncb {
     ekin_out = dmax( 0.0, ekin + deltaE );
   }
 
-  // The class tables of energy point `ie` addressed in place (no staging): used by the host build of these
-  // functions (tests/hostsim) -- the kernel builds the same struct with shared-memory pointers.
-  NCB_HD SabClassTabs sabClassTabsInPlace( const SabT& T, int ie )
-  {
-    const SabEPoint& ep = T.ep[ie];
-    SabClassTabs C;
-    C.bx = T.bx + ep.off_b; C.bpdf = T.bpdf + ep.off_b; C.bcdf = T.bcdf + ep.off_b;
-    C.guide = T.bguide + (size_t)ie*kSabGBStride;
-    C.heads = T.heads + (size_t)ie*T.nbeta;
-    C.ainfo = T.ainfo + (size_t)ie*T.nbeta;
-    C.beta = T.beta;
-    C.npts = ep.npts; C.ibeta_off = ep.ibeta_off; C.first_bin_endpoint = ep.first_bin_endpoint;
-    return C;
-  }
-
-  // Table path (E < Emax) of SABScatter::sampleScatterIsotropic through the staged functions: the sequence of
-  // attempts the class kernel runs for one neutron (k_sab_classes), as one loop.
-  NCB_HD void sabSampleScatterStaged( const SabT& T, double ekin, Rng& rng, double& ekin_out, double& mu, int& err )
+  // Table path (E < Emax) of SABScatter::sampleScatterIsotropic through the short-chain functions: the sequence of
+  // attempts k_sample_sab_refill runs for one neutron, as one loop (host build: tests/hostsim).
+  NCB_HD void sabSampleScatterFast( const SabT& T, double ekin, Rng& rng, double& ekin_out, double& mu, int& err )
   {
     bool ultra = false;
     const int ie = sabPickSampler( T, T.egrid, ekin, ultra );
-    const SabClassTabs C = sabClassTabsInPlace( T, ie );
+    const SabEPoint ep = T.ep[ie];
     const double ekin_div_kT = ekin / T.kT;
     const double sampling_ediv = ultra ? T.egrid[0] / T.kT : ekin_div_kT;
     int inner = 0, outer = 0;
@@ -597,8 +618,8 @@ namespace ncb {
     while ( true ) {
       double alpha = 0.0, beta = 0.0;
       bool inner_ok = true;
-      if ( C.npts != 0 )
-        inner_ok = sabAttemptStaged( T, C, sampling_ediv, rng, alpha, beta, err );
+      if ( ep.npts != 0 )
+        inner_ok = sabAttemptFast( T, ie, ep, sampling_ediv, rng, alpha, beta, err );
       if ( !inner_ok ) {
         if ( ++inner == 100 ) { err |= ERR_SAB_LOOP_INNER; return; }
         continue;

@@ -16,13 +16,15 @@ namespace ncb {
     const double* pb_fdm[kMaxPB];
     const double* sab_egrid[kMaxSab];
     const double* sab_xs[kMaxSab];
+    const uint16_t* pb_lut[kMaxPB];      // energy-key tables (KeyLut) of the two searches, or null
+    const uint16_t* sab_elut[kMaxSab];
     const ScBraggT* sc;   // the material's SCBragg tables, or `scv` (arrays staged in shared memory)
     ScBraggT scv;
   };
   NCB_HD void hotTabsFromMaterial( const Material& M, HotTabs& H )
   {
-    for ( int i = 0; i < kMaxPB; ++i ) { H.pb_e2d[i] = M.pb[i].e2d; H.pb_fdm[i] = M.pb[i].fdm; }
-    for ( int i = 0; i < kMaxSab; ++i ) { H.sab_egrid[i] = M.sab[i].egrid; H.sab_xs[i] = M.sab[i].xs; }
+    for ( int i = 0; i < kMaxPB; ++i ) { H.pb_e2d[i] = M.pb[i].e2d; H.pb_fdm[i] = M.pb[i].fdm; H.pb_lut[i] = M.pb[i].lut; }
+    for ( int i = 0; i < kMaxSab; ++i ) { H.sab_egrid[i] = M.sab[i].egrid; H.sab_xs[i] = M.sab[i].xs; H.sab_elut[i] = M.sab[i].elut; }
     H.sc = &M.sc;
   }
 
@@ -34,13 +36,13 @@ namespace ncb {
     switch ( c.kind ) {
     case KIND_POWDERBRAGG: {
       const PowderBraggT& T = M.pb[c.idx];
-      return pbXS( H.pb_e2d[c.idx], H.pb_fdm[c.idx], T.n, T.threshold, ekin, aux );
+      return pbXS( T, H.pb_e2d[c.idx], H.pb_fdm[c.idx], H.pb_lut[c.idx], ekin, aux );
     }
     case KIND_ELINC:
       return elincXS( M.elinc[c.idx], ekin, nullptr );
     case KIND_SAB: {
       const SabT& T = M.sab[c.idx];
-      return sabXS( T, H.sab_egrid[c.idx], H.sab_xs[c.idx], ekin, &aux );
+      return sabXS( T, H.sab_egrid[c.idx], H.sab_xs[c.idx], H.sab_elut[c.idx], ekin, &aux );
     }
     case KIND_FREEGAS:
       return fgXS( M.fg[c.idx], ekin );
@@ -86,7 +88,7 @@ namespace ncb {
         return;
       }
       if ( aux < 0 )
-        aux = pbLastValidPlane( H.pb_e2d[c.idx], T.n, ekin );
+        aux = pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
       mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], aux, ekin, rng );
       return;
     }

@@ -281,21 +281,40 @@ namespace ncb {
     return (uint16_t)upperBound( cumul_row, 0, nalpha, (double)b / scale );
   }
 
-  // ---- stage 4: gather-friendly copies for the class-staged sampling kernel (layout only, same values)
-  NCB_HD SabHead sabMakeHead( const SabAlphaInfo& info, const double* cumul_row, double ascale_row )
+  // ---- stage 4: gather-friendly copies for the table-sampling kernel (layout only, same values) + log guide
+  NCB_HD SabHead sabMakeHead( const SabAlphaInfo& info, const double* cumul_row, int nalpha )
   {
     SabHead h;
     h.prob_front = info.prob_front; h.prob_notback = info.prob_notback;
     h.f_idx = (uint32_t)info.f_idx; h.b_idx = (uint32_t)info.b_idx;
     h.clow = cumul_row[info.f_idx]; h.cupp = cumul_row[info.b_idx];
-    h.ascale = ascale_row;
+    const double tot = cumul_row[nalpha-1];
+    h.inv_total = ( tot > 0.0 && isFinite( 1.0/tot ) ) ? 1.0/tot : 0.0;
     return h;
+  }
+  NCB_HD void sabMakeTails( const SabAlphaInfo& info, SabTail* t2 )
+  {
+    t2[0].alpha = info.f_alpha; t2[0].sval = info.f_sval; t2[0].logsval = info.f_logsval; t2[0].pad = 0.0;
+    t2[1].alpha = info.b_alpha; t2[1].sval = info.b_sval; t2[1].logsval = info.b_logsval; t2[1].pad = 0.0;
   }
   NCB_HD SabPoint sabMakePoint( const double* agrid, const double* sab, const double* logsab, const double* cumul, int nalpha, size_t k )
   {
     SabPoint p;
     p.alpha = agrid[k % (size_t)nalpha]; p.sab = sab[k]; p.logsab = logsab[k]; p.cumul = cumul[k];
     return p;
+  }
+  // Log guide of one row: g[k] = number of grid points whose own key (computed exactly like the sampler computes the
+  // key of an area: cumul*inv_total) is below k.  Rounded multiplication by a positive constant is monotone, so for
+  // an area with key k every point counted by g[k] has cumul < area and every point from g[k+1] on has cumul > area:
+  // upper_bound(row, area) lies in [g[k], g[k+1]] -- exactly, no verification needed.
+  NCB_HD uint16_t sabLogGuideEntry( const double* cumul_row, int nalpha, double inv_total, int k )
+  {
+    int lo = 0, hi = nalpha;     // keys are non-decreasing along the row: binary search for the first key >= k
+    while ( lo < hi ) {
+      const int mid = lo + ( ( hi - lo ) >> 1 );
+      if ( sabLogKey( cumul_row[mid]*inv_total ) < k ) lo = mid + 1; else hi = mid;
+    }
+    return (uint16_t)lo;
   }
 
 }

@@ -22,6 +22,8 @@ namespace ncb {
     const double* fdm;   // m_fdm_commul[n]
     int n;
     double threshold;
+    const uint16_t* lut; // energy-key table over e2d (KeyLut, ncb_common.cuh), or null
+    int lut_key0, lut_shift, lut_nk;
   };
 
   // ref: NCElIncXS.hh (m_elm_data)
@@ -58,18 +60,46 @@ namespace ncb {
     double pad;                         // 80 bytes
   };
 
-  // Per (energy point, beta row): what SABSamplerAtE_Alg1::sampleAlpha needs to choose its case and to run the
-  // "whole bins" case, packed so that one overlay sampler's entries can be staged in shared memory (48 B, a
-  // multiple of 16 for the bulk copy).  clow/cupp/ascale are copies of cumul[row][f_idx], cumul[row][b_idx] and
-  // ascale[row]: they take two dependent gathers out of every alpha sample.
+  // ---- gather-friendly copies of the sampler tables (layout only; same values as the arrays above them).  A table
+  // attempt is a chain of dependent gathers from L2; these records put what one step of the chain needs into one
+  // 32-byte sector (or two adjacent ones), and carry copies of the values the next step's address depends on.
+  // Per (energy point, beta row): how SABSamplerAtE_Alg1::sampleAlpha chooses its case + what its "whole bins" case needs.
   struct SabHead {
     double prob_front, prob_notback;
-    double clow, cupp;
-    double ascale;
-    uint32_t f_idx, b_idx;
-  };
-  // Per (beta row, alpha grid point): everything sampleAlpha gathers at one grid point, in one 32-byte sector.
+    double clow, cupp;        // cumul[row][f_idx], cumul[row][b_idx]
+    double inv_total;         // 1 / cumul[row][nalpha-1] (0 for an all-zero row): scales an area to the row's log-guide key
+    uint32_t f_idx, b_idx;    // pt_front.alpha_idx, pt_back.alpha_idx
+  };                          // 48 B
+  // Per (energy point, beta row): pt_front and pt_back of AlphaSampleInfo (the two partial-bin "tails")
+  struct SabTail { double alpha, sval, logsval, pad; };   // [2] per row: front, back
+  // Per (beta row, alpha grid point): everything sampleAlpha gathers at one grid point
   struct SabPoint { double alpha, sab, logsab, cumul; };
+  // Per (energy point, point of its beta distribution)
+  struct SabBPoint { double x, pdf, cdf, pad; };
+
+  // Log-spaced guide over a row of cumulative alpha integrals: key = exponent and top 4 mantissa bits of
+  // area/total (16 buckets per octave, 32 octaves below 1).  The linear guide of r1 (256 buckets) left ~23-entry
+  // searches for heavy scatterers (Al: the kinematic window usually sits in the lowest percent of the row's
+  // integral); with this key the range is <= 2 entries for > 90 % of the lookups.
+  constexpr int kSabGLOct = 32;
+  constexpr int kSabGL = kSabGLOct*16 + 1;      // keys 0 .. kSabGL-1 (last: area/total >= 1)
+  constexpr int kSabGLStride = 520;             // uint16 entries per row (kSabGL+1 used)
+  inline
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
+  int sabLogKey( double x )
+  {
+    long long b;
+#if defined(__CUDA_ARCH__)
+    b = __double_as_longlong( x );
+#else
+    static_assert( sizeof(long long) == sizeof(double), "" );
+    __builtin_memcpy( &b, &x, sizeof(b) );
+#endif
+    const long long k = ( b >> 48 ) - (long long)( ( 1023 - kSabGLOct ) << 4 );   // (x >= 0: sign bit clear)
+    return k < 0 ? 0 : ( k > kSabGL-1 ? kSabGL-1 : (int)k );
+  }
 
   struct SabT {
     // SABScatter / SABXSProvider / SABSampler scalars
@@ -84,6 +114,8 @@ namespace ncb {
     int negrid, nalpha, nbeta;
     const double* egrid;   // [negrid]
     const double* xs;      // [negrid]
+    const uint16_t* elut;  // energy-key table over egrid (KeyLut), or null
+    int elut_key0, elut_shift, elut_nk;
     const double* alpha;   // [nalpha]
     const double* beta;    // [nbeta]
     const double* sab;     // [nbeta*nalpha]
@@ -100,10 +132,13 @@ namespace ncb {
     const uint16_t* aguide;    // [nbeta][kSabGA+1]   over each beta row of the cumulative alpha integrals
     const double* ascale;      // [nbeta]  kSabGA / cumul[row][nalpha-1]  (0 for an all-zero row)
     const SabHead* heads;      // [negrid*nbeta], indexed like ainfo
+    const SabTail* tails;      // [negrid*nbeta][2]
     const SabPoint* pts;       // [nbeta*nalpha]
-    int bstride;               // doubles between the beta-sampler rows of consecutive energy points (even: 16-byte rows)
+    const SabBPoint* bpts;     // [negrid*bstride], indexed like bx
+    const uint16_t* lguide;    // [nbeta][kSabGLStride]
+    int bstride;               // entries between the beta-sampler rows of consecutive energy points
   };
-  constexpr int kSabGBStride = 1032;   // uint16 entries between the beta guides of consecutive energy points (16-byte rows)
+  constexpr int kSabGBStride = 1032;   // uint16 entries between the beta guides of consecutive energy points
   inline int sabBStride( int nbeta ) { return ( nbeta + 2 ) & ~1; }
   constexpr int kSabGB = 1024;
   constexpr int kSabGA = 256;

@@ -75,13 +75,25 @@ namespace {
         for ( int b = 0; b <= kSabGA; ++b )
           aguide[(size_t)ib*( kSabGA+1 ) + b] = sabAlphaGuideEntry( row, na, ascale[ib], b );
       }
-      // stage 4: gather-friendly copies
+      // stage 4: gather-friendly copies + log guide
       SabHead* heads = reinterpret_cast<SabHead*>( base + pl.off_heads );
+      SabTail* tails = reinterpret_cast<SabTail*>( base + pl.off_tails );
       SabPoint* pts = reinterpret_cast<SabPoint*>( base + pl.off_pts );
-      for ( size_t k = 0; k < (size_t)ne*nb; ++k )
-        heads[k] = sabMakeHead( ainfo[k], cumul + ( k % (size_t)nb )*na, ascale[k % (size_t)nb] );
+      SabBPoint* bpts = reinterpret_cast<SabBPoint*>( base + pl.off_bpts );
+      uint16_t* lguide = reinterpret_cast<uint16_t*>( base + pl.off_lguide );
+      for ( size_t k = 0; k < (size_t)ne*nb; ++k ) {
+        heads[k] = sabMakeHead( ainfo[k], cumul + ( k % (size_t)nb )*na, na );
+        sabMakeTails( ainfo[k], tails + 2*k );
+      }
       for ( size_t k = 0; k < (size_t)nb*na; ++k )
         pts[k] = sabMakePoint( T.alpha, T.sab, logsab, cumul, na, k );
+      for ( size_t k = 0; k < (size_t)ne*T.bstride; ++k ) { bpts[k].x = bx[k]; bpts[k].pdf = bpdf[k]; bpts[k].cdf = bcdf[k]; bpts[k].pad = 0.0; }
+      for ( int ib = 0; ib < nb; ++ib ) {
+        const double* row = cumul + (size_t)ib*na;
+        const double inv = heads[ib].inv_total;      // (same for every energy point)
+        for ( int key = 0; key <= kSabGL; ++key )
+          lguide[(size_t)ib*kSabGLStride + key] = sabLogGuideEntry( row, na, inv, key );
+      }
     }
   }
 }
@@ -157,7 +169,7 @@ extern "C" {
     }
   }
 
-  // S(alpha,beta) leaf `c` through the class-staged variants of the table sampler (E below the table's Emax; above
+  // S(alpha,beta) leaf `c` through the short-chain variants of the table sampler (E below the table's Emax; above
   // it the plain path): must reproduce hostsim_sample_iso_leaf bit for bit
   void hostsim_sample_sab_staged( void* vh, int c, uint64_t seed, uint64_t first_index, const double* ekin, uint64_t n,
                                   double* ekin_out, double* mu_out, uint32_t* ndraws, int32_t* errs )
@@ -168,7 +180,7 @@ extern "C" {
       ncb::Rng rng; rng.init( seed, first_index + i );
       int err = 0;
       if ( ekin[i] < T.egrid[T.negrid-1] )
-        ncb::sabSampleScatterStaged( T, ekin[i], rng, ekin_out[i], mu_out[i], err );
+        ncb::sabSampleScatterFast( T, ekin[i], rng, ekin_out[i], mu_out[i], err );
       else
         ncb::sabSampleScatter( T, ekin[i], rng, ekin_out[i], mu_out[i], err );
       if ( ndraws ) ndraws[i] = rng.ndraws;
@@ -190,7 +202,7 @@ extern "C" {
     for ( uint64_t i = 0; i < n; ++i ) {
       ncb::Rng rng; rng.init( seed, i );
       int err = 0; double eo, mu;
-      if ( ekin[i] < T.egrid[T.negrid-1] ) ncb::sabSampleScatterStaged( T, ekin[i], rng, eo, mu, err );
+      if ( ekin[i] < T.egrid[T.negrid-1] ) ncb::sabSampleScatterFast( T, ekin[i], rng, eo, mu, err );
     }
     ncb::g_alpha_trace = nullptr; s_trace = nullptr;
     const uint64_t rows = std::min<uint64_t>( tr.size()/8, maxrows );
@@ -199,6 +211,41 @@ extern "C" {
   }
   void hostsim_sab_dims( void* vh, int c, int* dims ) { auto& M = static_cast<Handle*>(vh)->mat; const ncb::SabT& T = M.sab[M.comp[c].idx]; dims[0]=T.negrid; dims[1]=T.nalpha; dims[2]=T.nbeta; }
   void hostsim_sab_cumul( void* vh, int c, double* out ) { auto& M = static_cast<Handle*>(vh)->mat; const ncb::SabT& T = M.sab[M.comp[c].idx]; std::memcpy( out, T.cumul, (size_t)T.nalpha*T.nbeta*8 ); }
+
+  // energy-key lut (KeyLut) of component c's searched table: keyed vs plain upper_bound for arbitrary values;
+  // returns the number of lut buckets (0: the table has no lut)
+  int hostsim_keyed_upper_bound( void* vh, int c, const double* v, uint64_t n, int32_t* keyed, int32_t* plain )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    const ncb::Comp& cc = M.comp[c];
+    if ( cc.kind == ncb::KIND_POWDERBRAGG ) {
+      const ncb::PowderBraggT& T = M.pb[cc.idx];
+      for ( uint64_t i = 0; i < n; ++i ) {
+        keyed[i] = ncb::upperBoundKeyed( T.e2d, T.n, v[i], T.lut, T.lut_key0, T.lut_shift, T.lut_nk );
+        plain[i] = ncb::upperBound( T.e2d, 0, T.n, v[i] );
+      }
+      return T.lut ? T.lut_nk : 0;
+    }
+    if ( cc.kind == ncb::KIND_SAB ) {
+      const ncb::SabT& T = M.sab[cc.idx];
+      for ( uint64_t i = 0; i < n; ++i ) {
+        keyed[i] = ncb::upperBoundKeyed( T.egrid, T.negrid, v[i], T.elut, T.elut_key0, T.elut_shift, T.elut_nk );
+        plain[i] = ncb::upperBound( T.egrid, 0, T.negrid, v[i] );
+      }
+      return T.elut ? T.elut_nk : 0;
+    }
+    return -1;
+  }
+  int hostsim_table_values( void* vh, int c, double* out, int nmax )
+  {
+    auto& M = static_cast<Handle*>(vh)->mat;
+    const ncb::Comp& cc = M.comp[c];
+    const double* a = nullptr; int n = 0;
+    if ( cc.kind == ncb::KIND_POWDERBRAGG ) { a = M.pb[cc.idx].e2d; n = M.pb[cc.idx].n; }
+    else if ( cc.kind == ncb::KIND_SAB ) { a = M.sab[cc.idx].egrid; n = M.sab[cc.idx].negrid; }
+    for ( int i = 0; i < n && i < nmax; ++i ) out[i] = a[i];
+    return n;
+  }
 
   void hostsim_xs( void* vh, const double* ekin, const double* ux, const double* uy, const double* uz, uint64_t n, double* out )
   {

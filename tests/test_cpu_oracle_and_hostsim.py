@@ -191,10 +191,10 @@ def test_edge_energies_vs_reference(configs):
 
 
 @pytest.mark.parametrize("key", ["Al", "CH2", "H2O", "YAG"])
-def test_class_staged_sampler_equals_plain_sampler(key, configs):
-    """The class-staged variants of the S(alpha,beta) table sampler (SabHead / SabPoint gather records, the layout
-    k_sab_classes stages per overlay sampler) consume the same uniforms and give bit-identical outcomes as the plain
-    restatement, which the goldens pin against the reference -- for every S(alpha,beta) leaf of the material."""
+def test_short_chain_sampler_equals_plain_sampler(key, configs):
+    """The short-chain variants of the S(alpha,beta) table sampler (SabBPoint / SabHead / SabTail / SabPoint gather
+    records, log guide: what k_sample_sab_refill runs) consume the same uniforms and give bit-identical outcomes as
+    the plain restatement, which the goldens pin against the reference -- for every S(alpha,beta) leaf."""
     h = HostSim(_blob(configs[key]))
     ekin = np.concatenate([loguniform_energies(30000, seed=5), [1e-9, 1e-7, 4.99999, 5.0, 7.5]])
     nleaf = 0
@@ -207,3 +207,34 @@ def test_class_staged_sampler_equals_plain_sampler(key, configs):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
     assert nleaf >= 1
+
+
+@pytest.mark.parametrize("key", ["Al", "YAG", "H2O", "Ge"])
+def test_energy_key_lut_gives_the_exact_upper_bound(key, configs):
+    """The energy-key luts that replace the whole-table bisections of the cross-section path (PowderBragg 2dE table,
+    S(alpha,beta) energy grid) must give std::upper_bound exactly -- at, just below and just above every table value,
+    for random energies, and for the inputs outside the table (negative, zero, subnormal, inf, NaN)."""
+    import ctypes as C
+    h = HostSim(_blob(configs[key]))
+    L = HostSim.lib()
+    L.hostsim_keyed_upper_bound.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_uint64,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.hostsim_table_values.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    nlut = 0
+    for c in range(h.ncomp):
+        if h.component_kind(c) not in (1, 3):
+            continue
+        tab = np.empty(70000)
+        n = L.hostsim_table_values(h.h, c, tab.ctypes.data_as(dp), tab.size)
+        tab = tab[:n]
+        v = np.concatenate([tab, np.nextafter(tab, 0.0), np.nextafter(tab, np.inf), loguniform_energies(20000, seed=9, lo=1e-7, hi=1e3),
+                            [0.0, -0.0, -1.0, 5e-324, 1e-300, 1e300, np.inf, -np.inf, np.nan, tab[0] * 0.5, tab[-1] * 2]])
+        a, b = np.empty(v.size, dtype=np.int32), np.empty(v.size, dtype=np.int32)
+        nk = L.hostsim_keyed_upper_bound(h.h, c, v.ctypes.data_as(dp), v.size, a.ctypes.data_as(ip), b.ctypes.data_as(ip))
+        assert nk >= 0
+        nlut += nk > 0
+        assert np.array_equal(a, b)
+        fin = np.isfinite(v)
+        assert np.array_equal(b[fin], np.searchsorted(tab, v[fin], side="right"))
+    assert nlut >= 1
