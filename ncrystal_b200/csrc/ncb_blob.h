@@ -34,7 +34,9 @@ enum ncb_kind {
   NCB_KIND_ELINC       = 2, /* ref: src/elincscatter/NCElIncScatter.cc + src/phys_utils/NCElIncXS.cc */
   NCB_KIND_SAB         = 3, /* ref: src/sabscatter/NCSABScatter.cc + src/sab */
   NCB_KIND_FREEGAS     = 4, /* ref: src/freegas/NCFreeGas.cc + src/phys_utils/NCFreeGasUtils.cc */
-  NCB_KIND_SCBRAGG     = 5  /* ref: src/scbragg/NCSCBragg.cc + src/phys_utils/NCGaussMos.cc */
+  NCB_KIND_SCBRAGG     = 5, /* ref: src/scbragg/NCSCBragg.cc + src/phys_utils/NCGaussMos.cc */
+  NCB_KIND_LCBRAGG     = 7  /* ref: src/lcbragg/NCLCBragg.cc + src/extd_utils/NCLCUtils.cc (6 is taken by the
+                               loader-internal absorption kind) */
 };
 
 typedef struct {
@@ -135,6 +137,28 @@ typedef struct {
   uint64_t nfam, nnormals;
   uint64_t lut_sofcosd_n, lut_evalcosx_n;   /* number of (value,d2) pairs; CubicSpline::m_nm2 = n-2 */
 } ncb_scbragg_t;
+
+/* LCBragg (layered crystal, e.g. pyrolytic graphite; mode 0 = LCHelper, NCLCBragg.cc:52-69).  Followed by
+ *   planesets[7*nplanesets]   LCPlaneSet members in declaration order (NCLCUtils.hh:35-50): twodsp, inv_twodsp,
+ *                             cosalpha, sinalpha, cosalphaminus, cosalphaplus, fsq; sorted by d-spacing, largest first
+ *   lut_sofcosd[2*n], lut_evalcosx[2*n]   spline tables of the GaussOnSphere inside LCStdFrame::m_gm (as for SCBragg) */
+typedef struct {
+  double   ekin_low;           /* LCBragg::pimpl::m_ekin_low */
+  double   lcaxis_lab[3];      /* LCHelper::m_lcaxislab */
+  double   xsfact;             /* LCHelper::m_xsfact = 1/(V0*natoms) */
+  double   gos_cta, gos_sta;
+  double   gos_circleint_k1, gos_circleint_k2;
+  double   gos_numint_accuracy;
+  double   gos_prec;           /* GaussMos::precision() (accuracy of the phi integration, NCLCUtils.cc:469) */
+  double   gos_truncangle;
+  double   sofcosd_a, sofcosd_invdelta;
+  double   evalcosx_a, evalcosx_invdelta;
+  double   mos_fwhm;
+  double   reserved[3];
+  uint64_t nplanesets;
+  uint64_t lut_sofcosd_n, lut_evalcosx_n;
+  uint64_t reserved2;
+} ncb_lcbragg_t;
 
 static inline uint64_t ncb_align16(uint64_t x) { return (x + 15u) & ~(uint64_t)15u; }
 

@@ -420,6 +420,7 @@ namespace ncb {
       double xs = 0.0;
       if ( domainContains( c.dom_lo, c.dom_hi, ekin ) ) {
         if ( c.kind == KIND_SCBRAGG ) { xs = sc_xs; a = sc_n; }
+        else if ( c.kind == KIND_LCBRAGG ) { xs = sc_n ? M.lc.xsfact * sc_xs : 0.0; a = sc_n; }   // (sc_xs: sum over the ROIs, k_lc_scan)
         else xs = compXSIso( M, H, i, ekin, a );
       }
       tot += c.scale * xs;
@@ -478,6 +479,17 @@ namespace ncb {
             // no-scatter cases of SCBragg::sampleScatter (NCSCBragg.cc:306-318) finish here
             if ( !( ekin <= M.sc.threshold_ekin ) && aux[ich] > 0 && X.sc_xs[i] > 0.0 )
               cls = 3;
+          } else if ( c.kind == KIND_LCBRAGG ) {
+            // no-scatter cases of LCBragg::sampleScatter / LCHelper::genScatter (NCLCBragg.cc:129-136,
+            // NCLCUtils.cc:539-544) finish here: below the Bragg threshold the direction is returned as given,
+            // without ROIs it is returned normalised
+            LcNeutron N;
+            const Vec3 u = vunit( dir );
+            if ( !( ekin < M.lc.ekin_low ) && lcNeutronPars( M.lc, ekin, u, N ) ) {
+              o = u;
+              if ( aux[ich] > 0 && X.sc_xs[i] != 0.0 )
+                cls = 3;
+            }
           } else if ( c.kind == KIND_SAB ) {
             const SabT& T = M.sab[c.idx];
             cls = ( ekin < H.sab_egrid[c.idx][T.negrid-1] ) ? 1 : 2;

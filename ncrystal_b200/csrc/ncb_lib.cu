@@ -10,6 +10,7 @@
 // raises an error when no usable device is present.
 #include "ncb_kernels.cuh"
 #include "ncb_kernels_sc.cuh"
+#include "ncb_kernels_lc.cuh"
 #include "ncb_kernels_mmc.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
@@ -358,6 +359,8 @@ namespace {
     setSmemAttr( k_sc_sample );
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_find );
+    setSmemAttr( k_lc_scan );
+    setSmemAttr( k_lc_sample );
     setSmemAttr( k_tally_hist );
     done.push_back( device );
   }
@@ -842,6 +845,14 @@ namespace {
     return -1;
   }
 
+  int lcCompIndex( const Material& M )
+  {
+    for ( int i = 0; i < M.ncomp; ++i ) if ( M.comp[i].kind == KIND_LCBRAGG ) return i;
+    return -1;
+  }
+  // layered-crystal plane sets whose per-warp ROI lists fit shared memory (else: thread-per-neutron kernels)
+  bool lcWarpOk( const Material& M ) { return lcSmemBytes( M.lc.nplanes ) <= 160u*1024u; }
+
   // Batches below this size (the long tail of a transport run) are launch-latency bound: the all-in-one
   // thread-per-neutron kernels (1 launch instead of 2-8) are used for them.  NCB200_SMALL_V1 overrides (0 = never).
   uint64_t smallBatchV1()
@@ -895,13 +906,34 @@ namespace {
     CUDA_OK( cudaGetLastError() );
   }
 
+  // LCBragg scan (one warp per neutron) -> sc_xs (sum over the ROIs) / sc_n (number of ROIs)
+  void launchLcScan( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
+                     const double* uy, const double* uz, uint64_t n, cudaStream_t st, const uint32_t* n_dev = nullptr )
+  {
+    const int ilc = lcCompIndex( dm.mat );
+    s->ensureErrWord();
+    LcScanArgs LA;
+    LA.ekin = d_ekin; LA.ux = ux; LA.uy = uy; LA.uz = uz; LA.n = n; LA.lc_sum = qc.sc_xs; LA.lc_n = qc.sc_n;
+    LA.dom_lo = dm.mat.comp[ilc].dom_lo; LA.dom_hi = dm.mat.comp[ilc].dom_hi;
+    LA.err_flags = s->d_err; LA.n_dev = n_dev;
+    qc.sc_lists_valid = false;
+    const unsigned nsm = (unsigned)numSMs( dm.device );
+    const uint64_t need = ( n + kLcWarps - 1 ) / kLcWarps;
+    const unsigned grid = (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*16 );
+    { TimedLaunch tl( "k_lc_scan", st );
+      k_lc_scan<<< grid, 32*kLcWarps, lcSmemBytes( dm.mat.lc.nplanes ), st >>>( dm.mat, LA ); }
+    ++g_launches;
+    CUDA_OK( cudaGetLastError() );
+  }
+
   void launchXSAniso( Scatter* s, const double* d_ekin, const double* ux, const double* uy, const double* uz,
                       uint64_t n, double* d_out, cudaStream_t st, int ictx = kSlots )
   {
     if ( !n ) return;
     const DeviceMaterial& dm = *s->dm;
     const bool has_sc = scCompIndex( dm.mat ) >= 0;
-    if ( useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || n < smallBatchV1() ) {
+    const bool has_lc = lcCompIndex( dm.mat ) >= 0;
+    if ( useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || ( has_lc && !lcWarpOk( dm.mat ) ) || n < smallBatchV1() ) {
       DirArgs D; D.ux = ux; D.uy = uy; D.uz = uz; D.ox = D.oy = D.oz = nullptr;
       const int ctas = dm.sp.total > 56u*1024u ? 2 : 8;
       k_xs_aniso<<< gridFor( n, 128, dm.device, ctas ), 128, dm.sp.total, st >>>( dm.mat, dm.sp, d_ekin, D, n, d_out );
@@ -910,9 +942,12 @@ namespace {
       return;
     }
     const double* sc_xs = nullptr; const int32_t* sc_n = nullptr;
-    if ( has_sc ) {
+    if ( has_sc || has_lc ) {
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, n );
-      launchScScan( dm, qc, d_ekin, ux, uy, uz, n, st, s->n_dev_override );
+      if ( has_sc )
+        launchScScan( dm, qc, d_ekin, ux, uy, uz, n, st, s->n_dev_override );
+      else
+        launchLcScan( s, dm, qc, d_ekin, ux, uy, uz, n, st, s->n_dev_override );
       sc_xs = qc.sc_xs; sc_n = qc.sc_n;
     }
     const int ctas = dm.sp_iso.total > 56u*1024u ? 2 : 8;
@@ -933,7 +968,8 @@ namespace {
     int32_t* diag_comp = s->d_diag_comp;
     s->d_diag_ndraws = nullptr; s->d_diag_comp = nullptr;
     const bool has_sc = scCompIndex( dm.mat ) >= 0;
-    const bool v1 = useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || n < smallBatchV1();
+    const bool has_lc = lcCompIndex( dm.mat ) >= 0;
+    const bool v1 = useAnisoV1() || ( has_sc && !dm.sc_warp_ok ) || ( has_lc && !lcWarpOk( dm.mat ) ) || n < smallBatchV1();
     const uint64_t maxn = v1 ? n : ( (uint64_t)1 << kQueueIdxBits );
     for ( uint64_t done = 0; done < n; done += maxn ) {
       const uint64_t m = std::min<uint64_t>( maxn, n - done );
@@ -955,10 +991,12 @@ namespace {
       Scatter::QueueCtx& qc = s->ensureAnisoBuffers( ictx, m );
       if ( has_sc )
         launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
+      if ( has_lc )
+        launchLcScan( s, dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
       AnisoArgs X;
-      X.D = D; X.sc_xs = has_sc ? qc.sc_xs : nullptr; X.sc_n = has_sc ? qc.sc_n : nullptr;
+      X.D = D; X.sc_xs = ( has_sc || has_lc ) ? qc.sc_xs : nullptr; X.sc_n = ( has_sc || has_lc ) ? qc.sc_n : nullptr;
       X.mu_tmp = qc.mu_tmp; X.nd_tmp = qc.nd_tmp; X.q_sc = qc.q_sc; X.q_sc_count = qc.counts + 5;
       if ( has_sc && qc.sc_lists_valid ) { X.sc_wpos = qc.sc_wpos; X.sc_ncand = qc.sc_ncand; X.sc_cand = qc.sc_cand; }
       CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
@@ -982,6 +1020,12 @@ namespace {
         const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kScWarps - 1 )/kScWarps, (uint64_t)nsm*3 );
         { TimedLaunch tl( "k_sc_sample", st );
           k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off ); }
+        ++g_launches;
+      }
+      if ( has_lc ) {
+        const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kLcWarps - 1 )/kLcWarps, (uint64_t)nsm*16 );
+        { TimedLaunch tl( "k_lc_sample", st );
+          k_lc_sample<<< gs, 32*kLcWarps, lcSmemBytes( dm.mat.lc.nplanes ), st >>>( dm.mat, A, X ); }
         ++g_launches;
       }
       CUDA_OK( cudaGetLastError() );
@@ -1011,6 +1055,8 @@ namespace {
       throw Err( "CalcError", "Infinite looping in sampleAlphaBeta" );
     if ( flags & ERR_KIN_DENOM )
       throw Err( "CalcError", "convertAlphaBetaToDeltaEMu invalid for beta=-E/kT" );
+    if ( flags & ERR_LC_ROMBERG )
+      throw Err( "CalcError", "Romberg integration did not converge." );
   }
 
   // ---- pageable caller buffers.  Real callers of the *_many entry points (OpenMC, McStas, the reference's Python
@@ -1551,6 +1597,7 @@ extern "C" {
       case KIND_SAB: return "SABScatter";
       case KIND_FREEGAS: return "FreeGas";
       case KIND_SCBRAGG: return "SCBragg";
+      case KIND_LCBRAGG: return "LCBragg";
       case KIND_ABSOOV: return "AbsOOV";
       default: return "Process";
       }

@@ -77,6 +77,9 @@ namespace ncb {
       relocPtr( s.bguide, base ); relocPtr( s.aguide, base ); relocPtr( s.ascale, base );
       relocPtr( s.heads, base ); relocPtr( s.pts, base ); relocPtr( s.tails, base ); relocPtr( s.bpts, base ); relocPtr( s.lguide, base );
     }
+    if ( m.lc.nplanes ) {
+      relocPtr( m.lc.planes, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
+    }
     if ( m.sc.nfam ) {
       relocPtr( m.sc.fam_xsfact, base ); relocPtr( m.sc.fam_inv2d, base ); relocPtr( m.sc.fam_first, base );
       relocPtr( m.sc.normals, base ); relocPtr( m.sc.normals_f, base ); relocPtr( m.sc.sofcosd.data, base ); relocPtr( m.sc.evalcosx.data, base );
@@ -113,6 +116,7 @@ namespace ncb {
   }
 
   void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
+  void loadLcBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
 
   // Payload validation: the array counts inside a component payload come from the (untrusted) buffer; before any
   // copy the payload must hold its header plus `ndoubles` fp64 values.  Counts are bounded first so that the sums
@@ -282,6 +286,10 @@ namespace ncb {
       }
       case NCB_KIND_SCBRAGG:
         loadScBragg( lm, blob, c );
+        k.idx = 0;
+        break;
+      case NCB_KIND_LCBRAGG:
+        loadLcBragg( lm, blob, c );
         k.idx = 0;
         break;
       default:

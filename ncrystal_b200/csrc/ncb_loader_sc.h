@@ -51,4 +51,46 @@ namespace ncb {
     S.evalcosx.nm2 = (int)h.lut_evalcosx_n - 2;
     S.evalcosx.a = h.evalcosx_a; S.evalcosx.invdelta = h.evalcosx_invdelta;
   }
+
+  // LCBragg: plane sets + the mosaicity tables of its GaussMos (stored in Material::sc, which then has no families)
+  inline void loadLcBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c )
+  {
+    checkPayload( c, sizeof(ncb_lcbragg_t), {}, 0, "LCBragg" );
+    ncb_lcbragg_t h; std::memcpy( &h, blob + c.off, sizeof(h) );
+    checkPayload( c, sizeof(h), { h.nplanesets, h.lut_sofcosd_n, h.lut_evalcosx_n },
+                  kLcPlaneStride*h.nplanesets + 2*h.lut_sofcosd_n + 2*h.lut_evalcosx_n, "LCBragg" );
+    const double* arr = reinterpret_cast<const double*>( blob + c.off + sizeof(h) );
+    ScBraggT& S = lm.mat.sc;
+    LcBraggT& L = lm.mat.lc;
+    if ( S.nfam != 0 || L.nplanes != 0 )
+      throw std::runtime_error( "compiled material: more than one SCBragg/LCBragg component" );
+    if ( h.nplanesets == 0 || h.nplanesets > 32767 || h.lut_sofcosd_n < 4 || h.lut_evalcosx_n < 4 )
+      throw std::runtime_error( "compiled material: degenerate LCBragg tables" );
+    const size_t np = h.nplanesets;
+    for ( size_t i = 0; i < np; ++i ) {
+      const double* p = arr + kLcPlaneStride*i;
+      if ( !( p[0] > 0.0 ) || !( p[1] > 0.0 ) || ( i && p[0] > arr[kLcPlaneStride*(i-1)] ) )
+        throw std::runtime_error( "compiled material: LCBragg plane sets not sorted by d-spacing" );
+    }
+    L.ekin_low = h.ekin_low;
+    L.xsfact = h.xsfact;
+    L.acc = std::min( std::max( h.gos_prec, 1e-7 ), 1e-2 );
+    L.ax = h.lcaxis_lab[0]; L.ay = h.lcaxis_lab[1]; L.az = h.lcaxis_lab[2];
+    L.nplanes = (int)np;
+    L.planes = offAsPtr<double>( lm.put( arr, kLcPlaneStride*np*8 ) );
+    S.threshold_ekin = h.ekin_low;
+    S.cta = h.gos_cta;
+    S.sta = h.gos_sta;
+    S.circleint_k1 = h.gos_circleint_k1; S.circleint_k2 = h.gos_circleint_k2;
+    S.numint_accuracy = h.gos_numint_accuracy;
+    S.nfam = 0; S.nnormals = 0;
+    const double* l1 = arr + kLcPlaneStride*np;
+    const double* l2 = l1 + 2*h.lut_sofcosd_n;
+    S.sofcosd.data = offAsPtr<double>( lm.put( l1, 2*h.lut_sofcosd_n*8 ) );
+    S.sofcosd.nm2 = (int)h.lut_sofcosd_n - 2;
+    S.sofcosd.a = h.sofcosd_a; S.sofcosd.invdelta = h.sofcosd_invdelta;
+    S.evalcosx.data = offAsPtr<double>( lm.put( l2, 2*h.lut_evalcosx_n*8 ) );
+    S.evalcosx.nm2 = (int)h.lut_evalcosx_n - 2;
+    S.evalcosx.a = h.evalcosx_a; S.evalcosx.invdelta = h.evalcosx_invdelta;
+  }
 }

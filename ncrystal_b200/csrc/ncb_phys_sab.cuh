@@ -17,7 +17,8 @@ namespace ncb {
     ERR_SAB_LOOP_INNER = 4,  // SABSamplerAtE_Alg1: 100 tries (NCSABSamplerModels.cc:150)
     ERR_SAB_DISCARD = 8,     // sampleHighE: P_discardinside > 0.95 (NCSABSampler.cc:112)
     ERR_SAB_ISOFALLBACK = 16,// (warning only) isotropic fallback after 30 tries (NCSABSamplerModels.cc:99)
-    ERR_SAB_ROUTING = 32     // internal: E > Emax neutron reached the table-only kernel
+    ERR_SAB_ROUTING = 32,    // internal: E > Emax neutron reached the table-only kernel
+    ERR_LC_ROMBERG = 64      // LCBragg: phi integration did not converge (Romberg::convergenceError, NCRomberg.cc:48-61)
   };
 
   // sampleLogLinDist_fast, ref: NCSABUtils.hh:282-303

@@ -194,12 +194,15 @@ namespace ncb {
     return true;
   }
 
-  // Romberg::integrate specialised to GOSCircleInt, ref: NCRomberg.cc:62-146
-  NCB_HD_NOINLINE double gosRomberg( const ScBraggT& S, double sasg, double cacg, double acc, double a, double b )
+  // Romberg::integrate, ref: NCRomberg.cc:62-146, over an integrand object F with the three hooks of the reference's
+  // class: evalMany(fvals,n,offset,delta), evalManySum(n,offset,delta), accept(level,prev_estimate,estimate).
+  // `converged` is cleared when the last level is reached without acceptance (the reference's convergenceError).
+  template <class F>
+  NCB_HD double rombergIntegrate( F& f, double a, double b, bool& converged )
   {
     double h = ( b - a );
     double fvals[17];
-    gosEvalMany( S, sasg, cacg, fvals, 17, a, h*0.0625 );
+    f.evalMany( fvals, 17, a, h*0.0625 );
     h *= 0.5;
     const double R00 = (fvals[0] + fvals[16])*h;
     const double R10 = h*fvals[8] + 0.5*R00;
@@ -219,9 +222,9 @@ namespace ncb {
     const double R42 = (16./15.) * R41 + (-1./15.) * R31;
     const double R43 = (64./63.) * R42 + (-1./63.) * R32;
     const double R44 = (256./255.) * R43 + (-1./255.) * R33;
-    if ( gosAccept( acc, 4, R33, R44 ) )
+    if ( f.accept( 4, R33, R44 ) )
       return R44;
-    const double c5 = gosEvalManySum( S, sasg, cacg, 16, a+h*0.5, h );
+    const double c5 = f.evalManySum( 16, a+h*0.5, h );
     h *= 0.5;
     const double R50 = h*c5 + 0.5*R40;
     const double R51 = (4./3.) * R50 + (-1./3.)* R40;
@@ -229,7 +232,7 @@ namespace ncb {
     const double R53 = (64./63.) * R52 + (-1./63.) * R42;
     const double R54 = (256./255.) * R53 + (-1./255.) * R43;
     const double R55 = (1024./1023.) * R54 + (-1./1023.) * R44;
-    if ( gosAccept( acc, 5, R44, R55 ) )
+    if ( f.accept( 5, R44, R55 ) )
       return R55;
     constexpr unsigned maxlevel = 16;
     double cache1[maxlevel], cache2[maxlevel];
@@ -241,18 +244,34 @@ namespace ncb {
       const double hh = h;
       h *= 0.5;
       nj *= 2;
-      const double c = gosEvalManySum( S, sasg, cacg, nj, a+h, hh );
+      const double c = f.evalManySum( nj, a+h, hh );
       row[0] = h*c + 0.5*row_prev[0];
       double n_k = 1.;
       for ( unsigned j = 0; j < i; ++j ) {
         n_k *= 4.0;
         row[j+1] = ( n_k * row[j] - row_prev[j] ) / ( n_k - 1.0 );
       }
-      if ( gosAccept( acc, i, row_prev[i-1], row[i] ) )
+      if ( f.accept( i, row_prev[i-1], row[i] ) )
         return row[i];
       double* t = row_prev; row_prev = row; row = t;
     }
-    return row_prev[maxlevel-1]; // unreachable: gosAccept is always true for level >= 11
+    converged = false;
+    return row_prev[maxlevel-1];
+  }
+
+  // GOSCircleInt as integrand, ref: NCGaussOnSphere.cc:64-143
+  struct GosCircleIntegrand {
+    const ScBraggT& S;
+    double sasg, cacg, acc;
+    NCB_HD void evalMany( double* fvals, unsigned n, double offset, double delta ) const { gosEvalMany( S, sasg, cacg, fvals, n, offset, delta ); }
+    NCB_HD double evalManySum( unsigned n, double offset, double delta ) const { return gosEvalManySum( S, sasg, cacg, n, offset, delta ); }
+    NCB_HD bool accept( unsigned level, double prev_estimate, double estimate ) const { return gosAccept( acc, level, prev_estimate, estimate ); }
+  };
+  NCB_HD_NOINLINE double gosRomberg( const ScBraggT& S, double sasg, double cacg, double acc, double a, double b )
+  {
+    GosCircleIntegrand f{ S, sasg, cacg, acc };
+    bool converged = true;   // (gosAccept is always true for level >= 11)
+    return rombergIntegrate( f, a, b, converged );
   }
 
   // GaussOnSphere::circleIntegralSlow, ref: NCGaussOnSphere.cc:380-433

@@ -5,6 +5,7 @@
 #pragma once
 #include "ncb_phys_sab.cuh"
 #include "ncb_phys_scbragg.cuh"
+#include "ncb_phys_lcbragg.cuh"
 
 namespace ncb {
 
@@ -132,7 +133,8 @@ namespace ncb {
   // ProcComposition::crossSection (ref: NCProcImpl.cc:340-351) with updateCacheAnisotropic
   // (:206-249): isotropic leaves answer crossSection(E,dir) with their isotropic value
   // (NCProcImpl.hh:463).  aux[i]: PowderBragg plane index, or for SCBragg the number of
-  // contributing normals (entries of xs_commul); sc_total: SCBragg's unscaled xs.
+  // contributing normals (entries of xs_commul) / for LCBragg the number of ROIs; sc_total: SCBragg's unscaled xs /
+  // LCBragg's sum over the ROIs before the 1/(V0*natoms) factor.
   NCB_HD double matXS( const Material& M, const HotTabs& H, double ekin, const Vec3& dir,
                        double* cumul, int* aux, double* sc_total )
   {
@@ -147,6 +149,10 @@ namespace ncb {
         if ( c.kind == KIND_SCBRAGG ) {
           xs = scXS( *H.sc, ekin, dir, a );
           if ( sc_total ) *sc_total = xs;
+        } else if ( c.kind == KIND_LCBRAGG ) {
+          double raw; int lcerr = 0;
+          xs = lcXS( *H.sc, M.lc, ekin, dir, raw, a, lcerr );
+          if ( sc_total ) *sc_total = raw;
         } else {
           xs = compXSIso( M, H, i, ekin, a );
         }
@@ -176,6 +182,8 @@ namespace ncb {
     if ( M.comp[ichoice].kind == KIND_SCBRAGG ) {
       // (when the component's domain excludes E its xs pass was skipped: aux = -1 -> no entries)
       scSampleScatter( *H.sc, ekin, dir, aux[ichoice] > 0 ? aux[ichoice] : 0, sc_total, rng, outdir );
+    } else if ( M.comp[ichoice].kind == KIND_LCBRAGG ) {
+      lcSampleScatter( *H.sc, M.lc, ekin, dir, sc_total, aux[ichoice] > 0 ? aux[ichoice] : 0, rng, outdir, err );
     } else {
       // ScatterIsotropicMat::sampleScatter, ref: NCProcImpl.cc:29-37
       double mu;

@@ -10,7 +10,8 @@
 namespace ncb {
 
   enum Kind : int { KIND_NONE = 0, KIND_POWDERBRAGG = 1, KIND_ELINC = 2, KIND_SAB = 3, KIND_FREEGAS = 4, KIND_SCBRAGG = 5,
-                    KIND_ABSOOV = 6 /* 1/v absorption, ref: src/absoov/NCAbsOOV.cc:33-45; not a blob kind */ };
+                    KIND_ABSOOV = 6 /* 1/v absorption, ref: src/absoov/NCAbsOOV.cc:33-45; not a blob kind */,
+                    KIND_LCBRAGG = 7 /* layered crystal, ref: src/lcbragg/NCLCBragg.cc, src/extd_utils/NCLCUtils.cc */ };
 
   constexpr int kMaxComp = 8;
   constexpr int kMaxPB = 4, kMaxSab = 8;   // PowderBragg / S(alpha,beta) leaves per material (multiphase mixes)
@@ -164,6 +165,18 @@ namespace ncb {
     SplineLutT sofcosd, evalcosx;
   };
 
+  // ref: NCLCUtils.hh:35-50 (LCPlaneSet), :184-246 (LCHelper); the GaussMos of its LCStdFrame lives in Material::sc
+  // (nfam = 0: cta/sta, integration accuracy and the two spline tables only)
+  constexpr int kLcPlaneStride = 7;   // twodsp, inv_twodsp, cosalpha, sinalpha, cosalphaminus, cosalphaplus, fsq
+  struct LcBraggT {
+    double ekin_low;       // LCBragg::pimpl::m_ekin_low
+    double xsfact;         // LCHelper::m_xsfact
+    double acc;            // LCStdFrameIntegrator::m_acc = ncclamp(precision,1e-7,1e-2)
+    double ax, ay, az;     // LCHelper::m_lcaxislab
+    int nplanes;
+    const double* planes;  // [kLcPlaneStride*nplanes], d-spacing descending
+  };
+
   struct Comp {
     int kind;
     int idx;       // index into the per-kind arrays of Material
@@ -182,6 +195,7 @@ namespace ncb {
     FreeGasT fg[kMaxComp];   // (gas mixtures: one free-gas leaf per element)
     SabT sab[kMaxSab];
     ScBraggT sc;   // at most one SCBragg component (oriented materials only)
+    LcBraggT lc;   // at most one LCBragg component (then sc holds its mosaicity tables and has no families)
   };
 
 }

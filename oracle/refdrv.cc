@@ -130,6 +130,49 @@ namespace {
     return true;
   }
 
+  bool refdrv_compile_lcbragg( const NCPI::Process* p, ncb_comp_t& comp, Buf& buf, std::string& err )
+  {
+    auto lc = dynamic_cast<const NC::LCBragg*>( p );
+    if ( !lc )
+      return false;
+    auto pm = reinterpret_cast<const LCBraggMirrorPimpl*>( lc->m_pimpl.get() );
+    if ( pm->m_ekin_low != p->domain().elow.dbl() ) { err = "LCBragg pimpl mirror mismatch"; return true; }
+    if ( !pm->m_lchelper || pm->m_scmodel != nullptr ) { err = "LCBragg with lcmode!=0 (reference models built on SCBragg) is not supported"; return true; }
+    const NC::LCHelper& H = *pm->m_lchelper;
+    const NC::GaussMos& gm = H.m_lcstdframe.m_gm;
+    const NC::GaussOnSphere& gos = gm.m_gos;
+    comp.kind = NCB_KIND_LCBRAGG;
+    ncb_lcbragg_t h; std::memset(&h,0,sizeof(h));
+    h.ekin_low = pm->m_ekin_low;
+    h.lcaxis_lab[0] = H.m_lcaxislab.x(); h.lcaxis_lab[1] = H.m_lcaxislab.y(); h.lcaxis_lab[2] = H.m_lcaxislab.z();
+    h.xsfact = H.m_xsfact;
+    h.gos_cta = gos.m_cta; h.gos_sta = gos.m_sta;
+    h.gos_circleint_k1 = gos.m_circleint_k1; h.gos_circleint_k2 = gos.m_circleint_k2;
+    h.gos_numint_accuracy = gos.m_numint_accuracy;
+    h.gos_prec = gm.precision();
+    h.gos_truncangle = gos.m_truncangle;
+    h.sofcosd_a = gos.m_lt_sofcosd.m_a; h.sofcosd_invdelta = gos.m_lt_sofcosd.m_invdelta;
+    h.evalcosx_a = gos.m_lt_evalcosx.m_a; h.evalcosx_invdelta = gos.m_lt_evalcosx.m_invdelta;
+    h.mos_fwhm = gm.m_mos_fwhm.dbl();
+    h.nplanesets = H.m_planes.size();
+    std::vector<double> ps;
+    for ( auto& e : H.m_planes ) {
+      ps.push_back( e.twodsp ); ps.push_back( e.inv_twodsp ); ps.push_back( e.cosalpha ); ps.push_back( e.sinalpha );
+      ps.push_back( e.cosalphaminus ); ps.push_back( e.cosalphaplus ); ps.push_back( e.fsq );
+    }
+    auto lutdata = []( const NC::SplinedLookupTable& L ) {
+      std::vector<double> d;
+      for ( auto& e : L.m_spline.m_data ) { d.push_back(e.first); d.push_back(e.second); }
+      return d;
+    };
+    auto d1 = lutdata( gos.m_lt_sofcosd ), d2 = lutdata( gos.m_lt_evalcosx );
+    h.lut_sofcosd_n = d1.size()/2; h.lut_evalcosx_n = d2.size()/2;
+    comp.off = buf.reserve(sizeof(h));
+    buf.put(comp.off,&h,sizeof(h));
+    buf.appendv(ps); buf.appendv(d1); buf.appendv(d2);
+    return true;
+  }
+
   const NC::SAB::SABSamplerAtE_Alg1* firstAlg1( const NC::SABSampler& s )
   {
     for ( auto& up : s.m_samplers ) {
@@ -210,6 +253,9 @@ namespace {
       buf.appendv(sd.betaGrid());
       buf.appendv(sd.sab());
     } else if ( refdrv_compile_scbragg( p, comp, buf, err ) ) {
+      if ( !err.empty() )
+        return false;
+    } else if ( refdrv_compile_lcbragg( p, comp, buf, err ) ) {
       if ( !err.empty() )
         return false;
     } else {

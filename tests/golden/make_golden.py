@@ -51,6 +51,25 @@ def oriented_inputs(n):
     return e, ux, uy, uz
 
 
+def oriented_inputs_lc(n):
+    """Layered crystal (lcaxis = lab z): isotropic directions + log-uniform energies, plus the degenerate cases of the
+    ROI search -- neutrons along +-lcaxis (all crystallite rotations equivalent), almost along it, perpendicular to
+    it, non-normalised directions -- and energies at / just around the Bragg threshold."""
+    e = loguniform_energies(n, seed=781)
+    ux, uy, uz = isotropic_directions(n, seed=782)
+    k = 64
+    e[:k] = np.geomspace(1.5e-3, 8.0, k)
+    ux[:k] = 0.0; uy[:k] = 0.0; uz[:k] = 1.0
+    uz[k // 2:k] = -1.0
+    e[k:2 * k] = np.geomspace(1.5e-3, 8.0, k)
+    ux[k:2 * k] = 1e-11; uy[k:2 * k] = 0.0; uz[k:2 * k] = 1.0
+    e[2 * k:3 * k] = np.geomspace(1.5e-3, 8.0, k)
+    ux[2 * k:3 * k] = 0.6; uy[2 * k:3 * k] = 0.8; uz[2 * k:3 * k] = 0.0
+    ux[3 * k:4 * k] *= 3.0; uy[3 * k:4 * k] *= 3.0; uz[3 * k:4 * k] *= 3.0
+    e[4 * k:4 * k + 6] = [0.0018163, 0.0018164, 0.00181636, 0.002, 1e-5, 100.0]
+    return e, ux, uy, uz
+
+
 def main():
     only = sys.argv[1:]
     for key, cfg in list(CONFIGS.items()) + list(EXTRA_CONFIGS.items()):
@@ -58,7 +77,7 @@ def main():
             continue
         r = RefDrv(cfg)
         if RefDrv.lib().refdrv_isoriented(r.h):
-            e, ux, uy, uz = oriented_inputs(N)
+            e, ux, uy, uz = oriented_inputs_lc(N) if "LCBragg" in r.compnames() else oriented_inputs(N)
             xs = r.xs(e, ux, uy, uz)
             eo, ox, oy, oz, nd = r.sample(e, ux, uy, uz, seed=GOLDEN_SEED, first_index=0)
             out = os.path.join(HERE, "aniso_%s.npz" % key)
