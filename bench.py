@@ -278,6 +278,12 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.stream = torch.cuda.current_stream(self.dev)
         self.sp = C.c_void_p(self.stream.cuda_stream)
+        # library messages (e.g. the reference's "reverts to isotropic model" warning, raised on the device) go to
+        # stderr: stdout carries the one JSON line
+        from ncrystal_b200 import _lib
+        self._msgh = C.CFUNCTYPE(None, C.c_char_p, C.c_uint)(
+            lambda m, t: sys.stderr.write("[ncrystal_b200 %s] %s\n" % (("info", "warning", "raw")[min(t, 2)], m.decode(errors="replace"))))
+        _lib.lib().ncrystal_setmsghandler(C.cast(self._msgh, C.c_void_p))
 
     def event(self):
         return self.torch.cuda.Event(enable_timing=True)

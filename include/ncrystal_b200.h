@@ -130,6 +130,11 @@ void ncrystal_clearerror(void);
 int  ncrystal_setquietonerror( int );
 int  ncrystal_sethaltonerror( int );
 void ncrystal_seterrhandler( void (*handler)(char*,char*) );
+/* ncrystal.h:1051 -- library output (warnings raised on the device included) goes to stdout unless a handler is set;
+ * second argument: 0 info, 1 warning, 2 raw output.  NULL restores the default. */
+void ncrystal_setmsghandler( void (*handler)(const char*,unsigned) );
+/* extension (test hook): send a message through the handler */
+void ncb200_emit_message( const char* msg, unsigned msgtype );
 
 /* ncrystal.h:1067-1087 -- RNG control.  Host callbacks cannot be honoured on the
  * device: ncrystal_setrandgen raises an error.  The ncrystal_setbuiltinrandgen* calls set the seed (and restart the

@@ -10,10 +10,9 @@
 //
 // Semantics kept: units (eV, barn/atom), neutron = {ekin, ux, uy, uz} modified in place by sampleScatterUncached, no
 // client-side cache, calls on one ScatterProcess may come from several threads (serialised inside).
-// Semantics that differ, because a host callback cannot be evaluated on the device: the client's rng is not
-// consulted once per uniform; every sampleScatterUncached call draws exactly TWO numbers from it and uses them as the
-// key of that neutron's counter-based device stream.  Outcomes are therefore still a deterministic function of the
-// client's generator and independent between calls, but they do not replay the reference's draw-by-draw sequence.
+// The client's rng is consumed draw by draw exactly as by the reference (the device function runs with the numbers
+// drawn so far and asks for one more when it runs past them, csrc/ncb_replay.cu), so a client generator advances
+// identically under both libraries: tests/vapi_caller.cc reproduces the reference's tests/src/app_vapit1v1/test.log.
 // One neutron per call leaves the GPU idle: callers that can batch should use ncb200_crosssection_many /
 // ncb200_samplescatter_manydir (include/ncrystal_b200.h) -- this boundary exists so that they do not HAVE to.
 #ifndef NCRYSTAL_B200_VIRTAPI_HH

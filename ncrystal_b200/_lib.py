@@ -82,6 +82,8 @@ SIGNATURES = {
     "ncrystal_setquietonerror": (C.c_int, [C.c_int]),
     "ncrystal_sethaltonerror": (C.c_int, [C.c_int]),
     "ncrystal_seterrhandler": (None, [_vp]),
+    "ncrystal_setmsghandler": (None, [_vp]),
+    "ncb200_emit_message": (None, [C.c_char_p, C.c_uint]),
     "ncrystal_setrandgen": (None, [_vp]),
     "ncrystal_setbuiltinrandgen": (None, []),
     "ncrystal_setbuiltinrandgen_withseed": (None, [_ulong]),

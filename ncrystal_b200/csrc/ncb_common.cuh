@@ -144,6 +144,27 @@ namespace ncb {
     return *p;
 #endif
   }
+  // Streaming arrays (per-neutron inputs and outputs, each touched once per launch): evict-first loads / stores so
+  // that they do not displace the material tables from L2 (NCB_STREAM=0 compiles plain accesses, for A/B runs).
+#if !defined(NCB_STREAM)
+#  define NCB_STREAM 1
+#endif
+  NCB_HD double ldStream( const double* p )
+  {
+#if defined(__CUDA_ARCH__) && NCB_STREAM
+    return __ldcs( p );
+#else
+    return *p;
+#endif
+  }
+  NCB_HD void stStream( double* p, double v )
+  {
+#if defined(__CUDA_ARCH__) && NCB_STREAM
+    __stcs( p, v );
+#else
+    *p = v;
+#endif
+  }
   // upperBound / lowerBound over a table in global memory
   NCB_HD int upperBoundTable( const double* a, int lo, int hi, double v )
   {

@@ -103,12 +103,12 @@ namespace ncb {
     stageHotTabs( M, sp, smem, &mbar, H );
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double e = i < n ? ekin[i] : 0.0;
+    double e = i < n ? ldStream( ekin + i ) : 0.0;
     while ( i < n ) {
       // the next step's energy is requested before this step's arithmetic (the load latency was the top stall)
       const uint64_t inext = i + stride;
-      const double enext = inext < n ? ekin[inext] : 0.0;
-      out[i] = matXSIso( M, H, e, nullptr, nullptr );
+      const double enext = inext < n ? ldStream( ekin + inext ) : 0.0;
+      stStream( out + i, matXSIso( M, H, e, nullptr, nullptr ) );
       e = enext; i = inext;
     }
   }
@@ -211,13 +211,13 @@ namespace ncb {
     uint32_t c1 = 0, c2 = 0;                 // entries in the warp's two buffers (warp-uniform)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n = A.n;
-    double enext = ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x < n ) ? A.ekin[ (uint64_t)blockIdx.x * blockDim.x + threadIdx.x ] : 0.0;
+    double enext = ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x < n ) ? ldStream( A.ekin + ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x ) ) : 0.0;
     for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride ) {
       const uint64_t i = base + threadIdx.x;
       int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue
       uint32_t entry = 0;
       const double ekin = enext;
-      enext = ( i + stride < n ) ? A.ekin[i + stride] : 0.0;     // requested one step ahead
+      enext = ( i + stride < n ) ? ldStream( A.ekin + i + stride ) : 0.0;     // requested one step ahead
       if ( i < n ) {
         double eout = ekin, mu = 1.0, tot = 0.0;
         int ich = -1;
@@ -251,7 +251,7 @@ namespace ncb {
           }
           entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
         }
-        if ( A.xs_out ) A.xs_out[i] = tot;
+        if ( A.xs_out ) stStream( A.xs_out + i, tot );
         if ( A.component ) A.component[i] = ich;
         if ( cls == 0 ) {
           A.ekin_out[i] = eout;
@@ -1077,7 +1077,7 @@ namespace ncb {
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for ( uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride ) {
-      const double v = values[i];
+      const double v = ldStream( values + i );
       const double w = weights ? weights[i] : 1.0;
       const double rel = ( v - lo ) * invbinw;
       uint32_t b;

@@ -49,6 +49,17 @@ namespace {
   char g_errmsg[512];
   char g_errtype[64];
   void (*g_custom_error_handler)(char*,char*) = nullptr;
+  // message handler, ref: ncrystal.h:1051, ncrystal.cc:2428-2446, src/utils/NCMsg.cc:44-82 (0: info, 1: warning, 2: raw)
+  std::mutex g_msg_mtx;
+  void (*g_msg_handler)(const char*,unsigned) = nullptr;
+  void emitMsg( const char* msg, unsigned type )
+  {
+    std::lock_guard<std::mutex> g( g_msg_mtx );
+    if ( g_msg_handler ) { g_msg_handler( msg, type ); return; }
+    if ( type == 2 ) std::fputs( msg, stdout );
+    else std::printf( "%s%s\n", type == 1 ? "NCrystal WARNING: " : "NCrystal: ", msg );
+    std::fflush( stdout );
+  }
 
   void setError( const char* msg, const char* etype = nullptr ) noexcept
   {
@@ -1039,8 +1050,17 @@ namespace {
     if ( !s->d_err ) return 0;
     int flags = 0;
     CUDA_OK( cudaMemcpy( &flags, s->d_err, sizeof(int), cudaMemcpyDeviceToHost ) );
-    if ( flags & ~ERR_SAB_ISOFALLBACK )
+    if ( flags )
       CUDA_OK( cudaMemset( s->d_err, 0, sizeof(int) ) );
+    if ( flags & ERR_SAB_ISOFALLBACK ) {
+      // the reference's warning (NCSABSamplerModels.cc:96-105), through the message handler; at most 20 times.
+      // (One message per call in which the fallback happened: the device reports a flag, not a count.)
+      static std::atomic<unsigned> s_nfail{0};
+      const unsigned nfail = ++s_nfail;
+      if ( nfail <= 20 )
+        emitMsg( nfail == 20 ? "SABSampler reverts to isotropic model after 30 rejected attempts (suppressing further warnings of this type)"
+                             : "SABSampler reverts to isotropic model after 30 rejected attempts", 1 );
+    }
     return flags;
   }
 
@@ -1379,6 +1399,8 @@ extern "C" {
 
   // ---- error API (ref: ncrystal.cc:396-440)
   void ncrystal_seterrhandler( void (*handler)(char*,char*) ) { g_custom_error_handler = handler; }
+  void ncrystal_setmsghandler( void (*handler)(const char*,unsigned) ) { std::lock_guard<std::mutex> g( g_msg_mtx ); g_msg_handler = handler; }
+  void ncb200_emit_message( const char* msg, unsigned msgtype ) { if ( msg && msgtype <= 2 ) emitMsg( msg, msgtype ); }
   int ncrystal_error(void) { return g_waserror; }
   const char* ncrystal_lasterror(void) { return g_waserror ? g_errmsg : nullptr; }
   const char* ncrystal_lasterrortype(void) { return g_waserror ? g_errtype : nullptr; }

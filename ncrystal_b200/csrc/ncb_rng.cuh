@@ -23,6 +23,30 @@ namespace ncb {
 #endif
   }
 
+#if defined(NCB_RNG_REPLAY)
+  // Caller-supplied numbers instead of a Philox stream (ncb_replay.cu: ncrystal_samplescatter_rs and the virtual
+  // API hand the library a generator that must be consumed draw by draw).  The first `nu` numbers come from `u`;
+  // asking for more sets `overrun` -- the host then fetches one more number from the caller and repeats the
+  // neutron -- and returns throw-away values from a small generator so that rejection loops still terminate.
+  struct Rng {
+    const double* u;
+    uint32_t nu;
+    uint32_t ndraws;
+    uint32_t overrun;
+    uint32_t lcg;
+    NCB_HD void init( uint64_t, uint64_t, uint32_t = 0 ) { u = nullptr; nu = 0; ndraws = 0; overrun = 0; lcg = 12345u; }
+    NCB_HD void seek( uint32_t k ) { ndraws = k; }
+    NCB_HD double generate()
+    {
+      const uint32_t k = ndraws++;
+      if ( k < nu )
+        return u[k];
+      overrun = 1;
+      lcg = lcg*1664525u + 1013904223u;
+      return ( (double)( lcg >> 8 ) + 0.5 ) * ( 1.0/16777216.0 );
+    }
+  };
+#else
   struct Rng {
     uint32_t k0, k1;   // key  (seed)
     uint32_t c0, c1;   // counter words 0,1 (neutron index)
@@ -84,5 +108,6 @@ namespace ncb {
       return refill( k >> 1 );
     }
   };
+#endif
 
 }

@@ -131,6 +131,20 @@ def test_plain_c_caller_compiles_and_links_against_the_header(tmp_path):
     assert os.path.exists(_build_capi_caller(tmp_path))
 
 
+def _build_capi_crng(tmpdir):
+    import subprocess
+    exe = os.path.join(str(tmpdir), "capi_crng")
+    libdir = os.path.join(ROOT, "ncrystal_b200", "lib")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "capi_crng.c"), "-o", exe, "-L", libdir, "-lncrystal_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_caller_rng_program_compiles_and_links(tmp_path):
+    assert os.path.exists(_build_capi_crng(tmp_path))
+
+
 def _build_cxx_caller(tmpdir):
     import subprocess
     exe = os.path.join(str(tmpdir), "cxx_caller")

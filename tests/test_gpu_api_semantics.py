@@ -3,11 +3,12 @@ special energies, ragged sizes around the pipeline chunks, repeat ordering, erro
 handle life cycle.  Reference behaviour: ncrystal_core/src/cinterface/ncrystal.cc:280-306 (error handling),
 :1089-1282 (batch entry points), :474-496 (unref)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
-from conftest import CONFIG_KEYS_ISO
+from conftest import CONFIG_KEYS_ISO, HERE
 from _mmc import cached_oracle
 
 pytestmark = pytest.mark.gpu
@@ -202,22 +203,25 @@ def test_cxx_mirror_runs(tmp_path):
 
 
 def test_virtual_api_client_runs(tmp_path):
-    # OpenMC's boundary: the reference's own test of it (tests/src/app_vapit1v1/main.cc) with its golden cross sections;
-    # sampling draws two numbers from the client's generator per call (documented deviation), so the reference's
-    # printed directions are reproduced only where the physics fixes them: the first Ge scattering is the 591 barn
-    # Bragg reflection, whose outgoing direction the reference logs as (0.44452, 0.70709, 0.54993) (test.log)
+    # OpenMC's boundary: the reference's own test of it (tests/src/app_vapit1v1/main.cc) with its golden cross sections
+    # and -- the client's generator being consumed draw by draw like the reference does -- its pinned log of four
+    # successive Ge scatterings, verbatim (tests/golden/ref_app_vapit1v1_test.log)
     import subprocess
     from test_cpu_blob import _build_virtapi_caller
     out = subprocess.run([_build_virtapi_caller(tmp_path)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    kv = {l.split()[0]: l.split()[1:] for l in out.stdout.strip().splitlines()}
+    lines = out.stdout.strip().splitlines()
+    kv = {l.split()[0]: l.split()[1:] for l in lines}
     assert kv["bad_id_null"] == ["1"] and kv["al_xs_mismatches"] == ["0"] and kv["bad_cfg_throws"] == ["1"]
     assert float(kv["ge_xs"][0]) == pytest.approx(591.0263476502018, rel=1e-6)
     assert float(kv["ge_xs"][1]) == pytest.approx(1.667600586136298, rel=1e-6)
     assert kv["ge_deterministic"] == ["1"] and float(kv["ge_norm_dev"][0]) < 1e-9
-    wl, ux, uy, uz = [float(x) for x in kv["ge_first"]]
-    assert abs(wl - 1.54) < 1e-9
-    assert abs(abs(ux) - 0.44452) < 2e-3 and abs(uy - 0.70709) < 2e-3 and abs(uz - 0.54993) < 2e-3
+    ref = [l for l in open(os.path.join(HERE, "golden", "ref_app_vapit1v1_test.log")).read().splitlines() if l.startswith("Neutron state")]
+    got = [l[len("reflog "):] for l in lines if l.startswith("reflog Neutron state")]
+    assert len(ref) == 5 and got == ref, "\n".join(got)
+    # state of the client's generator after the four calls under the reference (35 numbers consumed: 3 + 7 + 7 + 7 + 11;
+    # obtained here by running the same sequence against oracle/_ref)
+    assert kv["reflog_rng_state"] == ["1583187185"]
     # Al at 25.3 meV: mean cosine of 1500 calls per client thread against the batched API (sigma of the mean ~0.015)
     import ncrystal_b200 as nc
     from __graft_entry__ import CONFIGS
@@ -227,40 +231,62 @@ def test_virtual_api_client_runs(tmp_path):
         assert abs(float(m) - mu.mean()) < 0.08
 
 
-def test_samplescatter_rs_uses_the_callers_generator(configs):
-    # ncrystal.h:792: the caller's generator decides the outcome (two numbers per call key the device stream),
-    # the handle's own stream is left where it was
+def test_caller_rng_log_of_the_reference(tmp_path):
+    # tests/src/app_crng (ncrystal_samplescatter_rs with a printing generator): the reference's pinned log, verbatim
+    import subprocess
+    from test_cpu_blob import _build_capi_crng
+    out = subprocess.run([_build_capi_crng(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ref = open(os.path.join(HERE, "golden", "ref_app_crng_test.log")).read()
+    assert out.stdout == ref
+
+
+@pytest.mark.parametrize("key", ["Al", "H2O", "Ge"])
+def test_samplescatter_rs_uses_the_callers_generator(configs, key):
+    # ncrystal.h:792: the caller's generator is consumed draw by draw.  Feeding it the numbers of the per-neutron
+    # Philox streams must therefore give the golden (reference) outcomes of the batch path AND ask for exactly as many
+    # numbers as the reference consumed; the handle's own stream is left where it was.
     import ctypes as C
     from ncrystal_b200 import _lib
     import ncrystal_b200 as nc
+    from _libs import HostSim
     L = _lib.lib()
-    sc = nc.Scatter(configs["Al"], seed=77)
+    aniso = key == "Ge"
+    g = np.load(os.path.join(HERE, "golden", ("aniso_%s.npz" if aniso else "iso_%s.npz") % key))
+    seed = int(g["seed"])
+    sc = nc.Scatter(configs[key], seed=77)
     RNGF = C.CFUNCTYPE(C.c_double, C.c_void_p)
-    calls = []
-
-    def make(seq):
-        it = iter(seq)
-
-        def f(_state):
-            v = next(it)
-            calls.append(v)
-            return v
-        return RNGF(f)
-
-    d_in = (C.c_double * 3)(0.0, 0.0, 1.0)
-
-    def one(seq):
-        ef, d_out = C.c_double(), (C.c_double * 3)()
-        L.ncrystal_samplescatter_rs(make(seq), None, sc._h, 0.0253, C.byref(d_in), C.byref(ef), C.byref(d_out))
-        return ef.value, tuple(d_out)
-
     before = sc.getRNGStream()
-    a = one([0.25, 0.75])
-    b = one([0.25, 0.75])
-    c = one([0.75, 0.25])
-    assert len(calls) == 6                       # exactly two numbers per call
-    assert a == b and a != c
-    assert abs(sum(x * x for x in a[1]) - 1.0) < 1e-12 and a[0] > 0
+    idx = [i for i in range(0, g["ekin"].size, 97)][:40]
+    for i in idx:
+        nd = int(g["ndraws"][i])
+        u = np.empty(nd + 64)
+        HostSim.lib().hostsim_uniforms(seed, i, u.size, u.ctypes.data_as(C.POINTER(C.c_double)))
+        calls = []
+
+        def f(_state, u=u, calls=calls):
+            calls.append(1)
+            return float(u[len(calls) - 1])
+        cb = RNGF(f)
+        d = (g["ux"][i], g["uy"][i], g["uz"][i]) if aniso else (0.0, 0.0, 1.0)
+        d_in = (C.c_double * 3)(*[float(x) for x in d])
+        ef, d_out = C.c_double(), (C.c_double * 3)()
+        L.ncrystal_samplescatter_rs(cb, None, sc._h, float(g["ekin"][i]), C.byref(d_in), C.byref(ef), C.byref(d_out))
+        nc.core._check_error()
+        if aniso:
+            assert len(calls) == nd, (i, len(calls), nd)
+            assert abs(ef.value - g["ekin_out"][i]) <= 1e-10 * abs(g["ekin_out"][i])
+            for a, b in zip(tuple(d_out), (g["ox"][i], g["oy"][i], g["oz"][i])):
+                assert abs(a - b) <= 1e-10
+        else:
+            # the isotropic golden file holds (E', mu); the oriented entry point then draws the azimuth
+            # (randDirectionGivenScatterMu: >= 2 more numbers) and mu is the cosine between the two directions
+            if nd == 0:
+                assert len(calls) == 0 and ef.value == g["ekin"][i] and tuple(d_out) == (0.0, 0.0, 1.0)
+            else:
+                assert len(calls) >= nd + 2, (i, len(calls), nd)
+                assert abs(ef.value - g["ekin_out"][i]) <= 1e-10 * abs(g["ekin_out"][i])
+                assert abs(d_out[2] - g["mu"][i]) <= 1e-10
     assert sc.getRNGStream() == before
 
 
@@ -385,3 +411,21 @@ def test_python_mirror_deprecated_spellings(configs):
     assert np.array_equal(sc.crossSectionNonOriented(e), sc.crossSectionIsotropic(e))
     ab = nc.Absorption(configs["Al"])
     assert ab.clone().crossSectionIsotropic(0.0253) == ab.crossSectionIsotropic(0.0253)
+
+
+def test_message_handler(configs):
+    # ncrystal.h:1051 / ncrystal.cc:2428-2446: messages (type 0 info, 1 warning, 2 raw) go to the registered handler;
+    # NULL restores the default (stdout)
+    from ncrystal_b200 import _lib
+    L = _lib.lib()
+    got = []
+    H = C.CFUNCTYPE(None, C.c_char_p, C.c_uint)
+    cb = H(lambda m, t: got.append((m.decode(), int(t))))
+    L.ncrystal_setmsghandler(C.cast(cb, C.c_void_p))
+    try:
+        L.ncb200_emit_message(b"hello", 1)
+        L.ncb200_emit_message(b"raw text", 2)
+        L.ncb200_emit_message(b"ignored", 7)
+    finally:
+        L.ncrystal_setmsghandler(None)
+    assert got == [("hello", 1), ("raw text", 2)]

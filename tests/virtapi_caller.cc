@@ -46,6 +46,25 @@ int main()
         for ( double v : n ) out.push_back( v );
       }
     };
+    {
+      // the sampling part of the reference's test on its exact cfg string, printed in its log format
+      // (app_vapit1v1/main.cc:109-139; the lines are compared with tests/golden/ref_app_vapit1v1_test.log)
+      auto ge_ref = api->createScatter( "stdlib::Ge_sg227.ncmat;dcutoff=0.5;mos=40.0arcsec;dir1=@crys_hkl:5,1,1@lab:0,0,1"
+                                        ";dir2=@crys_hkl:0,-1,1@lab:0,1,0" );
+      unsigned long state = 1789569706;
+      std::function<double()> fakerng = [&state]() {
+        state = ( 1103515245 * state + 12345 ) % 2147483648;
+        return state * ( 1.0 / 2147483648 );
+      };
+      fakerng(); fakerng(); fakerng();
+      double n[4] = { wl2ekin( 1.54 ), 0.0, 1.0, 1.0 };
+      for ( int k = 0; k < 5; ++k ) {
+        if ( k ) api->sampleScatterUncached( *ge_ref, fakerng, n );
+        std::printf( "reflog Neutron state: (wl=%.5g u=(%.5g, %.5g, %.5g)\n", std::sqrt( 0.081804209605330899 / n[0] ), n[1], n[2], n[3] );
+      }
+      std::printf( "reflog_rng_state %lu\n", state );
+      api->deallocateScatter( ge_ref );
+    }
     std::vector<double> a, b;
     run_ge( a ); run_ge( b );
     std::printf( "ge_deterministic %d\n", a == b ? 1 : 0 );
