@@ -671,18 +671,26 @@ def other_configs(cx, skip, steps=4):
                             "kernel_ms": {k: round(v["ms_avg"], 4) for k, v in r["ktimes"].items()},
                             "queue_units": r["qcounts"], "table_MB": r["table_MB"], "device_error_flags": r["flags"]}
             else:
-                n = 1 << 23     # short run: 8 Mi neutrons per GPU (the Ge line proper is `--config Ge`)
+                # BASELINE.json configs[4] as it is stated: 1e9 neutrons sharded over the ranks (strong scaling; 72 GB of
+                # resident arrays on one GPU, 9 GB per GPU on eight), one warm-up pass + `ge_steps` timed passes.
+                # NCB200_BENCH_GE_TOTAL overrides the total (smaller boxes).
                 from ncrystal_b200.sharding import shard_range
-                first = shard_range(cx.world * n, cx.rank, cx.world)[0]
-                r = measure_aniso(cx, key, n, first, steps, 2, headline=False)
+                n_total = int(os.environ.get("NCB200_BENCH_GE_TOTAL", w["n_total"]))
+                b0, b1 = shard_range(n_total, cx.rank, cx.world)
+                n, ge_steps = b1 - b0, 2
+                r = measure_aniso(cx, key, n, b0, ge_steps, 1, headline=False)
                 dom = dominant(r["ktimes"])
-                res[key] = {"workload": workload_text(key), "neutrons_per_gpu": n, "note": "short run; the sharded 1e9 line is --config Ge",
-                            "xs_per_s": cx.world * n / (r["ms_xs"] * 1e-3), "samples_per_s": cx.world * n / (r["ms_sample"] * 1e-3),
+                res[key] = {"workload": workload_text(key), "neutrons_total_per_step": n_total, "neutrons_per_gpu": n, "steps": ge_steps,
+                            "scaling": "strong", "ms_per_step": r["ms_total"] / ge_steps,
+                            "neutrons_per_s": n_total * ge_steps / (r["ms_total"] * 1e-3),
+                            "xs_per_s": n_total / (cx.max_over_ranks(r["ms_xs"])[0] * 1e-3),
+                            "samples_per_s": n_total / (cx.max_over_ranks(r["ms_sample"])[0] * 1e-3),
                             "xs_frac_of_hbm": n * BYTES["xs_aniso"] / (r["ms_xs"] * 1e-3) / 1e9 / peak,
                             "sample_frac_of_hbm": n * BYTES["sample_aniso"] / (r["ms_sample"] * 1e-3) / 1e9 / peak,
                             "dominant_kernel": dom[0] if dom else None, "dominant_ms": dom[1] if dom else None,
-                            "kernel_ms": {k: round(v["ms_avg"], 4) for k, v in r["ktimes"].items()},
+                            "kernel_ms_block": {k: round(v["ms_avg"], 4) for k, v in r["ktimes"].items()}, "kernel_block_neutrons": r["kt_block"],
                             "table_MB": r["table_MB"], "device_error_flags": r["flags"]}
+                r.pop("inputs", None); r.pop("sc", None)
             del r
             cx.torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

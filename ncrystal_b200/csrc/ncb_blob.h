@@ -111,7 +111,11 @@ typedef struct {
   double   k1, k2;         /* SABSampler::m_k1, m_k2 (NCSABSampler.cc:51-52) */
   double   egrid_margin;   /* SABSampler::m_egridMargin (1.05) */
   uint64_t negrid, nalpha, nbeta;
-  uint64_t reserved;
+  uint64_t auto_egrid;     /* 0: egrid[]/xs[] and k_extension, xs_at_emax, k1, k2 come from the reference.
+                              1: they are placeholders -- the library determines Emin/Emax (SABIntegrator::
+                              determineEMin/determineEMax, NCSABIntegrator.cc:147-200; egrid[0], egrid[1] hold a
+                              requested emin, emax -- an NCMAT "egrid" line -- or 0 = automatic), lays out the negrid-point
+                              geometric grid (:203-283) and integrates the cross sections itself */
 } ncb_sab_t;
 
 /* SCBragg (mosaic single crystal; NCSCBragg.cc:33-90 pimpl + GaussMos + GaussOnSphere).

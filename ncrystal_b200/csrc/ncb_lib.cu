@@ -14,6 +14,7 @@
 #include "ncb_kernels_mmc.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
+#include "ncb_sabgrid.h"
 #include "../../include/ncrystal_b200.h"
 
 #include <atomic>
@@ -284,7 +285,7 @@ namespace {
   {
     unsigned char* base = static_cast<unsigned char*>( dm.d_arena );
     for ( auto& pl : dm.sabplans ) {
-      const SabT& T = dm.mat.sab[pl.sab_index];
+      const SabT& T = dm.mat.sab[pl.sab_index];   // (reference into dm.mat: sees the updates of the auto-grid branch)
       const int na = T.nalpha, nb = T.nbeta, ne = T.negrid;
       double* logsab = reinterpret_cast<double*>( base + pl.off_logsab );
       double* cumul = reinterpret_cast<double*>( base + pl.off_cumul );
@@ -299,6 +300,55 @@ namespace {
       const size_t ntot = (size_t)na*nb;
       k_sab_logs<<< (unsigned)( ( ntot + 255 )/256 ), 256, 0, st >>>( T.sab, logsab, ntot );
       k_sab_cumul<<< ( nb + 63 )/64, 64, 0, st >>>( T.alpha, T.sab, logsab, na, nb, cumul );
+      if ( pl.auto_egrid ) {
+        // ---- energy grid from the scattering kernel alone (ncb_sabgrid.h): every point of a probe sequence is
+        // integrated in ONE pass of the table-build kernels (they run per energy point anyway)
+        SabT& Tm = dm.mat.sab[pl.sab_index];
+        double* d_egrid = reinterpret_cast<double*>( base + pl.off_egrid );
+        double* d_xs = reinterpret_cast<double*>( base + pl.off_xs );
+        auto sigmaAt = [&]( const std::vector<double>& e ) {
+          if ( e.empty() || (int)e.size() > ne )
+            throw Err( "CalcError", "SAB energy grid: probe sequence does not fit the table scratch" );
+          CUDA_OK( cudaMemcpyAsync( d_egrid, e.data(), e.size()*8, cudaMemcpyHostToDevice, st ) );
+          SabT Tp = Tm; Tp.negrid = (int)e.size();
+          k_sab_rows<<< dim3( ( nb + 127 )/128, (unsigned)e.size() ), 128, 0, st >>>( Tp, rows, ainfo );
+          k_sab_epoints<<< ( (int)e.size() + 31 )/32, 32, 0, st >>>( Tp, rows, ep, bx, bpdf, bcdf, xscheck, errs );
+          g_launches += 2;
+          std::vector<double> xs( e.size() );
+          std::vector<int> er( e.size() );
+          CUDA_OK( cudaMemcpyAsync( xs.data(), xscheck, e.size()*8, cudaMemcpyDeviceToHost, st ) );
+          CUDA_OK( cudaMemcpyAsync( er.data(), errs, e.size()*4, cudaMemcpyDeviceToHost, st ) );
+          CUDA_OK( cudaStreamSynchronize( st ) );
+          for ( int c : er ) if ( c ) throw Err( "CalcError", "S(alpha,beta) energy-point analysis failed on device (code "+std::to_string(c)+")" );
+          return xs;
+        };
+        // (alpha, beta grid ends for the kinematic limit of the table)
+        double bmin = 0.0, amax = 0.0;
+        CUDA_OK( cudaMemcpy( &bmin, T.beta, 8, cudaMemcpyDeviceToHost ) );
+        CUDA_OK( cudaMemcpy( &amax, T.alpha + ( na-1 ), 8, cudaMemcpyDeviceToHost ) );
+        std::vector<double> egrid;
+        try {
+          egrid = sabDetermineEnergyGrid( ne, T.kT, bmin, amax, pl.suggested_emax, pl.req_emin, pl.req_emax, T.ext, sigmaAt, []( const char* m ) { emitMsg( m, 1 ); } );
+        } catch ( std::runtime_error& e ) {
+          throw Err( "BadInput", e.what() );
+        }
+        CUDA_OK( cudaMemcpyAsync( d_egrid, egrid.data(), (size_t)ne*8, cudaMemcpyHostToDevice, st ) );
+        CUDA_OK( cudaStreamSynchronize( st ) );
+        // derived search aids of the grid (what the loader makes for a grid that comes with the blob)
+        {
+          const double l0 = std::log( egrid[0] ), l1 = std::log( egrid[ne-1] );
+          Tm.egrid_log0 = l0;
+          Tm.egrid_invdlog = l1 > l0 ? ( (double)ne - 1.0 )/( l1 - l0 ) : 0.0;
+          int key0 = 0, shift = 0, nk = 0;
+          const std::vector<uint16_t> lut = makeKeyLut( egrid.data(), (size_t)ne, key0, shift, nk );
+          if ( !lut.empty() && lut.size() <= kKeyLutMaxEntries ) {
+            CUDA_OK( cudaMemcpy( base + pl.off_elut, lut.data(), lut.size()*sizeof(uint16_t), cudaMemcpyHostToDevice ) );
+            Tm.elut = reinterpret_cast<const uint16_t*>( base + pl.off_elut );
+            Tm.elut_key0 = key0; Tm.elut_shift = shift; Tm.elut_nk = nk;
+          }
+        }
+        (void)d_xs;
+      }
       k_sab_rows<<< dim3( ( nb + 127 )/128, ne ), 128, 0, st >>>( T, rows, ainfo );
       k_sab_epoints<<< ( ne + 31 )/32, 32, 0, st >>>( T, rows, ep, bx, bpdf, bcdf, xscheck, errs );
       k_sab_guides<<< dim3( 4, ne + nb ), 256, 0, st >>>( T, ep, reinterpret_cast<uint16_t*>( base + pl.off_bguide ),
@@ -319,6 +369,19 @@ namespace {
       for ( int e : herrs )
         if ( e )
           throw Err( "CalcError", "S(alpha,beta) sampler table build failed on device (code "+std::to_string(e)+")" );
+      if ( pl.auto_egrid ) {
+        // cross sections of the grid = the integrals of the table build; constants of SABXSProvider::setData
+        // (NCSABXSProvider.cc:35-52) and SABSampler::setData (NCSABSampler.cc:41-57)
+        SabT& Tm = dm.mat.sab[pl.sab_index];
+        CUDA_OK( cudaMemcpy( base + pl.off_xs, xscheck, (size_t)ne*8, cudaMemcpyDeviceToDevice ) );
+        double emax = 0.0, xs_emax = 0.0;
+        CUDA_OK( cudaMemcpy( &emax, base + pl.off_egrid + (size_t)( ne-1 )*8, 8, cudaMemcpyDeviceToHost ) );
+        CUDA_OK( cudaMemcpy( &xs_emax, xscheck + ( ne-1 ), 8, cudaMemcpyDeviceToHost ) );
+        const double ext_emax = fgXS( Tm.ext, emax );
+        Tm.k_extension = ( xs_emax - ext_emax )*emax;
+        Tm.k1 = xs_emax*emax;
+        Tm.k2 = ext_emax*emax;
+      }
     }
   }
 
@@ -349,9 +412,9 @@ namespace {
     dm->sabplans = lm.sabplans;
     dm->blob = std::make_shared<const std::vector<unsigned char>>( static_cast<const unsigned char*>( blob ),
                                                                    static_cast<const unsigned char*>( blob ) + nbytes );
-    buildStagePlan( *dm );
     ensureKernelAttrs( dm->device );
     buildSabTablesOnDevice( *dm, 0 );
+    buildStagePlan( *dm );     // (after the build: an energy grid determined by the library has its key lut only now)
     return dm;
   }
 

@@ -22,7 +22,12 @@ namespace ncb {
     int sab_index;            // index into Material::sab
     size_t off_logsab, off_cumul, off_ep, off_bx, off_bpdf, off_bcdf, off_ainfo, off_rows, off_xscheck;
     size_t off_bguide, off_aguide, off_ascale, off_heads, off_pts, off_tails, off_bpts, off_lguide;
+    // energy grid determined by the library (ncb_sab_t::auto_egrid): where egrid / xs / the key lut live in the arena
+    bool auto_egrid = false;
+    double suggested_emax = 0.0, req_emin = 0.0, req_emax = 0.0;   // (request: first two entries of the placeholder egrid[])
+    size_t off_egrid = 0, off_xs = 0, off_elut = 0;
   };
+  constexpr size_t kKeyLutMaxEntries = 4100;   // uint16 entries reserved for a key lut that is built after the upload
 
   struct LoadedMaterial {
     Material mat;                       // pointers are OFFSETS into the arena until relocate()
@@ -113,6 +118,20 @@ namespace ncb {
       lut[k] = (uint16_t)i;
     }
     return lm.put( lut.data(), lut.size()*sizeof(uint16_t) );
+  }
+
+  // Same table as buildKeyLut, into a vector (for a grid that only exists after the upload)
+  inline std::vector<uint16_t> makeKeyLut( const double* a, size_t n, int& key0, int& shift, int& nk )
+  {
+    LoadedMaterial tmp;
+    tmp.reserve( 256 );
+    const size_t off = buildKeyLut( tmp, a, n, key0, shift, nk );
+    std::vector<uint16_t> lut;
+    if ( off ) {
+      lut.resize( (size_t)nk + 1 );
+      std::memcpy( lut.data(), tmp.arena.data() + off, lut.size()*sizeof(uint16_t) );
+    }
+    return lut;
   }
 
   void loadScBragg( LoadedMaterial& lm, const unsigned char* blob, const ncb_comp_t& c ); // ncb_loader_sc.h
@@ -225,7 +244,7 @@ namespace ncb {
         T.k_extension = h.k_extension;
         T.k1 = h.k1; T.k2 = h.k2;
         T.egrid_margin = h.egrid_margin;
-        {
+        if ( !h.auto_egrid ) {
           const double* eg = reinterpret_cast<const double*>( p + sizeof(h) );
           const double l0 = std::log( eg[0] ), l1 = std::log( eg[h.negrid-1] );
           T.egrid_log0 = l0;
@@ -238,14 +257,26 @@ namespace ncb {
         T.ext.mass_amu = h.ext_mass_amu;
         T.negrid = (int)h.negrid; T.nalpha = (int)h.nalpha; T.nbeta = (int)h.nbeta;
         const size_t ne = h.negrid, na = h.nalpha, nb = h.nbeta;
-        T.egrid = offAsPtr<double>( lm.put( arr, ne*8 ) );
-        T.xs    = offAsPtr<double>( lm.put( arr + ne, ne*8 ) );
-        T.elut  = offAsPtr<uint16_t>( buildKeyLut( lm, arr, ne, T.elut_key0, T.elut_shift, T.elut_nk ) );
+        const size_t off_egrid = lm.put( arr, ne*8 ), off_xs = lm.put( arr + ne, ne*8 );
+        T.egrid = offAsPtr<double>( off_egrid );
+        T.xs    = offAsPtr<double>( off_xs );
+        size_t off_elut = 0;
+        if ( h.auto_egrid ) {
+          if ( ne < 10 ) throw std::runtime_error( "compiled material: automatic SAB energy grid needs at least 10 points" );
+          off_elut = lm.reserve( kKeyLutMaxEntries*sizeof(uint16_t) );
+          T.elut = nullptr; T.elut_key0 = T.elut_shift = T.elut_nk = 0;
+          T.egrid_log0 = 0.0; T.egrid_invdlog = 0.0;
+        } else {
+          T.elut  = offAsPtr<uint16_t>( buildKeyLut( lm, arr, ne, T.elut_key0, T.elut_shift, T.elut_nk ) );
+        }
         T.alpha = offAsPtr<double>( lm.put( arr + 2*ne, na*8 ) );
         T.beta  = offAsPtr<double>( lm.put( arr + 2*ne + na, nb*8 ) );
         T.sab   = offAsPtr<double>( lm.put( arr + 2*ne + na + nb, na*nb*8 ) );
         SabBuildPlan pl;
         pl.sab_index = nsab;
+        pl.auto_egrid = h.auto_egrid != 0; pl.suggested_emax = h.suggested_emax;
+        if ( pl.auto_egrid ) { pl.req_emin = arr[0]; pl.req_emax = arr[1]; }
+        pl.off_egrid = off_egrid; pl.off_xs = off_xs; pl.off_elut = off_elut;
         pl.off_logsab = lm.reserve( na*nb*8 );
         pl.off_cumul  = lm.reserve( na*nb*8 );
         pl.off_ep     = lm.reserve( ne*sizeof(SabEPoint) );

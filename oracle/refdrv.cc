@@ -25,6 +25,7 @@
 #include "NCrystal/internal/sab/NCSABScatterHelper.hh"
 #include "NCrystal/internal/sab/NCSABSamplerModels.hh"
 #include "NCrystal/internal/sab/NCSABExtender.hh"
+#include "NCrystal/internal/sab/NCSABIntegrator.hh"
 #include "NCrystal/internal/freegas/NCFreeGas.hh"
 #include "NCrystal/internal/phys_utils/NCFreeGasUtils.hh"
 #include "NCrystal/internal/utils/NCPointwiseDist.hh"
@@ -496,6 +497,29 @@ extern "C" {
     }
     if (meta) { meta[0] = (double)a->m_ibetaOffset; meta[1] = a->m_firstBinKinematicEndpointValue; }
     return n;
+  }
+
+  // The reference's SABIntegrator run on a leaf's scattering kernel with a FULLY automatic energy grid (no "egrid"
+  // request; SABData::suggestedEmax still applies): what ncb_sabgrid.h restates.  egrid/xs: npts values each (300).
+  int refdrv_sab_auto_egrid( void* vh, int c, double* egrid, double* xs, int cap )
+  {
+    auto h = static_cast<Handle*>(vh);
+    auto sab = dynamic_cast<const NC::SABScatter*>( h->leaves.at(c).proc.get() );
+    if (!sab) return -1;
+    try {
+      auto alg1 = firstAlg1( sab->m_sh->sampler );
+      if (!alg1) return -1;
+      NC::shared_obj<const NC::SABData> data = alg1->m_common->data;
+      NC::SAB::SABIntegrator si( data );
+      NC::SABXSProvider xp = si.createXSProvider();
+      const int n = (int)xp.m_egrid.size();
+      if ( n > cap ) return -2;
+      for ( int i = 0; i < n; ++i ) { egrid[i] = xp.m_egrid[i]; xs[i] = xp.m_xs[i]; }
+      return n;
+    } catch ( std::exception& e ) {
+      g_err = e.what();
+      return -3;
+    }
   }
 
   // ---- (3) CPU baseline through the reference's own C-API --------------------

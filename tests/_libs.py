@@ -135,6 +135,16 @@ class RefDrv:
     def sab_sampler_dump(self, c, iE, nbeta):
         return _sab_dump(self.lib().refdrv_sab_sampler_dump, self.h, c, iE, nbeta)
 
+    def sab_auto_egrid(self, c, cap=1000):
+        """(egrid, xs) of the reference's SABIntegrator on leaf c's kernel with a fully automatic energy grid."""
+        eg, xs = np.zeros(cap), np.zeros(cap)
+        f = self.lib().refdrv_sab_auto_egrid
+        f.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int]
+        n = f(self.h, c, _d(eg), _d(xs), cap)
+        if n < 0:
+            raise RuntimeError("refdrv_sab_auto_egrid failed (%d)" % n)
+        return eg[:n], xs[:n]
+
     @classmethod
     def capi_sample_iso(cls, cfg, ekin, nthreads=None):
         """Independent-stream sampling through the reference's own C-API and builtin RNG
@@ -288,6 +298,14 @@ class HostSim:
     def sab_sampler_dump(self, c, iE, nbeta):
         return _sab_dump(self.lib().hostsim_sab_sampler_dump, self.h, c, iE, nbeta)
 
+    def sab_egrid(self, c, negrid):
+        out = np.zeros(negrid)
+        self.lib().hostsim_sab_egrid.argtypes = [C.c_void_p, C.c_int, _dp]
+        n = self.lib().hostsim_sab_egrid(self.h, c, _d(out))
+        if n < 0:
+            raise RuntimeError("egrid failed")
+        return out[:n]
+
     def sab_xscheck(self, c, negrid):
         out = np.zeros(negrid)
         n = self.lib().hostsim_sab_xscheck(self.h, c, _d(out))
@@ -309,3 +327,26 @@ def loguniform_energies(n, seed=12345, lo=1e-5, hi=10.0):
     rng = np.random.Generator(np.random.Philox(key=seed))
     u = rng.random(n)
     return 10.0 ** (np.log10(lo) + (np.log10(hi) - np.log10(lo)) * u)
+
+
+def strip_sab_energy_grids(blob, emax_request=0.0):
+    """A copy of a compiled material in which every S(alpha,beta) leaf has lost what the reference's SABIntegrator
+    derived for it -- the energy grid, the cross sections on it and the extension constants -- and asks the library to
+    determine them itself (ncb_sab_t::auto_egrid = 1).  The kernel (SABData), its extender constants and the number of
+    grid points stay.  emax_request: an Emax the material's file asks for ("egrid" line), 0 = automatic."""
+    import struct
+    b = bytearray(blob)
+    ncomp = struct.unpack_from("<I", b, 12)[0]
+    hdr_fixed = struct.calcsize("<QIIIIQdddddd176s")
+    comp_sz = struct.calcsize("<IIdddQQ")
+    for i in range(ncomp):
+        kind, _r, _s, _lo, _hi, off, _n = struct.unpack_from("<IIdddQQ", b, hdr_fixed + i * comp_sz)
+        if kind != 3:
+            continue
+        negrid = struct.unpack_from("<Q", b, off + 14 * 8)[0]
+        struct.pack_into("<4d", b, off + 9 * 8, 0.0, 0.0, 0.0, 0.0)       # k_extension, xs_at_emax, k1, k2
+        struct.pack_into("<Q", b, off + 14 * 8 + 3 * 8, 1)                   # auto_egrid
+        base = off + 14 * 8 + 4 * 8
+        b[base:base + 16 * negrid] = bytes(16 * negrid)                      # egrid[], xs[]
+        struct.pack_into("<2d", b, base, 0.0, float(emax_request))           # requested (emin, emax)
+    return bytes(b)

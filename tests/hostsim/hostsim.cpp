@@ -12,6 +12,7 @@
 #include "ncb_sabbuild.cuh"
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
+#include "ncb_sabgrid.h"
 #include "ncb_mmc.cuh"
 #include <memory>
 
@@ -48,6 +49,35 @@ namespace {
       double* bpdf = reinterpret_cast<double*>( base + pl.off_bpdf );
       double* bcdf = reinterpret_cast<double*>( base + pl.off_bcdf );
       double* xscheck = reinterpret_cast<double*>( base + pl.off_xscheck );
+      if ( pl.auto_egrid ) {
+        // energy grid determined from the kernel alone (ncb_sabgrid.h), as the product does on the device
+        SabT& Tm = h.mat.sab[pl.sab_index];
+        auto sigmaAt = [&]( const std::vector<double>& e ) {
+          std::vector<double> xs( e.size() );
+          std::vector<SabRow> r( nb );
+          std::vector<SabAlphaInfo> inf( nb );
+          std::vector<double> tx( T.bstride ), tp( T.bstride ), tc( T.bstride );
+          for ( size_t k = 0; k < e.size(); ++k ) {
+            for ( int ib = 0; ib < nb; ++ib )
+              r[ib] = sabAnalyseRow( T.alpha, na, T.beta, T.sab, logsab, cumul, e[k]/T.kT, ib, inf[ib] );
+            int err = 0; SabEPoint tmp;
+            xs[k] = sabAssembleEPoint( T.beta, nb, T.kT, T.bound_xs, e[k], r.data(), 0, 0, tmp, tx.data(), tp.data(), tc.data(), err );
+            if ( err ) throw std::runtime_error( "SAB energy-point analysis failed" );
+          }
+          return xs;
+        };
+        const std::vector<double> eg = sabDetermineEnergyGrid( ne, T.kT, T.beta[0], T.alpha[na-1], pl.suggested_emax, pl.req_emin, pl.req_emax, T.ext, sigmaAt, []( const char* ) {} );
+        std::memcpy( base + pl.off_egrid, eg.data(), (size_t)ne*8 );
+        const double l0 = std::log( eg[0] ), l1 = std::log( eg[ne-1] );
+        Tm.egrid_log0 = l0; Tm.egrid_invdlog = l1 > l0 ? ( (double)ne - 1.0 )/( l1 - l0 ) : 0.0;
+        int key0 = 0, shift = 0, nk = 0;
+        const std::vector<uint16_t> lut = makeKeyLut( eg.data(), (size_t)ne, key0, shift, nk );
+        if ( !lut.empty() && lut.size() <= kKeyLutMaxEntries ) {
+          std::memcpy( base + pl.off_elut, lut.data(), lut.size()*sizeof(uint16_t) );
+          Tm.elut = reinterpret_cast<const uint16_t*>( base + pl.off_elut );
+          Tm.elut_key0 = key0; Tm.elut_shift = shift; Tm.elut_nk = nk;
+        }
+      }
       for ( int ie = 0; ie < ne; ++ie ) {
         const double ekin_div_kT = T.egrid[ie] / T.kT;
         for ( int ib = 0; ib < nb; ++ib )
@@ -58,6 +88,13 @@ namespace {
                                          off_b, (uint32_t)( (size_t)ie*nb ), ep[ie], bx + off_b, bpdf + off_b, bcdf + off_b, err );
         if ( err )
           throw std::runtime_error( "SAB table build failed (err="+std::to_string(err)+")" );
+      }
+      if ( pl.auto_egrid ) {
+        SabT& Tm = h.mat.sab[pl.sab_index];
+        std::memcpy( base + pl.off_xs, xscheck, (size_t)ne*8 );
+        const double emax = T.egrid[ne-1], xs_emax = xscheck[ne-1], ext_emax = fgXS( Tm.ext, emax );
+        Tm.k_extension = ( xs_emax - ext_emax )*emax;
+        Tm.k1 = xs_emax*emax; Tm.k2 = ext_emax*emax;
       }
       // stage 3: guide tables
       uint16_t* bguide = reinterpret_cast<uint16_t*>( base + pl.off_bguide );
@@ -110,6 +147,7 @@ extern "C" {
       h->mat = ncb::relocated( h->lm, h->lm.arena.data() );
       ncb::hotTabsFromMaterial( h->mat, h->H );
       buildSabHost( *h );
+      ncb::hotTabsFromMaterial( h->mat, h->H );   // (again: an automatic energy grid sets its key lut during the build)
       return h.release();
     } catch ( std::exception& e ) {
       g_err = e.what();
@@ -302,6 +340,17 @@ extern "C" {
       }
     if ( meta ) { meta[0] = ep.ibeta_off; meta[1] = ep.first_bin_endpoint; }
     return n;
+  }
+
+  // energy grid of a S(alpha,beta) leaf (as loaded, or as determined by ncb_sabgrid.h)
+  int hostsim_sab_egrid( void* vh, int c, double* out )
+  {
+    auto* h = static_cast<Handle*>(vh);
+    auto& M = h->mat;
+    if ( c < 0 || c >= M.ncomp || M.comp[c].kind != ncb::KIND_SAB ) return -1;
+    const ncb::SabT& T = M.sab[M.comp[c].idx];
+    for ( int i = 0; i < T.negrid; ++i ) out[i] = T.egrid[i];
+    return T.negrid;
   }
 
   // total xs per energy point as recomputed by the native table builder

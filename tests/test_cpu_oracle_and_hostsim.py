@@ -238,3 +238,47 @@ def test_energy_key_lut_gives_the_exact_upper_bound(key, configs):
         fin = np.isfinite(v)
         assert np.array_equal(b[fin], np.searchsorted(tab, v[fin], side="right"))
     assert nlut >= 1
+
+
+@pytest.mark.parametrize("key", ["Al", "H2O", "CH2"])
+def test_sab_energy_grid_determined_from_the_kernel_alone(key):
+    """SABIntegrator::setupEnergyGrid / determineEMin / determineEMax (NCSABIntegrator.cc:147-283) restated
+    (csrc/ncb_sabgrid.h): a compiled material stripped of the reference's energy grids, grid cross sections and
+    extension constants must come out identical to the unstripped one -- grid points bit for bit, cross sections and
+    replayed samples likewise (host build: same libm as the reference)."""
+    from _libs import HostSim, strip_sab_energy_grids, loguniform_energies
+    from oracle_check import material_path
+    from __graft_entry__ import CONFIGS
+    blob = open(material_path(CONFIGS[key]), "rb").read()
+    # (the water file fixes Emax itself: "egrid 4.02", data/LiquidWaterH2O_T293.6K.ncmat:95; Emin is determined)
+    a, b = HostSim(blob), HostSim(strip_sab_energy_grids(blob, emax_request=4.02 if key == "H2O" else 0.0))
+    e = loguniform_energies(3000, seed=5)
+    e[:6] = [1e-9, 1e-7, 4.999, 5.001, 9.0, 100.0]
+    assert np.array_equal(a.xs_iso_components(e), b.xs_iso_components(e))
+    ra, rb = a.sample_iso(e, seed=3), b.sample_iso(e, seed=3)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
+@pytest.mark.parametrize("key", ["H2O", "D2O", "V"])
+def test_sab_energy_grid_fully_automatic_vs_live_reference(key):
+    """No Emax request and (water kernels) no suggested Emax in the table: determineEMax's walk down from the kinematic
+    limit decides the upper end.  The reference's SABIntegrator is run here on the same kernel with no "egrid" request."""
+    from _libs import HostSim, RefDrv, have_refdrv, strip_sab_energy_grids
+    from __graft_entry__ import CONFIGS, EXTRA_CONFIGS
+    if not have_refdrv():
+        pytest.skip("reference not built here")
+    cfg = CONFIGS.get(key) or EXTRA_CONFIGS[key]
+    r = RefDrv(cfg)
+    h = HostSim(strip_sab_energy_grids(r.compile()))
+    names = r.compnames()
+    nchecked = 0
+    for c, nm in enumerate(names):
+        if nm != "SABScatter":
+            continue
+        eg_ref, xs_ref = r.sab_auto_egrid(c)
+        eg = h.sab_egrid(c, 1000)
+        assert np.array_equal(eg, eg_ref), (key, c, eg[[0, -1]], eg_ref[[0, -1]])
+        assert np.array_equal(h.sab_xscheck(c, 1000), xs_ref)
+        nchecked += 1
+    assert nchecked >= 1

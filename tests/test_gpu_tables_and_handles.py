@@ -185,3 +185,27 @@ def test_plain_c_caller_uses_all_visible_gpus(tmp_path, configs):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert '"identical_to_one_device": true' in r.stdout
+
+
+@pytest.mark.parametrize("key", ["Al", "H2O", "CH2"])
+def test_sab_energy_grid_determined_on_the_device(key):
+    """A compiled material stripped of the reference's S(alpha,beta) energy grids / grid cross sections / extension
+    constants: the library determines them itself (csrc/ncb_sabgrid.h; all probe energies of determineEMin /
+    determineEMax integrated in one pass of the table-build kernels) and must behave like the unstripped material."""
+    import ncrystal_b200 as nc
+    from _libs import strip_sab_energy_grids, loguniform_energies
+    from _parity import assert_replay
+    from oracle_check import material_path
+    from __graft_entry__ import CONFIGS
+    blob = open(material_path(CONFIGS[key]), "rb").read()
+    a = nc.Scatter.fromBlob(blob, seed=4)
+    b = nc.Scatter.fromBlob(strip_sab_energy_grids(blob, emax_request=4.02 if key == "H2O" else 0.0), seed=4)
+    e = loguniform_energies(200000, seed=6)
+    e[:6] = [1e-9, 1e-7, 4.999, 5.001, 9.0, 100.0]
+    xa, xb = a.crossSectionIsotropic(e), b.crossSectionIsotropic(e)
+    rel = np.abs(xa - xb) / np.abs(xa)
+    print("%s: xs max rel %.2e between given and device-determined energy grid" % (key, rel.max()))
+    assert rel.max() <= 1e-12
+    a.setRNGStream(4, 0, 0); b.setRNGStream(4, 0, 0)
+    ra, rb = a.sampleScatterIsotropic(e), b.sampleScatterIsotropic(e)
+    assert_replay(rb, ra, None, None, "%s auto energy grid" % key)
