@@ -1,5 +1,5 @@
-// oracle/matcompile.cc -- command-line front end of the material compiler
-// (refdrv_compile in refdrv.cc):  ncb200_matcompile "<cfg-string>" out.ncb
+// bridge/matcompile.cc -- command-line front end of the material compiler
+// (refdrv_compile in matcompile_impl.icc):  ncb200_matcompile "<cfg-string>" out.ncb
 // TEST INFRASTRUCTURE / reference-side tooling; links the unmodified reference.
 #include <cstdio>
 #include <cstdint>

@@ -275,6 +275,11 @@ double   ncb200_fp64_fma_probe(void);
 /* SAB table builder check: per-energy-point total xs recomputed on the device while
  * building the sampler tables (compare with the xs grid of the compiled material). */
 int      ncb200_sab_xscheck( ncrystal_process_t, int component, double* out, int nmax );
+/* energy grid / grid cross sections / {k_extension, k1, k2, egrid_margin} of a S(alpha,beta) leaf: SABXSProvider::m_egrid,
+ * m_xs, m_kExtension and SABSampler::m_k1, m_k2, m_egridMargin (NCSABXSProvider.cc:35-52, NCSABSampler.cc:41-57), as
+ * delivered in the compiled material or as determined by the library itself (ncb_blob.h: ncb_sab_t::auto_egrid,
+ * restating NCSABIntegrator.cc:147-283).  Returns the number of grid points. */
+int      ncb200_sab_energy_grid( ncrystal_process_t, int component, double* egrid, double* xs, int nmax, double* consts4 );
 /* Copy of built sampler tables for one energy point (layout as oracle refdrv_sab_sampler_dump) */
 int      ncb200_sab_sampler_dump( ncrystal_process_t, int component, int iE, double* x, double* pdf, double* cdf,
                                   double* infos, double* meta );

@@ -131,6 +131,7 @@ SIGNATURES = {
     "ncb200_last_queue_counts": (C.c_int, [ncrystal_scatter_t, C.POINTER(C.c_uint32)]),
     "ncb200_version": (C.c_char_p, []),
     "ncb200_sab_xscheck": (C.c_int, [ncrystal_process_t, C.c_int, _dblp, C.c_int]),
+    "ncb200_sab_energy_grid": (C.c_int, [ncrystal_process_t, C.c_int, _dblp, _dblp, C.c_int, _dblp]),
     "ncb200_sab_sampler_dump": (C.c_int, [ncrystal_process_t, C.c_int, C.c_int, _dblp, _dblp, _dblp, _dblp, _dblp]),
     "ncb200_sab_selfcheck": (C.c_long, [ncrystal_process_t, C.c_int]),
     "ncb200_pin_host_buffer": (C.c_int, [_vp, _u64]),

@@ -49,6 +49,18 @@ namespace {
   int g_waserror = 0;
   char g_errmsg[512];
   char g_errtype[64];
+  // Kernel-tuning switches (chunk sizes, CTAs per SM, alternative kernel orderings: the A/B experiments recorded in
+  // DESIGN.md) are compiled out of the product: they are read from the environment only in a -DNCB200_TUNING=1 build.
+  // Run-time configuration that stays: NCB200_DATA_PATH (compiled materials), NCB200_COPY_THREADS (host copy pool).
+  inline const char* tuneEnv( const char* name )
+  {
+#if defined(NCB200_TUNING) && NCB200_TUNING
+    return std::getenv( name );
+#else
+    (void)name;
+    return nullptr;
+#endif
+  }
   void (*g_custom_error_handler)(char*,char*) = nullptr;
   // message handler, ref: ncrystal.h:1051, ncrystal.cc:2428-2446, src/utils/NCMsg.cc:44-82 (0: info, 1: warning, 2: raw)
   std::mutex g_msg_mtx;
@@ -305,7 +317,6 @@ namespace {
         // integrated in ONE pass of the table-build kernels (they run per energy point anyway)
         SabT& Tm = dm.mat.sab[pl.sab_index];
         double* d_egrid = reinterpret_cast<double*>( base + pl.off_egrid );
-        double* d_xs = reinterpret_cast<double*>( base + pl.off_xs );
         auto sigmaAt = [&]( const std::vector<double>& e ) {
           if ( e.empty() || (int)e.size() > ne )
             throw Err( "CalcError", "SAB energy grid: probe sequence does not fit the table scratch" );
@@ -320,6 +331,8 @@ namespace {
           CUDA_OK( cudaMemcpyAsync( er.data(), errs, e.size()*4, cudaMemcpyDeviceToHost, st ) );
           CUDA_OK( cudaStreamSynchronize( st ) );
           for ( int c : er ) if ( c ) throw Err( "CalcError", "S(alpha,beta) energy-point analysis failed on device (code "+std::to_string(c)+")" );
+          if ( tuneEnv( "NCB200_DEBUG_EGRID" ) )
+            for ( size_t k = 0; k < e.size(); ++k ) std::fprintf( stderr, "egrid-probe %zu %.17g %.17g\n", k, e[k], xs[k] );
           return xs;
         };
         // (alpha, beta grid ends for the kinematic limit of the table)
@@ -347,7 +360,6 @@ namespace {
             Tm.elut_key0 = key0; Tm.elut_shift = shift; Tm.elut_nk = nk;
           }
         }
-        (void)d_xs;
       }
       k_sab_rows<<< dim3( ( nb + 127 )/128, ne ), 128, 0, st >>>( T, rows, ainfo );
       k_sab_epoints<<< ( ne + 31 )/32, 32, 0, st >>>( T, rows, ep, bx, bpdf, bcdf, xscheck, errs );
@@ -449,7 +461,7 @@ namespace {
   constexpr size_t kChunkMax = (size_t)1 << 22; // staging capacity (neutrons) per pipeline slot of the host-pointer path
   size_t chunkSize()
   {
-    static const size_t c = []{ const char* e = std::getenv( "NCB200_CHUNK" ); size_t v = e ? (size_t)std::atoll(e) : ( (size_t)1 << 20 ); return std::min( std::max<size_t>( v, 1024 ), kChunkMax ); }();
+    static const size_t c = []{ const char* e = tuneEnv( "NCB200_CHUNK" ); size_t v = e ? (size_t)std::atoll(e) : ( (size_t)1 << 20 ); return std::min( std::max<size_t>( v, 1024 ), kChunkMax ); }();
     return c;
   }
   constexpr int kSlots = 3;
@@ -459,8 +471,8 @@ namespace {
   {
     static const PipeSchedule ps = []{
       PipeSchedule p;
-      const char* e0 = std::getenv( "NCB200_CHUNK0" );
-      const char* eg = std::getenv( "NCB200_CHUNK_GROWTH" );
+      const char* e0 = tuneEnv( "NCB200_CHUNK0" );
+      const char* eg = tuneEnv( "NCB200_CHUNK_GROWTH" );
       p.max = chunkSize();
       p.first = std::min<uint64_t>( p.max, std::max<uint64_t>( 4096, e0 ? (uint64_t)std::atoll(e0) : ( (uint64_t)1 << 18 ) ) );
       p.growth = std::max( 1.0, eg ? std::atof(eg) : 2.0 );
@@ -782,7 +794,7 @@ namespace {
   void partitionFgQueue( const DeviceMaterial& dm, Scatter::QueueCtx& qc, QueueArgs& Q, const double* d_ekin, uint64_t m,
                          cudaStream_t st )
   {
-    static const bool group = []{ const char* e = std::getenv( "NCB200_FG_GROUP" ); return !e || std::atoi(e) != 0; }();
+    static const bool group = []{ const char* e = tuneEnv( "NCB200_FG_GROUP" ); return !e || std::atoi(e) != 0; }();
     if ( !group || !dm.has_fg_leaf ) return;
     TimedLaunch tl( "k_fg_partition", st );
     uint32_t* cls = qc.counts + 8;                  // [16] class totals + [16] cursors (the sort's histogram area)
@@ -799,23 +811,26 @@ namespace {
   // two kernel tails less: measured better for the 1 Mi-neutron chunks of the host-pointer pipeline and for the
   // shrinking populations of a transport run; NCB200_FG_MODE=0 forces it).  The two refill cursors live in the (otherwise unused) sort-histogram area of the
   // counters, zeroed with them at the start of the launch sequence.
-  std::atomic<uint64_t> g_fg_staged_min{ []{ const char* e = std::getenv( "NCB200_FG_STAGED_MIN" );
+  std::atomic<uint64_t> g_fg_staged_min{ []{ const char* e = tuneEnv( "NCB200_FG_STAGED_MIN" );
                                              return e ? (uint64_t)std::atoll(e) : (uint64_t)4000000; }() };
   void launchFgSampling( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const SampleArgs& A, const QueueArgs& Q,
                          uint64_t m, cudaStream_t st, bool timed )
   {
-    static const int mode = []{ const char* e = std::getenv( "NCB200_FG_MODE" ); return e ? std::atoi(e) : 1; }();
-    static const int fgctas = []{ const char* e = std::getenv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
-    static const int fgminb = []{ const char* e = std::getenv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
-    static const int epl = []{ const char* e = std::getenv( "NCB200_FG_EPL" ); return e ? std::atoi(e) : 4; }();
+    static const int mode = []{ const char* e = tuneEnv( "NCB200_FG_MODE" ); return e ? std::atoi(e) : 1; }();
+    static const int fgctas = []{ const char* e = tuneEnv( "NCB200_FG_CTAS" ); return e ? std::atoi(e) : 16; }();
+    static const int fgminb = []{ const char* e = tuneEnv( "NCB200_FG_MINB" ); return e ? std::atoi(e) : 8; }();
+    static const int epl = []{ const char* e = tuneEnv( "NCB200_FG_EPL" ); return e ? std::atoi(e) : 4; }();
     const uint64_t minbatch = g_fg_staged_min.load();
     const unsigned nsm = (unsigned)numSMs( dm.device );
     auto timer = [&]( const char* name ) { return std::unique_ptr<TimedLaunch>( timed ? new TimedLaunch( name, st ) : nullptr ); };
     if ( mode == 0 || m < minbatch ) {
       const unsigned g = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*fgctas );
       auto tl = timer( "k_sample_fg" );
-      if ( fgminb >= 8 ) k_sample_fg<8><<< g, 128, 0, st >>>( dm.mat, A, Q );
-      else k_sample_fg<4><<< g, 128, 0, st >>>( dm.mat, A, Q );
+#if defined(NCB200_TUNING) && NCB200_TUNING
+      if ( fgminb < 8 ) k_sample_fg<4><<< g, 128, 0, st >>>( dm.mat, A, Q );
+      else
+#endif
+      k_sample_fg<8><<< g, 128, 0, st >>>( dm.mat, A, Q );
       ++g_launches;
       return;
     }
@@ -824,20 +839,26 @@ namespace {
     P.r = qc.fg_prep; P.cap = qc.fcap; P.w = qc.fg_nd;
     P.cursor = Q.counts + 8 + 48;
     P.epl = (uint32_t)std::max( 1, epl );
-    static const int batch = []{ const char* e = std::getenv( "NCB200_FG_BATCH" ); return e ? std::atoi(e) : 20; }();
+    static const int batch = []{ const char* e = tuneEnv( "NCB200_FG_BATCH" ); return e ? std::atoi(e) : 20; }();
     P.batch = (uint32_t)std::min( 32, std::max( 1, batch ) );
     const unsigned gflat = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*16 );
     const unsigned grefill = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*( fgminb >= 8 ? 8 : 6 ) );
     { auto tl = timer( "k_fg_prep" );
       k_fg_prep<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
     { auto tl = timer( "k_fg_beta" );
-      if ( fgminb >= 8 ) k_fg_beta<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
-      else k_fg_beta<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
+#if defined(NCB200_TUNING) && NCB200_TUNING
+      if ( fgminb < 8 ) k_fg_beta<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
+      else
+#endif
+      k_fg_beta<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
     { auto tl = timer( "k_fg_alpha_prep" );
       k_fg_alpha_prep<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
     { auto tl = timer( "k_fg_alpha" );
-      if ( fgminb >= 8 ) k_fg_alpha<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
-      else k_fg_alpha<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
+#if defined(NCB200_TUNING) && NCB200_TUNING
+      if ( fgminb < 8 ) k_fg_alpha<6><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P );
+      else
+#endif
+      k_fg_alpha<8><<< grefill, 128, 0, st >>>( dm.mat, A, Q, P ); }
     { auto tl = timer( "k_fg_finish" );
       k_fg_finish<<< gflat, 128, 0, st >>>( dm.mat, A, Q, P ); }
     g_launches += 5;
@@ -851,12 +872,15 @@ namespace {
                        uint64_t m, cudaStream_t st, bool timed )
   {
     const unsigned nsm = (unsigned)numSMs( dm.device );
-    static const int minb = []{ const char* e = std::getenv( "NCB200_SAB_MINB" ); return e ? std::atoi(e) : 8; }();
+    static const int minb = []{ const char* e = tuneEnv( "NCB200_SAB_MINB" ); return e ? std::atoi(e) : 8; }();
     const unsigned gr = (unsigned)std::min<uint64_t>( ( m + 127 )/128, (uint64_t)nsm*minb );
     std::unique_ptr<TimedLaunch> tl( timed ? new TimedLaunch( "k_sample_sab_refill", st ) : nullptr );
+#if defined(NCB200_TUNING) && NCB200_TUNING
     if ( minb == 6 ) k_sample_sab_refill<false,6><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
     else if ( minb == 7 ) k_sample_sab_refill<false,7><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
-    else k_sample_sab_refill<false,8><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
+    else
+#endif
+    k_sample_sab_refill<false,8><<< gr, 128, 0, st >>>( dm.mat, A, Q.q_sab, Q.counts + 0, Q.counts + 3 );
     ++g_launches;
   }
 
@@ -875,7 +899,7 @@ namespace {
     // Sub-launches of at most 2^26 neutrons (queue entries hold 28 index bits): bounds the scratch (index queues
     // 26 B and free-gas stage records 76 B per neutron of a sub-launch, ~7 GB) however large the batch is; results do
     // not depend on the split (streams are keyed by the global neutron index).  NCB200_SUBLAUNCH overrides (tests).
-    static const uint64_t sub = []{ const char* e = std::getenv( "NCB200_SUBLAUNCH" );
+    static const uint64_t sub = []{ const char* e = tuneEnv( "NCB200_SUBLAUNCH" );
                                     const uint64_t v = e ? (uint64_t)std::atoll(e) : ( (uint64_t)1 << 26 );
                                     return std::min<uint64_t>( std::max<uint64_t>( v, 1024 ), (uint64_t)1 << kQueueIdxBits ); }();
     for ( uint64_t done = 0; done < n; done += sub ) {
@@ -909,7 +933,7 @@ namespace {
 
   bool useAnisoV1()
   {
-    static const bool v1 = []{ const char* e = std::getenv( "NCB200_ANISO_V1" ); return e && *e && *e != '0'; }();
+    static const bool v1 = []{ const char* e = tuneEnv( "NCB200_ANISO_V1" ); return e && *e && *e != '0'; }();
     return v1;
   }
 
@@ -931,7 +955,7 @@ namespace {
   // thread-per-neutron kernels (1 launch instead of 2-8) are used for them.  NCB200_SMALL_V1 overrides (0 = never).
   uint64_t smallBatchV1()
   {
-    static const uint64_t v = []{ const char* e = std::getenv( "NCB200_SMALL_V1" ); return e ? (uint64_t)std::atoll(e) : (uint64_t)0; }();
+    static const uint64_t v = []{ const char* e = tuneEnv( "NCB200_SMALL_V1" ); return e ? (uint64_t)std::atoll(e) : (uint64_t)0; }();
     return v;
   }
 
@@ -940,7 +964,7 @@ namespace {
   void launchScScan( const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
                      const double* uy, const double* uz, uint64_t n, cudaStream_t st, const uint32_t* n_dev = nullptr )
   {
-    static const bool onekernel = []{ const char* e = std::getenv( "NCB200_SC_ONEKERNEL" ); return e && std::atoi(e) != 0; }();
+    static const bool onekernel = []{ const char* e = tuneEnv( "NCB200_SC_ONEKERNEL" ); return e && std::atoi(e) != 0; }();
     const int isc = scCompIndex( dm.mat );
     const uint64_t need = ( n + kScWarps - 1 ) / kScWarps;
     const unsigned nsm = (unsigned)numSMs( dm.device );
@@ -2068,6 +2092,25 @@ extern "C" {
           CUDA_OK( cudaMemcpy( out, static_cast<unsigned char*>( s->dm->d_arena ) + pl.off_xscheck, (size_t)m*8, cudaMemcpyDeviceToHost ) );
           return ne;
         }
+    } NCBCATCH;
+    return -1;
+  }
+
+  // energy grid, grid cross sections and extension constants {k_extension, k1, k2, egrid_margin} of a S(alpha,beta) leaf
+  // (as delivered in the compiled material, or as determined by the library: ncb_sab_t::auto_egrid)
+  int ncb200_sab_energy_grid( ncrystal_process_t p, int component, double* egrid, double* xs, int nmax, double* consts4 )
+  {
+    try {
+      Scatter* s = fromInternal( p.internal, "ncb200_sab_energy_grid" );
+      const Material& M = s->dm->mat;
+      if ( component < 0 || component >= M.ncomp || M.comp[component].kind != KIND_SAB ) return -1;
+      const SabT& T = M.sab[M.comp[component].idx];
+      const int m = T.negrid < nmax ? T.negrid : nmax;
+      DeviceGuard dg( s->dm->device );
+      if ( egrid ) CUDA_OK( cudaMemcpy( egrid, T.egrid, (size_t)m*8, cudaMemcpyDeviceToHost ) );
+      if ( xs ) CUDA_OK( cudaMemcpy( xs, T.xs, (size_t)m*8, cudaMemcpyDeviceToHost ) );
+      if ( consts4 ) { consts4[0] = T.k_extension; consts4[1] = T.k1; consts4[2] = T.k2; consts4[3] = T.egrid_margin; }
+      return T.negrid;
     } NCBCATCH;
     return -1;
   }

@@ -15,6 +15,8 @@
 #include "ncb_sabgrid.h"
 #include "ncb_mmc.cuh"
 #include <memory>
+#include <cstdio>
+#include <cstdlib>
 
 namespace ncb {
   double g_erfc_lut_host[kErfcLutLen];
@@ -64,6 +66,8 @@ namespace {
             xs[k] = sabAssembleEPoint( T.beta, nb, T.kT, T.bound_xs, e[k], r.data(), 0, 0, tmp, tx.data(), tp.data(), tc.data(), err );
             if ( err ) throw std::runtime_error( "SAB energy-point analysis failed" );
           }
+          if ( std::getenv( "NCB200_DEBUG_EGRID" ) )
+            for ( size_t k = 0; k < e.size(); ++k ) std::fprintf( stderr, "egrid-probe %zu %.17g %.17g\n", k, e[k], xs[k] );
           return xs;
         };
         const std::vector<double> eg = sabDetermineEnergyGrid( ne, T.kT, T.beta[0], T.alpha[na-1], pl.suggested_emax, pl.req_emin, pl.req_emax, T.ext, sigmaAt, []( const char* ) {} );
