@@ -266,6 +266,9 @@ int      ncb200_kernel_timing_report( char* buf, int buflen );
 /* Batches of at least nmin neutrons sample their free-gas queue with the staged kernels (k_fg_prep ... k_fg_finish),
  * smaller ones with the single neutron-per-lane kernel; identical results.  Default 4e6 ($NCB200_FG_STAGED_MIN). */
 void     ncb200_set_fg_staged_min( uint64_t nmin );
+/* test hook: 1 (default) = the tail of a transport run (<= 32 Ki live neutrons) is finished by the one-launch
+ * warp-per-history kernel, 0 = by groups of 16 steps of the multi-kernel sequence.  Same tallies either way. */
+void     ncb200_set_mmc_tail_mode( int persistent );
 /* sizes of the work queues of the most recent isotropic sampling launch: table path, free-gas path, table at Emax */
 int      ncb200_last_queue_counts( ncrystal_scatter_t, uint32_t* out3 );
 const char* ncb200_version(void);

@@ -125,6 +125,7 @@ SIGNATURES = {
     "ncb200_material_bulk": (None, [ncrystal_process_t, _dblp, _dblp, _dblp]),
     "ncb200_fp64_fma_probe": (C.c_double, []),
     "ncb200_set_fg_staged_min": (None, [C.c_uint64]),
+    "ncb200_set_mmc_tail_mode": (None, [C.c_int]),
     "ncb200_xs_and_samplescatterisotropic_many": (None, [ncrystal_scatter_t, _dblp, C.c_uint64, _dblp, _dblp, _dblp]),
     "ncb200_kernel_timing": (None, [C.c_int]),
     "ncb200_kernel_timing_report": (C.c_int, [C.c_char_p, C.c_int]),

@@ -250,3 +250,147 @@ namespace ncb {
   }
 
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tail of a transport run.  Once few neutrons are left (<= 32 Ki) a step is a dozen launches on nearly empty grids --
+// and a neutron caught between Bragg reflections of a single crystal can live for hundreds of steps (Ge sphere at
+// 3.2 Aa: 851 steps, 11,000 launches, 0.1 ms each).  k_mmc_tail finishes such a population in ONE launch: one warp
+// per history, looping over its steps until the history ends.  Per step it does what the launch sequence above does
+// for that neutron, with the same per-(source id, step) random streams -- hence the same tallies:
+//   cross section   isotropic leaves by every lane redundantly (same instruction stream, no extra issue cost),
+//                   the single-crystal leaf by the warp-cooperative walk of k_sc_scan (scWalkWarp);
+//   forward step    mmcForward;  exit tallies with global fp64 atomics, one lane per histogram;
+//   scattering      component pick; single crystal: second walk (mode 1) + GaussMos::genScat as in k_sc_sample;
+//                   other leaves: the thread-level samplers + randDirectionGivenScatterMu (ncb_proc.cuh: matSample);
+//   bookkeeping     k_mmc_post.
+// dynamic smem: [staged tables (sp.total)] [fam_of: nnormals bytes] [kMmcTailWarps x ScWarpScratch]
+constexpr int kMmcTailWarps = 8;
+struct MmcTailOut {
+  unsigned long long records;   // tally records made (= live neutrons summed over the steps)
+  unsigned int last_step;       // highest step index + 1 reached by any history
+  unsigned int pad;
+};
+
+namespace ncb {
+
+  __device__ __forceinline__ void mmcTallyAtomic( const MmcTally& T, double* __restrict__ tally, int lane,
+                                                  double ux, double uy, double uz, double ekin, double wt, int nscat, int ninel,
+                                                  double e0, double ux0, double uy0, double uz0 )
+  {
+    if ( lane >= T.nh ) return;
+    const MmcHist h = T.h[lane];
+    bool weighted;
+    const double val = mmcTallyValue( T, h.type, ux, uy, uz, ekin, wt, nscat, e0, ux0, uy0, uz0, weighted );
+    const double wgt = weighted ? wt : 1.0;
+    if ( !( wgt > 0.0 ) ) return;
+    const int nb2 = h.nbins + 2;
+    const int cls = mmcClass( nscat, ninel );
+    const int key = cls*nb2 + mmcValueToBin( h, val );
+    double* g = tally + h.off;
+    unsigned long long* gu = reinterpret_cast<unsigned long long*>( g );
+    atomicAdd( &g[key], wgt );
+    atomicAdd( &g[kMmcNClass*nb2 + key], wgt*wgt );
+    const int o = 2*kMmcNClass*nb2 + cls*kMmcNStat;
+    atomicAdd( &g[o+0], wgt ); atomicAdd( &g[o+1], wgt*val ); atomicAdd( &g[o+2], wgt*val*val );
+    atomicMin( &gu[o+3], mmcOrdered( val ) );
+    atomicMax( &gu[o+4], mmcOrdered( val ) );
+  }
+
+  __global__ void __launch_bounds__(32*kMmcTailWarps, 1)
+  k_mmc_tail( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+              const __grid_constant__ MmcGeom G, const __grid_constant__ MmcEngine E, const __grid_constant__ MmcTally T,
+              uint64_t seed, uint32_t step0, uint32_t max_steps, uint32_t n, MmcState A,
+              double* __restrict__ tally, double* __restrict__ meta, MmcTailOut* __restrict__ out, int* __restrict__ err_flags,
+              uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    int isc = -1;
+    for ( int c = 0; c < M.ncomp; ++c ) if ( M.comp[c].kind == KIND_SCBRAGG ) isc = c;
+    if ( isc >= 0 ) scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    else stageHotTabs( M, sp, smem, &mbar, H );
+    const ScBraggT& S = *H.sc;
+    ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * kMmcTailWarps;
+    unsigned long long records = 0;
+    unsigned int last_step = 0;
+    double sumw = 0.0;
+    int errs = 0;
+    for ( uint32_t ih = blockIdx.x * kMmcTailWarps + ( threadIdx.x >> 5 ); ih < n; ih += nwarps ) {
+      double x = A.x[ih], y = A.y[ih], z = A.z[ih], ux = A.ux[ih], uy = A.uy[ih], uz = A.uz[ih];
+      double w = A.w[ih], ekin = A.ekin[ih];
+      const double e0 = A.e0[ih];
+      double ux0 = 0, uy0 = 0, uz0 = 0;
+      if ( A.ux0 ) { ux0 = A.ux0[ih]; uy0 = A.uy0[ih]; uz0 = A.uz0[ih]; }
+      int nscat = A.nscat[ih], ninel = A.ninel[ih];
+      const uint64_t id = A.id[ih];
+      uint32_t step = step0;
+      while ( true ) {
+        if ( step - step0 >= max_steps ) { errs |= ERR_MMC_NOTERM; break; }
+        // ---- cross section at (E, dir): launchXSAniso
+        double sc_xs = 0.0; int sc_n = 0;
+        const Vec3 dir = { ux, uy, uz };
+        Vec3 dnorm = dir;
+        if ( isc >= 0 && domainContains( M.comp[isc].dom_lo, M.comp[isc].dom_hi, ekin ) && !( ekin <= S.threshold_ekin ) ) {
+          vnormalise( dnorm );
+          ScAccum acc; double wl;
+          scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 0, false, 0.0 );
+          sc_xs = acc.commul_last; sc_n = acc.n;
+        }
+        double cumul[kMaxComp]; int aux[kMaxComp];
+        const double xs = matXSPre( M, H, ekin, sc_xs, sc_n, cumul, aux );
+        // ---- forward step + exit tallies: k_mmc_forward, k_mmc_tally, k_mmc_sum_weights
+        Rng rng; rng.init( seed, id, kMmcSidBase + 2u*step );
+        const MmcStepOut o = mmcForward( G, E, rng, x, y, z, ux, uy, uz, w, ekin, nscat, xs );
+        mmcTallyAtomic( T, tally, lane, ux, uy, uz, ekin, o.wt, nscat, ninel, e0, ux0, uy0, uz0 );
+        sumw += o.wt; ++records;
+        ++step;
+        if ( !o.survives ) break;
+        x = o.x; y = o.y; z = o.z; w = o.w;
+        // ---- scattering: launchSampleAniso on the stream (id, step) with the odd stream id
+        double eout = ekin; Vec3 od = dir;
+        if ( domainContains( M.dom_lo, M.dom_hi, ekin ) ) {
+          Rng r2; r2.init( seed, id, kMmcSidBase + 2u*( step - 1u ) + 1u );
+          const int ich = ( M.ncomp == 1 ? 0 : pickIdxByWeight( r2.generate(), cumul, M.ncomp ) );
+          const Comp& c = M.comp[ich];
+          if ( c.kind == KIND_SCBRAGG ) {
+            if ( !( ekin <= M.sc.threshold_ekin ) && aux[ich] > 0 && sc_xs > 0.0 ) {
+              double choice = -1.0; bool linear = true;
+              if ( sc_n > 1 ) { choice = sc_xs * r2.generate(); linear = ( sc_n < 5 ); }
+              ScAccum acc; double wl;
+              scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 1, linear, choice );
+              const int in = acc.chosen_in;
+              const double sg = acc.chosen_sign ? 1.0 : -1.0;
+              const Vec3 pn = { sg*S.normals[3*in], sg*S.normals[3*in+1], sg*S.normals[3*in+2] };
+              const double inv2dsp = gmCacheRound( S.fam_inv2d[ fam_of[in] ] );
+              gmGenScat( S, r2, pn, inv2dsp, wl, dnorm, od );
+            }
+          } else {
+            double mu = 1.0; int err = 0;
+            compSampleIso( M, H, ich, aux[ich], ekin, r2, eout, mu, err );
+            errs |= err;
+            if ( !( err & ( ERR_SAB_LOOP_INNER | ERR_SAB_LOOP_OUTER | ERR_SAB_DISCARD | ERR_KIN_DENOM ) ) )
+              od = randDirectionGivenScatterMu( r2, mu, dir );
+            else { od = { 0.0, 0.0, 0.0 }; eout = -1.0; }
+          }
+        }
+        if ( !( eout >= 0.0 ) ) break;     // a sampler raised an error: the flags end the run on the host
+        // ---- k_mmc_post
+        const bool was_elastic = ( ekin == eout );
+        ux = od.x; uy = od.y; uz = od.z; ekin = eout;
+        ++nscat;
+        if ( !was_elastic ) ++ninel;
+      }
+      if ( step > last_step ) last_step = step;
+    }
+    if ( lane == 0 ) {
+      if ( records ) { atomicAdd( &out->records, records ); atomicAdd( &meta[0], sumw ); }
+      atomicMax( &out->last_step, last_step );
+    }
+    if ( errs ) atomicOr( err_flags, errs );
+  }
+
+}

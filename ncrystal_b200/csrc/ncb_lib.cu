@@ -445,6 +445,7 @@ namespace {
     setSmemAttr( k_sc_sample );
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_find );
+    setSmemAttr( k_mmc_tail );
     setSmemAttr( k_lc_scan );
     setSmemAttr( k_lc_sample );
     setSmemAttr( k_tally_hist );
@@ -1162,6 +1163,8 @@ namespace {
       throw Err( "CalcError", "Infinite looping in sampleAlphaBeta" );
     if ( flags & ERR_KIN_DENOM )
       throw Err( "CalcError", "convertAlphaBetaToDeltaEMu invalid for beta=-E/kT" );
+    if ( flags & ERR_MMC_NOTERM )
+      throw Err( "CalcError", "transport did not terminate" );
     if ( flags & ERR_LC_ROMBERG )
       throw Err( "CalcError", "Romberg integration did not converge." );
   }
@@ -1838,6 +1841,7 @@ extern "C" {
     } NCBCATCH;
   }
   void ncb200_set_fg_staged_min( uint64_t nmin ) { g_fg_staged_min.store( nmin ); }
+  void ncb200_set_mmc_tail_mode( int persistent ) { g_mmc_persistent_tail.store( persistent != 0 ); }
   void ncb200_get_rng_stream( ncrystal_scatter_t o, uint64_t* seed, uint32_t* stream_id, uint64_t* next_index )
   {
     try {

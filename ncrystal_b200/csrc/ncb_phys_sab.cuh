@@ -18,6 +18,7 @@ namespace ncb {
     ERR_SAB_DISCARD = 8,     // sampleHighE: P_discardinside > 0.95 (NCSABSampler.cc:112)
     ERR_SAB_ISOFALLBACK = 16,// (warning only) isotropic fallback after 30 tries (NCSABSamplerModels.cc:99)
     ERR_SAB_ROUTING = 32,    // internal: E > Emax neutron reached the table-only kernel
+    ERR_MMC_NOTERM = 128,    // transport: a history did not end within the step limit
     ERR_LC_ROMBERG = 64      // LCBragg: phi integration did not converge (Romberg::convergenceError, NCRomberg.cc:48-61)
   };
 

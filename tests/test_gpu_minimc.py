@@ -117,3 +117,28 @@ def test_full_size_run_properties(handles):
     got = res["output"]["tally"]["theta"]["breakdown"]["NOSCAT"]["stats"]["integral"] / n
     assert abs(got - expect) < 1e-9
     assert res["b200"]["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("key", ["al_4Aa", "scge", "thermal_h2o", "isoshell_ch2"])
+def test_tail_kernel_and_multi_kernel_tail_agree(handles, key):
+    # the one-launch warp-per-history kernel that finishes a run (k_mmc_tail, default) against the multi-kernel
+    # sequence in groups of 16 steps: same per-(source id, step) streams, hence the same tallies (sums in another
+    # order: 1e-10), record counts and step counts
+    sc = all_scenarios()[key]
+    s = handles(sc.material)
+    L = s._L
+    try:
+        L.ncb200_set_mmc_tail_mode(0)
+        r0 = s.minimc(sc.geomcfg, sc.srccfg(), sc.enginecfg())
+    finally:
+        L.ncb200_set_mmc_tail_mode(1)
+    r1 = s.minimc(sc.geomcfg, sc.srccfg(), sc.enginecfg())
+    h0, m0 = hists_from_json(r0, sc.tallies)
+    h1, m1 = hists_from_json(r1, sc.tallies)
+    assert m0["tallied"]["count"] == m1["tallied"]["count"] and m0["miss"]["count"] == m1["miss"]["count"]
+    assert abs(m0["tallied"]["weight"] - m1["tallied"]["weight"]) <= 1e-10 * m0["tallied"]["weight"]
+    assert r0["b200"]["steps"] == r1["b200"]["steps"]
+    assert r1["b200"]["kernel_launches"] < r0["b200"]["kernel_launches"]
+    for name, *_ in sc.tallies:
+        assert np.allclose(h0[name]["content"], h1[name]["content"], rtol=1e-10, atol=1e-9)
+        assert np.allclose(h0[name]["errsq"], h1[name]["errsq"], rtol=1e-10, atol=1e-9)
