@@ -13,6 +13,11 @@
 
 #include "../bridge/matcompile_impl.icc"
 #include "philox_ref.h"
+#include "NCrystal/internal/vdos/NCVDOSEval.hh"
+#include "NCrystal/internal/vdos/NCVDOSGn.hh"
+#include "NCrystal/internal/vdos/NCVDOSToScatKnl.hh"
+#include "NCrystal/internal/sab/NCSABUtils.hh"
+#include <algorithm>
 
 namespace {
   class PhiloxStream final : public NC::RNGStream {
@@ -187,6 +192,72 @@ extern "C" {
       g_err = e.what();
       return -3;
     }
+  }
+
+  // ---- VDOS -> S(alpha,beta) expansion of the reference, stage by stage (what csrc/ncb_vdos.h restates) -----
+  // The k'th DI_VDOS entry of the material's dynamic-info list.
+  static const NC::DI_VDOS* vdosEntry( const NC::Info& info, int k )
+  {
+    int i = 0;
+    for ( auto& di : info.getDynamicInfoList() )
+      if ( auto v = dynamic_cast<const NC::DI_VDOS*>( di.get() ) ) { if ( i++ == k ) return v; }
+    return nullptr;
+  }
+  // meta = { emin, emax, temperature, mass_amu, bound_xs }; returns the number of density points (or -1)
+  int refdrv_vdos_data( const char* cfg, int k, double* meta5, double* density, int cap )
+  {
+    try {
+      auto info = NC::createInfo( cfg );
+      auto v = vdosEntry( *info, k );
+      if ( !v ) return -1;
+      const NC::VDOSData& vd = v->vdosData();
+      meta5[0] = vd.vdos_egrid().first; meta5[1] = vd.vdos_egrid().second; meta5[2] = vd.temperature().dbl();
+      meta5[3] = vd.elementMassAMU().dbl(); meta5[4] = vd.boundXS().dbl();
+      const int n = (int)vd.vdos_density().size();
+      if ( n > cap ) return -2;
+      for ( int i = 0; i < n; ++i ) density[i] = vd.vdos_density()[i];
+      return n;
+    } catch ( std::exception& e ) { g_err = e.what(); return -3; }
+  }
+  // createScatteringKernel + transformKernelToStdFormat.  meta = { suggestedEmax, gamma0, msd, max order reached }.
+  int refdrv_vdos_expand( const char* cfg, int k, int vdoslux, double* alpha, int* nalpha, double* beta, int* nbeta,
+                          double* sab, int cap_sab, double* meta4 )
+  {
+    try {
+      auto info = NC::createInfo( cfg );
+      auto v = vdosEntry( *info, k );
+      if ( !v ) return -1;
+      const NC::VDOSData& vd = v->vdosData();
+      NC::VDOSEval ve( vd );
+      meta4[1] = ve.calcGamma0(); meta4[2] = ve.getMSD( meta4[1] );
+      auto sd = NC::SABUtils::transformKernelToStdFormat( NC::createScatteringKernel( vd, (unsigned)vdoslux ) );
+      meta4[0] = sd.suggestedEmax(); meta4[3] = 0.0;
+      const int na = (int)sd.alphaGrid().size(), nb = (int)sd.betaGrid().size();
+      if ( na*nb > cap_sab ) return -2;
+      *nalpha = na; *nbeta = nb;
+      for ( int i = 0; i < na; ++i ) alpha[i] = sd.alphaGrid()[i];
+      for ( int i = 0; i < nb; ++i ) beta[i] = sd.betaGrid()[i];
+      for ( int i = 0; i < na*nb; ++i ) sab[i] = sd.sab()[i];
+      return 0;
+    } catch ( std::exception& e ) { g_err = e.what(); return -3; }
+  }
+  // G_n spectrum of the reference (default truncation/thinning).  meta = { lower edge, bin width, max density }
+  int refdrv_vdos_gn( const char* cfg, int k, int order, double* spec, int cap, double* meta3 )
+  {
+    try {
+      auto info = NC::createInfo( cfg );
+      auto v = vdosEntry( *info, k );
+      if ( !v ) return -1;
+      NC::VDOSEval ve( v->vdosData() );
+      NC::VDOSGn gn( ve );
+      gn.growMaxOrder( (unsigned)order );
+      const auto& sp = gn.getRawSpectrum( (unsigned)order );
+      if ( (int)sp.size() > cap ) return -2;
+      for ( size_t i = 0; i < sp.size(); ++i ) spec[i] = sp[i];
+      meta3[0] = gn.eRange( (unsigned)order ).first; meta3[1] = gn.binWidth( (unsigned)order );
+      meta3[2] = *std::max_element( sp.begin(), sp.end() );
+      return (int)sp.size();
+    } catch ( std::exception& e ) { g_err = e.what(); return -3; }
   }
 
   // ---- (3) CPU baseline through the reference's own C-API --------------------
