@@ -3,20 +3,25 @@
 // TEST INFRASTRUCTURE / reference-side tooling; links the unmodified reference.
 #include <cstdio>
 #include <cstdint>
+#include <string>
 extern "C" {
   void* refdrv_create( const char* cfg );
   void refdrv_destroy( void* );
-  void* refdrv_compile( void*, uint64_t* nbytes );
+  void* refdrv_compile_ex( void*, uint64_t* nbytes, unsigned flags );
   void refdrv_free( void* );
   const char* refdrv_lasterror();
 }
 int main( int argc, char** argv )
 {
-  if ( argc != 3 ) { std::fprintf(stderr,"usage: %s \"<cfg-string>\" out.ncb\n",argv[0]); return 2; }
+  // --vdos: S(alpha,beta) leaves derived from a phonon density of states are delivered as that density; the
+  //         library expands them on the device (ncb_blob.h: NCB_KIND_SABVDOS)
+  unsigned flags = 0;
+  if ( argc == 4 && std::string(argv[1]) == "--vdos" ) { flags = 1; argv[1] = argv[2]; argv[2] = argv[3]; argc = 3; }
+  if ( argc != 3 ) { std::fprintf(stderr,"usage: %s [--vdos] \"<cfg-string>\" out.ncb\n",argv[0]); return 2; }
   void* h = refdrv_create( argv[1] );
   if (!h) { std::fprintf(stderr,"error: %s\n",refdrv_lasterror()); return 1; }
   uint64_t n = 0;
-  void* blob = refdrv_compile( h, &n );
+  void* blob = refdrv_compile_ex( h, &n, flags );
   if (!blob) { std::fprintf(stderr,"error: %s\n",refdrv_lasterror()); return 1; }
   FILE* f = std::fopen( argv[2], "wb" );
   if (!f) { std::perror("fopen"); return 1; }

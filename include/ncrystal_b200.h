@@ -290,6 +290,23 @@ int      ncb200_sab_sampler_dump( ncrystal_process_t, int component, int iE, dou
  * derived from, all read back from the device: number of violations (0 = consistent), -1 on error. */
 long     ncb200_sab_selfcheck( ncrystal_process_t, int component );
 
+/* ---- VDOS -> S(alpha,beta): the reference's own entry points for expanding a phonon density of states into a
+ * scattering kernel with Sjolander's method (ref: include/NCrystal/cinterface/ncrystal.h:885-925,
+ * src/cinterface/ncrystal.cc:755-883), same signatures and ownership (arrays are freed with
+ * ncrystal_dealloc_doubleptr).  The convolutions that produce the phonon-order spectra G_n and the sum over orders run
+ * on the device; the tables equal the reference's bit for bit. */
+void ncrystal_raw_vdos2gn( const double* vdos_egrid, const double* vdos_density, unsigned vdos_egrid_npts,
+                           unsigned vdos_density_npts, double scattering_xs, double mass_amu, double temperature,
+                           unsigned nvalue, double* res_gn_xmin, double* res_gn_xmax, unsigned* res_gn_npts,
+                           double** res_gn_vals );
+void ncrystal_raw_vdos2kernel( const double* vdos_egrid, const double* vdos_density, unsigned vdos_egrid_npts,
+                               unsigned vdos_density_npts, double scattering_xs, double mass_amu, double temperature,
+                               unsigned vdoslux, double (*order_weight_fct)( unsigned order ),
+                               unsigned* nalpha, unsigned* nbeta, double** alpha, double** beta, double** sab,
+                               double target_emax, double* suggested_emax );
+/* number of expansions run so far (raw calls and VDOS leaves of compiled materials, ncb_blob.h: NCB_KIND_SABVDOS) */
+unsigned long ncb200_vdos_expansion_count( void );
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,12 @@ SIGNATURES = {
     "ncb200_get_devices": (C.c_int, []),
     "ncb200_set_fanout_min": (None, [_u64]),
     "ncb200_tally_hist_many": (None, [_dblp, _dblp, _u64, C.c_double, C.c_double, C.c_uint32, _dblp, _dblp]),
+    "ncrystal_raw_vdos2gn": (None, [_dblp, _dblp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint,
+                                    _dblp, _dblp, C.POINTER(C.c_uint), C.POINTER(_dblp)]),
+    "ncrystal_raw_vdos2kernel": (None, [_dblp, _dblp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint,
+                                        _vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(_dblp),
+                                        C.POINTER(_dblp), C.POINTER(_dblp), C.c_double, _dblp]),
+    "ncb200_vdos_expansion_count": (C.c_ulong, []),
 }
 
 _lib = None

@@ -35,8 +35,11 @@ enum ncb_kind {
   NCB_KIND_SAB         = 3, /* ref: src/sabscatter/NCSABScatter.cc + src/sab */
   NCB_KIND_FREEGAS     = 4, /* ref: src/freegas/NCFreeGas.cc + src/phys_utils/NCFreeGasUtils.cc */
   NCB_KIND_SCBRAGG     = 5, /* ref: src/scbragg/NCSCBragg.cc + src/phys_utils/NCGaussMos.cc */
-  NCB_KIND_LCBRAGG     = 7  /* ref: src/lcbragg/NCLCBragg.cc + src/extd_utils/NCLCUtils.cc (6 is taken by the
+  NCB_KIND_LCBRAGG     = 7, /* ref: src/lcbragg/NCLCBragg.cc + src/extd_utils/NCLCUtils.cc (6 is taken by the
                                loader-internal absorption kind) */
+  NCB_KIND_SABVDOS     = 8  /* a SABScatter leaf delivered as the phonon density of states it derives from; the
+                               library runs the VDOS -> S(alpha,beta) expansion itself (ref: src/vdos/) and then
+                               treats the leaf as NCB_KIND_SAB with auto_egrid = 1 */
 };
 
 typedef struct {
@@ -117,6 +120,25 @@ typedef struct {
                               requested emin, emax -- an NCMAT "egrid" line -- or 0 = automatic), lays out the negrid-point
                               geometric grid (:203-283) and integrates the cross sections itself */
 } ncb_sab_t;
+
+/* SABScatter leaf given by its VDOS (DI_VDOS / DI_VDOSDebye, NCDynamicInfo; expansion: createScatteringKernel,
+ * src/vdos/NCVDOSToScatKnl.cc:787-944).  Followed by density[ndensity] (VDOSData::vdos_density(), regular grid
+ * over [emin, emax]). */
+typedef struct {
+  double   scale;           /* SABScatter::m_scale */
+  double   temperature;     /* VDOSData::temperature() [K] */
+  double   mass_amu;        /* VDOSData::elementMassAMU() */
+  double   bound_xs;        /* VDOSData::boundXS() */
+  double   ext_sigma_free, ext_ca, ext_temperature, ext_mass_amu;   /* free-gas extender, as in ncb_sab_t */
+  double   egrid_margin;    /* SABSampler::m_egridMargin (1.05) */
+  double   emin, emax;      /* VDOSData::vdos_egrid() */
+  double   target_emax;     /* Emax the expansion must reach (an "egrid" request of the material), 0 = by vdoslux */
+  double   req_emin, req_emax; /* request for the energy grid of the integrated cross sections, 0 = automatic */
+  uint64_t vdoslux;         /* 0..5 (for a Debye-model leaf: the reduced value the reference uses, max(0,vdoslux-3)) */
+  uint64_t negrid;          /* number of energy grid points (SABIntegrator, 300 by default) */
+  uint64_t ndensity;
+  uint64_t reserved;
+} ncb_sabvdos_t;
 
 /* SCBragg (mosaic single crystal; NCSCBragg.cc:33-90 pimpl + GaussMos + GaussOnSphere).
  * Followed by, in order:

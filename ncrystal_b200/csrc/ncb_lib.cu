@@ -15,6 +15,7 @@
 #include "ncb_loader.h"
 #include "ncb_loader_sc.h"
 #include "ncb_sabgrid.h"
+#include "ncb_vdos_api.h"
 #include "../../include/ncrystal_b200.h"
 
 #include <atomic>
@@ -397,6 +398,10 @@ namespace {
     }
   }
 
+#define NCB_LIB_VDOS_HELPERS
+#include "ncb_lib_vdos.inc"
+#undef NCB_LIB_VDOS_HELPERS
+
   std::shared_ptr<DeviceMaterial> uploadMaterial( const void* blob, size_t nbytes )
   {
     int ndev = 0;
@@ -404,6 +409,9 @@ namespace {
     if ( ce != cudaSuccess || ndev <= 0 )
       throw Err( "CalcError", std::string("ncrystal_b200 requires a CUDA device (no CPU fallback): ")
                  + ( ce != cudaSuccess ? cudaGetErrorString(ce) : "no devices found" ) );
+    // leaves delivered as a phonon density of states are expanded to S(alpha,beta) on the device first
+    std::vector<unsigned char> expanded;
+    if ( expandVdosLeaves( blob, nbytes, expanded ) ) { blob = expanded.data(); nbytes = expanded.size(); }
     LoadedMaterial lm;
     try {
       loadBlob( blob, nbytes, lm );
@@ -2223,6 +2231,11 @@ extern "C" {
 #define NCB_MMC_CAPI
 #include "ncb_lib_mmc.inc"
 #undef NCB_MMC_CAPI
+
+  // ---- VDOS -> S(alpha,beta) expansion on the device (ncrystal_raw_vdos2kernel / ncrystal_raw_vdos2gn)
+#define NCB_LIB_VDOS_ENTRYPOINTS
+#include "ncb_lib_vdos.inc"
+#undef NCB_LIB_VDOS_ENTRYPOINTS
 
 }
 

@@ -194,70 +194,7 @@ namespace ncb {
     return true;
   }
 
-  // Romberg::integrate, ref: NCRomberg.cc:62-146, over an integrand object F with the three hooks of the reference's
-  // class: evalMany(fvals,n,offset,delta), evalManySum(n,offset,delta), accept(level,prev_estimate,estimate).
-  // `converged` is cleared when the last level is reached without acceptance (the reference's convergenceError).
-  template <class F>
-  NCB_HD double rombergIntegrate( F& f, double a, double b, bool& converged )
-  {
-    double h = ( b - a );
-    double fvals[17];
-    f.evalMany( fvals, 17, a, h*0.0625 );
-    h *= 0.5;
-    const double R00 = (fvals[0] + fvals[16])*h;
-    const double R10 = h*fvals[8] + 0.5*R00;
-    const double R11 = (4./3.)*R10 + (-1./3.)*R00;
-    h *= 0.5;
-    const double R20 = h*(fvals[4]+fvals[12]) + 0.5*R10;
-    const double R21 = (4./3.) * R20 + (-1./3.)* R10;
-    const double R22 = (16./15.) * R21 + (-1./15.) * R11;
-    h *= 0.5;
-    const double R30 = h*((fvals[2]+fvals[6])+(fvals[10]+fvals[14])) + 0.5*R20;
-    const double R31 = (4./3.) * R30 + (-1./3.)* R20;
-    const double R32 = (16./15.) * R31 + (-1./15.) * R21;
-    const double R33 = (64./63.) * R32 + (-1./63.) * R22;
-    h *= 0.5;
-    const double R40 = h*(((fvals[1]+fvals[3])+(fvals[5]+fvals[7]))+((fvals[9]+fvals[11])+(fvals[13]+fvals[15]))) + 0.5*R30;
-    const double R41 = (4./3.) * R40 + (-1./3.)* R30;
-    const double R42 = (16./15.) * R41 + (-1./15.) * R31;
-    const double R43 = (64./63.) * R42 + (-1./63.) * R32;
-    const double R44 = (256./255.) * R43 + (-1./255.) * R33;
-    if ( f.accept( 4, R33, R44 ) )
-      return R44;
-    const double c5 = f.evalManySum( 16, a+h*0.5, h );
-    h *= 0.5;
-    const double R50 = h*c5 + 0.5*R40;
-    const double R51 = (4./3.) * R50 + (-1./3.)* R40;
-    const double R52 = (16./15.) * R51 + (-1./15.) * R41;
-    const double R53 = (64./63.) * R52 + (-1./63.) * R42;
-    const double R54 = (256./255.) * R53 + (-1./255.) * R43;
-    const double R55 = (1024./1023.) * R54 + (-1./1023.) * R44;
-    if ( f.accept( 5, R44, R55 ) )
-      return R55;
-    constexpr unsigned maxlevel = 16;
-    double cache1[maxlevel], cache2[maxlevel];
-    double *row_prev = &cache1[0], *row = &cache2[0];
-    row_prev[0] = R50; row_prev[1] = R51; row_prev[2] = R52;
-    row_prev[3] = R53; row_prev[4] = R54; row_prev[5] = R55;
-    unsigned nj = 16;
-    for ( unsigned i = 6; i < maxlevel; ++i ) {
-      const double hh = h;
-      h *= 0.5;
-      nj *= 2;
-      const double c = f.evalManySum( nj, a+h, hh );
-      row[0] = h*c + 0.5*row_prev[0];
-      double n_k = 1.;
-      for ( unsigned j = 0; j < i; ++j ) {
-        n_k *= 4.0;
-        row[j+1] = ( n_k * row[j] - row_prev[j] ) / ( n_k - 1.0 );
-      }
-      if ( f.accept( i, row_prev[i-1], row[i] ) )
-        return row[i];
-      double* t = row_prev; row_prev = row; row = t;
-    }
-    converged = false;
-    return row_prev[maxlevel-1];
-  }
+  // (rombergIntegrate: ncb_common.cuh)
 
   // GOSCircleInt as integrand, ref: NCGaussOnSphere.cc:64-143
   struct GosCircleIntegrand {

@@ -1,6 +1,8 @@
 // ncb_vdos.cu -- CUDA backend of the VDOS -> S(alpha,beta) expansion (ncb_vdos.h drives it, ncb_vdos_dev.cuh holds
 // the kernels).  Own translation unit of libncrystal_b200.so; entry points in ncb_vdos_api.h, C ABI in ncb_lib.cu
 // (ncrystal_raw_vdos2kernel / ncrystal_raw_vdos2gn, ref: include/NCrystal/cinterface/ncrystal.h:885-925).
+#define NCB_VDOS_KERNELS 1
+#define NCB_MATHFN __host__ __device__ __forceinline__   // (ncb_common.cuh: no second out-of-line copy of its libm wrappers)
 #include "ncb_vdos_dev.cuh"
 #include "ncb_vdos.h"
 #include "ncb_vdos_api.h"

@@ -20,8 +20,10 @@
 // the existing ones allow (n+1 .. 2n) goes into ONE batch of device work, and the reference's stopping rule is
 // applied to the statistics that come back.
 #pragma once
-#include "ncb_phys_scbragg.cuh"   // rombergIntegrate
+#include "ncb_common.cuh"   // rombergIntegrate, StableSum
 #include "ncb_vdos_dev.cuh"
+#include "ncb_blob.h"
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -954,6 +956,72 @@ namespace ncb { namespace vdos {
     K.max_order = max_order; K.gamma0 = gamma0; K.msd = msd;
     K.ntrimmed = trimZeroEdges( K );
     return K;
+  }
+
+  // A compiled material (ncb_blob.h) whose S(alpha,beta) leaves are given as phonon densities of states
+  // (NCB_KIND_SABVDOS) is re-assembled with ordinary NCB_KIND_SAB leaves: expandFn( Input, vdoslux, target_emax )
+  // returns the expanded kernel, the leaf's energy grid is left to the library (auto_egrid = 1).  Returns false when
+  // the material has no such leaf (or is not a readable material: the loader reports what is wrong with it).
+  template <class ExpandFn, class WarnFn>
+  inline bool rewriteVdosLeaves( const void* blob_, size_t nbytes, std::vector<unsigned char>& out, ExpandFn&& expandFn, WarnFn&& warn )
+  {
+    const unsigned char* blob = static_cast<const unsigned char*>( blob_ );
+    if ( nbytes < sizeof(ncb_header_t) ) return false;
+    ncb_header_t hdr;
+    std::memcpy( &hdr, blob, sizeof(hdr) );
+    if ( hdr.magic != NCB_MAGIC || hdr.version != NCB_VERSION || hdr.nbytes > nbytes || hdr.ncomp == 0 || hdr.ncomp > NCB_MAXCOMP )
+      return false;
+    bool any = false;
+    for ( uint32_t i = 0; i < hdr.ncomp; ++i ) any = any || hdr.comp[i].kind == NCB_KIND_SABVDOS;
+    if ( !any ) return false;
+    out.assign( sizeof(ncb_header_t), 0 );
+    ncb_header_t nh = hdr;
+    auto append = [&out]( const void* p, size_t n ) {
+      const size_t off = out.size();
+      out.resize( off + n );
+      std::memcpy( out.data() + off, p, n );
+    };
+    for ( uint32_t i = 0; i < hdr.ncomp; ++i ) {
+      const ncb_comp_t& c = hdr.comp[i];
+      if ( c.off > hdr.nbytes || c.nbytes > hdr.nbytes - c.off || c.off < sizeof(ncb_header_t) || c.off % 8 != 0 )
+        throw Error( "BadInput", "compiled material: component out of bounds" );
+      out.resize( ncb_align16( out.size() ), 0 );
+      nh.comp[i].off = out.size();
+      if ( c.kind != NCB_KIND_SABVDOS ) {
+        append( blob + c.off, c.nbytes );
+        nh.comp[i].nbytes = c.nbytes;
+        continue;
+      }
+      if ( c.nbytes < sizeof(ncb_sabvdos_t) ) throw Error( "BadInput", "compiled material: truncated VDOS payload" );
+      ncb_sabvdos_t v; std::memcpy( &v, blob + c.off, sizeof(v) );
+      if ( v.ndensity > ( (uint64_t)1 << 31 ) || ( c.nbytes - sizeof(v) )/8 < v.ndensity ) throw Error( "BadInput", "compiled material: truncated VDOS payload" );
+      if ( v.ndensity < 2 || v.negrid < 10 || v.negrid > 65535 || v.vdoslux > 5 ) throw Error( "BadInput", "compiled material: invalid VDOS leaf" );
+      Input in;
+      const double* dens = reinterpret_cast<const double*>( blob + c.off + sizeof(v) );
+      in.emin = v.emin; in.emax = v.emax; in.density.assign( dens, dens + v.ndensity );
+      in.temperature = v.temperature; in.mass_amu = v.mass_amu; in.bound_xs = v.bound_xs;
+      const Kernel K = expandFn( in, (unsigned)v.vdoslux, v.target_emax );
+      if ( K.ntrimmed )
+        warn( "Discarding "+std::to_string( K.ntrimmed )+" edges of provided kernel data due to missing S values." );
+      ncb_sab_t h; std::memset( &h, 0, sizeof(h) );
+      h.scale = v.scale; h.temperature = K.temperature; h.mass_amu = K.mass_amu; h.bound_xs = K.bound_xs;
+      h.suggested_emax = K.suggested_emax;
+      h.ext_sigma_free = v.ext_sigma_free; h.ext_ca = v.ext_ca; h.ext_temperature = v.ext_temperature; h.ext_mass_amu = v.ext_mass_amu;
+      h.egrid_margin = v.egrid_margin;
+      h.negrid = v.negrid; h.nalpha = K.alpha.size(); h.nbeta = K.beta.size(); h.auto_egrid = 1;
+      nh.comp[i].kind = NCB_KIND_SAB;
+      append( &h, sizeof(h) );
+      VectD placeholder( 2*(size_t)v.negrid, 0.0 );
+      placeholder[0] = v.req_emin; placeholder[1] = v.req_emax;
+      append( placeholder.data(), placeholder.size()*8 );
+      append( K.alpha.data(), K.alpha.size()*8 );
+      append( K.beta.data(), K.beta.size()*8 );
+      append( K.sab.data(), K.sab.size()*8 );
+      nh.comp[i].nbytes = out.size() - nh.comp[i].off;
+    }
+    nh.nbytes = out.size();
+    std::memcpy( out.data(), &nh, sizeof(nh) );
+    return true;
   }
 
 } }

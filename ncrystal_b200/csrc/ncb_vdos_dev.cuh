@@ -105,7 +105,7 @@ namespace ncb { namespace vdos {
     }
   }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && defined(NCB_VDOS_KERNELS)   // (the kernels belong to ncb_vdos.cu alone)
   constexpr int kFftLocalLog = 12;                 // stages done in shared memory
   constexpr int kFftThreads = 512;
 

@@ -43,6 +43,8 @@ class RefDrv:
             L.refdrv_lasterror.restype = C.c_char_p
             L.refdrv_compile.restype = C.c_void_p
             L.refdrv_compile.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+            L.refdrv_compile_ex.restype = C.c_void_p
+            L.refdrv_compile_ex.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_uint]
             L.refdrv_free.argtypes = [C.c_void_p]
             L.refdrv_ncomp.argtypes = [C.c_void_p]
             L.refdrv_compname.restype = C.c_char_p
@@ -83,9 +85,10 @@ class RefDrv:
     def compnames(self):
         return [self.lib().refdrv_compname(self.h, i).decode() for i in range(self.ncomp)]
 
-    def compile(self):
+    def compile(self, flags=0):
+        """flags & 1: S(alpha,beta) leaves derived from a phonon density of states are emitted as that density."""
         n = C.c_uint64(0)
-        p = self.lib().refdrv_compile(self.h, C.byref(n))
+        p = self.lib().refdrv_compile_ex(self.h, C.byref(n), flags)
         if not p:
             raise RuntimeError("refdrv_compile failed: %s" % self.lib().refdrv_lasterror().decode())
         try:

@@ -21,6 +21,7 @@
 namespace ncb {
   double g_erfc_lut_host[kErfcLutLen];
 }
+bool hostsim_expand_vdos_leaves( const void* blob, size_t nbytes, std::vector<unsigned char>& out );   // hostsim_vdos.cpp
 
 namespace {
   struct Handle {
@@ -147,6 +148,8 @@ extern "C" {
   {
     try {
       auto h = std::make_unique<Handle>();
+      std::vector<unsigned char> expanded;   // leaves given as a phonon density of states: expanded first (hostsim_vdos.cpp)
+      if ( hostsim_expand_vdos_leaves( blob, nbytes, expanded ) ) { blob = expanded.data(); nbytes = expanded.size(); }
       ncb::loadBlob( blob, nbytes, h->lm );
       h->mat = ncb::relocated( h->lm, h->lm.arena.data() );
       ncb::hotTabsFromMaterial( h->mat, h->H );

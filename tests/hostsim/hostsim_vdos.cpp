@@ -127,6 +127,13 @@ namespace {
   }
 }
 
+bool hostsim_expand_vdos_leaves( const void* blob, size_t nbytes, std::vector<unsigned char>& out )
+{
+  return rewriteVdosLeaves( blob, nbytes, out,
+    []( const Input& in, unsigned vdoslux, double target_emax ) { HostBackend be; return expand( in, vdoslux, target_emax, be ); },
+    []( const std::string& ) {} );
+}
+
 extern "C" {
 
   const char* hostsim_vdos_lasterror() { return g_verr.c_str(); }
