@@ -723,6 +723,47 @@ def transport_figure(cx, sc):
         return {"error": str(e)}
 
 
+def vdos_figure(cx):
+    """Secondary figure (rank 0): VDOS -> S(alpha,beta) expansion of the Al curve through
+    ncrystal_raw_vdos2kernel of the library -- FFT convolutions and the sum over phonon orders on the device -- beside the
+    same call of the compiled reference on the host, and whether the two tables are bit-identical.  The input curve is
+    read from the committed golden file (tests/golden/vdos_reference.npz)."""
+    if cx.rank != 0:
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import numpy as np
+        import _vdos
+        from ncrystal_b200 import _lib
+        g = _vdos.load_golden()
+        egrid, density = g["in_Al_egrid"], g["in_Al_density"]
+        sigma, mass, T = [float(x) for x in g["in_Al_meta"]]
+        prod = _vdos.RawVdosAPI(_lib.lib())
+        prod.kernel(egrid, density, sigma, mass, T, 1)     # warm-up (module load, memory pool)
+        l0 = int(_lib.lib().ncb200_kernel_launch_count())
+        best, out = 1e9, None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            out = prod.kernel(egrid, density, sigma, mass, T, 3)
+            best = min(best, time.perf_counter() - t0)
+        launches = (int(_lib.lib().ncb200_kernel_launch_count()) - l0) // 3
+        rec = {"workload": "Al_sg225 VDOS (%d points), 293.15 K, vdoslux 3 -> %dx%d table" % (density.size, out[0].size, out[1].size),
+               "api": "ncrystal_raw_vdos2kernel", "seconds": best, "expansions_per_s": 1.0 / best, "gpu_launches": launches,
+               "sab_sha256_matches_reference_golden": _vdos.sha(out[2]) == str(g["out_Al_lux3_sab_sha"])}
+        if _vdos.have_reference():
+            ref = _vdos.reference_api()
+            rb = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                r = ref.kernel(egrid, density, sigma, mass, T, 3)
+                rb = min(rb, time.perf_counter() - t0)
+            rec.update(reference_seconds=rb, reference_threads="reference's own thread pool",
+                       bit_identical_to_live_reference=bool(np.array_equal(out[2], r[2])))
+        return rec
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_iso(args, key, cx):
     from ncrystal_b200 import _lib
     L = _lib.lib()
@@ -730,6 +771,7 @@ def run_iso(args, key, cx):
     r = measure_iso(cx, key, n, args.steps, args.warmup, headline=True)
     e2e, mean_mu = e2e_iso(cx, r["sc"], r["d_e"][0], n, max(2, min(args.steps, 10)))
     transport = transport_figure(cx, r["sc"]) if key == "Al" else None
+    vdosfig = vdos_figure(cx) if key == "Al" else None
     others = other_configs(cx, key) if not args.no_other_configs else None
     if cx.rank != 0:
         return None
@@ -762,6 +804,7 @@ def run_iso(args, key, cx):
             "rng": "Philox4x32-10 per-neutron streams", "device_error_flags": r["flags"],
             "tally_total": r["hist_total"], "mean_mu_e2e": mean_mu, "table_MB": r["table_MB"],
             "transport_step": transport,
+            "vdos_expansion": vdosfig,
             "other_configs": others,
         },
         "e2e": e2e, "gpu_launches": int(r["launches"]), "clocks": r["clocks"], "roofline": roof,

@@ -20,30 +20,27 @@ namespace ncb { namespace vdos {
     }
 #define VDOS_CUDA_OK(x) cudaOk( (x), #x )
 
+    // device scratch comes from the stream-ordered pool of the device (cudaMallocAsync): after the first expansion
+    // the blocks are recycled, an expansion then costs no cudaMalloc / cudaFree round trips
     template <class T> struct DevBuf {
-      T* p = nullptr; size_t cap = 0;
-      ~DevBuf() { if ( p ) cudaFree( p ); }
+      T* p = nullptr; size_t cap = 0; cudaStream_t st = 0;
+      ~DevBuf() { if ( p ) cudaFreeAsync( p, st ); }
       void need( size_t n )
       {
         if ( n <= cap ) return;
-        if ( p ) { cudaFree( p ); p = nullptr; cap = 0; }
+        if ( p ) { cudaFreeAsync( p, st ); p = nullptr; cap = 0; }
         size_t c = std::max<size_t>( n, 1024 );
-        VDOS_CUDA_OK( cudaMalloc( &p, c*sizeof(T) ) );
+        VDOS_CUDA_OK( cudaMallocAsync( &p, c*sizeof(T), st ) );
         cap = c;
       }
-      DevBuf() = default;
+      explicit DevBuf( cudaStream_t s ) : st( s ) {}
       DevBuf( const DevBuf& ) = delete; DevBuf& operator=( const DevBuf& ) = delete;
     };
 
     class CudaBackend {
     public:
-      explicit CudaBackend( cudaStream_t st ) : m_st( st )
+      explicit CudaBackend( cudaStream_t st ) : m_st( st ), m_work( st ), m_w( st ), m_ytmp( st ), m_jobs( st ), m_stats( st )
       {
-        int ndev = 0;
-        cudaError_t ce = cudaGetDeviceCount( &ndev );
-        if ( ce != cudaSuccess || ndev <= 0 )
-          throw Error( "CalcError", std::string( "ncrystal_b200 requires a CUDA device (no CPU fallback): " )
-                       + ( ce != cudaSuccess ? cudaGetErrorString( ce ) : "no devices found" ) );
         static std::mutex mtx; static std::map<int,bool> done;
         int dev = 0; VDOS_CUDA_OK( cudaGetDevice( &dev ) );
         std::lock_guard<std::mutex> g( mtx );
@@ -51,10 +48,14 @@ namespace ncb { namespace vdos {
           const int smem = (int)( sizeof(Cplx) << kFftLocalLog );
           VDOS_CUDA_OK( cudaFuncSetAttribute( k_vdos_fft_local<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem ) );
           VDOS_CUDA_OK( cudaFuncSetAttribute( k_vdos_fft_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem ) );
+          cudaMemPool_t pool;
+          VDOS_CUDA_OK( cudaDeviceGetDefaultMemPool( &pool, dev ) );
+          unsigned long long keep = (unsigned long long)256 << 20;    // freed scratch stays with the pool up to 256 MB
+          VDOS_CUDA_OK( cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &keep ) );
           done[dev] = true;
         }
       }
-      ~CudaBackend() { for ( double* p : m_pools ) cudaFree( p ); }
+      ~CudaBackend() { for ( double* p : m_pools ) cudaFreeAsync( p, m_st ); }
       unsigned launches = 0;
 
       void setSpectrum( unsigned order, const VectD& spec )
@@ -147,7 +148,8 @@ namespace ncb { namespace vdos {
           const GnMeta& m = P.meta[n-1];
           gn[n-1] = GnDev{ m_spec.at( n-1 ), (unsigned long long)m.n, m.lower, m.upper, 1.0/m.binwidth };
         }
-        DevBuf<GnDev> d_gn; DevBuf<double> d_scale, d_af, d_beta, d_expb, d_sab; DevBuf<int> d_first, d_end; DevBuf<unsigned char> d_skip; DevBuf<unsigned> d_groups;
+        DevBuf<GnDev> d_gn( m_st ); DevBuf<double> d_scale( m_st ), d_af( m_st ), d_beta( m_st ), d_expb( m_st ), d_sab( m_st );
+        DevBuf<int> d_first( m_st ), d_end( m_st ); DevBuf<unsigned char> d_skip( m_st ); DevBuf<unsigned> d_groups( m_st );
         d_gn.need( norders ); d_scale.need( norders ); d_first.need( norders ); d_end.need( norders ); d_skip.need( norders );
         d_beta.need( nrows ); d_expb.need( nrows ); d_sab.need( na*nb );
         auto up = [&]( void* d, const void* h, size_t n ) { VDOS_CUDA_OK( cudaMemcpyAsync( d, h, n, cudaMemcpyHostToDevice, m_st ) ); };
@@ -207,7 +209,7 @@ namespace ncb { namespace vdos {
         if ( m_pool_left < capacity ) {
           const size_t sz = std::max<size_t>( capacity, m_next_pool );
           double* p = nullptr;
-          VDOS_CUDA_OK( cudaMalloc( &p, sz*8 ) );
+          VDOS_CUDA_OK( cudaMallocAsync( &p, sz*8, m_st ) );
           m_pools.push_back( p ); m_pool_cur = p; m_pool_left = sz;
         }
         m_spec[order-1] = m_pool_cur; m_pool_cur += capacity; m_pool_left -= capacity;
@@ -227,20 +229,42 @@ namespace ncb { namespace vdos {
     };
   }
 
+  namespace {
+    // the expansion runs on a stream of its own; the guard waits for the stream-ordered frees before destroying it
+    struct StreamGuard {
+      cudaStream_t st = nullptr;
+      StreamGuard()
+      {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount( &ndev );
+        if ( ce != cudaSuccess || ndev <= 0 )
+          throw Error( "CalcError", std::string( "ncrystal_b200 requires a CUDA device (no CPU fallback): " )
+                       + ( ce != cudaSuccess ? cudaGetErrorString( ce ) : "no devices found" ) );
+        VDOS_CUDA_OK( cudaStreamCreateWithFlags( &st, cudaStreamNonBlocking ) );
+      }
+      ~StreamGuard() { if ( st ) { cudaStreamSynchronize( st ); cudaStreamDestroy( st ); } }
+    };
+  }
+
   Kernel expandOnDevice( const Input& in, unsigned vdoslux, double target_emax, const std::function<double(unsigned)>& scaleFct, unsigned* launches )
   {
-    CudaBackend be( 0 );
-    Kernel K = expand( in, vdoslux, target_emax, be, scaleFct );
-    if ( launches ) *launches = be.launches;
+    StreamGuard sg;
+    Kernel K;
+    {
+      CudaBackend be( sg.st );
+      K = expand( in, vdoslux, target_emax, be, scaleFct );
+      if ( launches ) *launches = be.launches;
+    }
     return K;
   }
 
   VectD gnOnDevice( const Input& in, unsigned order, double& xmin, double& xmax )
   {
     if ( order < 1 || order >= 100000 ) throw Error( "BadInput", "invalid phonon order" );
-    CudaBackend be( 0 );
+    StreamGuard sg;
+    CudaBackend be( sg.st );
     Eval ev( in );
-    Ladder<CudaBackend> Gn( ev, be, TruncThin(), 1e-9 );
+    Ladder<CudaBackend> Gn( ev, ev.calcGamma0(), be, TruncThin(), 1e-9 );
     Gn.grow( order, 0 );
     const PairDD r = Gn.eRange( order );
     xmin = r.first; xmax = r.second;

@@ -36,6 +36,16 @@
 #include <utility>
 #include <vector>
 
+#ifdef NCB_VDOS_TIMING   // (development aid: host-side stage times of expand() on stderr)
+#include <chrono>
+#include <cstdio>
+#define NCB_VDOS_TICK(label) do { auto t_now = std::chrono::steady_clock::now(); std::fprintf( stderr, "vdos-timing %-28s %8.3f ms\n", label, std::chrono::duration<double,std::milli>( t_now - t_last ).count() ); t_last = t_now; } while (0)
+#define NCB_VDOS_TICK_INIT auto t_last = std::chrono::steady_clock::now()
+#else
+#define NCB_VDOS_TICK(label) do {} while (0)
+#define NCB_VDOS_TICK_INIT do {} while (0)
+#endif
+
 namespace ncb { namespace vdos {
 
   // physics constants, spelled like the reference so that the compile-time products round identically
@@ -140,43 +150,53 @@ namespace ncb { namespace vdos {
   }
 
   // Thin a sampled curve to targetN points, removing the least important interior point first (importance =
-  // area change x (change of the log-curve area)^2); among equal scores the one scored first goes first.
+  // area change x (change of the log-curve area)^2).  Among equal scores the one scored first goes first -- the
+  // order a std::multimap gives the reference; here the ranking is a binary heap of (score, sequence number) keys
+  // over an index-linked list, stale entries skipped when they surface.
   inline std::pair<VectD,VectD> reducePoints( const VectD& x, const VectD& y, size_t targetN )
   {
-    if ( targetN >= x.size() ) return { x, y };
+    const size_t n = x.size();
+    if ( targetN >= n ) return { x, y };
     const double inv_ymax = 1.0 / *std::max_element( y.begin(), y.end() );
-    struct Pt { double x, y, lny; std::pair<double,uint64_t> key; bool scored; };
-    std::list<Pt> pts;
-    for ( size_t i = 0; i < x.size(); ++i )
-      pts.push_back( Pt{ x[i], y[i], std::log( std::max<double>( 1e-20, y[i]*inv_ymax ) ), {0.0,0}, false } );
-    typedef std::list<Pt>::iterator It;
-    auto cmp = []( const std::pair<std::pair<double,uint64_t>,It>& a, const std::pair<std::pair<double,uint64_t>,It>& b ) { return a.first < b.first; };
-    std::set<std::pair<std::pair<double,uint64_t>,It>,decltype(cmp)> ranking( cmp );
+    VectD lny( n );
+    for ( size_t i = 0; i < n; ++i ) lny[i] = std::log( std::max<double>( 1e-20, y[i]*inv_ymax ) );
+    std::vector<uint32_t> prev( n ), next( n );
+    std::vector<uint64_t> cur( n, ~(uint64_t)0 );      // sequence number of a point's live heap entry
+    for ( size_t i = 0; i < n; ++i ) { prev[i] = (uint32_t)( i - 1 ); next[i] = (uint32_t)( i + 1 ); }
+    struct Entry { double score; uint64_t seq; uint32_t idx; };
+    auto later = []( const Entry& a, const Entry& b ) { return a.score > b.score || ( a.score == b.score && a.seq > b.seq ); };
+    std::vector<Entry> heap;
+    heap.reserve( 3*n );
     uint64_t seq = 0;
-    auto score = []( It it ) {
-      const Pt& p1 = *it; const Pt& p0 = *std::prev( it ); const Pt& p2 = *std::next( it );
-      const double area = std::fabs( p0.x*( p1.y - p2.y ) + p1.x*( p2.y - p0.y ) + p2.x*( p0.y - p1.y ) );
-      const double larea = std::fabs( p0.x*( p1.lny - p2.lny ) + p1.x*( p2.lny - p0.lny ) + p2.x*( p0.lny - p1.lny ) );
+    auto score = [&]( uint32_t i ) {
+      const uint32_t i0 = prev[i], i2 = next[i];
+      const double area = std::fabs( x[i0]*( y[i] - y[i2] ) + x[i]*( y[i2] - y[i0] ) + x[i2]*( y[i0] - y[i] ) );
+      const double larea = std::fabs( x[i0]*( lny[i] - lny[i2] ) + x[i]*( lny[i2] - lny[i0] ) + x[i2]*( lny[i0] - lny[i] ) );
       return area*larea*larea;
     };
-    auto enter = [&]( It it ) { it->key = { score( it ), seq++ }; it->scored = true; ranking.insert( { it->key, it } ); };
-    for ( It it = std::next( pts.begin() ), last = std::prev( pts.end() ); it != last; ++it ) enter( it );
-    auto rescore = [&]( It it ) {
-      if ( !it->scored ) return;           // end points
-      ranking.erase( { it->key, it } );
-      enter( it );
+    auto enter = [&]( uint32_t i ) {
+      if ( i == 0 || i == n - 1 ) return;               // end points are never candidates
+      cur[i] = seq;
+      heap.push_back( Entry{ score( i ), seq++, i } );
+      std::push_heap( heap.begin(), heap.end(), later );
     };
-    while ( pts.size() > targetN ) {
-      auto first = ranking.begin();
-      It it = first->second;
-      It before = std::prev( it ), after = std::next( it );
-      ranking.erase( first );
-      pts.erase( it );
-      rescore( before );
-      rescore( after );
+    for ( uint32_t i = 1; i + 1 < n; ++i ) enter( i );
+    size_t left = n;
+    while ( left > targetN ) {
+      std::pop_heap( heap.begin(), heap.end(), later );
+      const Entry e = heap.back();
+      heap.pop_back();
+      if ( cur[e.idx] != e.seq ) continue;              // re-scored or removed since
+      const uint32_t before = prev[e.idx], after = next[e.idx];
+      next[before] = after; prev[after] = before;
+      cur[e.idx] = ~(uint64_t)0;
+      --left;
+      enter( before );
+      enter( after );
     }
     VectD nx, ny;
-    for ( auto& p : pts ) { nx.push_back( p.x ); ny.push_back( p.y ); }
+    nx.reserve( left ); ny.reserve( left );
+    for ( uint32_t i = 0; i < n; i = next[i] ) { nx.push_back( x[i] ); ny.push_back( y[i] ); }
     return { nx, ny };
   }
 
@@ -464,7 +484,8 @@ namespace ncb { namespace vdos {
   template <class Backend>
   class Ladder {
   public:
-    Ladder( const Eval& ev, Backend& be, TruncThin tt, double relthr ) : m_be( be ), m_tt( tt ), m_relthr( relthr ), m_kT( ev.kT() )
+    // gamma0 = ev.calcGamma0() (passed in: the caller needs it as well and it is an integral over the whole curve)
+    Ladder( const Eval& ev, double gamma0, Backend& be, TruncThin tt, double relthr ) : m_be( be ), m_tt( tt ), m_relthr( relthr ), m_kT( ev.kT() )
     {
       unsigned long nbins = ev.nptsExtended() - 1;
       constexpr unsigned long min_nbins = 400;
@@ -474,7 +495,6 @@ namespace ncb { namespace vdos {
       const VectD egrid = linSpace( 0.0, ev.emax(), (unsigned)( nbins + 1 ) );
       const double binwidth = egrid.back()/nbins;
       VectD g1( egrid.size()*2 - 1, 0.0 );
-      const double gamma0 = ev.calcGamma0();
       for ( size_t i = 0; i < egrid.size(); ++i ) {
         const PairDD v = ev.g1AsymmetricPair( egrid[i], gamma0 );
         g1[nbins+i] = v.second;
@@ -887,14 +907,18 @@ namespace ncb { namespace vdos {
     if ( !( targetEmax_requested >= 0.0 ) ) throw Error( "BadInput", "target Emax must be non-negative" );
     constexpr double lux2emax[6] = { 0.5, 1.0, 3.0, 5.0, 8.0, 12.0 };
     double targetEmax = targetEmax_requested > 0.0 ? targetEmax_requested : lux2emax[vdoslux];
+    NCB_VDOS_TICK_INIT;
     Eval ev( in );
+    NCB_VDOS_TICK( "Eval (normalisation)" );
     const double kT = ev.kT(), invkT = 1.0/kT;
     const double gamma0 = ev.calcGamma0();
+    NCB_VDOS_TICK( "gamma0" );
     const double msd = ev.getMSD( gamma0 );
     double targetEmax_div_kT = targetEmax*invkT;
     unsigned max_order = 4;
     const double relcontriblvl = std::pow( 10.0, -( 3.0 + 2.0*vdoslux ) );
-    Ladder<Backend> Gn( ev, be, tt, relcontriblvl );
+    Ladder<Backend> Gn( ev, gamma0, be, tt, relcontriblvl );
+    NCB_VDOS_TICK( "G1" );
     Gn.grow( max_order );
     unsigned order_limit = 1000;
     if ( targetEmax_requested > 0.0 || vdoslux == 5 ) order_limit *= 10;
@@ -925,6 +949,7 @@ namespace ncb { namespace vdos {
       }
     }
     Gn.grow( max_order );
+    NCB_VDOS_TICK( "order loop" );
     double betaMin = 0.0, alphaMax = 0.0;
     for ( unsigned n = 1; n <= max_order; ++n ) {
       PairDD ar, br;
@@ -935,6 +960,7 @@ namespace ncb { namespace vdos {
     }
     if ( !( betaMin < 0.0 && alphaMax > 0.0 ) ) throw Error( "CalcError", "VDOS expansion: empty kinematic region" );
     const double upper_beta = -betaMin*1.01, upper_alpha = alphaMax*1.01;
+    NCB_VDOS_TICK( "alpha/beta reach" );
     // (orders beyond max_order may exist in the ladder -- produced ahead in a batch; the reference's maxOrder() is max_order)
     struct View {
       const Ladder<Backend>& L; unsigned n;
@@ -946,15 +972,19 @@ namespace ncb { namespace vdos {
     } view{ Gn, max_order };
     Kernel K;
     K.beta = setupBetaGrid( view, upper_beta, vdoslux );
+    NCB_VDOS_TICK( "beta grid" );
     K.alpha = setupAlphaGrid( kT, msd, upper_alpha, (unsigned)( K.beta.size()/2 ) );
     std::vector<GnMeta> meta( Gn.allMeta().begin(), Gn.allMeta().begin() + max_order );
     const FillPlan P = planFill( meta, kT, msd, K.alpha, K.beta, scaleFct );
+    NCB_VDOS_TICK( "alpha grid + fill plan" );
     be.fill( P, K.sab );
+    NCB_VDOS_TICK( "fill" );
     K.suggested_emax = targetEmax;
     if ( scaleFct && scaleFct( max_order ) == 0.0 ) K.suggested_emax = 0.0;
     K.temperature = ev.temperature(); K.bound_xs = in.bound_xs; K.mass_amu = in.mass_amu;
     K.max_order = max_order; K.gamma0 = gamma0; K.msd = msd;
     K.ntrimmed = trimZeroEdges( K );
+    NCB_VDOS_TICK( "trim" );
     return K;
   }
 

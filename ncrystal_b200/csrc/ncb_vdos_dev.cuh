@@ -108,6 +108,7 @@ namespace ncb { namespace vdos {
 #if defined(__CUDACC__) && defined(NCB_VDOS_KERNELS)   // (the kernels belong to ncb_vdos.cu alone)
   constexpr int kFftLocalLog = 12;                 // stages done in shared memory
   constexpr int kFftThreads = 512;
+  constexpr unsigned kSumChunk = 4096;             // bins staged per round of the serial area sum
 
   // blockIdx = (chunk, job, which input).  INV: transform of b1*b2 into bo with conjugated twiddles.
   template <bool INV>
@@ -186,6 +187,7 @@ namespace ncb { namespace vdos {
     __shared__ double sd[16];
     __shared__ long long sl[16];
     __shared__ double s_inv;
+    __shared__ double s_chunk[kSumChunk];
     const JobDev J = jobs[blockIdx.x];
     const unsigned nout = J.nout;
     auto fmaxop = []( double a, double b ) { return a > b ? a : b; };
@@ -223,12 +225,27 @@ namespace ncb { namespace vdos {
       len = ( len + extra - 1 )/extra;
       dt *= (double)extra;
     }
-    // unit area: the bins are summed in index order (one thread), as the reference sums them
-    if ( threadIdx.x == 0 ) {
+    // unit area: the bins are summed in index order by ONE thread, as the reference sums them (a tree reduction would
+    // round differently); the CTA stages the bins through shared memory so that the serial chain runs at the latency
+    // of a shared-memory load + one DADD per bin instead of an L2 round trip
+    {
       double area = 0.;
-      for ( unsigned long long m = 0; m < len; ++m ) area += J.ytmp[lo + m*extra];
-      area *= dt;
-      s_inv = 1.0/area;
+      for ( unsigned long long m0 = 0; m0 < len; m0 += kSumChunk ) {
+        const unsigned cnt = (unsigned)( len - m0 < kSumChunk ? len - m0 : kSumChunk );
+        for ( unsigned m = threadIdx.x; m < cnt; m += blockDim.x ) s_chunk[m] = J.ytmp[lo + ( m0 + m )*extra];
+        __syncthreads();
+        if ( threadIdx.x == 0 ) {
+          unsigned m = 0;
+          for ( ; m + 8 <= cnt; m += 8 ) {
+            const double v0 = s_chunk[m], v1 = s_chunk[m+1], v2 = s_chunk[m+2], v3 = s_chunk[m+3],
+                         v4 = s_chunk[m+4], v5 = s_chunk[m+5], v6 = s_chunk[m+6], v7 = s_chunk[m+7];
+            area += v0; area += v1; area += v2; area += v3; area += v4; area += v5; area += v6; area += v7;
+          }
+          for ( ; m < cnt; ++m ) area += s_chunk[m];
+        }
+        __syncthreads();
+      }
+      if ( threadIdx.x == 0 ) { area *= dt; s_inv = 1.0/area; }
     }
     __syncthreads();
     const double inv = s_inv;

@@ -163,7 +163,7 @@ extern "C" {
     try {
       HostBackend be;
       Eval ev( makeInput( egrid, negrid, density, ndensity, temperature, mass_amu, bound_xs ) );
-      Ladder<HostBackend> Gn( ev, be, TruncThin(), 1e-9 );
+      Ladder<HostBackend> Gn( ev, ev.calcGamma0(), be, TruncThin(), 1e-9 );
       Gn.grow( (unsigned)order, 0 );
       const VectD s = be.spectrum( (unsigned)order );
       if ( (int)s.size() > cap ) return -2;

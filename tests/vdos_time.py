@@ -6,7 +6,9 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, __file__.rsplit("/", 1)[0])
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _vdos  # noqa: E402
 
 g = _vdos.load_golden()
@@ -21,7 +23,7 @@ for curve, T, lux in cases:
     sigma, mass, _ = [float(x) for x in g["in_%s_meta" % curve]]
     best = 1e9
     for _ in range(3):
-        l0 = L.ncb200_launch_count() if hasattr(L, "ncb200_launch_count") else 0
+        l0 = L.ncb200_kernel_launch_count() if hasattr(L, "ncb200_launch_count") else 0
         t = time.perf_counter()
         a, b, s, e = prod.kernel(egrid, density, sigma, mass, T, lux)
         best = min(best, time.perf_counter() - t)
