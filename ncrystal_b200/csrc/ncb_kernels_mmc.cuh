@@ -273,7 +273,10 @@ struct MmcTailOut {
 
 namespace ncb {
 
-  __device__ __forceinline__ void mmcTallyAtomic( const MmcTally& T, double* __restrict__ tally, int lane,
+  // s_stat: the CTA's running statistics [histogram][class][kMmcNStat] in shared memory -- every record of a class
+  // updates the same five words, so with global atomics all warps of the grid serialised on a handful of L2
+  // addresses (Ge tail: 17 ms); the bins themselves are spread and stay global.
+  __device__ __forceinline__ void mmcTallyAtomic( const MmcTally& T, double* __restrict__ tally, double* s_stat, int lane,
                                                   double ux, double uy, double uz, double ekin, double wt, int nscat, int ninel,
                                                   double e0, double ux0, double uy0, double uz0 )
   {
@@ -287,24 +290,34 @@ namespace ncb {
     const int cls = mmcClass( nscat, ninel );
     const int key = cls*nb2 + mmcValueToBin( h, val );
     double* g = tally + h.off;
-    unsigned long long* gu = reinterpret_cast<unsigned long long*>( g );
     atomicAdd( &g[key], wgt );
     atomicAdd( &g[kMmcNClass*nb2 + key], wgt*wgt );
-    const int o = 2*kMmcNClass*nb2 + cls*kMmcNStat;
-    atomicAdd( &g[o+0], wgt ); atomicAdd( &g[o+1], wgt*val ); atomicAdd( &g[o+2], wgt*val*val );
-    atomicMin( &gu[o+3], mmcOrdered( val ) );
-    atomicMax( &gu[o+4], mmcOrdered( val ) );
+    double* st = s_stat + ( lane*kMmcNClass + cls )*kMmcNStat;
+    unsigned long long* stu = reinterpret_cast<unsigned long long*>( st );
+    atomicAdd( &st[0], wgt ); atomicAdd( &st[1], wgt*val ); atomicAdd( &st[2], wgt*val*val );
+    atomicMin( &stu[3], mmcOrdered( val ) );
+    atomicMax( &stu[4], mmcOrdered( val ) );
   }
 
-  __global__ void __launch_bounds__(32*kMmcTailWarps, 1)
+  template <int kMinBlocks>
+  __global__ void __launch_bounds__(32*kMmcTailWarps, kMinBlocks)
   k_mmc_tail( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
               const __grid_constant__ MmcGeom G, const __grid_constant__ MmcEngine E, const __grid_constant__ MmcTally T,
               uint64_t seed, uint32_t step0, uint32_t max_steps, uint32_t n, MmcState A,
               double* __restrict__ tally, double* __restrict__ meta, MmcTailOut* __restrict__ out, int* __restrict__ err_flags,
-              uint32_t fam_of_off, uint32_t scratch_off )
+              uint32_t fam_of_off, uint32_t scratch_off, uint32_t* __restrict__ next_history )
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
+    __shared__ double s_stat[TALLY_NTYPES*kMmcNClass*kMmcNStat];
+    {
+      unsigned long long* su = reinterpret_cast<unsigned long long*>( s_stat );
+      for ( int k = threadIdx.x; k < TALLY_NTYPES*kMmcNClass*kMmcNStat; k += blockDim.x ) {
+        const int stat = k % kMmcNStat;
+        if ( stat == 3 ) su[k] = ~0ull; else if ( stat == 4 ) su[k] = 0ull; else s_stat[k] = 0.0;
+      }
+    }
+    __syncthreads();
     HotTabs H;
     uint8_t* fam_of = smem + fam_of_off;
     int isc = -1;
@@ -314,12 +327,16 @@ namespace ncb {
     const ScBraggT& S = *H.sc;
     ScWarpScratch& ws = reinterpret_cast<ScWarpScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
     const int lane = threadIdx.x & 31;
-    const uint32_t nwarps = gridDim.x * kMmcTailWarps;
     unsigned long long records = 0;
     unsigned int last_step = 0;
     double sumw = 0.0;
     int errs = 0;
-    for ( uint32_t ih = blockIdx.x * kMmcTailWarps + ( threadIdx.x >> 5 ); ih < n; ih += nwarps ) {
+    // histories differ in length by three orders of magnitude: warps fetch them one at a time from a global counter
+    while ( true ) {
+      uint32_t ih = 0;
+      if ( lane == 0 ) ih = atomicAdd( next_history, 1u );
+      ih = __shfl_sync( 0xffffffffu, ih, 0 );
+      if ( ih >= n ) break;
       double x = A.x[ih], y = A.y[ih], z = A.z[ih], ux = A.ux[ih], uy = A.uy[ih], uz = A.uz[ih];
       double w = A.w[ih], ekin = A.ekin[ih];
       const double e0 = A.e0[ih];
@@ -345,7 +362,7 @@ namespace ncb {
         // ---- forward step + exit tallies: k_mmc_forward, k_mmc_tally, k_mmc_sum_weights
         Rng rng; rng.init( seed, id, kMmcSidBase + 2u*step );
         const MmcStepOut o = mmcForward( G, E, rng, x, y, z, ux, uy, uz, w, ekin, nscat, xs );
-        mmcTallyAtomic( T, tally, lane, ux, uy, uz, ekin, o.wt, nscat, ninel, e0, ux0, uy0, uz0 );
+        mmcTallyAtomic( T, tally, s_stat, lane, ux, uy, uz, ekin, o.wt, nscat, ninel, e0, ux0, uy0, uz0 );
         sumw += o.wt; ++records;
         ++step;
         if ( !o.survives ) break;
@@ -391,6 +408,20 @@ namespace ncb {
       atomicMax( &out->last_step, last_step );
     }
     if ( errs ) atomicOr( err_flags, errs );
+    // the CTA's running statistics -> global (one set of atomics per histogram and class that was filled)
+    __syncthreads();
+    for ( int k = threadIdx.x; k < T.nh*kMmcNClass; k += blockDim.x ) {
+      const int ih = k / kMmcNClass, cls = k % kMmcNClass;
+      const double* st = s_stat + k*kMmcNStat;
+      const unsigned long long* stu = reinterpret_cast<const unsigned long long*>( st );
+      if ( stu[3] == ~0ull ) continue;
+      const MmcHist h = T.h[ih];
+      double* g = tally + h.off + 2*kMmcNClass*( h.nbins + 2 ) + cls*kMmcNStat;
+      unsigned long long* gu = reinterpret_cast<unsigned long long*>( g );
+      atomicAdd( &g[0], st[0] ); atomicAdd( &g[1], st[1] ); atomicAdd( &g[2], st[2] );
+      atomicMin( &gu[3], stu[3] );
+      atomicMax( &gu[4], stu[4] );
+    }
   }
 
 }

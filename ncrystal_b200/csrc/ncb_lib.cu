@@ -453,7 +453,8 @@ namespace {
     setSmemAttr( k_sc_sample );
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_find );
-    setSmemAttr( k_mmc_tail );
+    setSmemAttr( k_mmc_tail<1> );
+    setSmemAttr( k_mmc_tail<2> );
     setSmemAttr( k_lc_scan );
     setSmemAttr( k_lc_sample );
     setSmemAttr( k_tally_hist );
@@ -1849,7 +1850,7 @@ extern "C" {
     } NCBCATCH;
   }
   void ncb200_set_fg_staged_min( uint64_t nmin ) { g_fg_staged_min.store( nmin ); }
-  void ncb200_set_mmc_tail_mode( int persistent ) { g_mmc_persistent_tail.store( persistent != 0 ); }
+  void ncb200_set_mmc_tail_mode( int persistent ) { g_mmc_persistent_tail.store( persistent != 0 ); if ( persistent > 0 ) g_mmc_tail_ctas.store( persistent >= 2 ? 2 : 1 ); }
   void ncb200_get_rng_stream( ncrystal_scatter_t o, uint64_t* seed, uint32_t* stream_id, uint64_t* next_index )
   {
     try {

@@ -106,3 +106,28 @@ def test_material_with_vdos_leaves(key, configs):
     assert np.max(np.abs(xs[ok] - g["xs"][ok]) / np.abs(g["xs"][ok])) <= 1e-12
     b.setRNGStream(int(g["seed"]), 0, 0)
     assert_replay(b.sampleScatterIsotropic(g["ekin"]), (g["ekin_out"], g["mu"]), what=key + " vs golden")
+
+
+@pytest.mark.skipif(not _vdos.have_reference(), reason="compiled reference (oracle/_ref) not present")
+def test_data_library_sweep_subset(product):
+    """Every 7th phonon density of states of the reference's embedded data library (tests/vdos_sweep.py runs all 211;
+    results under profiles/): device table == reference table, bit for bit."""
+    from _libs import RefDrv, _d
+    ref = _vdos.reference_api()
+    n, strs = C.c_uint(0), C.POINTER(C.c_char_p)()
+    ref.L.ncrystal_get_file_list.argtypes = [C.POINTER(C.c_uint), C.POINTER(C.POINTER(C.c_char_p))]
+    ref.L.ncrystal_get_file_list(C.byref(n), C.byref(strs))
+    names = sorted({strs[i].decode() for i in range(0, n.value, 4) if strs[i].decode().endswith(".ncmat")})
+    L = RefDrv.lib()
+    L.refdrv_vdos_data.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+    done = 0
+    for name in names[::7]:
+        meta, dens = np.zeros(5), np.zeros(200000)
+        m = L.refdrv_vdos_data(name.encode(), 0, _d(meta), _d(dens), dens.size)
+        if m <= 0:
+            continue
+        args = (meta[:2].copy(), dens[:m].copy(), float(meta[4]), float(meta[3]), float(meta[2]), 1)
+        r, g = ref.kernel(*args), product.kernel(*args)
+        assert all(a.shape == b.shape and np.array_equal(a, b) for a, b in zip(r[:3], g[:3])) and r[3] == g[3], name
+        done += 1
+    assert done >= 10
