@@ -304,6 +304,10 @@ void ncrystal_raw_vdos2kernel( const double* vdos_egrid, const double* vdos_dens
                                unsigned vdoslux, double (*order_weight_fct)( unsigned order ),
                                unsigned* nalpha, unsigned* nbeta, double** alpha, double** beta, double** sab,
                                double target_emax, double* suggested_emax );
+void ncrystal_raw_vdos2knl( const double* vdos_egrid, const double* vdos_density, unsigned vdos_egrid_npts,
+                            unsigned vdos_density_npts, double scattering_xs, double mass_amu, double temperature,
+                            unsigned vdoslux, double (*order_weight_fct)( unsigned order ),
+                            unsigned* nalpha, unsigned* nbeta, double** alpha, double** beta, double** sab ); /* obsolete spelling */
 /* number of expansions run so far (raw calls and VDOS leaves of compiled materials, ncb_blob.h: NCB_KIND_SABVDOS) */
 unsigned long ncb200_vdos_expansion_count( void );
 

@@ -146,6 +146,9 @@ SIGNATURES = {
     "ncrystal_raw_vdos2kernel": (None, [_dblp, _dblp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint,
                                         _vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(_dblp),
                                         C.POINTER(_dblp), C.POINTER(_dblp), C.c_double, _dblp]),
+    "ncrystal_raw_vdos2knl": (None, [_dblp, _dblp, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint,
+                                     _vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(_dblp),
+                                     C.POINTER(_dblp), C.POINTER(_dblp)]),
     "ncb200_vdos_expansion_count": (C.c_ulong, []),
 }
 

@@ -5,12 +5,13 @@
  * ProcComposition (ref: ncrystal_core/include/NCrystal/interfaces/NCProcImpl.hh:310-373,
  * flattened by ProcComposition::consumeAndCombine, src/interfaces/NCProcImpl.cc:410-454)
  * with, per leaf, exactly the immutable tables its crossSection/sampleScatter
- * methods read.  Producing it (NCMAT parsing, HKL lists, VDOS->S(alpha,beta)) is
- * the reference's setup pipeline and is out of scope here; the reference-side
- * producer is oracle/matcompile.cc (the binding a maintainer would add, see
+ * methods read.  Producing it (NCMAT parsing, HKL lists) is the reference's setup
+ * pipeline and is out of scope here; the reference-side producer is
+ * bridge/matcompile_impl.icc (the binding a maintainer would add, see
  * INTEGRATION.md).  Everything derived that the hot path needs beyond these
- * inputs (S(alpha,beta) sampler tables) is built natively at load time
- * (csrc/sab_build.cpp).
+ * inputs is built natively on the device at load time: the S(alpha,beta) sampler
+ * tables and energy grids (csrc/ncb_sabbuild.cuh, ncb_sabgrid.h) and, for leaves
+ * delivered as a phonon density of states, S(alpha,beta) itself (csrc/ncb_vdos.h).
  *
  * Layout: one contiguous little-endian buffer.  ncb_header_t at offset 0, then
  * one payload per component at comp[i].off (byte offset from the start of the

@@ -345,20 +345,43 @@ namespace ncb {
       int nscat = A.nscat[ih], ninel = A.ninel[ih];
       const uint64_t id = A.id[ih];
       uint32_t step = step0;
+      double iso_ekin = -1.0, iso_xs[kMaxComp]; int iso_aux[kMaxComp];
       while ( true ) {
         if ( step - step0 >= max_steps ) { errs |= ERR_MMC_NOTERM; break; }
         // ---- cross section at (E, dir): launchXSAniso
-        double sc_xs = 0.0; int sc_n = 0;
+        double sc_xs = 0.0, sc_wl = 0.0; int sc_n = 0;
         const Vec3 dir = { ux, uy, uz };
         Vec3 dnorm = dir;
         if ( isc >= 0 && domainContains( M.comp[isc].dom_lo, M.comp[isc].dom_hi, ekin ) && !( ekin <= S.threshold_ekin ) ) {
           vnormalise( dnorm );
           ScAccum acc; double wl;
-          scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 0, false, 0.0 );
-          sc_xs = acc.commul_last; sc_n = acc.n;
+          scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 2, false, 0.0 );     // (mode 2: the entries are recorded)
+          sc_xs = acc.commul_last; sc_n = acc.n; sc_wl = wl;
         }
+        // composition sum (matXSPre).  The isotropic leaves depend on the energy alone, and a neutron caught between
+        // Bragg reflections keeps its energy for hundreds of steps: their values are kept while ekin does not change
+        // (same values, same summation order).
         double cumul[kMaxComp]; int aux[kMaxComp];
-        const double xs = matXSPre( M, H, ekin, sc_xs, sc_n, cumul, aux );
+        double xs = 0.0;
+        if ( domainContains( M.dom_lo, M.dom_hi, ekin ) ) {
+          const bool fresh = !( ekin == iso_ekin );
+          for ( int i = 0; i < M.ncomp; ++i ) {
+            const Comp& c = M.comp[i];
+            int a = -1;
+            double v = 0.0;
+            if ( domainContains( c.dom_lo, c.dom_hi, ekin ) ) {
+              if ( c.kind == KIND_SCBRAGG ) { v = sc_xs; a = sc_n; }
+              else if ( c.kind == KIND_LCBRAGG ) { v = sc_n ? M.lc.xsfact * sc_xs : 0.0; a = sc_n; }
+              else {
+                if ( fresh ) { iso_xs[i] = compXSIso( M, H, i, ekin, a ); iso_aux[i] = a; }
+                v = iso_xs[i]; a = iso_aux[i];
+              }
+            }
+            xs += c.scale * v;
+            cumul[i] = xs; aux[i] = a;
+          }
+          iso_ekin = ekin;
+        }
         // ---- forward step + exit tallies: k_mmc_forward, k_mmc_tally, k_mmc_sum_weights
         Rng rng; rng.init( seed, id, kMmcSidBase + 2u*step );
         const MmcStepOut o = mmcForward( G, E, rng, x, y, z, ux, uy, uz, w, ekin, nscat, xs );
@@ -377,10 +400,26 @@ namespace ncb {
             if ( !( ekin <= M.sc.threshold_ekin ) && aux[ich] > 0 && sc_xs > 0.0 ) {
               double choice = -1.0; bool linear = true;
               if ( sc_n > 1 ) { choice = sc_xs * r2.generate(); linear = ( sc_n < 5 ); }
-              ScAccum acc; double wl;
-              scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 1, linear, choice );
-              const int in = acc.chosen_in;
-              const double sg = acc.chosen_sign ? 1.0 : -1.0;
+              // the plane is selected among the entries the cross-section walk of this step recorded (same rule as
+              // the second walk of k_sc_sample: linear search '>' below five entries, lower_bound '>=' above); only a
+              // neutron with more contributing planes than the record holds is walked again
+              int in, sgn;
+              double wl = sc_wl;
+              if ( sc_n <= kScRecCap ) {
+                __syncwarp();
+                int k = 0;
+                for ( ; k < sc_n - 1; ++k ) {
+                  const double cum = ws.rec_cumul[k];
+                  if ( linear ? ( cum > choice ) : !( cum < choice ) ) break;
+                }
+                const int e = ws.rec_entry[k];
+                in = e & 0x7fff; sgn = e >> 15;
+              } else {
+                ScAccum acc;
+                scWalkWarp( S, ws, fam_of, ekin, dnorm, wl, acc, 1, linear, choice );
+                in = acc.chosen_in; sgn = acc.chosen_sign;
+              }
+              const double sg = sgn ? 1.0 : -1.0;
               const Vec3 pn = { sg*S.normals[3*in], sg*S.normals[3*in+1], sg*S.normals[3*in+2] };
               const double inv2dsp = gmCacheRound( S.fam_inv2d[ fam_of[in] ] );
               gmGenScat( S, r2, pn, inv2dsp, wl, dnorm, od );

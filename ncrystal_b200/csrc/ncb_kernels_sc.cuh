@@ -23,6 +23,7 @@ namespace ncb {
 
   constexpr int kScMaxFam = 128;      // families whose per-neutron parameters fit the per-warp scratch
   constexpr int kScCandCap = 64;
+  constexpr int kScRecCap = 32;
   constexpr int kScWarps = 8;         // warps per CTA (they share the staged tables)
 
   struct ScWarpScratch {
@@ -34,6 +35,10 @@ namespace ncb {
     double spt[kScMaxFam];
     double vals[2*kScCandCap];        // raw xs of (-normal, +normal) per candidate
     uint16_t cand[kScCandCap];
+    // record of a cross-section walk (mode 2): cumulative sum and (normal, sign) of every contributing entry, so that a
+    // caller that goes on to scatter on this crystal selects among them without walking again (transport tail kernel)
+    double rec_cumul[kScRecCap];
+    uint16_t rec_entry[kScRecCap];    // normal index | sign << 15
   };
 
   // state of the ordered accumulation (warp-uniform)
@@ -47,6 +52,7 @@ namespace ncb {
 
   // Evaluate the `count` recorded candidates (lanes in parallel), then accumulate in order.
   // mode 0: total/count.  mode 1: stop at the entry selected by `choice` (rule: linear '>' / lower_bound '>=').
+  // mode 2: as 0, and the first kScRecCap contributing entries are recorded in the scratch (rec_cumul / rec_entry).
   __device__ __forceinline__ void scFlush( const ScBraggT& S, ScWarpScratch& ws, const uint8_t* fam_of,
                                            double wl, const Vec3& d, int count, ScAccum& acc,
                                            int mode, bool linear, double choice )
@@ -73,7 +79,7 @@ namespace ncb {
     }
     __syncwarp();
     // ordered accumulation, all lanes redundantly (<= 128 values)
-    for ( int k = 0; k < count && !( mode && acc.found ); ++k ) {
+    for ( int k = 0; k < count && !( mode == 1 && acc.found ); ++k ) {
       const int in = ws.cand[k];
       const int f = fam_of[in];
       if ( f != acc.cur_fam ) { acc.cur_fam = f; acc.xsoffset = acc.commul_last; acc.xssum = 0.0; }
@@ -82,7 +88,9 @@ namespace ncb {
         if ( xs ) {
           acc.commul_last = acc.xsoffset + ( acc.xssum += xs );
           ++acc.n;
-          if ( mode ) {
+          if ( mode == 2 ) {
+            if ( acc.n <= kScRecCap && lane == 0 ) { ws.rec_cumul[acc.n-1] = acc.commul_last; ws.rec_entry[acc.n-1] = (uint16_t)( in | ( sgn << 15 ) ); }
+          } else if ( mode ) {
             acc.chosen_in = in; acc.chosen_sign = sgn;
             if ( linear ? ( acc.commul_last > choice ) : !( acc.commul_last < choice ) ) { acc.found = true; break; }
           }
@@ -169,7 +177,7 @@ namespace ncb {
           if ( count > kScCandCap - 32 ) {
             scFlush( S, ws, fam_of, wl, d, count, acc, mode, linear, choice );
             count = 0;
-            if ( mode && acc.found ) return;
+            if ( mode == 1 && acc.found ) return;
           }
         }
       }

@@ -39,7 +39,7 @@ namespace ncb { namespace vdos {
 
     class CudaBackend {
     public:
-      explicit CudaBackend( cudaStream_t st ) : m_st( st ), m_work( st ), m_w( st ), m_ytmp( st ), m_jobs( st ), m_stats( st )
+      explicit CudaBackend( cudaStream_t st ) : m_st( st ), m_work( st ), m_ytmp( st ), m_jobs( st ), m_stats( st )
       {
         static std::mutex mtx; static std::map<int,bool> done;
         int dev = 0; VDOS_CUDA_OK( cudaGetDevice( &dev ) );
@@ -113,17 +113,17 @@ namespace ncb { namespace vdos {
         const unsigned nchunks = 1u << ( maxlog - llog );
         const size_t smem = sizeof(Cplx) << llog;
         const unsigned wsize = 1u << m_wlog;
-        k_vdos_fft_local<false><<< dim3( nchunks, (unsigned)nj, 2 ), kFftThreads, smem, m_st >>>( m_jobs.p, m_w.p, wsize );
+        k_vdos_fft_local<false><<< dim3( nchunks, (unsigned)nj, 2 ), kFftThreads, smem, m_st >>>( m_jobs.p, m_wdev, wsize );
         ++launches;
         const unsigned bfblocks = maxlog > 0 ? ( ( 1u << ( maxlog - 1 ) ) + 255 )/256 : 1;
         for ( int i = kFftLocalLog; i < maxlog; ++i ) {
-          k_vdos_fft_stage<false><<< dim3( bfblocks, (unsigned)nj, 2 ), 256, 0, m_st >>>( m_jobs.p, m_w.p, wsize, i );
+          k_vdos_fft_stage<false><<< dim3( bfblocks, (unsigned)nj, 2 ), 256, 0, m_st >>>( m_jobs.p, m_wdev, wsize, i );
           ++launches;
         }
-        k_vdos_fft_local<true><<< dim3( nchunks, (unsigned)nj, 1 ), kFftThreads, smem, m_st >>>( m_jobs.p, m_w.p, wsize );
+        k_vdos_fft_local<true><<< dim3( nchunks, (unsigned)nj, 1 ), kFftThreads, smem, m_st >>>( m_jobs.p, m_wdev, wsize );
         ++launches;
         for ( int i = kFftLocalLog; i < maxlog; ++i ) {
-          k_vdos_fft_stage<true><<< dim3( bfblocks, (unsigned)nj, 1 ), 256, 0, m_st >>>( m_jobs.p, m_w.p, wsize, i );
+          k_vdos_fft_stage<true><<< dim3( bfblocks, (unsigned)nj, 1 ), 256, 0, m_st >>>( m_jobs.p, m_wdev, wsize, i );
           ++launches;
         }
         k_vdos_finish<<< (unsigned)nj, 512, 0, m_st >>>( m_jobs.p, m_stats.p );
@@ -195,7 +195,8 @@ namespace ncb { namespace vdos {
       std::vector<double*> m_pools;
       double* m_pool_cur = nullptr; size_t m_pool_left = 0, m_next_pool = (size_t)1 << 16;
       std::vector<size_t> m_len;
-      DevBuf<Cplx> m_work, m_w;
+      DevBuf<Cplx> m_work;
+      const Cplx* m_wdev = nullptr;
       DevBuf<double> m_ytmp;
       DevBuf<JobDev> m_jobs;
       DevBuf<JobStat> m_stats;
@@ -216,15 +217,26 @@ namespace ncb { namespace vdos {
         return m_spec[order-1];
       }
       void reservePool( size_t ndoubles ) { m_next_pool = std::max<size_t>( ndoubles, (size_t)1 << 16 ); m_pool_left = 0; }
+      // device copy of the twiddle table: one per device for the life of the process, grown on demand
       void needTwiddles( int logn )
       {
         if ( logn <= m_wlog ) return;
-        const int l = std::max( logn, 13 );
-        const std::vector<Cplx> w = makeTwiddles( (unsigned)l );
-        m_w.need( w.size() );
-        VDOS_CUDA_OK( cudaMemcpyAsync( m_w.p, w.data(), w.size()*sizeof(Cplx), cudaMemcpyHostToDevice, m_st ) );
-        VDOS_CUDA_OK( cudaStreamSynchronize( m_st ) );
-        m_wlog = l;
+        static std::mutex mtx;
+        struct DevTable { Cplx* p = nullptr; int log = -1; };
+        static std::map<int,DevTable> cache;
+        int dev = 0; VDOS_CUDA_OK( cudaGetDevice( &dev ) );
+        std::lock_guard<std::mutex> g( mtx );
+        DevTable& t = cache[dev];
+        if ( t.log < logn ) {
+          const int l = std::max( logn, 13 );
+          const std::vector<Cplx>& w = twiddles( (unsigned)l );
+          Cplx* p = nullptr;
+          VDOS_CUDA_OK( cudaMalloc( &p, w.size()*sizeof(Cplx) ) );
+          VDOS_CUDA_OK( cudaMemcpy( p, w.data(), w.size()*sizeof(Cplx), cudaMemcpyHostToDevice ) );
+          // (a smaller table stays allocated: an expansion on another thread may still be reading it)
+          t.p = p; t.log = l;
+        }
+        m_wdev = t.p; m_wlog = t.log;
       }
     };
   }

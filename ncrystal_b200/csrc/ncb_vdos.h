@@ -30,6 +30,7 @@
 #include <functional>
 #include <limits>
 #include <list>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -220,8 +221,33 @@ namespace ncb { namespace vdos {
     const PairDD a = calcPhase( 1, n ), b = calcPhase( k - 1, n );
     return PairDD( a.first*b.first - a.second*b.second, a.first*b.second + a.second*b.first );
   }
-  // W[k] = exp(i 2 pi k / size); the entries do not depend on the table size they were generated for
-  // (W_2N[2k] == W_N[k] exactly), so one table of the largest size serves every transform length.
+  // W[k] = exp(i 2 pi k / size), the reference's twiddle table (initWTable: even entries from calcPhase, odd entries
+  // = W[1] * previous entry).  The entries do not depend on the table size they were generated for: calcPhase strips
+  // common factors of two, so W_2N[2k] == W_N[k] exactly, and an odd entry is the same product in either
+  // formulation.  Hence (a) one table of the largest size serves every transform length (stride access) and (b) the
+  // table of size 2N follows from the table of size N in one pass -- which is how it is built here (the recursive
+  // definition costs ~popcount(k) complex products per entry: 5 ms for 65536 entries, more than all the FFTs of an
+  // expansion).  Process-wide cache, grown on demand.
+  inline const std::vector<Cplx>& twiddles( unsigned log2size )
+  {
+    static std::mutex mtx;
+    static std::vector<std::vector<Cplx>> tables;     // [L] = table of size 2^L (kept: references stay valid)
+    std::lock_guard<std::mutex> g( mtx );
+    if ( tables.empty() ) { tables.reserve( 32 ); tables.push_back( std::vector<Cplx>( 1, Cplx{ 1.0, 0.0 } ) ); }
+    while ( tables.size() <= log2size ) {
+      const unsigned L = (unsigned)tables.size();
+      const std::vector<Cplx>& half = tables.back();
+      const PairDD p1 = calcPhase( 1, L );
+      std::vector<Cplx> w( (size_t)1 << L );
+      for ( size_t i = 0; i < w.size(); i += 2 ) {
+        w[i] = half[i/2];
+        w[i+1] = Cplx{ p1.first*w[i].re - p1.second*w[i].im, p1.first*w[i].im + p1.second*w[i].re };
+      }
+      tables.push_back( std::move( w ) );
+    }
+    return tables[log2size];
+  }
+  // the same table by the reference's own recipe (kept for the unit test of the construction above)
   inline std::vector<Cplx> makeTwiddles( unsigned log2size )
   {
     const unsigned size = 1u << log2size;

@@ -66,7 +66,7 @@ namespace {
       const size_t nout = J.n1 + J.n2 - 1;
       int logn = 0;
       while ( ( (size_t)1 << logn ) < nout ) ++logn;
-      if ( logn > m_wlog ) { m_w = makeTwiddles( (unsigned)logn ); m_wlog = logn; }
+      if ( logn > m_wlog ) { m_w = twiddles( (unsigned)logn ); m_wlog = logn; }
       const size_t N = (size_t)1 << logn;
       const VectD& a1 = at( J.o1 ); const VectD& a2 = at( J.o2 );
       std::vector<Cplx> b1( N ), b2( N ), bo( N );
@@ -172,6 +172,16 @@ extern "C" {
       meta4[0] = m.lower; meta4[1] = m.upper; meta4[2] = m.binwidth; meta4[3] = m.maxval;
       return (int)s.size();
     } catch ( std::exception& e ) { g_verr = e.what(); return -3; }
+  }
+
+  // twiddle table built by doubling == table built by the reference's recipe (number of differing entries)
+  int hostsim_vdos_twiddle_check( int log2size )
+  {
+    const std::vector<Cplx>& a = twiddles( (unsigned)log2size );
+    const std::vector<Cplx> b = makeTwiddles( (unsigned)log2size );
+    int bad = a.size() == b.size() ? 0 : 1;
+    for ( size_t i = 0; i < a.size() && i < b.size(); ++i ) if ( a[i].re != b[i].re || a[i].im != b[i].im ) ++bad;
+    return bad;
   }
 
   // regulariseVDOSGrid alone

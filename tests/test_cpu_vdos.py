@@ -70,3 +70,11 @@ def test_material_with_vdos_leaves_equals_material_with_expanded_leaves(cfg):
     eb, mb, nb = b.sample_iso(e, seed=11)[:3]
     same = (np.abs(ea - eb) <= 1e-10 * np.abs(ea)) & (np.abs(ma - mb) <= 1e-10) & (na == nb)
     assert same.all(), "%d of %d replayed samples differ" % ((~same).sum(), e.size)
+
+
+def test_twiddle_table_by_doubling_equals_reference_recipe():
+    """csrc/ncb_vdos.h builds the FFT twiddle table of size 2N from the table of size N (one pass); it must equal the
+    table the reference's recursive recipe gives (NCFastConvolve.cc:183-215,466-564), entry for entry."""
+    L = HostSim.lib()
+    for log2size in (1, 2, 5, 12, 16, 18):
+        assert L.hostsim_vdos_twiddle_check(log2size) == 0

@@ -60,6 +60,17 @@ def test_python_mirror_and_error_convention(golden):
     assert k["suggested_emax"] is None and _vdos.sha(k["sab"]) == str(golden["out_Be_lux2_weights_sab_sha"])
     (xmin, xmax), gn = vdos.extractGn((egrid, density), order, mass, T, scatxs=sigma, expand_egrid=False)
     assert (xmin, xmax) == tuple(golden["out_Be_lux2_weights_gn_range"]) and _vdos.sha(gn) == str(golden["out_Be_lux2_weights_gn_sha"])
+    # obsolete spelling ncrystal_raw_vdos2knl (ncrystal.h:897-907): same table, no Emax arguments
+    L = nc._lib.lib()
+    dp = C.POINTER(C.c_double)
+    na, nb, pa, pb, ps = C.c_uint(0), C.c_uint(0), dp(), dp(), dp()
+    L.ncrystal_raw_vdos2knl(egrid.ctypes.data_as(dp), density.ctypes.data_as(dp), egrid.size, density.size, sigma, mass, T, 1,
+                            None, C.byref(na), C.byref(nb), C.byref(pa), C.byref(pb), C.byref(ps))
+    k1 = vdos.extractKnl((egrid, density), mass, T, vdoslux=1, scatxs=sigma)
+    assert na.value == k1["alpha"].size and nb.value == k1["beta"].size
+    assert np.array_equal(np.ctypeslib.as_array(ps, (na.value * nb.value,)), k1["sab"])
+    for p_ in (pa, pb, ps):
+        L.ncrystal_dealloc_doubleptr(p_)
     with pytest.raises(nc.NCBadInput):
         vdos.extractKnl((np.array([1e-7, 0.03]), density), mass, T)
     with pytest.raises(nc.NCBadInput):
