@@ -747,12 +747,15 @@ namespace {
     dirs.push_back( libDir() + "/data" );
     const std::string stem = cfgToStem( cfg );
     std::string tried;
-    for ( auto& d : dirs ) {
-      const std::string path = d + "/" + stem + ".ncb";
-      auto data = readFile( path );
-      if ( !data.empty() ) return data;
-      tried += " " + path;
-    }
+    // <stem>.ncb, else <stem>.vdos.ncb: the same material with its S(alpha,beta) leaves delivered as phonon
+    // densities of states (a fraction of the size; expanded on the device when the material is created)
+    for ( const char* ext : { ".ncb", ".vdos.ncb" } )
+      for ( auto& d : dirs ) {
+        const std::string path = d + "/" + stem + ext;
+        auto data = readFile( path );
+        if ( !data.empty() ) return data;
+        if ( ext[1] == 'n' ) tried += " " + path;
+      }
     // second chance: same cfg spelled with another parameter order or the "stdlib::" prefix
     const std::string key = looseCfgKey( stem );
     for ( auto& d : dirs ) {

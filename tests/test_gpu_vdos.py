@@ -142,3 +142,34 @@ def test_data_library_sweep_subset(product):
         assert all(a.shape == b.shape and np.array_equal(a, b) for a, b in zip(r[:3], g[:3])) and r[3] == g[3], name
         done += 1
     assert done >= 10
+
+
+def test_create_scatter_falls_back_to_the_vdos_form(configs, tmp_path):
+    """ncrystal_create_scatter(cfg) looks for <stem>.ncb and then for <stem>.vdos.ncb: a data directory that holds only
+    the density-of-states form of a material (43 KB instead of 2.6 MB for Al) serves the cfg string."""
+    import shutil
+    import ncrystal_b200 as nc
+    from ncrystal_b200 import _lib
+    from _libs import loguniform_energies
+    L = _lib.lib()
+    cfg = configs["Al"]
+    alias = cfg + ";vdoslux=3"                       # same material, a spelling no compiled file exists for
+    buf = C.create_string_buffer(512)
+    L.ncb200_cfg_to_filestem(cfg.encode(), buf, 512)
+    src = os.path.join(_lib.DATA_DIR, buf.value.decode() + ".vdos.ncb")
+    if not os.path.exists(src):
+        pytest.skip("vdos form not built")
+    L.ncb200_cfg_to_filestem(alias.encode(), buf, 512)
+    shutil.copy(src, tmp_path / (buf.value.decode() + ".vdos.ncb"))
+    with pytest.raises(nc.NCFileNotFound):
+        nc.Scatter(alias, seed=1)
+    e = loguniform_energies(5000, seed=8)
+    ref = nc.Scatter(cfg, seed=1).crossSectionIsotropic(e)
+    n0 = L.ncb200_vdos_expansion_count()
+    L.ncb200_set_data_path((str(tmp_path) + ":" + _lib.DATA_DIR).encode())
+    try:
+        xs = nc.Scatter(alias, seed=1).crossSectionIsotropic(e)
+    finally:
+        L.ncb200_set_data_path(os.environ.get("NCB200_DATA_PATH", _lib.DATA_DIR).encode())
+    assert L.ncb200_vdos_expansion_count() == n0 + 1
+    assert np.max(np.abs(xs - ref) / ref) < 1e-12
