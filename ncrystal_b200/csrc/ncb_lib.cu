@@ -257,13 +257,13 @@ namespace {
       // k_sc_find stages the float normals (slot of the double normals) and nothing else
       std::memset( &dm.sp_find, 0, sizeof(StagePlan) );
       {
-        const uint32_t nn4 = ( (uint32_t)M.sc.nnormals + 3u ) & ~3u;
-        const uint32_t nb = 3u*nn4*(uint32_t)sizeof(float);
+        const uint32_t nnp = ( (uint32_t)M.sc.nnormals + 127u ) & ~127u;
+        const uint32_t nb = 4u*nnp*(uint32_t)sizeof(float);
         dm.sp_find.src[kHotSlotsIso] = M.sc.normals_f; dm.sp_find.nbytes[kHotSlotsIso] = nb; dm.sp_find.off[kHotSlotsIso] = 0;
         dm.sp_find.copy_bytes = nb;
         dm.sp_find.total = ( nb + 127u ) & ~127u;
-        dm.sc_find_famof_off = dm.sp_find.total;
-        dm.sc_find_scratch_off = ( dm.sc_find_famof_off + (uint32_t)M.sc.nnormals + 127u ) & ~127u;
+        dm.sc_find_famof_off = dm.sp_find.total;     // (no family map: the records carry the family index)
+        dm.sc_find_scratch_off = dm.sp_find.total;
         dm.sc_find_smem = dm.sc_find_scratch_off + (uint32_t)( kScFindWarps*sizeof(ScFindScratch) );
       }
     }

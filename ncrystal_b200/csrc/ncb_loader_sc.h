@@ -36,10 +36,17 @@ namespace ncb {
     const double* pn = arr + 2*nf + nf + 1;
     S.normals = offAsPtr<double>( lm.put( pn, 3*nn*8 ) );
     {
-      const size_t nn4 = ( nn + 3 ) & ~(size_t)3;          // rows padded to 16 bytes
-      std::vector<float> nf32( 3*nn4, 0.0f );
-      for ( size_t i = 0; i < nn; ++i )
-        for ( int k = 0; k < 3; ++k ) nf32[k*nn4 + i] = (float)pn[3*i+k];
+      // single-precision copy for the pre-filter of k_sc_find: one 16-byte record per normal, (x, y, z, family index
+      // as integer bits), padded to a multiple of 128 records with normals that can never pass (x=y=z=0)
+      const size_t nnp = ( nn + 127 ) & ~(size_t)127;
+      std::vector<float> nf32( 4*nnp, 0.0f );
+      size_t f = 0;
+      for ( size_t i = 0; i < nn; ++i ) {
+        while ( f + 1 < nf && (int)i >= first[f+1] ) ++f;
+        for ( int k = 0; k < 3; ++k ) nf32[4*i + k] = (float)pn[3*i+k];
+        const uint32_t fi = (uint32_t)f;
+        std::memcpy( &nf32[4*i + 3], &fi, 4 );
+      }
       S.normals_f = offAsPtr<float>( lm.put( nf32.data(), nf32.size()*sizeof(float) ) );
     }
     const double* l1 = pn + 3*nn;

@@ -161,7 +161,8 @@ namespace ncb {
     const double* fam_inv2d;          // [nfam] ascending
     const int* fam_first;             // [nfam+1]
     const double* normals;            // [3*nnormals] lab frame
-    const float* normals_f;           // [3][nnormals] single-precision copy, SoA (pre-filter of k_sc_find only)
+    const float* normals_f;           // single-precision copy for the pre-filter of k_sc_find: float4 records (x, y, z, family
+                                      // index as integer bits), padded to a multiple of 128 records
     SplineLutT sofcosd, evalcosx;
   };
 
