@@ -257,6 +257,7 @@ namespace ncb {
     double dom_lo, dom_hi;
     double* sc_xs; int32_t* sc_n;      // zeroed here for neutrons without candidates
     uint32_t* work; uint32_t* work_count; uint8_t* ncand; uint16_t* cand;   // work list (bit 31: overflow)
+    uint32_t* overflow_count;          // number of work items flagged "overflow"
     int32_t* wpos;                     // per neutron: its work-list position, -1 none, -2 overflow (for k_sc_sample)
   };
 
@@ -356,6 +357,7 @@ namespace ncb {
         pos = __shfl_sync( 0xffffffffu, pos, 0 );
         if ( lane == 0 ) {
           A.work[pos] = (uint32_t)i | ( overflow ? 0x80000000u : 0u );
+          if ( overflow ) atomicAdd( A.overflow_count, 1u );
           A.ncand[pos] = (uint8_t)( overflow ? 0 : count );
           A.wpos[i] = overflow ? -2 : (int32_t)pos;
         }
@@ -366,12 +368,89 @@ namespace ncb {
     }
   }
 
+  // Evaluation of the recorded candidates, EIGHT LANES PER NEUTRON (four neutrons per warp): a neutron has 1-3
+  // candidate planes on average, so with a warp per neutron 29 of 32 lanes idled through the circle integrals (ncu:
+  // 13 of 32 lanes active, 24 % occupancy at 128 registers).  The lanes of a group evaluate the group's candidates
+  // in parallel (raw cross sections of -normal / +normal), then the group accumulates them in plane order exactly as
+  // scFlush does.  Work items flagged "overflow" (more than kScFindCap candidates) are left to k_sc_eval below.
+  // dynamic smem: [staged tables (sp.total)] [fam_of: nnormals bytes] [kScWarps x 4 x ScGroupScratch]
+  struct ScGroupScratch { double vals[2*kScFindCap]; };
   __global__ void __launch_bounds__(32*kScWarps, 2)
-  k_sc_eval( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
-             const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off )
+  k_sc_eval_groups( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                    const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off )
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
+    ScGroupScratch& gs = reinterpret_cast<ScGroupScratch*>( smem + scratch_off )[ ( threadIdx.x >> 5 )*4 + grp ];
+    const uint32_t nwork = *A.work_count;
+    const uint32_t nitems = gridDim.x * kScWarps * 4;
+    for ( uint32_t w0 = ( blockIdx.x * kScWarps + ( threadIdx.x >> 5 ) )*4; w0 < nwork; w0 += nitems ) {
+      const uint32_t w = w0 + grp;
+      uint32_t entry = 0x80000000u;
+      int count = 0;
+      if ( w < nwork ) { entry = A.work[w]; if ( !( entry & 0x80000000u ) ) count = A.ncand[w]; }
+      const uint32_t i = entry & 0x7fffffffu;
+      Vec3 d = { 0, 0, 1 };
+      double wl = 0.0;
+      if ( count ) {
+        d = Vec3{ A.ux[i], A.uy[i], A.uz[i] };
+        vnormalise( d );
+        const double ekin = scCacheRound( A.ekin[i] );
+        wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+      }
+      const int maxcount = __reduce_max_sync( 0xffffffffu, count );
+      const uint16_t* cand = A.cand + (size_t)w*kScFindCap;
+      for ( int k0 = 0; k0 < maxcount; k0 += 8 ) {
+        const int k = k0 + sl;
+        if ( k < count ) {
+          const int in = cand[k];
+          const int f = fam_of[in];
+          InteractionPars ip;
+          ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+          const double nx = S.normals[3*in], ny = S.normals[3*in+1], nz = S.normals[3*in+2];
+          const double dot = nx*d.x + ny*d.y + nz*d.z;
+          const double sdotcptsq = ( 1.0 - dot*dot )*ip.cos_perfect_theta_sq;
+          const double ds = dot * ip.sin_perfect_theta;
+          double xm = 0.0, xp = 0.0;
+          const double Am = dmax( 0.0, S.cta - ds );
+          if ( sdotcptsq > Am*Am ) xm = gmRawXS( S, ip, dot );     // anti-normal
+          const double Ap = dmax( 0.0, S.cta + ds );
+          if ( sdotcptsq > Ap*Ap ) xp = gmRawXS( S, ip, -dot );    // normal
+          gs.vals[2*k] = xm; gs.vals[2*k+1] = xp;
+        }
+      }
+      __syncwarp();
+      if ( count && sl == 0 ) {
+        // ordered accumulation (scFlush, mode 0)
+        int cur_fam = -1, n = 0;
+        double xsoffset = 0.0, xssum = 0.0, commul_last = 0.0;
+        for ( int k = 0; k < count; ++k ) {
+          const int f = fam_of[ cand[k] ];
+          if ( f != cur_fam ) { cur_fam = f; xsoffset = commul_last; xssum = 0.0; }
+          for ( int sgn = 0; sgn < 2; ++sgn ) {
+            const double xs = gs.vals[2*k+sgn];
+            if ( xs ) { commul_last = xsoffset + ( xssum += xs ); ++n; }
+          }
+        }
+        A.sc_xs[i] = commul_last; A.sc_n[i] = n;
+      }
+      __syncwarp();
+    }
+  }
+
+  // warp-per-neutron evaluation: all work items (only_overflow = 0), or just the ones k_sc_eval_groups leaves
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_eval( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+             const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off, int only_overflow )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    if ( only_overflow && *A.overflow_count == 0 ) return;
     HotTabs H;
     uint8_t* fam_of = smem + fam_of_off;
     scBlockSetup( M, sp, smem, &mbar, H, fam_of );
@@ -382,6 +461,7 @@ namespace ncb {
     const uint32_t nwarps = gridDim.x * kScWarps;
     for ( uint32_t w = blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); w < nwork; w += nwarps ) {
       const uint32_t entry = A.work[w];
+      if ( only_overflow && !( entry & 0x80000000u ) ) continue;
       const uint32_t i = entry & 0x7fffffffu;
       Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
       vnormalise( d );

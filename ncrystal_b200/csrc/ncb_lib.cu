@@ -452,6 +452,7 @@ namespace {
     setSmemAttr( k_sc_scan );
     setSmemAttr( k_sc_sample );
     setSmemAttr( k_sc_eval );
+    setSmemAttr( k_sc_eval_groups );
     setSmemAttr( k_sc_find );
     setSmemAttr( k_mmc_tail<1> );
     setSmemAttr( k_mmc_tail<2> );
@@ -1000,20 +1001,27 @@ namespace {
     FA.ekin = d_ekin; FA.ux = ux; FA.uy = uy; FA.uz = uz; FA.n = n;
     FA.dom_lo = dm.mat.comp[isc].dom_lo; FA.dom_hi = dm.mat.comp[isc].dom_hi;
     FA.sc_xs = qc.sc_xs; FA.sc_n = qc.sc_n;
-    FA.work = qc.sc_work; FA.work_count = qc.counts + 6; FA.ncand = qc.sc_ncand; FA.cand = qc.sc_cand;
+    FA.work = qc.sc_work; FA.work_count = qc.counts + 6; FA.overflow_count = qc.counts + 7; FA.ncand = qc.sc_ncand; FA.cand = qc.sc_cand;
     FA.wpos = qc.sc_wpos;
     qc.sc_lists_valid = true;
-    CUDA_OK( cudaMemsetAsync( qc.counts + 6, 0, sizeof(uint32_t), st ) );
+    CUDA_OK( cudaMemsetAsync( qc.counts + 6, 0, 2*sizeof(uint32_t), st ) );
     const int cf = std::min( 3, std::max( 1, (int)( ( 220u*1024u ) / std::max( dm.sc_find_smem, 1u ) ) ) );
     const uint64_t need_f = ( n + kScFindWarps - 1 ) / kScFindWarps;
     const int ce = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( dm.sc_smem, 1u ) ) ) );
     { TimedLaunch tl( "k_sc_find", st );
       k_sc_find<<< (unsigned)std::min<uint64_t>( need_f, (uint64_t)nsm*cf ), 32*kScFindWarps, dm.sc_find_smem, st >>>(
         dm.mat, dm.sp_find, FA, dm.sc_find_famof_off, dm.sc_find_scratch_off ); }
+    // evaluation: eight lanes per neutron; the (rare) neutrons with more candidates than the record holds are
+    // flagged in the work list (the find kernel counts them) and walked again by the warp-per-neutron kernel
     { TimedLaunch tl( "k_sc_eval", st );
-      k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
+      const uint32_t gsmem = dm.sc_scratch_off + (uint32_t)( kScWarps*4*sizeof(ScGroupScratch) );
+      const int cg = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( gsmem, 1u ) ) ) );
+      k_sc_eval_groups<<< (unsigned)std::min<uint64_t>( ( need + 3 )/4, (uint64_t)nsm*cg ), 32*kScWarps, gsmem, st >>>(
         dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off ); }
-    g_launches += 2;
+    { TimedLaunch tl( "k_sc_eval_overflow", st );
+      k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
+        dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off, 1 ); }
+    g_launches += 3;
     CUDA_OK( cudaGetLastError() );
   }
 

@@ -20,3 +20,13 @@ def t(fn, reps=5):
 txs = t(lambda: L.ncb200_crosssection_many_dev(sc._p, e.data_ptr(), ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), m, xs.data_ptr(), sp))
 tsm = t(lambda: L.ncb200_samplescatter_manydir_dev(sc._h, e.data_ptr(), ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), m, eo.data_ptr(), ox.data_ptr(), oy.data_ptr(), oz.data_ptr(), sp))
 print("Ge 4M: xs %.2f ms (%.3e /s)  sample %.2f ms (%.3e /s)  xs checksum %.12e" % (txs, m / txs * 1e3, tsm, m / tsm * 1e3, float(xs.sum())))
+import json
+buf = C.create_string_buffer(1 << 16)
+for name, fn in (("xs", lambda: L.ncb200_crosssection_many_dev(sc._p, e.data_ptr(), ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), m, xs.data_ptr(), sp)),
+                 ("sample", lambda: L.ncb200_samplescatter_manydir_dev(sc._h, e.data_ptr(), ux.data_ptr(), uy.data_ptr(), uz.data_ptr(), m, eo.data_ptr(), ox.data_ptr(), oy.data_ptr(), oz.data_ptr(), sp))):
+    L.ncb200_kernel_timing(1)
+    fn(); torch.cuda.synchronize()
+    L.ncb200_kernel_timing_report(buf, len(buf))
+    L.ncb200_kernel_timing(0)
+    kt = json.loads(buf.value.decode())
+    print(name, {k: round(v["launches"] * v["ms_avg"], 3) for k, v in kt.items()})
