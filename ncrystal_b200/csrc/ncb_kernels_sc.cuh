@@ -614,12 +614,85 @@ namespace ncb {
       atomicOr( A.err_flags, errs );
   }
 
-  // one queued neutron per warp: choose the normal (second walk) and generate the scattering
+  // One queued neutron per THREAD: the planes that can contribute were recorded by k_sc_find (1-3 on average), the
+  // thread evaluates them in order until the entry picked by pickRandIdxByWeight is reached (same values, same order
+  // and stop rule as scFlush in mode 1) and generates the scattering (GaussMos::genScat).  With a warp per neutron
+  // (k_sc_sample below, r1) all 32 lanes repeated the thread-level part.  Neutrons without a recorded list (more
+  // candidates than the record holds) are left to the warp-per-neutron kernel.
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_sample_threads( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                       const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X,
+                       uint32_t fam_of_off, uint32_t* __restrict__ n_left )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    const uint32_t nq = *X.q_sc_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t left = 0;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
+      const uint32_t i = X.q_sc[j] & kQueueIdxMask;
+      const int32_t wp = X.sc_wpos ? X.sc_wpos[i] : -2;
+      if ( wp < 0 ) { ++left; continue; }
+      const double ekin = A.ekin[i];
+      Vec3 d = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
+      vnormalise( d );
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
+      rng.seek( M.ncomp > 1 ? 1u : 0u );
+      const int nent = X.sc_n[i];
+      const double total = X.sc_xs[i];
+      double choice = -1.0; bool linear = true;
+      if ( nent > 1 ) { choice = total * rng.generate(); linear = ( nent < 5 ); }
+      const double ekr = scCacheRound( ekin );
+      const double wl = ekr ? sqrt( kWl2Ekin / ekr ) : kInf;
+      const int count = X.sc_ncand[wp];
+      const uint16_t* cand = X.sc_cand + (size_t)wp*kScFindCap;
+      int cur_fam = -1, chosen_in = 0, chosen_sign = 1;
+      double xsoffset = 0.0, xssum = 0.0, commul_last = 0.0;
+      bool found = false;
+      for ( int k = 0; k < count && !found; ++k ) {
+        const int in = cand[k];
+        const int f = fam_of[in];
+        InteractionPars ip;
+        ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+        const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
+        const double sdotcptsq = ( 1.0 - dot*dot )*ip.cos_perfect_theta_sq;
+        const double ds = dot * ip.sin_perfect_theta;
+        if ( f != cur_fam ) { cur_fam = f; xsoffset = commul_last; xssum = 0.0; }
+        for ( int sgn = 0; sgn < 2 && !found; ++sgn ) {
+          const double Aa = dmax( 0.0, sgn ? S.cta + ds : S.cta - ds );
+          double xs = 0.0;
+          if ( sdotcptsq > Aa*Aa ) xs = gmRawXS( S, ip, sgn ? -dot : dot );     // sgn 0: anti-normal, 1: normal
+          if ( xs ) {
+            commul_last = xsoffset + ( xssum += xs );
+            chosen_in = in; chosen_sign = sgn;
+            if ( linear ? ( commul_last > choice ) : !( commul_last < choice ) ) found = true;
+          }
+        }
+      }
+      const double sg = chosen_sign ? 1.0 : -1.0;
+      const Vec3 pn = { sg*S.normals[3*chosen_in], sg*S.normals[3*chosen_in+1], sg*S.normals[3*chosen_in+2] };
+      const double inv2dsp = gmCacheRound( S.fam_inv2d[ fam_of[chosen_in] ] );
+      Vec3 o;
+      gmGenScat( S, rng, pn, inv2dsp, wl, d, o );
+      A.ekin_out[i] = ekin;
+      X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
+      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+    }
+    if ( left ) atomicAdd( n_left, left );
+  }
+
+  // one queued neutron per warp: choose the normal (second walk) and generate the scattering.  only_unlisted: just the
+  // neutrons k_sc_sample_threads left (no recorded candidate list); *n_left == 0: nothing to do
   __global__ void __launch_bounds__(32*kScWarps, 2)
   k_sc_sample( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
                const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X,
-               uint32_t fam_of_off, uint32_t scratch_off )
+               uint32_t fam_of_off, uint32_t scratch_off, int only_unlisted, const uint32_t* __restrict__ n_left )
   {
+    if ( only_unlisted && *n_left == 0 ) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
     HotTabs H;
@@ -632,6 +705,7 @@ namespace ncb {
     const uint32_t nwarps = gridDim.x * kScWarps;
     for ( uint32_t j = blockIdx.x * kScWarps + ( threadIdx.x >> 5 ); j < nq; j += nwarps ) {
       const uint32_t i = X.q_sc[j] & kQueueIdxMask;
+      if ( only_unlisted && X.sc_wpos && X.sc_wpos[i] >= 0 ) continue;
       const double ekin = A.ekin[i];
       Vec3 d = { X.D.ux[i], X.D.uy[i], X.D.uz[i] };
       vnormalise( d );

@@ -451,6 +451,7 @@ namespace {
     setSmemAttr( k_classify_aniso );
     setSmemAttr( k_sc_scan );
     setSmemAttr( k_sc_sample );
+    setSmemAttr( k_sc_sample_threads );
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_eval_groups );
     setSmemAttr( k_sc_find );
@@ -1137,9 +1138,22 @@ namespace {
       g_launches += 3;
       if ( has_sc ) {
         const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kScWarps - 1 )/kScWarps, (uint64_t)nsm*3 );
-        { TimedLaunch tl( "k_sc_sample", st );
-          k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off ); }
-        ++g_launches;
+        // neutrons with a recorded candidate list: one per thread; the others (none, normally): one per warp
+        uint32_t* n_left = qc.counts + 7;
+        CUDA_OK( cudaMemsetAsync( n_left, 0, sizeof(uint32_t), st ) );
+        if ( X.sc_wpos ) {
+          const uint32_t tsmem = dm.sc_famof_off + ( ( (uint32_t)dm.mat.sc.nnormals + 127u ) & ~127u );
+          const unsigned gt = (unsigned)std::min<uint64_t>( ( m + 32*kScWarps - 1 )/( 32*kScWarps ), (uint64_t)nsm*2 );
+          { TimedLaunch tl( "k_sc_sample", st );
+            k_sc_sample_threads<<< gt, 32*kScWarps, tsmem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, n_left ); }
+          { TimedLaunch tl( "k_sc_sample_unlisted", st );
+            k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off, 1, n_left ); }
+          g_launches += 2;
+        } else {
+          { TimedLaunch tl( "k_sc_sample", st );
+            k_sc_sample<<< gs, 32*kScWarps, dm.sc_smem, st >>>( dm.mat, dm.sp_sc, A, X, dm.sc_famof_off, dm.sc_scratch_off, 0, n_left ); }
+          ++g_launches;
+        }
       }
       if ( has_lc ) {
         const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kLcWarps - 1 )/kLcWarps, (uint64_t)nsm*16 );
