@@ -276,6 +276,8 @@ namespace ncb {
     const int lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t)gridDim.x * kScFindWarps;
     const double cta = S.cta;
+    double scratch_ekin = -1.0;     // energy the windows in the scratch were computed for (warp-uniform)
+    int nfam_act = 0;
     for ( uint64_t i = (uint64_t)blockIdx.x * kScFindWarps + ( threadIdx.x >> 5 ); i < A.n; i += nwarps ) {
       const double ekin_raw = A.ekin[i];
       int count = 0;
@@ -286,27 +288,32 @@ namespace ncb {
         const double ekin = scCacheRound( ekin_raw );
         const double wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
         if ( wl != 0 ) {
-          const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
-          int nfam_act = 0;
-          for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
-            const int f = f0 + lane;
-            const bool act = ( f < S.nfam ) && ( S.fam_inv2d[f] < inv2dcutoff );
-            if ( act ) {
-              InteractionPars ip;
-              ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
-              const double spt = ip.sin_perfect_theta, cpt = sqrt( ip.cos_perfect_theta_sq );
-              const double slo = spt*cta - cpt*S.sta, shi = spt*cta + cpt*S.sta;
-              const bool open_hi = !( cpt*cta - spt*S.sta > 1e-6 );
-              // (the window is compared with a float dot product: widened by 4e-6)
-              ws.lohi[f] = make_float2( (float)( slo - 4e-6 ), open_hi ? 2.0f : (float)( shi + 4e-6 ) );
-              ws.cptsq[f] = ip.cos_perfect_theta_sq;
-              ws.spt[f] = spt;
+          // per-family windows: functions of the energy alone, kept in the warp's scratch while consecutive neutrons
+          // have the same energy (a mono-energetic beam in a transport run: every neutron of the first steps)
+          if ( !( ekin == scratch_ekin ) ) {
+            const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
+            nfam_act = 0;
+            for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
+              const int f = f0 + lane;
+              const bool act = ( f < S.nfam ) && ( S.fam_inv2d[f] < inv2dcutoff );
+              if ( act ) {
+                InteractionPars ip;
+                ip.set( wl, S.fam_inv2d[f], S.fam_xsfact[f] );
+                const double spt = ip.sin_perfect_theta, cpt = sqrt( ip.cos_perfect_theta_sq );
+                const double slo = spt*cta - cpt*S.sta, shi = spt*cta + cpt*S.sta;
+                const bool open_hi = !( cpt*cta - spt*S.sta > 1e-6 );
+                // (the window is compared with a float dot product: widened by 4e-6)
+                ws.lohi[f] = make_float2( (float)( slo - 4e-6 ), open_hi ? 2.0f : (float)( shi + 4e-6 ) );
+                ws.cptsq[f] = ip.cos_perfect_theta_sq;
+                ws.spt[f] = spt;
+              }
+              const uint32_t m = __ballot_sync( 0xffffffffu, act );
+              nfam_act += __popc( m );
+              if ( m != 0xffffffffu ) break;
             }
-            const uint32_t m = __ballot_sync( 0xffffffffu, act );
-            nfam_act += __popc( m );
-            if ( m != 0xffffffffu ) break;
+            scratch_ekin = ekin;
+            __syncwarp();
           }
-          __syncwarp();
           const int n_act = nfam_act ? S.fam_first[nfam_act] : 0;
           const float dxf = (float)d.x, dyf = (float)d.y, dzf = (float)d.z;
           // Four 32-normal slices per pass.  The pre-filter runs in single precision on the packed records (one
