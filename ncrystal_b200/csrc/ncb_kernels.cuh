@@ -155,6 +155,10 @@ namespace ncb {
     uint32_t* q_fg;     // free-gas leaf and S(alpha,beta) above Emax
     uint32_t* q_emax;   // pairs (entry, draws consumed): table sampling at E=Emax requested by the high-E analysis
     uint32_t* counts;   // [0] = #q_sab, [1] = #q_fg, [2] = #q_emax (pairs), [3],[4] refill cursors
+    // elastic leaves (isotropic sampling): neutrons whose chosen component is PowderBragg / ElIncScatter, sampled by
+    // k_sample_elastic; null = sampled in place by k_sample_classify
+    uint32_t* q_pb = nullptr;  uint32_t* q_el = nullptr;
+    uint32_t* counts_el = nullptr;   // [0] = #q_pb, [1] = #q_el
   };
 
   // Monotonic energy bin: exponent + top 4 mantissa bits of the double (16 bins per octave).
@@ -182,8 +186,9 @@ namespace ncb {
   // writes them out in runs (one global atomic and a coalesced copy per ~100 entries).  No CTA barrier on the
   // path (r1: three __syncthreads per CTA iteration, `barrier` was the top stall reason of the kernel).
   constexpr int kWarpBuf = 128;            // entries per warp and queue; flushed when fewer than 32 slots are left
+  template <int kQueues>
   struct WarpQueueBuf {
-    uint32_t e[2][kWarpBuf];
+    uint32_t e[kQueues][kWarpBuf];     // S(alpha,beta) table, free gas [, PowderBragg, ElIncScatter]
   };
   __device__ __forceinline__ void warpBufFlush( const uint32_t* buf, uint32_t n, uint32_t* q, uint32_t* counter )
   {
@@ -197,24 +202,26 @@ namespace ncb {
     __syncwarp();
   }
 
+  template <bool kDeferElastic>
   __global__ void __launch_bounds__(256, 8)
   k_sample_classify( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
                      const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q )
   {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar;
-    __shared__ WarpQueueBuf s_wq[8];
+    __shared__ WarpQueueBuf<kDeferElastic ? 4 : 2> s_wq[8];
     HotTabs H;
     stageHotTabs( M, sp, smem, &mbar, H );
     const int lane = threadIdx.x & 31;
-    WarpQueueBuf& wq = s_wq[threadIdx.x >> 5];
-    uint32_t c1 = 0, c2 = 0;                 // entries in the warp's two buffers (warp-uniform)
+    auto& wq = s_wq[threadIdx.x >> 5];
+    uint32_t c1 = 0, c2 = 0, c3 = 0, c4 = 0; // entries in the warp's buffers (warp-uniform)
+    constexpr bool defer_elastic = kDeferElastic;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n = A.n;
     double enext = ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x < n ) ? ldStream( A.ekin + ( (uint64_t)blockIdx.x * blockDim.x + threadIdx.x ) ) : 0.0;
     for ( uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride ) {
       const uint64_t i = base + threadIdx.x;
-      int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue
+      int cls = 0;            // 0: done here, 1: SAB table queue, 2: free-gas queue, 3: PowderBragg queue, 4: ElInc queue
       uint32_t entry = 0;
       const double ekin = enext;
       enext = ( i + stride < n ) ? ldStream( A.ekin + i + stride ) : 0.0;     // requested one step ahead
@@ -239,15 +246,24 @@ namespace ncb {
             cls = 2;
           } else if ( c.kind == KIND_POWDERBRAGG ) {
             // PowderBragg::sampleScatterIsotropic, ref: NCPowderBragg.cc:202-216
+            // The elastic leaves are sampled by k_sample_elastic over their own queues (r2): in place, every warp
+            // walked the PowderBragg path, the ElInc path and the queue pushes one after the other for a third of
+            // its lanes (ncu: 19.9 of 32 lanes active).  A neutron below the Bragg threshold needs no sampling.
             const PowderBraggT& T = M.pb[c.idx];
             if ( !( ekin < T.threshold || !isFinite(ekin) ) ) {
-              const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
-              mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
+              if ( defer_elastic ) cls = 3;
+              else {
+                const int iv = aux[ich] >= 0 ? aux[ich] : pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
+                mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
+              }
             }
             nd = rng.ndraws;
           } else if ( c.kind == KIND_ELINC ) {
-            mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
-            nd = rng.ndraws;
+            if ( defer_elastic ) cls = 4;
+            else {
+              mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
+              nd = rng.ndraws;
+            }
           }
           entry = (uint32_t)i | ( (uint32_t)ich << kQueueIdxBits );
         }
@@ -267,9 +283,58 @@ namespace ncb {
       c1 += __popc( m1 ); c2 += __popc( m2 );
       if ( c1 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[0], c1, Q.q_sab, Q.counts + 0 ); c1 = 0; }
       if ( c2 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[1], c2, Q.q_fg, Q.counts + 1 ); c2 = 0; }
+      if constexpr ( kDeferElastic ) {
+        const uint32_t m3 = __ballot_sync( 0xffffffffu, cls == 3 );
+        const uint32_t m4 = __ballot_sync( 0xffffffffu, cls == 4 );
+        if ( cls == 3 ) wq.e[2][ c3 + __popc( m3 & lt ) ] = entry;
+        if ( cls == 4 ) wq.e[3][ c4 + __popc( m4 & lt ) ] = entry;
+        c3 += __popc( m3 ); c4 += __popc( m4 );
+        if ( c3 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[2], c3, Q.q_pb, Q.counts_el + 0 ); c3 = 0; }
+        if ( c4 > (uint32_t)( kWarpBuf - 32 ) ) { warpBufFlush( wq.e[3], c4, Q.q_el, Q.counts_el + 1 ); c4 = 0; }
+      }
     }
     if ( c1 ) warpBufFlush( wq.e[0], c1, Q.q_sab, Q.counts + 0 );
     if ( c2 ) warpBufFlush( wq.e[1], c2, Q.q_fg, Q.counts + 1 );
+    if constexpr ( kDeferElastic ) {
+      if ( c3 ) warpBufFlush( wq.e[2], c3, Q.q_pb, Q.counts_el + 0 );
+      if ( c4 ) warpBufFlush( wq.e[3], c4, Q.q_el, Q.counts_el + 1 );
+    }
+  }
+
+  // Elastic leaves over their queues: blockIdx.y = 0 PowderBragg (genScatterMu: one draw, search in the cumulative
+  // structure-factor table staged in shared memory), 1 = ElIncScatter.  One entry per thread, all lanes on one path.
+  __global__ void __launch_bounds__(256)
+  k_sample_elastic( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                    const __grid_constant__ SampleArgs A, const __grid_constant__ QueueArgs Q )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    const bool is_pb = blockIdx.y == 0;
+    const uint32_t nq = Q.counts_el[is_pb ? 0 : 1];
+    if ( blockIdx.x * blockDim.x >= nq ) return;       // (before any staging: surplus CTAs leave at once)
+    HotTabs H;
+    if ( is_pb ) stageHotTabs( M, sp, smem, &mbar, H );
+    const uint32_t* q = is_pb ? Q.q_pb : Q.q_el;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
+      const uint32_t entry = q[j];
+      const uint32_t i = entry & kQueueIdxMask;
+      const Comp& c = M.comp[ entry >> kQueueIdxBits ];
+      const double ekin = A.ekin[i];
+      Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
+      rng.seek( M.ncomp > 1 ? 1u : 0u );
+      double mu;
+      if ( is_pb ) {
+        const PowderBraggT& T = M.pb[c.idx];
+        const int iv = pbLastValidPlane( T, H.pb_e2d[c.idx], H.pb_lut[c.idx], ekin );
+        mu = pbSampleMu( H.pb_e2d[c.idx], H.pb_fdm[c.idx], iv, ekin, rng );
+      } else {
+        mu = elincSampleMu( M.elinc[c.idx], ekin, rng );
+      }
+      A.ekin_out[i] = ekin;
+      A.mu_out[i] = mu;
+      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
+    }
   }
 
   // S(alpha,beta) table path, attempt-level scheduling ("lane refill").  The reference's

@@ -444,7 +444,9 @@ namespace {
     std::lock_guard<std::mutex> g( m );
     for ( int d : done ) if ( d == device ) return;
     setSmemAttr( k_xs_iso );
-    setSmemAttr( k_sample_classify );
+    setSmemAttr( k_sample_classify<true> );
+    setSmemAttr( k_sample_classify<false> );
+    setSmemAttr( k_sample_elastic );
     setSmemAttr( k_xs_aniso );
     setSmemAttr( k_sample_aniso );
     setSmemAttr( k_xs_aniso_pre );
@@ -572,7 +574,7 @@ namespace {
       if ( c.cap < n ) {
         if ( c.q ) { CUDA_OK( cudaDeviceSynchronize() ); CUDA_OK( cudaFree( c.q ) ); c.q = nullptr; }
         c.cap = n + n/8 + 1024;
-        CUDA_OK( cudaMalloc( &c.q, 6*c.cap*sizeof(uint32_t) ) );
+        CUDA_OK( cudaMalloc( &c.q, 8*c.cap*sizeof(uint32_t) ) );     // (q_sab, q_fg, q_emax x2, -, fg partition, q_pb, q_el)
       }
       return c;
     }
@@ -930,9 +932,26 @@ namespace {
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
       CUDA_OK( cudaMemsetAsync( qc.counts, 0, ( 8 + 2*kSortBins )*sizeof(uint32_t), st ) );
+      // Elastic leaves: sampled in place by the classify kernel, or -- for materials whose incoherent-elastic leaf
+      // has several elements (its sampler then re-evaluates the per-element contributions: the in-place code costs
+      // every warp that path) -- over their own queues by k_sample_elastic.  Measured per 1e7 neutrons (classify +
+      // elastic kernel against classify with in-place sampling): polyethylene 0.47 + 0.17 against 0.86 ms, YAG
+      // 0.87 + 0.14 against 1.01 ms, Al (one element, 171 planes) 0.39 + 0.10 against 0.47 ms: the scattered
+      // re-read / write-back of the queue kernel costs what the converged lanes save unless the paths are heavy.
+      bool multi_elinc = false;
+      for ( int ic = 0; ic < dm.mat.ncomp; ++ic )
+        if ( dm.mat.comp[ic].kind == KIND_ELINC && dm.mat.elinc[dm.mat.comp[ic].idx].n >= 2 ) multi_elinc = true;
+      const bool defer_elastic = multi_elinc && m >= ( (uint64_t)1 << 18 );
+      if ( defer_elastic ) { Q.q_pb = qc.q + 6*qc.cap; Q.q_el = qc.q + 7*qc.cap; Q.counts_el = qc.counts + 8 + 64; }
       { TimedLaunch tl( "k_sample_classify", st );
-        k_sample_classify<<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
+        if ( defer_elastic ) k_sample_classify<true><<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q );
+        else k_sample_classify<false><<< gridFor( m, 256, dm.device, ctas ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q ); }
       ++g_launches;
+      if ( defer_elastic ) {
+        TimedLaunch tl( "k_sample_elastic", st );
+        k_sample_elastic<<< dim3( gridFor( m, 256, dm.device, ctas ), 2 ), 256, dm.sp.total, st >>>( dm.mat, dm.sp, A, Q );
+        ++g_launches;
+      }
       launchSabQueue( s, dm, qc, A, Q, m, st, true );
       partitionFgQueue( dm, qc, Q, A.ekin, m, st );
       launchFgSampling( s, dm, qc, A, Q, m, st, true );
