@@ -78,6 +78,12 @@ namespace ncb {
     double dom_lo, dom_hi;
     int* err_flags;
     const uint32_t* n_dev = nullptr;
+    // sampling calls: the scan also makes the choice a scattering on this leaf would make among its rotation ranges
+    // (pickRandIdxByWeight with the neutron's uniform number `pick_draw` of its stream) and stores the chosen range,
+    // so that the sampling pass does not have to build the list a second time (k_lc_sample_threads); null = off
+    LcRoi* pick_roi = nullptr;
+    uint64_t seed = 0, first_index = 0; uint32_t sid = 0, pick_draw = 0;
+    const uint64_t* ids = nullptr;
   };
 
   __global__ void __launch_bounds__(32*kLcWarps)
@@ -104,51 +110,54 @@ namespace ncb {
           if ( nroi ) sum = commul[nroi-1];
         }
       }
+      if ( A.pick_roi ) {
+        LcRoi chosen; chosen.rotmin = chosen.rotmax = 0.0; chosen.ips = -1; chosen.sign = 1;
+        if ( nroi > 0 && sum ) {
+          int idx = 0;
+          if ( nroi > 1 ) {
+            Rng rng; rng.init( A.seed, A.ids ? A.ids[i] : A.first_index + i, A.sid );
+            rng.seek( A.pick_draw );
+            idx = pickIdxByWeight( rng.generate(), commul, nroi );
+          }
+          chosen = rois[idx];
+        }
+        if ( lane == 0 ) A.pick_roi[i] = chosen;
+      }
       if ( lane == 0 ) { A.lc_sum[i] = sum; A.lc_n[i] = nroi; }
     }
     if ( err && A.err_flags )
       atomicOr( A.err_flags, err );
   }
 
-  // one queued neutron per warp
-  __global__ void __launch_bounds__(32*kLcWarps)
-  k_lc_sample( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X )
+  // One queued neutron per THREAD, for sampling calls whose scan recorded the chosen rotation range: the scattering
+  // itself (overlay sampling of the crystallite rotation, GaussMos::genScat, rotation to the lab frame) is
+  // thread-level work; building the list of ranges a second time -- what k_lc_sample below does, one warp per
+  // neutron -- cost as much as the cross-section scan.
+  __global__ void __launch_bounds__(128)
+  k_lc_sample_threads( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X,
+                       const LcRoi* __restrict__ pick_roi )
   {
-    extern __shared__ __align__(128) unsigned char smem[];
     const ScBraggT& S = M.sc;
     const LcBraggT& L = M.lc;
-    const uint32_t cap = lcRoiCap( L.nplanes );
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    LcRoi* rois = reinterpret_cast<LcRoi*>( smem ) + (size_t)w*cap;
-    double* commul = reinterpret_cast<double*>( smem + (size_t)kLcWarps*cap*sizeof(LcRoi) ) + (size_t)w*cap;
     const uint32_t nq = *X.q_sc_count;
-    const uint32_t nwarps = gridDim.x * kLcWarps;
-    int err = 0;
-    for ( uint32_t j = blockIdx.x * kLcWarps + w; j < nq; j += nwarps ) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for ( uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += stride ) {
       const uint32_t i = X.q_sc[j] & kQueueIdxMask;
       const double ekin = A.ekin[i];
       const Vec3 u = vunit( Vec3{ X.D.ux[i], X.D.uy[i], X.D.uz[i] } );
       Vec3 o = u;
+      const LcRoi roi = pick_roi[i];
       Rng rng; rng.init( A.seed, A.streamIndex( i ), A.sid );
-      rng.seek( M.ncomp > 1 ? 1u : 0u );
+      // (the pick among the ranges consumed one number when there was more than one range)
+      rng.seek( ( M.ncomp > 1 ? 1u : 0u ) + ( roi.ips >= 0 && X.sc_n[i] > 1 ? 1u : 0u ) );
       LcNeutron N;
-      if ( lcNeutronPars( L, ekin, u, N ) ) {
-        const int nroi = lcBuildWarp( S, L, N, rois, commul, err );
-        if ( nroi > 0 && commul[nroi-1] ) {
-          // pickRandIdxByWeight over m_roixs_commul (NCLCUtils.cc:546), every lane with the same stream
-          const int idx = ( nroi == 1 ? 0 : pickIdxByWeight( rng.generate(), commul, nroi ) );
-          const LcRoi roi = rois[idx];
-          lcGenScatterRoi( S, L, N, roi, u, rng, o );
-        }
-      }
-      if ( lane == 0 ) {
-        A.ekin_out[i] = ekin;
-        X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
-        if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
-      }
+      if ( roi.ips >= 0 && lcNeutronPars( L, ekin, u, N ) )
+        lcGenScatterRoi( S, L, N, roi, u, rng, o );
+      A.ekin_out[i] = ekin;
+      X.D.ox[i] = o.x; X.D.oy[i] = o.y; X.D.oz[i] = o.z;
+      if ( A.ndraws ) A.ndraws[i] = rng.ndraws;
     }
-    if ( err )
-      atomicOr( A.err_flags, err );
   }
+
 
 }

@@ -460,7 +460,6 @@ namespace {
     setSmemAttr( k_mmc_tail<1> );
     setSmemAttr( k_mmc_tail<2> );
     setSmemAttr( k_lc_scan );
-    setSmemAttr( k_lc_sample );
     setSmemAttr( k_tally_hist );
     done.push_back( device );
   }
@@ -1047,7 +1046,8 @@ namespace {
 
   // LCBragg scan (one warp per neutron) -> sc_xs (sum over the ROIs) / sc_n (number of ROIs)
   void launchLcScan( Scatter* s, const DeviceMaterial& dm, Scatter::QueueCtx& qc, const double* d_ekin, const double* ux,
-                     const double* uy, const double* uz, uint64_t n, cudaStream_t st, const uint32_t* n_dev = nullptr )
+                     const double* uy, const double* uz, uint64_t n, cudaStream_t st, const uint32_t* n_dev = nullptr,
+                     const SampleArgs* pick = nullptr )
   {
     const int ilc = lcCompIndex( dm.mat );
     s->ensureErrWord();
@@ -1055,6 +1055,14 @@ namespace {
     LA.ekin = d_ekin; LA.ux = ux; LA.uy = uy; LA.uz = uz; LA.n = n; LA.lc_sum = qc.sc_xs; LA.lc_n = qc.sc_n;
     LA.dom_lo = dm.mat.comp[ilc].dom_lo; LA.dom_hi = dm.mat.comp[ilc].dom_hi;
     LA.err_flags = s->d_err; LA.n_dev = n_dev;
+    if ( pick ) {
+      // (a material has either a single-crystal or a layered-crystal leaf: the candidate buffer of the former, 64
+      //  bytes per neutron, holds the chosen ranges of the latter)
+      static_assert( sizeof(LcRoi) <= kScFindCap*sizeof(uint16_t), "chosen rotation ranges must fit the candidate buffer" );
+      LA.pick_roi = reinterpret_cast<LcRoi*>( qc.sc_cand );
+      LA.seed = pick->seed; LA.first_index = pick->first_index; LA.sid = pick->sid; LA.ids = pick->ids;
+      LA.pick_draw = dm.mat.ncomp > 1 ? 1u : 0u;
+    }
     qc.sc_lists_valid = false;
     const unsigned nsm = (unsigned)numSMs( dm.device );
     const uint64_t need = ( n + kLcWarps - 1 ) / kLcWarps;
@@ -1131,7 +1139,7 @@ namespace {
       if ( has_sc )
         launchScScan( dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
       if ( has_lc )
-        launchLcScan( s, dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override );
+        launchLcScan( s, dm, qc, A.ekin, D.ux, D.uy, D.uz, m, st, s->n_dev_override, &A );
       QueueArgs Q;
       Q.q_sab = qc.q; Q.q_fg = qc.q + qc.cap; Q.q_emax = qc.q + 2*qc.cap; Q.counts = qc.counts;
       AnisoArgs X;
@@ -1175,9 +1183,8 @@ namespace {
         }
       }
       if ( has_lc ) {
-        const unsigned gs = (unsigned)std::min<uint64_t>( ( m + kLcWarps - 1 )/kLcWarps, (uint64_t)nsm*16 );
         { TimedLaunch tl( "k_lc_sample", st );
-          k_lc_sample<<< gs, 32*kLcWarps, lcSmemBytes( dm.mat.lc.nplanes ), st >>>( dm.mat, A, X ); }
+          k_lc_sample_threads<<< gridFor( m, 128, dm.device, 8 ), 128, 0, st >>>( dm.mat, A, X, reinterpret_cast<const LcRoi*>( qc.sc_cand ) ); }
         ++g_launches;
       }
       CUDA_OK( cudaGetLastError() );
