@@ -8,10 +8,11 @@
 //      before anti-normal) into the warp's shared-memory list with shuffle prefix sums;
 //   2. lanes stride that list and integrate their ROIs in parallel;
 //   3. the running sum (m_roixs_commul) is formed in list order.
-//   k_lc_scan    per neutron: sum over the ROIs + their number (what crossSection and the component pick need)
-//   k_lc_sample  per neutron whose chosen component is LCBragg: the list again, pickRandIdxByWeight over the
-//                cumulative values, then the scattering in the chosen ROI (overlay rejection sampling of phi,
-//                GaussMos::genScat, rotation to the lab frame)
+//   k_lc_scan            per neutron: sum over the ROIs + their number (what crossSection and the component pick need);
+//                        in a sampling call also the ROI that pickRandIdxByWeight over the cumulative values would
+//                        choose with the neutron's own uniform number
+//   k_lc_sample_threads  per neutron whose chosen component is LCBragg (one per thread): the scattering in the
+//                        recorded ROI (overlay rejection sampling of phi, GaussMos::genScat, rotation to the lab frame)
 #pragma once
 #include "ncb_kernels_sc.cuh"
 
@@ -131,8 +132,8 @@ namespace ncb {
 
   // One queued neutron per THREAD, for sampling calls whose scan recorded the chosen rotation range: the scattering
   // itself (overlay sampling of the crystallite rotation, GaussMos::genScat, rotation to the lab frame) is
-  // thread-level work; building the list of ranges a second time -- what k_lc_sample below does, one warp per
-  // neutron -- cost as much as the cross-section scan.
+  // thread-level work; building the list of ranges a second time, one warp per neutron (r2 first version), cost half
+  // as much again as the cross-section scan.
   __global__ void __launch_bounds__(128)
   k_lc_sample_threads( const __grid_constant__ Material M, const __grid_constant__ SampleArgs A, const __grid_constant__ AnisoArgs X,
                        const LcRoi* __restrict__ pick_roi )
