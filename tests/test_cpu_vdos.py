@@ -78,3 +78,37 @@ def test_twiddle_table_by_doubling_equals_reference_recipe():
     L = HostSim.lib()
     for log2size in (1, 2, 5, 12, 16, 18):
         assert L.hostsim_vdos_twiddle_check(log2size) == 0
+
+
+@pytest.mark.skipif(not have_refdrv(), reason="compiled reference (oracle/_ref) not present")
+def test_corrupt_vdos_leaf_is_refused_not_read_out_of_bounds():
+    """The array count and the parameters inside a VDOS leaf come from the (untrusted) buffer: a truncated or
+    inconsistent leaf must raise, never read past the payload (same rule as for the other leaf kinds, ncb_loader.h)."""
+    import struct
+    blob = bytearray(RefDrv("Be_sg194.ncmat;vdoslux=0").compile(flags=1))
+    ncomp = struct.unpack_from("<I", blob, 12)[0]
+    hdr_fixed = struct.calcsize("<QIIIIQdddddd176s")
+    comp_sz = struct.calcsize("<IIdddQQ")
+    leaf = None
+    for i in range(ncomp):
+        kind, _r, _s, _lo, _hi, off, nbytes = struct.unpack_from("<IIdddQQ", blob, hdr_fixed + i * comp_sz)
+        if kind == 8:
+            leaf = (i, off, nbytes)
+    assert leaf is not None
+    i, off, nbytes = leaf
+    o_vdoslux = off + 14 * 8          # 14 doubles, then vdoslux, negrid, ndensity, reserved
+    HostSim(bytes(blob))              # the intact material loads
+
+    def broken(mutate):
+        b = bytearray(blob)
+        mutate(b)
+        with pytest.raises(RuntimeError):
+            HostSim(bytes(b))
+
+    broken(lambda b: struct.pack_into("<Q", b, o_vdoslux + 16, 10**9))                   # ndensity beyond the payload
+    broken(lambda b: struct.pack_into("<Q", b, o_vdoslux + 16, 1))                       # too few density points
+    broken(lambda b: struct.pack_into("<Q", b, o_vdoslux, 9))                            # vdoslux out of range
+    broken(lambda b: struct.pack_into("<Q", b, o_vdoslux + 8, 3))                        # energy grid too short
+    broken(lambda b: struct.pack_into("<Q", b, hdr_fixed + i * comp_sz + 40, 64))        # payload shorter than its header
+    broken(lambda b: struct.pack_into("<d", b, off + 9 * 8, 1e-9))                       # emin below 1e-5 eV
+    broken(lambda b: struct.pack_into("<d", b, off + 8, -5.0))                           # negative temperature
