@@ -3,6 +3,7 @@ density of states of every NCMAT file the compiled reference embeds is expanded 
 
    python tests/vdos_sweep.py device [vdoslux]     the product (libncrystal_b200.so, CUDA)
    python tests/vdos_sweep.py host   [vdoslux]     the TEST-ONLY host build of the same code (no GPU needed)
+   (optional third argument n: every n-th file of the library only)
 
 and by the live reference; the tables must be bit-identical.  One JSON line per curve, a summary line at the end."""
 import ctypes as C
@@ -20,6 +21,7 @@ from _libs import RefDrv, _d  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "host"
 lux = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+every = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # take every n-th file only
 if which == "device":
     from ncrystal_b200 import _lib
     api = _vdos.RawVdosAPI(_lib.lib())
@@ -35,7 +37,7 @@ L = RefDrv.lib()
 L.refdrv_vdos_data.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
 ncurves = nbad = nfail = 0
 t_dev = t_ref = 0.0
-for name in names:
+for name in names[::every]:
     for k in range(16):
         meta, dens = np.zeros(5), np.zeros(200000)
         m = L.refdrv_vdos_data(name.encode(), k, _d(meta), _d(dens), dens.size)
