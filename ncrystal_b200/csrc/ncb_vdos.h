@@ -34,6 +34,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -451,14 +452,30 @@ namespace ncb { namespace vdos {
     template <class Fn> void integrateBins( Fn f, StableSum& sum ) const
     {
       const unsigned nbins = (unsigned)m_density.size() - 1;
-      for ( unsigned ibin = 0; ibin < nbins; ++ibin ) {
+      auto binIntegral = [this,&f,nbins]( unsigned ibin ) {
         const double d0 = m_density[ibin], d1 = m_density[ibin+1];
         const double e0 = m_emin + m_binwidth*ibin;
         const double e1 = ( ibin + 1 == nbins ? m_emax : m_emin + m_binwidth*( ibin + 1 ) );
         const double A = ( d1 - d0 )*m_invbinwidth, B = d0 - e0*A;
         auto g = [&f,A,B]( double e ) { return f( e )*( A*e + B ); };
-        sum.add( romberg17( g, e0, e1 ) );
+        return romberg17( g, e0, e1 );
+      };
+      const unsigned nthreads = nbins >= 2000 ? std::min<unsigned>( 8, std::max<unsigned>( 1, std::thread::hardware_concurrency() ) ) : 1;
+      if ( nthreads <= 1 ) {
+        for ( unsigned ibin = 0; ibin < nbins; ++ibin ) sum.add( binIntegral( ibin ) );
+        return;
       }
+      // finely binned curve: the bin integrals are independent (host threads); they are ADDED in bin order
+      VectD contrib( nbins );
+      std::vector<std::thread> pool;
+      const unsigned per = ( nbins + nthreads - 1 )/nthreads;
+      for ( unsigned t = 0; t < nthreads; ++t ) {
+        const unsigned b0 = t*per, b1 = std::min( nbins, b0 + per );
+        if ( b0 >= b1 ) break;
+        pool.emplace_back( [&contrib,&binIntegral,b0,b1]() { for ( unsigned ibin = b0; ibin < b1; ++ibin ) contrib[ibin] = binIntegral( ibin ); } );
+      }
+      for ( auto& th : pool ) th.join();
+      for ( unsigned ibin = 0; ibin < nbins; ++ibin ) sum.add( contrib[ibin] );
     }
   };
 
@@ -852,14 +869,29 @@ namespace ncb { namespace vdos {
     P.expbeta.resize( P.beta_nonpos.size() );
     for ( size_t i = 0; i < P.beta_nonpos.size(); ++i ) P.expbeta[i] = std::exp( P.beta_nonpos[i] );
     for ( unsigned n = 1; n <= norders; ++n ) {
-      double* af = &P.alpha_factor[(size_t)( n-1 )*na];
       P.scale[n-1] = scaleFct ? scaleFct( n ) : 1.0;
       if ( !( P.scale[n-1] >= 0.0 ) ) throw Error( "BadInput", "order weight function must return non-negative values" );
+    }
+    // one row of the table: orders below 16 by the recursion (sequential), the others independently of each other
+    auto positiveRun = [&P,na]( unsigned n ) {
+      const double* af = &P.alpha_factor[(size_t)( n-1 )*na];
+      size_t first = 0;
+      while ( first != na && !( af[first] > 0.0 ) ) ++first;
+      size_t end = first;
+      while ( end != na && af[end] > 0.0 ) ++end;
+      P.a_first[n-1] = (int)first; P.a_end[n-1] = (int)end;
+    };
+    for ( unsigned n = 1; n <= norders && n < stirling_threshold; ++n ) {
+      double* af = &P.alpha_factor[(size_t)( n-1 )*na];
       const double invn = 1.0/n;
-      if ( n < stirling_threshold ) {
-        for ( size_t i = 0; i < na; ++i ) fxn[i] *= x[i]*invn;
-        for ( size_t i = 0; i < na; ++i ) af[i] = fxn[i]*expmhalfx[i]*kT;
-      } else {
+      for ( size_t i = 0; i < na; ++i ) fxn[i] *= x[i]*invn;
+      for ( size_t i = 0; i < na; ++i ) af[i] = fxn[i]*expmhalfx[i]*kT;
+      positiveRun( n );
+    }
+    auto stirlingRows = [&]( unsigned n0, unsigned n1 ) {
+      for ( unsigned n = n0; n <= n1; ++n ) {
+        double* af = &P.alpha_factor[(size_t)( n-1 )*na];
+        const double invn = 1.0/n;
         const double gn = stirlingSeries9( invn );
         const double fact = kT*kInvSqrt2Pi/( std::sqrt( n )*gn );
         if ( !fact ) { P.skip[n-1] = 1; continue; }
@@ -868,12 +900,26 @@ namespace ncb { namespace vdos {
           const double exparg = n*( logx[i] - logn + 1.0 ) - x[i];
           af[i] = fact*std::exp( exparg );
         }
+        positiveRun( n );
       }
-      size_t first = 0;
-      while ( first != na && !( af[first] > 0.0 ) ) ++first;
-      size_t end = first;
-      while ( end != na && af[end] > 0.0 ) ++end;
-      P.a_first[n-1] = (int)first; P.a_end[n-1] = (int)end;
+    };
+    if ( norders >= stirling_threshold ) {
+      // (a vdoslux-5 expansion has ~1e3 orders x 1600 alpha points: the exponentials are spread over host threads;
+      //  every row is computed by one thread, so the values do not depend on the split)
+      const size_t work = (size_t)( norders - stirling_threshold + 1 )*na;
+      unsigned nthreads = work > 200000 ? std::min<unsigned>( 8, std::max<unsigned>( 1, std::thread::hardware_concurrency() ) ) : 1;
+      if ( nthreads <= 1 ) {
+        stirlingRows( stirling_threshold, norders );
+      } else {
+        std::vector<std::thread> pool;
+        const unsigned total = norders - stirling_threshold + 1, per = ( total + nthreads - 1 )/nthreads;
+        for ( unsigned t = 0; t < nthreads; ++t ) {
+          const unsigned n0 = stirling_threshold + t*per, n1 = std::min<unsigned>( norders, n0 + per - 1 );
+          if ( n0 > norders ) break;
+          pool.emplace_back( stirlingRows, n0, n1 );
+        }
+        for ( auto& th : pool ) th.join();
+      }
     }
     // fixed groups of >= 16 orders (independent of any thread count), summed group by group
     const unsigned njobs = ( norders <= 16 ? 1 : norders/16 );
