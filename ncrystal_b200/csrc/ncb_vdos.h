@@ -163,12 +163,13 @@ namespace ncb { namespace vdos {
     VectD lny( n );
     for ( size_t i = 0; i < n; ++i ) lny[i] = std::log( std::max<double>( 1e-20, y[i]*inv_ymax ) );
     std::vector<uint32_t> prev( n ), next( n );
-    std::vector<uint64_t> cur( n, ~(uint64_t)0 );      // sequence number of a point's live heap entry
     for ( size_t i = 0; i < n; ++i ) { prev[i] = (uint32_t)( i - 1 ); next[i] = (uint32_t)( i + 1 ); }
-    struct Entry { double score; uint64_t seq; uint32_t idx; };
-    auto later = []( const Entry& a, const Entry& b ) { return a.score > b.score || ( a.score == b.score && a.seq > b.seq ); };
-    std::vector<Entry> heap;
-    heap.reserve( 3*n );
+    // indexed binary min-heap over the interior points, ordered by ( score, sequence number of the scoring ): a
+    // point whose neighbour was removed is re-scored IN PLACE (sift up or down), so the heap never holds stale entries
+    std::vector<double> sc( n, 0.0 );
+    std::vector<uint64_t> sq( n, 0 );
+    std::vector<uint32_t> heap, pos( n, 0 );
+    heap.reserve( n );
     uint64_t seq = 0;
     auto score = [&]( uint32_t i ) {
       const uint32_t i0 = prev[i], i2 = next[i];
@@ -176,25 +177,53 @@ namespace ncb { namespace vdos {
       const double larea = std::fabs( x[i0]*( lny[i] - lny[i2] ) + x[i]*( lny[i2] - lny[i0] ) + x[i2]*( lny[i0] - lny[i] ) );
       return area*larea*larea;
     };
-    auto enter = [&]( uint32_t i ) {
-      if ( i == 0 || i == n - 1 ) return;               // end points are never candidates
-      cur[i] = seq;
-      heap.push_back( Entry{ score( i ), seq++, i } );
-      std::push_heap( heap.begin(), heap.end(), later );
+    auto before = [&]( uint32_t a, uint32_t b ) { return sc[a] < sc[b] || ( sc[a] == sc[b] && sq[a] < sq[b] ); };
+    auto siftUp = [&]( size_t k ) {
+      const uint32_t v = heap[k];
+      while ( k > 0 ) {
+        const size_t parent = ( k - 1 )/2;
+        if ( !before( v, heap[parent] ) ) break;
+        heap[k] = heap[parent]; pos[heap[k]] = (uint32_t)k;
+        k = parent;
+      }
+      heap[k] = v; pos[v] = (uint32_t)k;
     };
-    for ( uint32_t i = 1; i + 1 < n; ++i ) enter( i );
+    auto siftDown = [&]( size_t k ) {
+      const uint32_t v = heap[k];
+      const size_t m = heap.size();
+      while ( true ) {
+        size_t c = 2*k + 1;
+        if ( c >= m ) break;
+        if ( c + 1 < m && before( heap[c+1], heap[c] ) ) ++c;
+        if ( !before( heap[c], v ) ) break;
+        heap[k] = heap[c]; pos[heap[k]] = (uint32_t)k;
+        k = c;
+      }
+      heap[k] = v; pos[v] = (uint32_t)k;
+    };
+    for ( uint32_t i = 1; i + 1 < n; ++i ) {              // (end points are never candidates)
+      sc[i] = score( i ); sq[i] = seq++;
+      heap.push_back( i );
+      siftUp( heap.size() - 1 );
+    }
+    auto rescore = [&]( uint32_t i ) {
+      if ( i == 0 || i == n - 1 ) return;
+      sc[i] = score( i ); sq[i] = seq++;
+      const size_t k = pos[i];
+      siftUp( k );
+      if ( pos[i] == k ) siftDown( k );
+    };
     size_t left = n;
     while ( left > targetN ) {
-      std::pop_heap( heap.begin(), heap.end(), later );
-      const Entry e = heap.back();
+      const uint32_t idx = heap.front();
+      heap.front() = heap.back(); pos[heap.front()] = 0;
       heap.pop_back();
-      if ( cur[e.idx] != e.seq ) continue;              // re-scored or removed since
-      const uint32_t before = prev[e.idx], after = next[e.idx];
-      next[before] = after; prev[after] = before;
-      cur[e.idx] = ~(uint64_t)0;
+      if ( !heap.empty() ) siftDown( 0 );
+      const uint32_t pb = prev[idx], pa = next[idx];
+      next[pb] = pa; prev[pa] = pb;
       --left;
-      enter( before );
-      enter( after );
+      rescore( pb );
+      rescore( pa );
     }
     VectD nx, ny;
     nx.reserve( left ); ny.reserve( left );
