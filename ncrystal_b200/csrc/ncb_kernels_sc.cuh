@@ -276,22 +276,42 @@ namespace ncb {
     const int lane = threadIdx.x & 31;
     const uint64_t nwarps = (uint64_t)gridDim.x * kScFindWarps;
     const double cta = S.cta;
-    double scratch_ekin = -1.0;     // energy the windows in the scratch were computed for (warp-uniform)
+    double scratch_wl = -1.0;       // wavelength the windows in the scratch were computed for (warp-uniform)
     int nfam_act = 0;
-    for ( uint64_t i = (uint64_t)blockIdx.x * kScFindWarps + ( threadIdx.x >> 5 ); i < A.n; i += nwarps ) {
-      const double ekin_raw = A.ekin[i];
+    // The warp takes its neutrons 32 at a time: the part of a neutron's set-up that depends on its energy alone
+    // (wavelength, d-spacing cut: a division, a square root and another division in double precision) is done by
+    // ONE LANE PER NEUTRON for the whole batch and handed out with shuffles -- with the whole warp repeating it for
+    // each neutron it was a fifth of the kernel's instructions.
+    // Batches are 32 CONSECUTIVE neutrons (coalesced reads of the energies, neighbouring direction reads hit the
+    // same sectors), dealt out to the warps round-robin.
+    for ( uint64_t ib = 32*( (uint64_t)blockIdx.x * kScFindWarps + ( threadIdx.x >> 5 ) ); ib < A.n; ib += 32*nwarps ) {
+      double wl_mine = 0.0, cut_mine = 0.0;      // wl == 0: nothing to search for this neutron
+      int count_mine = 0;                        // lane k: number of candidates of the batch's k-th neutron
+      const uint64_t im = ib + lane;
+      {
+        if ( im < A.n ) {
+          const double ekin_raw = A.ekin[im];
+          if ( domainContains( A.dom_lo, A.dom_hi, ekin_raw ) && !( ekin_raw <= S.threshold_ekin ) ) {
+            const double ekin = scCacheRound( ekin_raw );
+            wl_mine = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+            if ( wl_mine != 0 ) cut_mine = ( 1.0 - 2*kDblEps )/wl_mine;
+          }
+        }
+      }
+    for ( int kb = 0; kb < 32; ++kb ) {
+      const uint64_t i = ib + kb;
+      if ( i >= A.n ) break;
+      const double wl = __shfl_sync( 0xffffffffu, wl_mine, kb );
       int count = 0;
       bool overflow = false;
-      if ( domainContains( A.dom_lo, A.dom_hi, ekin_raw ) && !( ekin_raw <= S.threshold_ekin ) ) {
-        Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
-        vnormalise( d );
-        const double ekin = scCacheRound( ekin_raw );
-        const double wl = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+      {
         if ( wl != 0 ) {
-          // per-family windows: functions of the energy alone, kept in the warp's scratch while consecutive neutrons
+          Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
+          vnormalise( d );
+          // per-family windows: functions of the wavelength alone, kept in the warp's scratch while consecutive neutrons
           // have the same energy (a mono-energetic beam in a transport run: every neutron of the first steps)
-          if ( !( ekin == scratch_ekin ) ) {
-            const double inv2dcutoff = ( 1.0 - 2*kDblEps )/wl;
+          if ( !( wl == scratch_wl ) ) {
+            const double inv2dcutoff = __shfl_sync( 0xffffffffu, cut_mine, kb );
             nfam_act = 0;
             for ( int f0 = 0; f0 < S.nfam; f0 += 32 ) {
               const int f = f0 + lane;
@@ -311,7 +331,7 @@ namespace ncb {
               nfam_act += __popc( m );
               if ( m != 0xffffffffu ) break;
             }
-            scratch_ekin = ekin;
+            scratch_wl = wl;
             __syncwarp();
           }
           const int n_act = nfam_act ? S.fam_first[nfam_act] : 0;
@@ -356,9 +376,8 @@ namespace ncb {
           __syncwarp();
         }
       }
-      if ( count == 0 ) {
-        if ( lane == 0 ) { A.sc_xs[i] = 0.0; A.sc_n[i] = 0; A.wpos[i] = -1; }
-      } else {
+      if ( lane == kb ) count_mine = count;
+      if ( count != 0 ) {
         uint32_t pos = 0;
         if ( lane == 0 ) pos = atomicAdd( A.work_count, 1u );
         pos = __shfl_sync( 0xffffffffu, pos, 0 );
@@ -372,6 +391,9 @@ namespace ncb {
           A.cand[(size_t)pos*kScFindCap + lane] = ws.cand[lane];
       }
       __syncwarp();
+    }
+      // neutrons without candidates: zeroed by the lane that owns them, one coalesced store per array and batch
+      if ( im < A.n && count_mine == 0 ) { A.sc_xs[im] = 0.0; A.sc_n[im] = 0; A.wpos[im] = -1; }
     }
   }
 
