@@ -340,7 +340,9 @@ namespace ncb {
           // 16-byte and one 8-byte shared-memory load, three multiply-adds and two compares per normal; it only has
           // to be a superset of the exact test).  Planes pass it rarely, so the pass votes ONCE on "any lane has a
           // survivor"; only then the reference's test runs in double precision from the fp64 normals and the
-          // candidates are compacted in index order.  (r2: 32 -> ~9 warp instructions per normal tested.)
+          // candidates are compacted in index order.  (r2: 32 -> ~9 warp instructions per normal tested.)  The last
+          // pass may run over slots beyond n_act (families that are not active, whose windows in the scratch are stale,
+          // or padding): the pre-filter does not test for that -- four compares per pass -- the exact test does.
           for ( int base = 0; base < n_act; base += 128 ) {
             bool pre[4];
             int fam[4];
@@ -351,14 +353,14 @@ namespace ncb {
               fam[u] = __float_as_int( r.w );
               const float2 w = ws.lohi[fam[u]];
               const float xf = fabsf( __fmaf_rn( r.x, dxf, __fmaf_rn( r.y, dyf, r.z*dzf ) ) );
-              pre[u] = ( in < n_act ) & ( xf > w.x ) & ( xf < w.y );
+              pre[u] = ( xf > w.x ) & ( xf < w.y );      // (slots beyond n_act in the last pass: sorted out below)
             }
             if ( !__any_sync( 0xffffffffu, pre[0] | pre[1] | pre[2] | pre[3] ) ) continue;
 #pragma unroll
             for ( int u = 0; u < 4; ++u ) {
               const int in = base + 32*u + lane;
               bool c = false;
-              if ( pre[u] ) {
+              if ( pre[u] && in < n_act ) {
                 const int f = fam[u];
                 const double dot = S.normals[3*in]*d.x + S.normals[3*in+1]*d.y + S.normals[3*in+2]*d.z;
                 double sd, ds;
