@@ -474,6 +474,116 @@ namespace ncb {
     }
   }
 
+  // Evaluation of the recorded candidates, ONE CANDIDATE PER LANE.  With eight lanes per neutron (k_sc_eval_groups
+  // above) the raw cross sections -- the bulk of the kernel -- still ran with 2.8 of 32 lanes active (source-level
+  // profile: a neutron has 1-3 candidates, seven of the eight lanes of its group idled).  Here a warp takes 32 work
+  // items at a time: lane j prepares neutron j (direction, wavelength) into the warp's scratch, the candidates of
+  // all 32 neutrons are numbered consecutively (prefix sum of the counts) and evaluated 32 at a time, every lane
+  // its own candidate of whatever neutron; then lane j accumulates neutron j's values in plane order exactly as
+  // scFlush does.  A round holds kScFlatVals candidates; a batch with more (rare) takes several rounds.
+  // dynamic smem: [staged tables (sp.total)] [fam_of: nnormals bytes] [kScWarps x ScFlatScratch]
+  constexpr int kScFlatVals = 256;
+  struct ScFlatScratch {
+    double par[32][4];                 // per work item of the batch: normalised direction, wavelength
+    double vals[2*kScFlatVals];        // raw cross sections (anti-normal, normal) per candidate slot of the round
+    int off[32];                       // first slot of each item of the round
+  };
+  __global__ void __launch_bounds__(32*kScWarps, 2)
+  k_sc_eval_flat( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,
+                  const __grid_constant__ ScFindArgs A, uint32_t fam_of_off, uint32_t scratch_off )
+  {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    HotTabs H;
+    uint8_t* fam_of = smem + fam_of_off;
+    scBlockSetup( M, sp, smem, &mbar, H, fam_of );
+    const ScBraggT& S = *H.sc;
+    const int lane = threadIdx.x & 31;
+    ScFlatScratch& fs = reinterpret_cast<ScFlatScratch*>( smem + scratch_off )[ threadIdx.x >> 5 ];
+    const uint32_t nwork = *A.work_count;
+    const uint32_t stride = gridDim.x * kScWarps * 32;
+    for ( uint32_t w0 = ( blockIdx.x * kScWarps + ( threadIdx.x >> 5 ) )*32; w0 < nwork; w0 += stride ) {
+      const uint32_t w = w0 + lane;
+      uint32_t entry = 0x80000000u;
+      int count = 0;
+      if ( w < nwork ) { entry = A.work[w]; if ( !( entry & 0x80000000u ) ) count = A.ncand[w]; }
+      const uint32_t i = entry & 0x7fffffffu;
+      __syncwarp();     // (the scratch is reused from the previous batch)
+      if ( count ) {
+        Vec3 d = { A.ux[i], A.uy[i], A.uz[i] };
+        vnormalise( d );
+        const double ekin = scCacheRound( A.ekin[i] );
+        fs.par[lane][0] = d.x; fs.par[lane][1] = d.y; fs.par[lane][2] = d.z;
+        fs.par[lane][3] = ekin ? sqrt( kWl2Ekin / ekin ) : kInf;
+      }
+      int incl = count;      // inclusive prefix sum of the counts over the lanes
+      #pragma unroll
+      for ( int dd = 1; dd < 32; dd <<= 1 ) {
+        const int v = __shfl_up_sync( 0xffffffffu, incl, dd );
+        if ( lane >= dd ) incl += v;
+      }
+      int start = 0, base_slots = 0;
+      while ( start < 32 ) {
+        // items [start, end) of the batch: as many as fit the slot table (the prefix sum does not decrease, so the
+        // lanes that fit form one run from `start`; a single item always fits: count <= kScFindCap)
+        const uint32_t fits = __ballot_sync( 0xffffffffu, lane >= start && incl - base_slots <= kScFlatVals );
+        const int end = start + __popc( fits );
+        const int total = __shfl_sync( 0xffffffffu, incl, end - 1 ) - base_slots;
+        const bool mine = lane >= start && lane < end;
+        if ( mine ) fs.off[lane] = incl - count - base_slots;
+        __syncwarp();
+        for ( int c0 = 0; c0 < total; c0 += 32 ) {
+          const int c = c0 + lane;
+          if ( c < total ) {
+            // owner: the last item of the round whose first slot is <= c (items without candidates share the
+            // first slot of their successor and are passed over)
+            int lo = start, hi = end - 1;
+            while ( lo < hi ) {
+              const int mid = ( lo + hi + 1 ) >> 1;
+              if ( fs.off[mid] <= c ) lo = mid; else hi = mid - 1;
+            }
+            const int k = c - fs.off[lo];
+            const int in = A.cand[ (size_t)( w0 + lo )*kScFindCap + k ];
+            const int f = fam_of[in];
+            const double* P = fs.par[lo];
+            InteractionPars ip;
+            ip.set( P[3], S.fam_inv2d[f], S.fam_xsfact[f] );
+            const double nx = S.normals[3*in], ny = S.normals[3*in+1], nz = S.normals[3*in+2];
+            const double dot = nx*P[0] + ny*P[1] + nz*P[2];
+            const double sdotcptsq = ( 1.0 - dot*dot )*ip.cos_perfect_theta_sq;
+            const double ds = dot * ip.sin_perfect_theta;
+            double xm = 0.0, xp = 0.0;
+            const double Am = dmax( 0.0, S.cta - ds );
+            if ( sdotcptsq > Am*Am ) xm = gmRawXS( S, ip, dot );     // anti-normal
+            const double Ap = dmax( 0.0, S.cta + ds );
+            if ( sdotcptsq > Ap*Ap ) xp = gmRawXS( S, ip, -dot );    // normal
+            fs.vals[2*c] = xm; fs.vals[2*c+1] = xp;
+          }
+        }
+        __syncwarp();
+        if ( mine && count ) {
+          // ordered accumulation (scFlush, mode 0)
+          const uint16_t* cand = A.cand + (size_t)w*kScFindCap;
+          const double* v = fs.vals + 2*fs.off[lane];
+          int cur_fam = -1, n = 0;
+          double xsoffset = 0.0, xssum = 0.0, commul_last = 0.0;
+          for ( int k = 0; k < count; ++k ) {
+            const int f = fam_of[ cand[k] ];
+            if ( f != cur_fam ) { cur_fam = f; xsoffset = commul_last; xssum = 0.0; }
+            for ( int sgn = 0; sgn < 2; ++sgn ) {
+              const double xs = v[2*k+sgn];
+              if ( xs ) { commul_last = xsoffset + ( xssum += xs ); ++n; }
+            }
+          }
+          A.sc_xs[i] = commul_last; A.sc_n[i] = n;
+        }
+        base_slots += total;
+        start = end;
+        __syncwarp();
+      }
+    }
+  }
+
   // warp-per-neutron evaluation: all work items (only_overflow = 0), or just the ones k_sc_eval_groups leaves
   __global__ void __launch_bounds__(32*kScWarps, 2)
   k_sc_eval( const __grid_constant__ Material M, const __grid_constant__ StagePlan sp,

@@ -456,6 +456,7 @@ namespace {
     setSmemAttr( k_sc_sample_threads );
     setSmemAttr( k_sc_eval );
     setSmemAttr( k_sc_eval_groups );
+    setSmemAttr( k_sc_eval_flat );
     setSmemAttr( k_sc_find );
     setSmemAttr( k_mmc_tail<1> );
     setSmemAttr( k_mmc_tail<2> );
@@ -1033,10 +1034,18 @@ namespace {
     // evaluation: eight lanes per neutron; the (rare) neutrons with more candidates than the record holds are
     // flagged in the work list (the find kernel counts them) and walked again by the warp-per-neutron kernel
     { TimedLaunch tl( "k_sc_eval", st );
-      const uint32_t gsmem = dm.sc_scratch_off + (uint32_t)( kScWarps*4*sizeof(ScGroupScratch) );
-      const int cg = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( gsmem, 1u ) ) ) );
-      k_sc_eval_groups<<< (unsigned)std::min<uint64_t>( ( need + 3 )/4, (uint64_t)nsm*cg ), 32*kScWarps, gsmem, st >>>(
-        dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off ); }
+      static const bool groups = []{ const char* e = tuneEnv( "NCB200_SC_EVAL_GROUPS" ); return e && std::atoi(e) != 0; }();
+      if ( groups ) {       // (r2 first form: eight lanes per neutron)
+        const uint32_t gsmem = dm.sc_scratch_off + (uint32_t)( kScWarps*4*sizeof(ScGroupScratch) );
+        const int cg = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( gsmem, 1u ) ) ) );
+        k_sc_eval_groups<<< (unsigned)std::min<uint64_t>( ( need + 3 )/4, (uint64_t)nsm*cg ), 32*kScWarps, gsmem, st >>>(
+          dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+      } else {              // one candidate per lane
+        const uint32_t fsmem = dm.sc_scratch_off + (uint32_t)( kScWarps*sizeof(ScFlatScratch) );
+        const int cg = std::min( 2, std::max( 1, (int)( ( 200u*1024u ) / std::max( fsmem, 1u ) ) ) );
+        k_sc_eval_flat<<< (unsigned)std::min<uint64_t>( ( need + 31 )/32, (uint64_t)nsm*cg ), 32*kScWarps, fsmem, st >>>(
+          dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off );
+      } }
     { TimedLaunch tl( "k_sc_eval_overflow", st );
       k_sc_eval<<< (unsigned)std::min<uint64_t>( need, (uint64_t)nsm*ce ), 32*kScWarps, dm.sc_smem, st >>>(
         dm.mat, dm.sp_sc, FA, dm.sc_famof_off, dm.sc_scratch_off, 1 ); }
