@@ -554,9 +554,16 @@ namespace ncb {
             const double ds = dot * ip.sin_perfect_theta;
             double xm = 0.0, xp = 0.0;
             const double Am = dmax( 0.0, S.cta - ds );
-            if ( sdotcptsq > Am*Am ) xm = gmRawXS( S, ip, dot );     // anti-normal
             const double Ap = dmax( 0.0, S.cta + ds );
-            if ( sdotcptsq > Ap*Ap ) xp = gmRawXS( S, ip, -dot );    // normal
+            const bool pm = sdotcptsq > Am*Am;      // anti-normal contributes
+            const bool pp = sdotcptsq > Ap*Ap;      // normal contributes
+            // (usually one of the two: the lanes make their first -- mostly only -- evaluation together, whichever
+            //  side it is for; the value does not depend on which side is evaluated first)
+            if ( pm || pp ) {
+              const double x1 = gmRawXS( S, ip, pm ? dot : -dot );
+              if ( pm ) xm = x1; else xp = x1;
+            }
+            if ( pm && pp ) xp = gmRawXS( S, ip, -dot );
             fs.vals[2*c] = xm; fs.vals[2*c+1] = xp;
           }
         }
