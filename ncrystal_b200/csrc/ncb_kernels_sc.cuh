@@ -9,7 +9,13 @@
 // integrals are evaluated by different lanes in parallel, and the running cumulative sums
 // ("xs_commul") are then formed in the reference's order.
 //
-//   k_sc_scan        per neutron: SCBragg cross section + number of contributing normals
+//   k_sc_scan        per neutron: SCBragg cross section + number of contributing normals (small batches); large
+//                    batches take the two-stage form:
+//   k_sc_find        candidate search, a warp per neutron in batches of 32 consecutive neutrons (single-precision
+//                    pre-filter on packed records, exact test on the survivors) -> work list + candidate lists
+//   k_sc_eval_flat   evaluation of the recorded candidates, one candidate per lane, accumulated per neutron in
+//                    plane order (k_sc_eval_groups: the eight-lanes-per-neutron form it replaced, tuning builds;
+//                    k_sc_eval: warp per neutron, for the rare lists longer than the record)
 //   k_classify_aniso per neutron (one per lane): composition sum with that result, component pick,
 //                    PowderBragg/ElInc sampled in place (+direction), S(a,b)/free-gas -> queues,
 //                    SCBragg-chosen -> queue
